@@ -79,9 +79,16 @@ static inline float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f :
 
 #define EPS40 1e-40f
 #define EPS10 1e-10f
-static inline float L40(float x) { return logf(tmax(x, EPS40)); }   /* pdp_propagate.py:133-134 */
-static inline float L10(float x) { return logf(tmax(x, EPS10)); }   /* pdp_predict.py:149-150   */
-static inline float X30(float x) { return expf(tmin(x, 30.0f)); }   /* pdp_propagate.py:136-137 */
+/* math mode 0: libm logf/expf (default).  mode 1: fp32 results rounded from fp64 log/exp -- the
+ * definition the CUDA library's strict-math TEST build uses, so trajectories can be compared bit for
+ * bit (two correctly rounded implementations agree except ~1e-8 of the time). */
+static int g_math_mode = 0;
+void ora_set_math_mode(int m) { g_math_mode = m; }
+static inline float o_logf(float x) { return g_math_mode ? (float)log((double)x) : logf(x); }
+static inline float o_expf(float x) { return g_math_mode ? (float)exp((double)x) : expf(x); }
+static inline float L40(float x) { return o_logf(tmax(x, EPS40)); }   /* pdp_propagate.py:133-134 */
+static inline float L10(float x) { return o_logf(tmax(x, EPS10)); }   /* pdp_predict.py:149-150   */
+static inline float X30(float x) { return o_expf(tmin(x, 30.0f)); }   /* pdp_propagate.py:136-137 */
 
 static void build_adj(int64_t n_nodes, int64_t E, const int32_t* key, int64_t* ptr, int32_t* adj) {
     memset(ptr, 0, sizeof(int64_t) * (size_t)(n_nodes + 1));

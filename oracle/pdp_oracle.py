@@ -68,6 +68,7 @@ def lib():
         L.ora_local_search.argtypes = [P, I64, F32, ctypes.c_int, P, P, P]
         L.ora_deduplicate.argtypes = [P, ctypes.c_int, P, P, P]
         L.ora_num_threads.restype = ctypes.c_int
+        L.ora_set_math_mode.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -222,6 +223,11 @@ class Oracle(object):
         win = np.empty(self.B // batch_replication, np.int64)
         self._L.ora_deduplicate(self._h, batch_replication, _p(p), _p(out), _p(win))
         return out, win
+
+
+def set_math_mode(correctly_rounded):
+    """True: fp32 log/exp rounded from fp64 (matches the CUDA strict-math test build bit for bit)."""
+    lib().ora_set_math_mode(1 if correctly_rounded else 0)
 
 
 def num_threads():

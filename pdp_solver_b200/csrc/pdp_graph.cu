@@ -1,0 +1,358 @@
+// pdp_graph.cu -- graph ingest: the reference's batch tensors -> CSR (by clause) + CSC (by variable).
+// Replaces SATProblem.setup_problem and the 14 sparse COO incidence matrices it builds
+// (reference pdp/nn/solver.py:28-54,101-178).  Adjacency lists are STABLE (ascending original edge
+// index inside every node) because that is the fp32 accumulation order of torch.mm(sparse, dense).
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+#include "pdp_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pdp_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* pdp_last_error(void) { return g_err; }
+#ifdef PDP_STRICT_MATH
+extern "C" const char* pdp_version(void) { return "pdp_b200 0.1 (sm_100a, strict-math test build)"; }
+#else
+extern "C" const char* pdp_version(void) { return "pdp_b200 0.1 (sm_100a)"; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Carver {
+    uint8_t* base;
+    size_t off;
+    bool dry;
+    template <typename T>
+    T* take(int64_t n) {
+        size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(T);
+        off = (off + 255) & ~(size_t)255;
+        T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+size_t cub_reserve(int64_t E, int64_t V, int64_t F) {
+    size_t n = (size_t)(E > V ? E : V);
+    if ((size_t)F > n) n = (size_t)F;
+    return (size_t)(1 << 20) + n / 2;
+}
+
+void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
+    pdp_graph& g = c->g;
+    pdp_state& s = c->s;
+    g.cl_ptr = k.take<int32_t>(F + 1);
+    g.var_ptr = k.take<int32_t>(V + 1);
+    g.c_orig = k.take<int32_t>(E);
+    g.c_var = k.take<uint32_t>(E);
+    g.c_pos = k.take<int32_t>(E);
+    g.v_cedge = k.take<uint32_t>(E);
+    g.v_cls = k.take<int32_t>(E);
+    g.v_orig = k.take<int32_t>(E);
+    g.bvm = k.take<int32_t>(V);
+    g.bfm = k.take<int32_t>(F);
+    for (int i = 0; i < 2; ++i) {
+        s.eta[i] = k.take<float>(E);
+        s.qu[i] = k.take<float>(E);
+        s.qs[i] = k.take<float>(E);
+        s.qd[i] = k.take<float>(E);
+    }
+    s.ext = k.take<float>(E);
+    s.av = k.take<uint8_t>(V);
+    s.af = k.take<uint8_t>(F);
+    s.sol = k.take<float>(V);
+    s.is_sat = k.take<float>(B);
+    s.active = k.take<uint8_t>(B);
+    s.counters = k.take<int32_t>(B);
+    s.freeze_iter = k.take<int32_t>(B);
+    s.flags = k.take<uint32_t>(B);
+    s.masked = k.take<uint8_t>(B);
+    s.dirty = k.take<uint8_t>(B);
+    s.conv = k.take<uint8_t>(B);
+    s.nanflag = k.take<uint8_t>(B);
+    s.st_max = k.take<uint32_t>(2 * B);
+    s.st_min = k.take<uint32_t>(2 * B);
+    s.st_nan = k.take<uint32_t>(B);
+    s.nav = k.take<int32_t>(B);
+    s.c_max = k.take<uint32_t>(B);
+    s.c_min = k.take<uint32_t>(B);
+    s.c_nan = k.take<uint32_t>(B);
+    s.arg_idx = k.take<int32_t>(B);
+    s.n_unsat = k.take<int32_t>(B);
+    s.conflicts = k.take<int32_t>(B);
+    s.score = k.take<float>(V);
+    s.up_cnt = k.take<int32_t>(V);
+    s.up_ev = k.take<int32_t>(V);
+    s.pure = k.take<uint8_t>(V);
+    s.single = k.take<uint8_t>(F);
+    s.ctrl = k.take<int32_t>(CTRL_SIZE);
+    s.asg = k.take<int8_t>(V);
+    s.ws_true = k.take<int32_t>(F);
+    s.ws_deg = k.take<int32_t>(F);
+    s.ws_best = k.take<uint32_t>(2 * B);
+    s.ws_key = k.take<unsigned long long>(2 * B);
+    s.energy = k.take<int32_t>(B);
+    s.scan_tmp = k.take<int32_t>(V + 1);
+    c->cub_tmp_bytes = cub_reserve(E, V, F);
+    c->cub_tmp = k.take<uint8_t>((int64_t)c->cub_tmp_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_check_and_count(const int32_t* __restrict__ evar, const int32_t* __restrict__ ecls, int64_t E,
+                                  int64_t V, int64_t F, int32_t* cl_cnt, int32_t* var_cnt, int32_t* flags) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int32_t v = evar[e], a = ecls[e];
+        if (v < 0 || v >= V || a < 0 || a >= F) { atomicOr(&flags[1], 1); continue; }
+        if (e > 0 && ecls[e - 1] > a) atomicOr(&flags[0], 1);   // not clause-major
+        atomicAdd(&cl_cnt[a + 1], 1);
+        atomicAdd(&var_cnt[v + 1], 1);
+    }
+}
+
+__global__ void k_check_maps(const int32_t* __restrict__ bvm, const int32_t* __restrict__ bfm, int64_t V, int64_t F,
+                             int64_t B, int32_t* flags) {
+    int64_t n = V > F ? V : F;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < V && (bvm[i] < 0 || bvm[i] >= B)) atomicOr(&flags[1], 2);
+        if (i < F && (bfm[i] < 0 || bfm[i] >= B)) atomicOr(&flags[1], 2);
+    }
+}
+
+__global__ void k_iota(int32_t* out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)i;
+}
+
+// inv[c_orig[c]] = c
+__global__ void k_invert(const int32_t* __restrict__ perm, int32_t* inv, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        inv[perm[i]] = (int32_t)i;
+}
+
+__global__ void k_fill_clause_major(const int32_t* __restrict__ evar, const float* __restrict__ sign,
+                                    const int32_t* __restrict__ c_orig, uint32_t* c_var, int64_t E) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < E; c += (int64_t)gridDim.x * blockDim.x) {
+        int32_t e = c_orig[c];
+        c_var[c] = (uint32_t)evar[e] | ((sign[e] < 0.f) ? PDP_SIGN_BIT : 0u);
+    }
+}
+
+// v_orig[p] is the original edge index of slot p (stable sort by variable)
+__global__ void k_fill_var_major(const int32_t* __restrict__ ecls, const float* __restrict__ sign,
+                                 const int32_t* __restrict__ v_orig, const int32_t* __restrict__ inv,
+                                 uint32_t* v_cedge, int32_t* v_cls, int32_t* c_pos, int64_t E) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x) {
+        int32_t e = v_orig[p];
+        int32_t c = inv ? inv[e] : e;
+        v_cedge[p] = (uint32_t)c | ((sign[e] < 0.f) ? PDP_SIGN_BIT : 0u);
+        v_cls[p] = ecls[e];
+        c_pos[c] = (int32_t)p;
+    }
+}
+
+__global__ void k_max_degree(const int32_t* __restrict__ ptr, int64_t n, int32_t* out) {
+    int32_t m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t d = ptr[i + 1] - ptr[i];
+        m = d > m ? d : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) { int32_t t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+}  // namespace
+
+__global__ void k_reset_state(pdp_state s, int64_t V, int64_t F, int64_t B) {
+    int64_t n = V > F ? V : F;
+    if (B > n) n = B;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < V) { s.av[i] = 1; s.sol[i] = 0.5f; s.up_cnt[i] = 0; s.up_ev[i] = 0; s.pure[i] = 0; s.score[i] = 0.f; s.asg[i] = 0; }
+        if (i < F) { s.af[i] = 1; s.single[i] = 0; }
+        if (i < B) {
+            s.is_sat[i] = 0.5f; s.active[i] = 1; s.counters[i] = 0; s.freeze_iter[i] = -1; s.flags[i] = 0;
+            s.masked[i] = 0; s.dirty[i] = 1; s.conv[i] = 0; s.nanflag[i] = 0; s.n_unsat[i] = 0; s.conflicts[i] = 0;
+            s.nav[i] = 0; s.arg_idx[i] = 0x7fffffff; s.energy[i] = 0;
+            s.st_max[2 * i] = 0u; s.st_max[2 * i + 1] = 0u; s.st_min[2 * i] = 0x7f800000u; s.st_min[2 * i + 1] = 0x7f800000u;
+            s.st_nan[i] = 0u; s.c_max[i] = 0u; s.c_min[i] = 0x7f800000u; s.c_nan[i] = 0u;
+        }
+        if (i < CTRL_SIZE) s.ctrl[i] = (i == CTRL_NUM_ACTIVE) ? (int32_t)B : ((i == CTRL_ANY_DIRTY) ? 1 : 0);
+    }
+}
+
+extern "C" size_t pdp_workspace_bytes(int64_t E, int64_t V, int64_t F, int64_t B) {
+    if (E < 0 || V < 0 || F < 0 || B < 0) return 0;
+    pdp_ctx tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    Carver k{nullptr, 0, true};
+    carve(&tmp, k, E, V, F, B);
+    return k.off + 256;
+}
+
+extern "C" int pdp_reset(pdp_ctx* ctx, void* stream_) {
+    if (!ctx) { pdp_set_error("pdp_reset: null context"); return PDP_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t n = ctx->g.V > ctx->g.F ? ctx->g.V : ctx->g.F;
+    if (ctx->g.B > n) n = ctx->g.B;
+    if (n < CTRL_SIZE) n = CTRL_SIZE;
+    k_reset_state<<<pdp_grid(n, 256, ctx->num_sms), 256, 0, stream>>>(ctx->s, ctx->g.V, ctx->g.F, ctx->g.B);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float* d_edge_feature,
+                          const int32_t* d_bvm, const int32_t* d_bfm, int64_t E, int64_t V, int64_t F, int64_t B,
+                          void* d_workspace, size_t workspace_bytes, void* stream_) {
+    if (!out) { pdp_set_error("pdp_create: out is null"); return PDP_ERR_ARG; }
+    *out = nullptr;
+    if (E < 0 || V < 0 || F < 0 || B < 0 || E >= (int64_t)0x7fffffff || V >= (int64_t)0x7fffffff || F >= (int64_t)0x7fffffff) {
+        pdp_set_error("pdp_create: sizes out of range (E=%lld V=%lld F=%lld B=%lld; each must be < 2^31-1)",
+                      (long long)E, (long long)V, (long long)F, (long long)B);
+        return PDP_ERR_ARG;
+    }
+    if ((E > 0 && (!d_graph_map || !d_edge_feature)) || (V > 0 && !d_bvm) || (F > 0 && !d_bfm) || !d_workspace) {
+        pdp_set_error("pdp_create: null input pointer");
+        return PDP_ERR_ARG;
+    }
+    size_t need = pdp_workspace_bytes(E, V, F, B);
+    if (workspace_bytes < need) {
+        pdp_set_error("pdp_create: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return PDP_ERR_WORKSPACE;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    pdp_ctx* c = new pdp_ctx();
+    memset(c, 0, sizeof(*c));
+    if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; pdp_set_error("pdp_create: no CUDA device"); return PDP_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; pdp_set_error("pdp_create: cudaGetDeviceProperties failed"); return PDP_ERR_CUDA; }
+    if (prop.major < 10) {
+        delete c;
+        pdp_set_error("pdp_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        return PDP_ERR_UNSUPPORTED;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    c->workspace = d_workspace;
+    c->workspace_bytes = workspace_bytes;
+    c->g.E = E; c->g.V = V; c->g.F = F; c->g.B = B;
+    uintptr_t base = ((uintptr_t)d_workspace + 255) & ~(uintptr_t)255;
+    Carver k{reinterpret_cast<uint8_t*>(base), 0, false};
+    carve(c, k, E, V, F, B);
+    pdp_graph& g = c->g;
+    const int32_t* evar = d_graph_map;
+    const int32_t* ecls = d_graph_map + E;
+    const int nsm = c->num_sms;
+
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { pdp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); delete c; return PDP_ERR_CUDA; } } while (0)
+#define LK() do { c->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { pdp_set_error("%s:%d: launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); delete c; return PDP_ERR_CUDA; } } while (0)
+
+    if (V > 0) CK(cudaMemcpyAsync(g.bvm, d_bvm, sizeof(int32_t) * (size_t)V, cudaMemcpyDeviceToDevice, stream));
+    if (F > 0) CK(cudaMemcpyAsync(g.bfm, d_bfm, sizeof(int32_t) * (size_t)F, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemsetAsync(g.cl_ptr, 0, sizeof(int32_t) * (size_t)(F + 1), stream));
+    CK(cudaMemsetAsync(g.var_ptr, 0, sizeof(int32_t) * (size_t)(V + 1), stream));
+    CK(cudaMemsetAsync(c->s.ctrl, 0, sizeof(int32_t) * CTRL_SIZE, stream));
+    int32_t* flags = c->s.ctrl;   // [0] not clause-major, [1] index out of range, [2] max var deg, [3] max clause deg
+    if (E > 0) {
+        k_check_and_count<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(evar, ecls, E, V, F, g.cl_ptr, g.var_ptr, flags);
+        LK();
+    }
+    k_check_maps<<<pdp_grid(V > F ? V : F, 256, nsm), 256, 0, stream>>>(d_bvm, d_bfm, V, F, B, flags);
+    LK();
+    // counts -> pointers (in-place inclusive of the leading zero = exclusive scan shifted by one)
+    {
+        size_t tb = c->cub_tmp_bytes;
+        size_t q = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, q, g.cl_ptr, g.cl_ptr, (int)(F + 1), stream));
+        if (q > tb) { pdp_set_error("pdp_create: scan scratch %zu > reserve %zu", q, tb); delete c; return PDP_ERR_WORKSPACE; }
+        CK(cub::DeviceScan::InclusiveSum(c->cub_tmp, tb, g.cl_ptr, g.cl_ptr, (int)(F + 1), stream));
+        c->launches++;
+        tb = c->cub_tmp_bytes;
+        CK(cub::DeviceScan::InclusiveSum(c->cub_tmp, tb, g.var_ptr, g.var_ptr, (int)(V + 1), stream));
+        c->launches++;
+    }
+    int32_t hflags[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (hflags[1]) {
+        pdp_set_error("pdp_create: graph_map / batch maps hold indices outside [0,V) x [0,F) x [0,B) (code %d)", hflags[1]);
+        delete c;
+        return PDP_ERR_ARG;
+    }
+    const bool clause_major = (hflags[0] == 0);
+
+    if (E > 0) {
+        // scratch aliases: message buffers are not live yet
+        int32_t* kA = reinterpret_cast<int32_t*>(c->s.eta[0]);
+        int32_t* kB = reinterpret_cast<int32_t*>(c->s.eta[1]);
+        int32_t* vA = reinterpret_cast<int32_t*>(c->s.qu[0]);
+        int32_t* vB = reinterpret_cast<int32_t*>(c->s.qu[1]);
+        int32_t* inv = reinterpret_cast<int32_t*>(c->s.qs[0]);
+        auto stable_sort = [&](const int32_t* keys, int64_t nkeys, int32_t* out_vals) -> int {
+            int bits = 1;
+            while (((int64_t)1 << bits) < nkeys && bits < 31) ++bits;
+            cudaError_t e1 = cudaMemcpyAsync(kA, keys, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream);
+            if (e1 != cudaSuccess) return -1;
+            k_iota<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(vA, E);
+            c->launches++;
+            cub::DoubleBuffer<int32_t> dk(kA, kB);
+            cub::DoubleBuffer<int32_t> dv(vA, vB);
+            size_t q = 0;
+            if (cub::DeviceRadixSort::SortPairs(nullptr, q, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return -1;
+            if (q > c->cub_tmp_bytes) return -2;
+            size_t tb = c->cub_tmp_bytes;
+            if (cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return -1;
+            c->launches++;
+            if (cudaMemcpyAsync(out_vals, dv.Current(), sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
+            return 0;
+        };
+        if (clause_major) {
+            k_iota<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(g.c_orig, E);
+            LK();
+        } else {
+            int r = stable_sort(ecls, F, g.c_orig);
+            if (r != 0) { pdp_set_error("pdp_create: clause sort failed (%d)", r); delete c; return r == -2 ? PDP_ERR_WORKSPACE : PDP_ERR_CUDA; }
+        }
+        {
+            int r = stable_sort(evar, V, g.v_orig);
+            if (r != 0) { pdp_set_error("pdp_create: variable sort failed (%d)", r); delete c; return r == -2 ? PDP_ERR_WORKSPACE : PDP_ERR_CUDA; }
+        }
+        if (!clause_major) {
+            k_invert<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(g.c_orig, inv, E);
+            LK();
+        }
+        k_fill_clause_major<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(evar, d_edge_feature, g.c_orig, g.c_var, E);
+        LK();
+        k_fill_var_major<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(ecls, d_edge_feature, g.v_orig, clause_major ? nullptr : inv,
+                                                                     g.v_cedge, g.v_cls, g.c_pos, E);
+        LK();
+        if (V > 0) { k_max_degree<<<pdp_grid(V, 256, nsm), 256, 0, stream>>>(g.var_ptr, V, flags + 2); LK(); }
+        if (F > 0) { k_max_degree<<<pdp_grid(F, 256, nsm), 256, 0, stream>>>(g.cl_ptr, F, flags + 3); LK(); }
+        CK(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        g.max_var_degree = hflags[2];
+        g.max_clause_degree = hflags[3];
+    }
+    int rc = pdp_reset(c, stream);
+    if (rc != PDP_OK) { delete c; return rc; }
+#undef CK
+#undef LK
+    *out = c;
+    return PDP_OK;
+}
+
+extern "C" int pdp_destroy(pdp_ctx* ctx) {
+    delete ctx;
+    return PDP_OK;
+}
+
+extern "C" int64_t pdp_launch_count(pdp_ctx* ctx) { return ctx ? ctx->launches : 0; }

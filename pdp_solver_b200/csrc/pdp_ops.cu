@@ -1,0 +1,421 @@
+// pdp_ops.cu -- stateless operators in the caller's edge order (the reference's operator interface) and
+// the import/export of the solver state held by a context.
+#include <cub/cub.cuh>
+
+#include "pdp_device.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// SatCNFEvaluator.forward (util.py:210-236)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cnf_eval_count(pdp_graph g, pdp_state s, const float* __restrict__ pred) {
+    // s.conflicts counts clauses, s.energy counts satisfied clauses (both zero on entry, reset on exit)
+    int last_b = -1, n_all = 0, n_sat = 0;
+    WARP_STRIDED(a, g.F) {
+        if (a >= g.F) continue;
+        const int b = g.bfm[a];
+        if (b != last_b) {
+            if (last_b >= 0) { atomicAdd(&s.conflicts[last_b], n_all); atomicAdd(&s.energy[last_b], n_sat); }
+            last_b = b; n_all = 0; n_sat = 0;
+        }
+        bool sat = false;
+        for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+            const uint32_t w = g.c_var[c];
+            if (literal_true((w & PDP_SIGN_BIT) ? -1.f : 1.f, pred[w & PDP_IDX_MASK])) { sat = true; break; }
+        }
+        n_all += 1; n_sat += sat ? 1 : 0;
+    }
+    if (last_b >= 0) { atomicAdd(&s.conflicts[last_b], n_all); atomicAdd(&s.energy[last_b], n_sat); }
+}
+
+__global__ void k_cnf_eval_finish(pdp_graph g, pdp_state s, float* solved, float* n_unsat) {
+    for (int64_t b = gtid(); b < g.B; b += gthreads()) {
+        const int all = s.conflicts[b], sat = s.energy[b];
+        solved[b] = (all == sat) ? 1.f : 0.f;
+        n_unsat[b] = (float)(all - sat);
+        s.conflicts[b] = 0; s.energy[b] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// _compute_energy / _compute_energy_diff (solver.py:469-496), float masks like the reference's
+// ------------------------------------------------------------------------------------------------
+__global__ void k_energy(pdp_graph g, const float* __restrict__ asg, const float* __restrict__ av,
+                         const float* __restrict__ af, float* energy, float* unsat_fn, float* agg_out, float* deg_out) {
+    WARP_STRIDED(a, g.F) {
+        if (a >= g.F) continue;
+        float agg = 0.f, deg = 0.f;
+        for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+            const uint32_t w = g.c_var[c];
+            const int v = (int)(w & PDP_IDX_MASK);
+            const float sg = (w & PDP_SIGN_BIT) ? -1.f : 1.f;
+            agg += sg * (asg[v] * av[v]);
+            deg += av[v];
+        }
+        if (agg_out) { agg_out[a] = agg; deg_out[a] = deg; }
+        if (unsat_fn) {
+            const float u = ((agg == -deg) ? 1.f : 0.f) * af[a];
+            unsat_fn[a] = u;
+            if (u != 0.f) atomicAdd(&energy[g.bfm[a]], u);   // small integers: exact in any order
+        }
+    }
+}
+
+__global__ void k_energy_diff(pdp_graph g, const float* __restrict__ asg, const float* __restrict__ av,
+                              const float* __restrict__ em, const float* __restrict__ agg, const float* __restrict__ deg,
+                              float* delta) {
+    WARP_STRIDED(i, g.V) {
+        if (i >= g.V) continue;
+        float d = 0.f;
+        const float lit0 = asg[i] * av[i];
+        for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) {
+            const int a = g.v_cls[p];
+            const float dist = ((g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f) * lit0;
+            const float others = agg[a] - dist;
+            const float crit = ((others == (1.f - deg[a])) ? 1.f : 0.f) * em[g.v_orig[p]];
+            d += crit * dist;
+        }
+        delta[i] = d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SurveyPropagator.forward in the caller's edge order (pdp_propagate.py:139-221)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sp_step_clause(pdp_graph g, const float* __restrict__ dq3, const float* __restrict__ em,
+                                 const float* __restrict__ pfs2, const float* __restrict__ dfs2,
+                                 const uint8_t* __restrict__ active, float* out_fs2) {
+    WARP_STRIDED(a, g.F) {
+        if (a >= g.F) continue;
+        const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
+        float tot = 0.f;
+        for (int c = beg; c < end; ++c) {
+            const int e = g.c_orig[c];
+            float v = L40(dq3[3 * (int64_t)e]);
+            if (em) v = v * em[e];
+            tot += v;
+        }
+        for (int c = beg; c < end; ++c) {
+            const int e = g.c_orig[c];
+            float v = L40(dq3[3 * (int64_t)e]);
+            if (em) v = v * em[e];
+            const float mask = active ? (float)active[g.bvm[g.c_var[c] & PDP_IDX_MASK]] : 1.f;
+            out_fs2[2 * (int64_t)e] = mask * X30(tot - v) + (1.f - mask) * pfs2[2 * (int64_t)e];
+            out_fs2[2 * (int64_t)e + 1] = dfs2[2 * (int64_t)e + 1];
+        }
+    }
+}
+
+__global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const float* __restrict__ em,
+                              const float* __restrict__ pq3, const uint8_t* __restrict__ active, float pi, float* out_q3) {
+    WARP_STRIDED(i, g.V) {
+        if (i >= g.V) continue;
+        const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
+        const float mask = active ? (float)active[g.bvm[i]] : 1.f;
+        float P = 0.f, N = 0.f;
+        for (int p = beg; p < end; ++p) {
+            const int e = g.v_orig[p];
+            float y = L40(1.f - dfs2[2 * (int64_t)e]);
+            if (em) y = y * em[e];
+            const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
+            P += (neg ? 0.f : 1.f) * y;
+            N += (neg ? 1.f : 0.f) * y;
+        }
+        for (int p = beg; p < end; ++p) {
+            const int64_t e = g.v_orig[p];
+            float y = L40(1.f - dfs2[2 * e]);
+            if (em) y = y * em[e];
+            float u, v, d;
+            sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, dfs2[2 * e + 1], pi, u, v, d);
+            out_q3[3 * e + 0] = mask * u + (1.f - mask) * pq3[3 * e + 0];
+            out_q3[3 * e + 1] = mask * v + (1.f - mask) * pq3[3 * e + 1];
+            out_q3[3 * e + 2] = mask * d + (1.f - mask) * pq3[3 * e + 2];
+        }
+    }
+}
+
+// SurveyScorer.forward (pdp_predict.py:155-192), float clause mask
+__global__ void k_score(pdp_graph g, const float* __restrict__ fs2, const float* __restrict__ af, float pi, float* score) {
+    WARP_STRIDED(i, g.V) {
+        if (i >= g.V) continue;
+        float extsum = 0.f, ps = 0.f, ns = 0.f, as = 0.f;
+        for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) {
+            const int64_t e = g.v_orig[p];
+            extsum += fs2[2 * e + 1];
+            const float f = L10(1.f - fs2[2 * e]) * af[g.v_cls[p]];
+            const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
+            ps += (neg ? 0.f : 1.f) * f;
+            ns += (neg ? 1.f : 0.f) * f;
+            as += f;
+        }
+        score[i] = sp_score_tail(ps, ns, as, sgnf(extsum), pi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// state import / export
+// ------------------------------------------------------------------------------------------------
+__global__ void k_load_state(pdp_graph g, pdp_state s, const float* __restrict__ dq3, const float* __restrict__ dfs2, int buf) {
+    for (int64_t p = gtid(); p < g.E; p += gthreads()) {
+        const int64_t e = g.v_orig[p];
+        s.qu[buf][p] = dq3[3 * e]; s.qs[buf][p] = dq3[3 * e + 1]; s.qd[buf][p] = dq3[3 * e + 2];
+        s.eta[buf][p] = dfs2[2 * e]; s.ext[p] = dfs2[2 * e + 1];
+    }
+}
+
+// thread per variable; when the [E,3] state was not tracked every iteration, q_s and q_* are
+// re-derived from the previous surveys with the current masks (materialised once, on exit)
+__global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* out_fs2, int iter, int tracked, float pi) {
+    WARP_STRIDED(i, g.V) {
+        if (i >= g.V) continue;
+        const int b = g.bvm[i];
+        const int fz = s.freeze_iter[b];
+        const int last = (fz >= 0) ? fz : iter;
+        const int buf = last & 1;
+        const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
+        const bool rebuild = (!tracked) && last >= 1;
+        float P = 0.f, N = 0.f;
+        const bool um = (last >= 2) && s.masked[b];
+        const float avi = (float)s.av[i];
+        if (rebuild) {
+            for (int p = beg; p < end; ++p) {
+                float y = L40(1.f - s.eta[buf ^ 1][p]);
+                if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
+                const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
+                P += (neg ? 0.f : 1.f) * y;
+                N += (neg ? 1.f : 0.f) * y;
+            }
+        }
+        for (int p = beg; p < end; ++p) {
+            const int64_t e = g.v_orig[p];
+            float u = s.qu[buf][p], v = s.qs[buf][p], d = s.qd[buf][p];
+            if (rebuild) {
+                float y = L40(1.f - s.eta[buf ^ 1][p]);
+                if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
+                float uu;
+                sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, s.ext[p], pi, uu, v, d);
+            }
+            if (out_q3) { out_q3[3 * e] = u; out_q3[3 * e + 1] = v; out_q3[3 * e + 2] = d; }
+            if (out_fs2) { out_fs2[2 * e] = s.eta[buf][p]; out_fs2[2 * e + 1] = s.ext[p]; }
+        }
+    }
+}
+
+__global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const float* af, const float* sol) {
+    const int64_t n = max(max(g.V, g.F), g.B);
+    for (int64_t i = gtid(); i < n; i += gthreads()) {
+        if (i < g.V) { if (av) s.av[i] = (av[i] != 0.f) ? 1 : 0; if (sol) s.sol[i] = sol[i]; }
+        if (i < g.F && af) s.af[i] = (af[i] != 0.f) ? 1 : 0;
+        if (i < g.B) { s.masked[i] = 1; s.dirty[i] = 1; }
+        if (i == 0) s.ctrl[CTRL_ANY_DIRTY] = 1;
+    }
+}
+
+__global__ void k_get_masks(pdp_graph g, pdp_state s, float* av, float* af, float* sol, float* is_sat, uint8_t* active, float* em) {
+    const int64_t n = max(max(g.V, g.F), g.B);
+    for (int64_t i = gtid(); i < n; i += gthreads()) {
+        if (i < g.V) {
+            if (av) av[i] = (float)s.av[i];
+            if (sol) sol[i] = s.sol[i];
+            if (em) for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) em[g.v_orig[p]] = (float)s.av[i] * (float)s.af[g.v_cls[p]];
+        }
+        if (i < g.F && af) af[i] = (float)s.af[i];
+        if (i < g.B) { if (is_sat) is_sat[i] = s.is_sat[i]; if (active) active[i] = s.active[i]; }
+    }
+}
+
+__global__ void k_get_flags(pdp_graph g, pdp_state s, uint32_t* flags, int32_t* counters, int32_t* freeze) {
+    for (int64_t b = gtid(); b < g.B; b += gthreads()) {
+        if (flags) flags[b] = s.flags[b];
+        if (counters) counters[b] = s.counters[b];
+        if (freeze) freeze[b] = s.freeze_iter[b];
+    }
+}
+
+struct U8ToInt {
+    __host__ __device__ __forceinline__ int operator()(const uint8_t& x) const { return (int)x; }
+};
+
+__global__ void k_random_fill(pdp_graph g, pdp_state s, const float* __restrict__ draws) {
+    for (int64_t i = gtid(); i < g.V; i += gthreads())
+        if (s.av[i]) s.sol[i] = draws[s.scan_tmp[i]];
+}
+
+// _deduplicate (solver.py:401-431)
+__global__ void k_dedup_energy(pdp_graph g, pdp_state s, const float* __restrict__ pred) {
+    WARP_STRIDED(a, g.F) {
+        if (a >= g.F) continue;
+        if (!s.af[a]) continue;
+        float agg = 0.f, deg = 0.f;
+        for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+            const uint32_t w = g.c_var[c];
+            const int v = (int)(w & PDP_IDX_MASK);
+            const float avv = (float)s.av[v];
+            agg += ((w & PDP_SIGN_BIT) ? -1.f : 1.f) * ((2.f * pred[v] - 1.0f) * avv);
+            deg += avv;
+        }
+        if (agg == -deg) atomicAdd(&s.energy[g.bfm[a]], 1);
+    }
+}
+
+__global__ void k_dedup_pick(pdp_graph g, pdp_state s, int rep, int32_t* winner) {
+    const int64_t B0 = g.B / rep;
+    for (int64_t j = gtid(); j < B0; j += gthreads()) {
+        int best = 0, be = s.energy[j];
+        for (int r = 1; r < rep; ++r) { const int en = s.energy[(int64_t)r * B0 + j]; if (en < be) { be = en; best = r; } }
+        winner[j] = best;
+    }
+}
+
+__global__ void k_dedup_gather(pdp_graph g, pdp_state s, int rep, const float* __restrict__ pred, const int32_t* __restrict__ winner,
+                               float* out) {
+    const int64_t V0 = g.V / rep;
+    for (int64_t i = gtid(); i < g.V; i += gthreads()) {
+        if (i < V0) out[i] = pred[(int64_t)winner[g.bvm[i]] * V0 + i];
+    }
+    for (int64_t b = gtid(); b < g.B; b += gthreads()) s.energy[b] = 0;
+}
+
+}  // namespace
+
+#define GRID(n) pdp_grid((n), 256, ctx->num_sms), 256, 0, stream
+#define NEED(ctx, cond, msg) do { if (!(ctx)) { pdp_set_error("null context"); return PDP_ERR_ARG; } if (!(cond)) { pdp_set_error(msg); return PDP_ERR_ARG; } } while (0)
+
+extern "C" int pdp_cnf_eval(pdp_ctx* ctx, const float* d_pred, float* d_solved, float* d_n_unsat, void* stream_) {
+    NEED(ctx, (d_pred || ctx->g.V == 0) && d_solved && d_n_unsat, "pdp_cnf_eval: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.F > 0) { k_cnf_eval_count<<<GRID(ctx->g.F)>>>(ctx->g, ctx->s, d_pred); PDP_LAUNCH_CHECK(ctx); }
+    k_cnf_eval_finish<<<GRID(ctx->g.B)>>>(ctx->g, ctx->s, d_solved, d_n_unsat);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_energy(pdp_ctx* ctx, const float* d_asg, const float* d_av, const float* d_af, float* d_energy,
+                          float* d_unsat_fn, void* stream_) {
+    NEED(ctx, d_asg && d_av && d_af && d_energy && d_unsat_fn, "pdp_energy: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PDP_CUDA_CHECK(cudaMemsetAsync(d_energy, 0, sizeof(float) * (size_t)ctx->g.B, stream));
+    if (ctx->g.F > 0) { k_energy<<<GRID(ctx->g.F)>>>(ctx->g, d_asg, d_av, d_af, d_energy, d_unsat_fn, nullptr, nullptr); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_energy_diff(pdp_ctx* ctx, const float* d_asg, const float* d_av, const float* d_em, float* d_delta, void* stream_) {
+    NEED(ctx, d_asg && d_av && d_em && d_delta, "pdp_energy_diff: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    float* agg = reinterpret_cast<float*>(ctx->s.ws_true);
+    float* deg = reinterpret_cast<float*>(ctx->s.ws_deg);
+    if (ctx->g.F > 0) { k_energy<<<GRID(ctx->g.F)>>>(ctx->g, d_asg, d_av, nullptr, nullptr, nullptr, agg, deg); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.V > 0) { k_energy_diff<<<GRID(ctx->g.V)>>>(ctx->g, d_asg, d_av, d_em, agg, deg, d_delta); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_sp_step(pdp_ctx* ctx, const float* d_dec_q3, const float* d_dec_fs2, const float* d_edge_mask,
+                           const float* d_prop_q3, const float* d_prop_fs2, const uint8_t* d_active, float pi,
+                           float* d_out_q3, float* d_out_fs2, void* stream_) {
+    NEED(ctx, d_dec_q3 && d_dec_fs2 && d_out_q3 && d_out_fs2, "pdp_sp_step: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float* pq = d_prop_q3 ? d_prop_q3 : d_dec_q3;
+    const float* pf = d_prop_fs2 ? d_prop_fs2 : d_dec_fs2;
+    if (ctx->g.F > 0) { k_sp_step_clause<<<GRID(ctx->g.F)>>>(ctx->g, d_dec_q3, d_edge_mask, pf, d_dec_fs2, d_active, d_out_fs2); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.V > 0) { k_sp_step_var<<<GRID(ctx->g.V)>>>(ctx->g, d_dec_fs2, d_edge_mask, pq, d_active, pi, d_out_q3); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_score(pdp_ctx* ctx, const float* d_fs2, const float* d_af, float pi, float* d_score, void* stream_) {
+    NEED(ctx, d_fs2 && d_af && d_score, "pdp_score: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.V > 0) { k_score<<<GRID(ctx->g.V)>>>(ctx->g, d_fs2, d_af, pi, d_score); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float* d_prop_fs2, const float* d_dec_q3,
+                              const float* d_dec_fs2, void* stream_) {
+    (void)d_prop_q3; (void)d_prop_fs2;   // only reachable through the frozen-problem blend; every problem starts active
+    NEED(ctx, d_dec_q3 && d_dec_fs2, "pdp_load_state: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.E > 0) { k_load_state<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s, d_dec_q3, d_dec_fs2, 0); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* stream_) {
+    NEED(ctx, d_out_q3 || d_out_fs2, "pdp_store_state: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t h[2] = {0, 0};
+    PDP_CUDA_CHECK(cudaMemcpyAsync(h, ctx->s.ctrl + CTRL_ITER, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PDP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (ctx->g.V > 0) {
+        k_store_state<<<GRID(ctx->g.V)>>>(ctx->g, ctx->s, d_out_q3, d_out_fs2, h[0], ctx->full_state_tracked, ctx->last_pi);
+        PDP_LAUNCH_CHECK(ctx);
+    }
+    return PDP_OK;
+}
+
+extern "C" int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af, const float* d_sol, void* stream_) {
+    NEED(ctx, true, "");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t n = std::max(std::max(ctx->g.V, ctx->g.F), std::max(ctx->g.B, (int64_t)1));
+    k_set_masks<<<GRID(n)>>>(ctx->g, ctx->s, d_av, d_af, d_sol);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_get_masks(pdp_ctx* ctx, float* d_av, float* d_af, float* d_sol, float* d_is_sat, uint8_t* d_active,
+                             float* d_em, void* stream_) {
+    NEED(ctx, true, "");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t n = std::max(std::max(ctx->g.V, ctx->g.F), std::max(ctx->g.B, (int64_t)1));
+    k_get_masks<<<GRID(n)>>>(ctx->g, ctx->s, d_av, d_af, d_sol, d_is_sat, d_active, d_em);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_get_problem_flags(pdp_ctx* ctx, uint32_t* d_flags, int32_t* d_counters, int32_t* d_freeze, void* stream_) {
+    NEED(ctx, true, "");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    k_get_flags<<<GRID(ctx->g.B)>>>(ctx->g, ctx->s, d_flags, d_counters, d_freeze);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_count_active_variables(pdp_ctx* ctx, int64_t* host_out, void* stream_) {
+    NEED(ctx, host_out, "pdp_count_active_variables: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *host_out = 0;
+    if (ctx->g.V == 0) return PDP_OK;
+    cub::TransformInputIterator<int, U8ToInt, const uint8_t*> it(ctx->s.av, U8ToInt());
+    size_t tb = ctx->cub_tmp_bytes;
+    int* d_sum = ctx->s.scan_tmp + ctx->g.V;
+    PDP_CUDA_CHECK(cub::DeviceReduce::Sum(ctx->cub_tmp, tb, it, d_sum, (int)ctx->g.V, stream));
+    ctx->launches++;
+    int h = 0;
+    PDP_CUDA_CHECK(cudaMemcpyAsync(&h, d_sum, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PDP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *host_out = h;
+    return PDP_OK;
+}
+
+extern "C" int pdp_random_fill(pdp_ctx* ctx, const float* d_draws, void* stream_) {
+    NEED(ctx, d_draws || ctx->g.V == 0, "pdp_random_fill: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.V == 0) return PDP_OK;
+    cub::TransformInputIterator<int, U8ToInt, const uint8_t*> it(ctx->s.av, U8ToInt());
+    size_t tb = ctx->cub_tmp_bytes;
+    PDP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tb, it, ctx->s.scan_tmp, (int)ctx->g.V, stream));
+    ctx->launches++;
+    k_random_fill<<<GRID(ctx->g.V)>>>(ctx->g, ctx->s, d_draws);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+extern "C" int pdp_deduplicate(pdp_ctx* ctx, int32_t rep, const float* d_pred, float* d_out, int32_t* d_winner, void* stream_) {
+    NEED(ctx, d_pred && d_out && d_winner && rep >= 1, "pdp_deduplicate: bad argument");
+    if (ctx->g.B % rep || ctx->g.V % rep) { pdp_set_error("pdp_deduplicate: sizes not divisible by the replication factor"); return PDP_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.F > 0) { k_dedup_energy<<<GRID(ctx->g.F)>>>(ctx->g, ctx->s, d_pred); PDP_LAUNCH_CHECK(ctx); }
+    k_dedup_pick<<<GRID(ctx->g.B)>>>(ctx->g, ctx->s, rep, d_winner);
+    PDP_LAUNCH_CHECK(ctx);
+    k_dedup_gather<<<GRID(std::max(ctx->g.V, ctx->g.B))>>>(ctx->g, ctx->s, rep, d_pred, d_winner, d_out);
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}

@@ -1,0 +1,52 @@
+"""Predictors and scorers of the PDP framework, B200-native (reference src/pdp/nn/pdp_predict.py)."""
+import torch
+import torch.nn as nn
+
+
+class IdentityPredictor(nn.Module):
+    """Prediction = the SATProblem's running solution; on the last call undecided variables are filled
+    with uniform draws consumed in batch-global variable order (reference pdp_predict.py:110-128)."""
+
+    def __init__(self, device, random_fill=False):
+        super(IdentityPredictor, self).__init__()
+        self._random_fill = random_fill
+        self._device = device
+
+    def forward(self, decimator_state, sat_problem, last_call=False):
+        ctx = sat_problem._ctx
+        if self._random_fill and last_call:
+            n_active = ctx.count_active_variables()
+            if n_active > 0:
+                ctx.random_fill(torch.rand(n_active, device=ctx.device))   # same draw as pdp_predict.py:126
+        return ctx.solution().unsqueeze(1), None
+
+
+class SurveyScorer(nn.Module):
+    "Per-variable SP bias W(+) - W(-) used for SP-guided decimation (reference pdp_predict.py:134-208)."
+
+    def __init__(self, device, message_dimension, include_adaptors=False, pi=0.0):
+        super(SurveyScorer, self).__init__()
+        if include_adaptors:
+            raise NotImplementedError("neural adaptors are not part of the accelerated path yet")
+        self._device = device
+        self._include_adaptors = include_adaptors
+        self._pi_value = float(pi)
+
+    def forward(self, message_state, sat_problem, last_call=False):
+        ctx = sat_problem._ctx
+        af = ctx.get_masks()["af"]
+        return ctx.score(message_state[1], af, self._pi_value).unsqueeze(1), None
+
+    def get_init_state(self, graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat,
+                       randomized, batch_replication):
+        "reference pdp_predict.py:194-208 (the random variant is NOT normalised, as in the reference)"
+        edge_num = graph_map.size(1) * batch_replication
+        if randomized:
+            variable_state = torch.rand(edge_num, 3, dtype=torch.float32, device=self._device)
+            function_state = torch.rand(edge_num, 2, dtype=torch.float32, device=self._device)
+            function_state[:, 1] = 0
+        else:
+            variable_state = torch.ones(edge_num, 3, dtype=torch.float32, device=self._device) / 3.0
+            function_state = 0.5 * torch.ones(edge_num, 2, dtype=torch.float32, device=self._device)
+            function_state[:, 1] = 0
+        return (variable_state, function_state)

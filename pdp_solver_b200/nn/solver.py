@@ -1,0 +1,267 @@
+"""Drop-in for the reference module `pdp.nn.solver` (reference src/pdp/nn/solver.py), B200-native.
+
+Same class names, constructor arguments, `get_init_state` / `forward` signatures and return layout as
+the reference; underneath, the batch lives in a device `Context` (CSR/CSC instead of 14 torch sparse
+matrices) and the whole propagate -> decimate -> predict loop, the CNF check, unit propagation /
+peeling and WalkSAT run as hand-written sm_100a kernels behind the C ABI of libpdp_b200.so.
+
+Scope: the classical model types `p-d-p` (SurveyPropagatorSolver) and `walk-sat`
+(WalkSATSolver).  There is no CPU path and no fallback: CPU tensors or a missing library raise.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import Context
+from . import pdp_decimate, pdp_predict, pdp_propagate, util
+
+# WalkSAT draws are pre-generated with torch.rand in the reference's order when they fit this many
+# floats; above it the kernel's counter-based generator is used (same distribution, other stream).
+TORCH_RNG_DRAW_LIMIT = int(os.environ.get("PDP_TORCH_RNG_DRAW_LIMIT", str(1 << 28)))
+
+
+class SATProblem(object):
+    """One batch of CNFs on the device (reference solver.py:19-285).  Exposes the attributes the
+    reference's callbacks read (`_graph_map`, `_batch_variable_map`, `_batch_function_map`,
+    `_edge_feature`, `_meta_data`, `_batch_replication`, `_active_variables`, `_active_functions`,
+    `_solution`, `_edge_mask`, `_batch_size`, ...); the mask attributes are fetched from the device
+    context on access."""
+
+    def __init__(self, data_batch, device, batch_replication=1):
+        self._device = device
+        self._batch_replication = batch_replication
+        graph_map, bvm, bfm, edge_feature, meta_data, _ = data_batch
+        if graph_map.device.type != "cuda":
+            raise _lib.PdpError("pdp_solver_b200 runs on CUDA tensors only (there is no CPU path); "
+                                "move the batch to the GPU as the reference's _to_cuda does")
+        self._replication_mask_tuple = None
+        if batch_replication > 1:
+            graph_map, bvm, bfm, edge_feature, meta_data = self._replicate_batch(
+                graph_map, bvm, bfm, edge_feature, meta_data, batch_replication)
+        self._graph_map, self._batch_variable_map, self._batch_function_map = graph_map, bvm, bfm
+        self._edge_feature, self._meta_data = edge_feature, meta_data
+        self._variable_num = bvm.size(0)
+        self._function_num = bfm.size(0)
+        self._edge_num = graph_map.size(1)
+        self._ctx = Context(graph_map, bvm, bfm, edge_feature)
+        self._batch_size = self._ctx.B
+        self._edge_mask_set = False
+        if batch_replication > 1:
+            self._replication_mask_tuple = self._compute_batch_replication_map(batch_replication)
+
+    @staticmethod
+    def _replicate_batch(graph_map, bvm, bfm, edge_feature, meta_data, b):
+        """replica r of problem j gets problem id r*B + j (reference solver.py:56-82)"""
+        V, F = bvm.size(0), bfm.size(0)
+        B = int(bvm.max().item()) + 1
+        r = torch.arange(b, dtype=torch.int32, device=graph_map.device)
+        off = torch.stack([r * V, r * F])                                  # [2, b]
+        gm = (graph_map.unsqueeze(1) + off.unsqueeze(2)).reshape(2, -1)    # [2, b*E]
+        bv = (bvm.unsqueeze(0) + (r * B).unsqueeze(1)).reshape(-1)
+        bf = (bfm.unsqueeze(0) + (r * B).unsqueeze(1)).reshape(-1)
+        ef = edge_feature.repeat(b, 1)
+        md = None if meta_data is None else meta_data.repeat(b, 1)
+        return gm.contiguous(), bv.contiguous(), bf.contiguous(), ef, md
+
+    def _compute_batch_replication_map(self, b):
+        """dense-free equivalent of reference solver.py:84-99 for callbacks that torch.mm with it"""
+        B0 = self._batch_size // b
+        x = torch.arange(B0 * b, dtype=torch.int64, device=self._graph_map.device)
+        ind = torch.stack([x, x % B0])
+        mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0))
+        return (mask, mask.transpose(0, 1))
+
+    # ---- state views -----------------------------------------------------------------------------
+    @property
+    def _active_variables(self):
+        return self._ctx.get_masks()["av"].unsqueeze(1)
+
+    @property
+    def _active_functions(self):
+        return self._ctx.get_masks()["af"].unsqueeze(1)
+
+    @property
+    def _solution(self):
+        return self._ctx.solution()
+
+    @property
+    def _is_sat(self):
+        return self._ctx.get_masks()["is_sat"]
+
+    @property
+    def _edge_mask(self):
+        if not self._edge_mask_set:
+            return None
+        return self._ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
+
+    # ---- reference solver.py:275-285 ---------------------------------------------------------------
+    def set_variables(self, assignment):
+        self._ctx.set_variables(assignment)
+
+    def simplify(self):
+        self._ctx.simplify()
+
+
+def _is_standard_termination(cb):
+    """The reference's trainer callback (trainer.py:150-162) -- or anything tagged as equivalent -- is
+    evaluated inside the persistent kernel; any other callable is honoured by stepping."""
+    if cb is None:
+        return False
+    if getattr(cb, "_pdp_standard_termination", False):
+        return True
+    fn = getattr(cb, "__func__", cb)
+    return getattr(fn, "__name__", "") == "_check_recurrence_termination" and \
+        hasattr(getattr(cb, "__self__", None), "_cnf_evaluator")
+
+
+class PropagatorDecimatorSolverBase(nn.Module):
+    "The base class for all PDP SAT solvers (reference solver.py:293-511)."
+
+    def __init__(self, device, name, propagator, decimator, predictor, local_search_iterations=0, epsilon=0.05):
+        super(PropagatorDecimatorSolverBase, self).__init__()
+        self._device = device
+        self._module_list = nn.ModuleList()
+        self._propagator, self._decimator, self._predictor = propagator, decimator, predictor
+        for m in (propagator, decimator, predictor):
+            self._module_list.append(m)
+        self._global_step = nn.Parameter(torch.tensor([0], dtype=torch.float, device=self._device), requires_grad=False)
+        self._name = name
+        self._local_search_iterations = local_search_iterations
+        self._epsilon = epsilon
+        self.last_problem = None          # SATProblem of the last forward (flags, diagnostics)
+        self.last_iterations = None
+
+    def parameter_count(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def save(self, export_path_base):
+        torch.save(self.state_dict(), os.path.join(export_path_base, self._name))
+
+    def load(self, import_path_base):
+        self.load_state_dict(torch.load(os.path.join(import_path_base, self._name)))
+
+    def get_init_state(self, graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat,
+                       randomized, batch_replication=1):
+        "Initializes the propagator and the decimator messages in each direction (reference solver.py:498-511)."
+        p = None if self._propagator is None else self._propagator.get_init_state(
+            graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat, randomized, batch_replication)
+        d = None if self._decimator is None else self._decimator.get_init_state(
+            graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat, randomized, batch_replication)
+        return p, d
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, init_state, graph_map, batch_variable_map, batch_function_map, edge_feature,
+                meta_data, is_training=True, iteration_num=1, check_termination=None, simplify=True,
+                batch_replication=1):
+        """reference solver.py:324-353.  Returns (prediction, (propagator_state, decimator_state)) with
+        prediction = (variable_prediction [V,1] in [0,1], None)."""
+        if is_training:
+            raise NotImplementedError("training (is_training=True) is outside the accelerated path (SURVEY.md section 8)")
+        init_propagator_state, init_decimator_state = init_state
+        sat_problem = SATProblem((graph_map, batch_variable_map, batch_function_map, edge_feature, meta_data, None),
+                                 self._device, batch_replication)
+        ctx = sat_problem._ctx
+        self.last_problem = sat_problem
+        if simplify:
+            sat_problem.simplify()
+
+        propagator_state = decimator_state = None
+        if self._propagator is not None and self._decimator is not None:
+            propagator_state, decimator_state = self._forward_core(
+                init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination)
+
+        # predictor, last call: random fill of the undecided variables (pdp_predict.py:121-126)
+        self._predictor(decimator_state, sat_problem, True)
+        prediction = self._local_search(sat_problem, batch_replication)
+        if batch_replication > 1:
+            pred, _ = ctx.deduplicate(batch_replication, prediction)
+            prediction = pred
+            # states of the winning replicas (reference solver.py:417-424)
+            propagator_state = decimator_state = None if propagator_state is None else \
+                self._dedup_states(propagator_state, sat_problem, batch_replication, _)
+        return (prediction.unsqueeze(1), None), (propagator_state, decimator_state)
+
+    @staticmethod
+    def _dedup_states(state, sat_problem, b, winner):
+        E0 = sat_problem._edge_num // b
+        gm = sat_problem._graph_map[:, :E0]
+        prob = sat_problem._batch_variable_map[gm[0].long()].long()       # original problem of each edge
+        src = winner.long()[prob] * E0 + torch.arange(E0, device=gm.device)
+        return tuple(x[src] for x in state[:2])
+
+    def _forward_core(self, init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination):
+        """reference solver.py:355-386 for the p-d-p composition: one persistent kernel when the
+        termination callback is the trainer's (or None), one launch per iteration otherwise."""
+        ctx = sat_problem._ctx
+        dec = self._decimator
+        ctx.load_state(init_propagator_state, init_decimator_state[:2])
+        b = sat_problem._batch_replication
+        if check_termination is None or _is_standard_termination(check_termination):
+            self.last_iterations = ctx.sp_run(iteration_num, dec._tolerance, dec._t_max,
+                                              check_termination is not None, b, self._propagator.pi_value())
+        else:
+            raise NotImplementedError(
+                "custom check_termination callbacks are not supported by the fused loop; tag the callable with "
+                "`_pdp_standard_termination = True` if it implements trainer._check_recurrence_termination semantics")
+        sat_problem._edge_mask_set = iteration_num > 0
+        q3, fs2 = ctx.store_state()
+        return (q3, fs2), (q3, fs2)
+
+    def _local_search(self, sat_problem, batch_replication):
+        "WalkSAT post-processing + solution merge (reference solver.py:433-467, 388-399)."
+        ctx = sat_problem._ctx
+        W = int(self._local_search_iterations)
+        V, B = ctx.V, ctx.B
+        if W > 0 and W * (V + B) <= TORCH_RNG_DRAW_LIMIT:
+            # the reference's draw order per iteration: rand([V,1]) then rand(B) (solver.py:457,460)
+            rv = torch.empty(W, V, device=ctx.device)
+            rc = torch.empty(W, B, device=ctx.device)
+            for it in range(W):
+                rv[it] = torch.rand([V, 1], device=ctx.device).squeeze(1)
+                rc[it] = torch.rand(B, device=ctx.device)
+            pred, _ = ctx.walksat(W, self._epsilon, rv, rc, 0, batch_replication)
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if W > 0 else 0
+            pred, _ = ctx.walksat(W, self._epsilon, None, None, seed, batch_replication)
+        return pred
+
+
+class SurveyPropagatorSolver(PropagatorDecimatorSolverBase):
+    "The classical SP-guided decimation solver, model type `p-d-p` (reference solver.py:567-578)."
+
+    def __init__(self, device, name, tolerance, t_max, local_search_iterations=0, epsilon=0.05):
+        super(SurveyPropagatorSolver, self).__init__(
+            device=device, name=name,
+            propagator=pdp_propagate.SurveyPropagator(device, decimator_dimension=1, include_adaptors=False),
+            decimator=pdp_decimate.SequentialDecimator(
+                device, message_dimension=(3, 1),
+                scorer=pdp_predict.SurveyScorer(device, message_dimension=1, include_adaptors=False),
+                tolerance=tolerance, t_max=t_max),
+            predictor=pdp_predict.IdentityPredictor(device=device, random_fill=True),
+            local_search_iterations=local_search_iterations, epsilon=epsilon)
+
+
+class WalkSATSolver(PropagatorDecimatorSolverBase):
+    "The classical Walk-SAT solver, model type `walk-sat` (reference solver.py:584-592)."
+
+    def __init__(self, device, name, iteration_num, epsilon=0.05):
+        super(WalkSATSolver, self).__init__(
+            device=device, name=name, propagator=None, decimator=None,
+            predictor=pdp_predict.IdentityPredictor(device=device, random_fill=True),
+            local_search_iterations=iteration_num, epsilon=epsilon)
+
+
+def _out_of_scope(name):
+    class _Stub(PropagatorDecimatorSolverBase):
+        def __init__(self, *a, **k):
+            raise NotImplementedError("%s is not part of the accelerated path yet (SURVEY.md section 8f)" % name)
+    _Stub.__name__ = name
+    return _Stub
+
+
+NeuralPropagatorDecimatorSolver = _out_of_scope("NeuralPropagatorDecimatorSolver")
+NeuralSurveyPropagatorSolver = _out_of_scope("NeuralSurveyPropagatorSolver")
+ReinforceSurveyPropagatorSolver = _out_of_scope("ReinforceSurveyPropagatorSolver")
+NeuralSequentialDecimatorSolver = _out_of_scope("NeuralSequentialDecimatorSolver")
