@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""bench.py -- SATYR p-d-p hot path on B200: SP edge-updates/s (+ CNFs solved/s), % of HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on at 1/2/4/8 B200): the
+p-d-p model (Survey Propagation + sequential decimation) plus 100 iterations of WalkSAT on uniform
+random 3-SAT with n = 1,000,000 variables at m/n = 4.2, `--problems` (default 8) problems per GPU,
+T = 100 iterations.  One step = one whole forward() of SurveyPropagatorSolver over that batch: graph
+ingest, simplify, T x [SP sweep, decimation statistics/decisions, termination check], random fill,
+WalkSAT, solution merge.  Weak scaling: every rank owns its own problems, no data-path collective.
+
+`value`  : device-resident inputs; SP edge-updates (sum over problems of executed iterations x edges)
+           divided by the time of the whole step, max over ranks.
+`e2e`    : the same through the public API with HOST (pinned) batch tensors; H2D of the batch and D2H
+           of the prediction + verdicts are inside the timed region.
+`roofline`: the persistent SP kernel (k_sp_run) timed alone with CUDA events on its stream.
+`--impl reference`: the reference algorithm on the host cores (the C oracle port, OpenMP, all
+           threads; the Python reference cannot travel to the GPU box) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_EDGE_UPDATE = 20.0   # q_u r + eta r + index r + eta' w + q_u' w
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--problems", type=int, default=8, help="problems per GPU")
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--alpha", type=float, default=4.2)
+    ap.add_argument("--iterations", type=int, default=100)
+    ap.add_argument("--walksat", type=int, default=100)
+    ap.add_argument("--epsilon", type=float, default=0.5)
+    ap.add_argument("--tolerance", type=float, default=0.02)
+    ap.add_argument("--t_max", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-problem-n", type=int, default=0, help="n of the CPU sample problem (default: --n)")
+    ap.add_argument("--cpu-iterations", type=int, default=3)
+    ap.add_argument("--cpu-walksat", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "p-d-p SP + %d-iteration WalkSAT, random %d-SAT n=%d m/n=%.2f, %d problems/GPU, T=%d" % (
+        a.walksat, a.k, a.n, a.alpha, a.problems, a.iterations)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for nme, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_forward(batch, T, W, tol, t_max, eps, seed):
+    """one forward() of the reference algorithm on the CPU; returns (seconds, edge_updates, solved)"""
+    from oracle import pdp_oracle as po
+    gm, bvm, bfm, ef = batch
+    E = gm.shape[1]
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    o = po.Oracle(gm, bvm, bfm, ef, strict=False)
+    o.simplify()
+    o.set_state(*po.init_state(E, False))
+    done = o.run(T, tol, t_max, True)
+    n_act = o.count_active_variables()
+    if n_act:
+        o.random_fill(rng.random(n_act, dtype=np.float32))
+    rv = rng.random((max(W, 1), o.V), dtype=np.float32)
+    rc = rng.random((max(W, 1), o.B), dtype=np.float32)
+    pred, _ = o.local_search(W, eps, rv, rc)
+    solved, _ = o.cnf_eval(pred)
+    dt = time.perf_counter() - t0
+    return dt, float(done) * E, int(solved.sum())
+
+
+def cpu_sample(a):
+    from pdp_solver_b200 import cnfgen
+    n = a.cpu_problem_n or a.n
+    return cnfgen.random_batch(1, n, a.k, a.alpha, a.seed + 999), n
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    from oracle import pdp_oracle as po
+    po.build()
+    batch, n = cpu_sample(a)
+    sample = "1 problem n=%d, T=%d SP iterations + %d WalkSAT iterations per step (bounded sample of the workload)" % (
+        n, a.cpu_iterations, a.cpu_walksat)
+    for _ in range(min(a.warmup, 1)):
+        cpu_forward(batch, 1, 1, a.tolerance, a.t_max, a.epsilon, a.seed)
+    tot_t, tot_u = 0.0, 0.0
+    for s in range(a.steps):
+        dt, upd, _ = cpu_forward(batch, a.cpu_iterations, a.cpu_walksat, a.tolerance, a.t_max, a.epsilon, a.seed + s)
+        tot_t += dt
+        tot_u += upd
+    val = tot_u / tot_t
+    line = {"impl": "reference", "metric": "sp_edge_updates_per_s", "value": val, "unit": "edge-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(a.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a)},
+            "cpu_baseline": {"value": val, "unit": "edge-updates/s", "cores": po.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.nn import solver as pdp_solver
+    from pdp_solver_b200.nn import util as pdp_util
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic batch (host, pinned) -----------------------------------------------------------
+    batch = cnfgen.random_batch(a.problems, a.n, a.k, a.alpha, a.seed + 17 * rank)
+    host = [torch.from_numpy(x).pin_memory() for x in batch]
+    E, V, F, B = batch[0].shape[1], batch[1].shape[0], batch[2].shape[0], a.problems
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in host)
+    resident = [t.to(dev, non_blocking=True) for t in host]
+    torch.cuda.synchronize()
+
+    model = pdp_solver.SurveyPropagatorSolver(dev, "p-d-p", tolerance=a.tolerance, t_max=a.t_max,
+                                              local_search_iterations=a.walksat, epsilon=a.epsilon)
+    evaluator = pdp_util.SatCNFEvaluator(dev)
+
+    def termination(active, prediction, sat_problem):   # evaluated inside the persistent kernel
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+
+    stats = {"updates": 0.0, "solved": 0, "launches": 0, "loop_ms": 0.0, "loop_updates": 0.0, "ws_ms": 0.0}
+
+    def one_step(tensors, from_host, timed):
+        torch.manual_seed(1 + rank)
+        if from_host:
+            gm, bvm, bfm, ef = [t.to(dev, non_blocking=True) for t in tensors]
+        else:
+            gm, bvm, bfm, ef = tensors
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=1)
+        (pred, _), _ = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                             edge_feature=ef, meta_data=None, is_training=False, iteration_num=a.iterations,
+                             check_termination=termination, batch_replication=1)
+        ctx = model.last_problem._ctx
+        solved, _ = ctx.cnf_eval(pred)
+        if from_host:
+            pred_h = pred.to("cpu", non_blocking=False)
+            solved_h = solved.cpu()
+        else:
+            solved_h = None
+        if timed:
+            _, _, freeze = ctx.problem_flags()
+            iters = int(model.last_iterations.item())
+            per = torch.where(freeze >= 0, freeze, torch.full_like(freeze, iters)).double()
+            bvm_l = bvm.long()
+            epp = torch.bincount(bvm_l[gm[0].long()], minlength=B).double()
+            upd = float((per * epp).sum().item())
+            stats["updates"] += upd
+            stats["solved"] += int(solved.sum().item())
+            stats["launches"] += ctx.launch_count() + 2   # + the evaluator's two kernels
+            t = model.last_problem._ctx.timing
+            if t:
+                stats["loop_ms"] += t.get("sp_run", 0.0)
+                stats["ws_ms"] += t.get("walksat", 0.0)
+                stats["loop_updates"] += upd
+        return pred
+
+    def timed_region(tensors, from_host):
+        for k in stats:
+            stats[k] = 0 if isinstance(stats[k], int) else 0.0
+        for _ in range(a.warmup):
+            one_step(tensors, from_host, False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            one_step(tensors, from_host, True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            agg = torch.tensor([stats["updates"], stats["solved"], stats["launches"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            tot_upd, tot_solved, tot_launch = [float(x) for x in agg.tolist()]
+        else:
+            tot_upd, tot_solved, tot_launch = stats["updates"], stats["solved"], stats["launches"]
+        return ms, tot_upd, tot_solved, tot_launch, dict(stats)
+
+    os.environ["PDP_B200_TIMING"] = "1"
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, upd, solved, launches, st = timed_region(resident, False)
+    ms_e, upd_e, solved_e, _, _ = timed_region(host, True)
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    loop_s = st["loop_ms"] / 1e3
+    achieved = ALG_BYTES_PER_EDGE_UPDATE * st["loop_updates"] / loop_s / 1e9 if loop_s > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_sp_run_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "sp_edge_updates_per_s", "value": upd / (ms / 1e3), "unit": "edge-updates/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "model_type": "p-d-p", "edges_per_gpu": E, "variables_per_gpu": V,
+                   "clauses_per_gpu": F, "init": "deterministic (predict path)", "rng": "torch" if a.walksat * (V + B) <= pdp_solver.TORCH_RNG_DRAW_LIMIT else "philox",
+                   "l2": "inputs larger than L2 (%.1f GB message+topology working set per GPU)" % (E * 48 / 1e9),
+                   "sharding": "problems sharded across ranks, no per-iteration collective"},
+        "cnfs_solved_per_s": solved / (ms / 1e3), "cnfs_per_s": world * B * a.steps / (ms / 1e3),
+        "sp_loop_edge_updates_per_s_rank0": st["loop_updates"] / loop_s if loop_s > 0 else None,
+        "phase_ms_per_step_rank0": {"sp_loop": st["loop_ms"] / a.steps, "walksat": st["ws_ms"] / a.steps,
+                                    "other(ingest,simplify,fill,io)": (ms - st["loop_ms"] - st["ws_ms"]) / a.steps},
+        "e2e": {"value": upd_e / (ms_e / 1e3), "unit": "edge-updates/s", "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": (V * 4 + B * 4) * world, "ms_per_step": ms_e / a.steps,
+                "cnfs_solved_per_s": solved_e / (ms_e / 1e3)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_sp_run (persistent SP propagate/decimate loop)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_edge_update": ALG_BYTES_PER_EDGE_UPDATE,
+                     "edge_updates_per_launch": st["loop_updates"] / a.steps, "launch_ms": st["loop_ms"] / a.steps},
+        "clocks": sampler.summary(),
+    }
+    if not a.no_cpu_baseline and world == 1:
+        from oracle import pdp_oracle as po
+        po.build()
+        cb, n = cpu_sample(a)
+        dt, u, _ = cpu_forward(cb, a.cpu_iterations, a.cpu_walksat, a.tolerance, a.t_max, a.epsilon, a.seed)
+        line["cpu_baseline"] = {"value": u / dt, "unit": "edge-updates/s", "cores": po.num_threads(), "kind": "port",
+                                "sample": "1 problem n=%d, T=%d SP iterations + %d WalkSAT iterations (%.1f s)" % (
+                                    n, a.cpu_iterations, a.cpu_walksat, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+    if world == 1 and a.gpus > 1:
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531"] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_b200_arm(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

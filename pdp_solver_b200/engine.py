@@ -5,6 +5,7 @@ kernels.  There is no fallback path: without a CUDA device or without the built 
 raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -58,6 +59,26 @@ class Context(object):
         self._h = h
         self._iters = torch.zeros(2, dtype=torch.int32, device=dev)
         self._trace = None
+        # optional CUDA-event timing of the two persistent kernels (bench.py's roofline numbers)
+        self._events = {} if os.environ.get("PDP_B200_TIMING") == "1" else None
+
+    def _timed(self, name, fn):
+        if self._events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self._events.setdefault(name, []).append((e0, e1))
+        return r
+
+    @property
+    def timing(self):
+        """name -> total milliseconds (synchronises); None unless PDP_B200_TIMING=1"""
+        if self._events is None:
+            return None
+        torch.cuda.synchronize(self.device)
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self._events.items()}
 
     def __del__(self):
         try:
@@ -177,7 +198,8 @@ class Context(object):
         int32 tensor holding the number of executed iterations (or the int when sync=True)."""
         prm = SpParams(int(iterations), float(tolerance), int(t_max), float(pi), 1 if check_termination else 0,
                        int(batch_replication), 1 if full_state else 0, 0)
-        check(self._L.pdp_sp_run(self._h, ctypes.byref(prm), _ptr(self._iters), _stream()), "pdp_sp_run")
+        self._timed("sp_run", lambda: check(
+            self._L.pdp_sp_run(self._h, ctypes.byref(prm), _ptr(self._iters), _stream()), "pdp_sp_run"))
         if sync:
             return int(self._iters[0].item())
         return self._iters[:1]
@@ -195,9 +217,10 @@ class Context(object):
         rv = None if rand_var is None else _f32(rand_var, self.device).reshape(-1)
         rc = None if rand_coin is None else _f32(rand_coin, self.device).reshape(-1)
         pred = self._new(self.V)
-        check(self._L.pdp_walksat(self._h, int(iterations), float(epsilon), int(batch_replication), _ptr(rv), _ptr(rc),
-                                  int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(pred), _ptr(self._iters[1:]), _stream()),
-              "pdp_walksat")
+        self._timed("walksat", lambda: check(
+            self._L.pdp_walksat(self._h, int(iterations), float(epsilon), int(batch_replication), _ptr(rv), _ptr(rc),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(pred), _ptr(self._iters[1:]), _stream()),
+            "pdp_walksat"))
         if sync:
             return pred, int(self._iters[1].item())
         return pred, self._iters[1:]
