@@ -178,6 +178,7 @@ def run_b200_arm(a, rank, world, local_rank):
     E, V, F, B = batch[0].shape[1], batch[1].shape[0], batch[2].shape[0], a.problems
     h2d_bytes = sum(int(t.numel() * t.element_size()) for t in host)
     resident = [t.to(dev, non_blocking=True) for t in host]
+    edges_per_problem = torch.bincount(resident[1].long()[resident[0][0].long()], minlength=B).double()
     torch.cuda.synchronize()
 
     model = pdp_solver.SurveyPropagatorSolver(dev, "p-d-p", tolerance=a.tolerance, t_max=a.t_max,
@@ -211,9 +212,7 @@ def run_b200_arm(a, rank, world, local_rank):
             _, _, freeze = ctx.problem_flags()
             iters = int(model.last_iterations.item())
             per = torch.where(freeze >= 0, freeze, torch.full_like(freeze, iters)).double()
-            bvm_l = bvm.long()
-            epp = torch.bincount(bvm_l[gm[0].long()], minlength=B).double()
-            upd = float((per * epp).sum().item())
+            upd = float((per * edges_per_problem).sum().item())
             stats["updates"] += upd
             stats["solved"] += int(solved.sum().item())
             stats["launches"] += ctx.launch_count() + 2   # + the evaluator's two kernels

@@ -47,14 +47,45 @@ struct KeyedReducer {
             acc.reset();
         }
     }
-    // call once, by ALL threads of the block, outside of divergent code
+    // call once, by ALL threads of the block, outside of divergent code.  Warps whose lanes all hold
+    // the same problem merge in registers and hand their partial to a block-level merge in shared
+    // memory (one commit per block and problem run: a 1M-variable problem costs ~600 atomics per
+    // pass instead of ~10^5); mixed warps commit per lane group.
     __device__ __forceinline__ void finish(const pdp_state& s) {
-        unsigned m = __match_any_sync(0xffffffffu, key);
-        acc.merge_shfl(m);
-        bool leader = (lane_id() == (__ffs(m) - 1));
-        if (leader && key >= 0) acc.commit(s, key);
+        __shared__ ACC sm_acc[32];
+        __shared__ int sm_key[32];
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const bool uniform = (m == 0xffffffffu);
+        const int warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        if (uniform) {
+            acc.merge_full();
+            if (lane_id() == 0) { sm_acc[warp] = acc; sm_key[warp] = key; }
+        } else {
+            acc.merge_group(m);
+            if (lane_id() == (__ffs(m) - 1) && key >= 0) acc.commit(s, key);
+            if (lane_id() == 0) sm_key[warp] = -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int w = 0;
+            while (w < nwarp) {
+                const int k = sm_key[w];
+                if (k < 0) { ++w; continue; }
+                ACC a = sm_acc[w];
+                int v = w + 1;
+                while (v < nwarp && sm_key[v] == k) { a.merge(sm_acc[v]); ++v; }
+                a.commit(s, k);
+                w = v;
+            }
+        }
+        __syncthreads();
     }
 };
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, o), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), o);
+    return ((unsigned long long)hi << 32) | lo;
+}
 
 // ------------------------------------------------------------------------------------------------
 // accumulators
@@ -71,6 +102,11 @@ struct StatAcc {   // SequentialDecimator statistics: per problem max/min of two
         mx0 = __reduce_max_sync(m, mx0); mn0 = __reduce_min_sync(m, mn0);
         mx1 = __reduce_max_sync(m, mx1); mn1 = __reduce_min_sync(m, mn1);
         nan = __reduce_or_sync(m, nan); nav = __reduce_add_sync(m, nav);
+    }
+    __device__ __forceinline__ void merge_full() { merge_shfl(0xffffffffu); }
+    __device__ __forceinline__ void merge_group(unsigned m) { merge_shfl(m); }
+    __device__ __forceinline__ void merge(const StatAcc& o) {
+        mx0 = max(mx0, o.mx0); mn0 = min(mn0, o.mn0); mx1 = max(mx1, o.mx1); mn1 = min(mn1, o.mn1); nan |= o.nan; nav += o.nav;
     }
     __device__ __forceinline__ void commit(const pdp_state& s, int b) const {
         atomicMax(&s.st_max[2 * b], mx0); atomicMin(&s.st_min[2 * b], mn0);
@@ -89,6 +125,9 @@ struct CoefAcc {   // decimation coefficients |score| * active: per problem max 
     __device__ __forceinline__ void merge_shfl(unsigned m) {
         mx = __reduce_max_sync(m, mx); mn = __reduce_min_sync(m, mn); nan = __reduce_or_sync(m, nan);
     }
+    __device__ __forceinline__ void merge_full() { merge_shfl(0xffffffffu); }
+    __device__ __forceinline__ void merge_group(unsigned m) { merge_shfl(m); }
+    __device__ __forceinline__ void merge(const CoefAcc& o) { mx = max(mx, o.mx); mn = min(mn, o.mn); nan |= o.nan; }
     __device__ __forceinline__ void commit(const pdp_state& s, int b) const {
         atomicMax(&s.c_max[b], mx); atomicMin(&s.c_min[b], mn);
         if (nan) atomicOr(&s.c_nan[b], nan);
@@ -99,6 +138,9 @@ struct CountAcc {  // integer count into s.n_unsat
     int n;
     __device__ __forceinline__ void reset() { n = 0; }
     __device__ __forceinline__ void merge_shfl(unsigned m) { n = __reduce_add_sync(m, n); }
+    __device__ __forceinline__ void merge_full() { merge_shfl(0xffffffffu); }
+    __device__ __forceinline__ void merge_group(unsigned m) { merge_shfl(m); }
+    __device__ __forceinline__ void merge(const CountAcc& o) { n += o.n; }
     __device__ __forceinline__ void commit(const pdp_state& s, int b) const { if (n) atomicAdd(&s.n_unsat[b], n); }
 };
 
@@ -106,7 +148,50 @@ struct EnergyAcc { // integer count into s.energy
     int n;
     __device__ __forceinline__ void reset() { n = 0; }
     __device__ __forceinline__ void merge_shfl(unsigned m) { n = __reduce_add_sync(m, n); }
+    __device__ __forceinline__ void merge_full() { merge_shfl(0xffffffffu); }
+    __device__ __forceinline__ void merge_group(unsigned m) { merge_shfl(m); }
+    __device__ __forceinline__ void merge(const EnergyAcc& o) { n += o.n; }
     __device__ __forceinline__ void commit(const pdp_state& s, int b) const { if (n) atomicAdd(&s.energy[b], n); }
+};
+
+// WalkSAT candidate selection (solver.py:453-458): per problem
+//   kg = min over variables of (delta, index)            -> first index of the minimum energy delta
+//   kr = max over variables of (fl(x+1) bits, ~index)    -> first index of the maximum random key
+//   mn / mx = min / max of x (float bits) for the exact handling of min x > 0
+struct PickAcc {
+    unsigned long long kg, kr;
+    uint32_t mn, mx;
+    __device__ __forceinline__ void reset() { kg = ~0ull; kr = 0ull; mn = 0x7f800000u; mx = 0u; }
+    __device__ __forceinline__ void add(unsigned long long g, unsigned long long r, uint32_t xb) {
+        kg = g < kg ? g : kg; kr = r > kr ? r : kr; mn = min(mn, xb); mx = max(mx, xb);
+    }
+    __device__ __forceinline__ void merge(const PickAcc& o) {
+        kg = o.kg < kg ? o.kg : kg; kr = o.kr > kr ? o.kr : kr; mn = min(mn, o.mn); mx = max(mx, o.mx);
+    }
+    __device__ __forceinline__ void merge_full() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long g = shfl_xor_u64(kg, o), r = shfl_xor_u64(kr, o);
+            kg = g < kg ? g : kg; kr = r > kr ? r : kr;
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    }
+    // mixed warp: serialise over the (few) distinct keys; every lane of a group ends with the group's result
+    __device__ __forceinline__ void merge_group(unsigned m) {
+        mn = __reduce_min_sync(m, mn); mx = __reduce_max_sync(m, mx);
+        unsigned todo = m;
+        unsigned long long g = kg, r = kr;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            const unsigned long long og = __shfl_sync(m, g, src), orr = __shfl_sync(m, r, src);
+            kg = og < kg ? og : kg; kr = orr > kr ? orr : kr;
+            todo &= todo - 1;
+        }
+    }
+    __device__ __forceinline__ void commit(const pdp_state& s, int b) const {
+        atomicMin(&s.ws_key[2 * b], kg); atomicMax(&s.ws_key[2 * b + 1], kr);
+        atomicMin(&s.ws_best[2 * b], mn); atomicMax(&s.ws_best[2 * b + 1], mx);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -182,182 +182,6 @@ __global__ void __launch_bounds__(256) k_set_variables(const __grid_constant__ K
     closure(A, grid);
 }
 
-// ------------------------------------------------------------------------------------------------
-// WalkSAT (solver.py:433-467) as a cooperative kernel; one flip per still-unsatisfied problem and
-// iteration, exactly as the reference schedules it.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
-
-// Philox-4x32-10 counter based generator: (seed, counter) -> uniform float in [0,1)
-__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x5eed5eedu;
-#pragma unroll
-    for (int rnd = 0; rnd < 10; ++rnd) {
-        const uint32_t hi0 = mulhi32(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-        const uint32_t hi1 = mulhi32(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-        const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
-        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return (float)(x0 >> 8) * (1.0f / 16777216.0f);
-}
-
-struct WsArgs {
-    int32_t W;
-    float epsilon;
-    int32_t rep;
-    const float* rand_var;    // [W,V] or null
-    const float* rand_coin;   // [W,B] or null
-    uint64_t seed;
-    float* prediction;        // [V]
-    int32_t* iters_done;
-};
-
-__device__ __forceinline__ float ws_rand_var(const WsArgs& w, int it, int64_t i, int64_t V) {
-    return w.rand_var ? w.rand_var[(int64_t)it * V + i] : philox_uniform(w.seed, (uint32_t)i, (uint32_t)it, 0x76617231u);
-}
-__device__ __forceinline__ float ws_rand_coin(const WsArgs& w, int it, int64_t b, int64_t B) {
-    return w.rand_coin ? w.rand_coin[(int64_t)it * B + b] : philox_uniform(w.seed, (uint32_t)b, (uint32_t)it, 0x636f696eu);
-}
-
-__global__ void __launch_bounds__(256) k_walksat(const __grid_constant__ KArgs A, const __grid_constant__ WsArgs wa) {
-    cg::grid_group grid = cg::this_grid();
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    const int rep = wa.rep > 1 ? wa.rep : 1;
-    const int64_t B0 = g.B / rep;
-    // solver.py:436-437
-    WARP_STRIDED(i, g.V) {
-        if (i < g.V) s.asg[i] = s.av[i] ? ((s.sol[i] > 0.5f) ? (int8_t)1 : (int8_t)-1) : (int8_t)0;
-    }
-    WARP_STRIDED(b, g.B) { if (b < g.B) s.energy[b] = 0; }
-    if (gtid() == 0) { s.ctrl[CTRL_WS_UNSAT] = 0; s.ctrl[CTRL_WS_UNSAT + 1] = 0; s.ctrl[CTRL_WS_REDO] = 0; s.ctrl[CTRL_WS_REDO + 1] = 0; }
-    grid.sync();
-    int it = 0;
-    for (; it < wa.W; ++it) {
-        const int slot = it & 1;
-        // ---- energy (solver.py:486-496): clause unsatisfied iff sum of its literals == -(#active variables)
-        {
-            KeyedReducer<EnergyAcc> red;
-            WARP_STRIDED(a, g.F) {
-                if (a >= g.F) continue;
-                const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
-                int agg = 0, deg = 0;
-                for (int c = beg; c < end; ++c) {
-                    const uint32_t w = g.c_var[c];
-                    const int v = (int)(w & PDP_IDX_MASK);
-                    const int lit = (int)s.asg[v];
-                    agg += (w & PDP_SIGN_BIT) ? -lit : lit;
-                    deg += s.av[v];
-                }
-                const bool unsat = (agg == -deg) && s.af[a];
-                s.ws_true[a] = agg; s.ws_deg[a] = deg; s.single[a] = unsat ? 1 : 0;
-                if (unsat) { red.touch(s, g.bfm[a]); red.acc.n += 1; }
-            }
-            red.finish(s);
-        }
-        grid.sync();
-        // ---- which problems are still unsatisfied (solver.py:444-451)
-        WARP_STRIDED(j, B0) {
-            if (j >= B0) continue;
-            bool all_unsat = true;
-            for (int r = 0; r < rep; ++r) if (!(s.energy[(int64_t)r * B0 + j] > 0)) all_unsat = false;
-            if (all_unsat) s.ctrl[CTRL_WS_UNSAT + slot] = 1;
-            for (int r = 0; r < rep; ++r) {
-                const int64_t b = (int64_t)r * B0 + j;
-                s.ws_key[2 * b] = ~0ull; s.ws_key[2 * b + 1] = 0ull;
-                s.ws_best[2 * b] = 0x7f800000u; s.ws_best[2 * b + 1] = 0u;
-            }
-        }
-        if (gtid() == 0) { s.ctrl[CTRL_WS_UNSAT + (slot ^ 1)] = 0; s.ctrl[CTRL_WS_REDO + (slot ^ 1)] = 0; }
-        grid.sync();
-        if (!s.ctrl[CTRL_WS_UNSAT + slot]) break;
-        // ---- energy delta and the two candidate picks (solver.py:453-458)
-        WARP_STRIDED(i, g.V) {
-            if (i >= g.V) continue;
-            const int b = g.bvm[i];
-            if (!(s.energy[b] > 0)) continue;
-            const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
-            const int ai = (int)s.asg[i];
-            const int avi = s.av[i];
-            int delta = 0, uv = 0;
-            for (int p = beg; p < end; ++p) {
-                const int a = g.v_cls[p];
-                const int lit = (g.v_cedge[p] & PDP_SIGN_BIT) ? -ai : ai;
-                const bool crit = (s.ws_true[a] - lit == 1 - s.ws_deg[a]) && avi && s.af[a];
-                if (crit) delta += lit;
-                uv += s.single[a];
-            }
-            uv *= avi;
-            // greedy: first index of the minimum delta (argmax of -delta; integers, exact)
-            const unsigned long long kg = ((unsigned long long)(uint32_t)(delta + 0x40000000) << 32) | (uint32_t)i;
-            atomicMin(&s.ws_key[2 * b], kg);
-            // random: first index of max fl(fl(x - min x) + 1); computed here for min x == 0
-            const float x = ((uv > 0) ? 1.f : 0.f) * ws_rand_var(wa, it, i, g.V);
-            const float key = argmax_key(x, 0.f);
-            const unsigned long long kr = ((unsigned long long)f2u(key) << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
-            atomicMax(&s.ws_key[2 * b + 1], kr);
-            atomicMin(&s.ws_best[2 * b], f2u(x));
-            atomicMax(&s.ws_best[2 * b + 1], f2u(x));
-        }
-        grid.sync();
-        // min x > 0 (every variable of the problem sits in an unsatisfied clause): redo exactly
-        WARP_STRIDED(b, g.B) {
-            if (b >= g.B) continue;
-            if (s.energy[b] > 0 && s.ws_best[2 * b] != 0u && s.ws_best[2 * b] != 0x7f800000u) {
-                s.ctrl[CTRL_WS_REDO + slot] = 1;
-                s.ws_key[2 * b + 1] = ~0ull;   // becomes an atomicMin over the index
-            }
-        }
-        grid.sync();
-        if (s.ctrl[CTRL_WS_REDO + slot]) {
-            WARP_STRIDED(i, g.V) {
-                if (i >= g.V) continue;
-                const int b = g.bvm[i];
-                if (!(s.energy[b] > 0) || s.ws_best[2 * b] == 0u || s.ws_best[2 * b] == 0x7f800000u) continue;
-                const float m = u2f(s.ws_best[2 * b]);
-                const float kmax = argmax_key(u2f(s.ws_best[2 * b + 1]), m);
-                int uv = 0;
-                for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) uv += s.single[g.v_cls[p]];
-                uv *= s.av[i];
-                const float x = ((uv > 0) ? 1.f : 0.f) * ws_rand_var(wa, it, i, g.V);
-                if (argmax_key(x, m) == kmax) atomicMin(&s.ws_key[2 * b + 1], (unsigned long long)(uint32_t)i);
-            }
-            grid.sync();
-        }
-        // ---- flip (solver.py:460-465)
-        WARP_STRIDED(b, g.B) {
-            if (b >= g.B) continue;
-            if (s.energy[b] > 0) {
-                const bool redo = (s.ws_best[2 * b] != 0u && s.ws_best[2 * b] != 0x7f800000u);
-                const uint32_t gi = (uint32_t)(s.ws_key[2 * b] & 0xffffffffull);
-                const uint32_t lo = (uint32_t)(s.ws_key[2 * b + 1] & 0xffffffffull);
-                const uint32_t ri = redo ? lo : (0xffffffffu - lo);
-                const bool coin = ws_rand_coin(wa, it, b, g.B) > wa.epsilon;
-                const uint32_t ind = coin ? gi : ri;
-                if (ind < (uint32_t)g.V) s.asg[ind] = (int8_t)(-s.asg[ind]);
-            }
-            s.energy[b] = 0;
-        }
-        grid.sync();
-    }
-    // solver.py:467 + _update_solution (solver.py:388-399)
-    WARP_STRIDED(i, g.V) {
-        if (i >= g.V) continue;
-        const float avf = (float)s.av[i];
-        const float walk = ((float)s.asg[i] + 1.f) / 2.0f;
-        const float merged = avf * walk + (1.0f - avf) * s.sol[i];
-        if (s.av[i]) s.sol[i] = merged;
-        if (wa.prediction) wa.prediction[i] = merged;
-    }
-    WARP_STRIDED(a, g.F) { if (a < g.F) s.single[a] = 0; }
-    WARP_STRIDED(b, g.B) { if (b < g.B) { s.energy[b] = 0; s.dirty[b] = 1; } }
-    if (gtid() == 0) {
-        s.ctrl[CTRL_WS_ITERS] = it; s.ctrl[CTRL_ANY_DIRTY] = 1;
-        if (wa.iters_done) *wa.iters_done = it;
-    }
-}
-
 template <typename K>
 int coop_blocks(pdp_ctx* ctx, K kernel) {
     int per_sm = 0;
@@ -425,25 +249,6 @@ extern "C" int pdp_set_variables(pdp_ctx* ctx, const float* d_assignment, void* 
     int blocks = coop_blocks(ctx, k_set_variables);
     if (blocks < 1) { pdp_set_error("pdp_set_variables: occupancy query failed"); return PDP_ERR_CUDA; }
     PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_set_variables, dim3(blocks), dim3(256), args, 0, (cudaStream_t)stream_));
-    PDP_LAUNCH_CHECK(ctx);
-    return PDP_OK;
-}
-
-extern "C" int pdp_walksat(pdp_ctx* ctx, int32_t W, float epsilon, int32_t batch_replication, const float* d_rand_var,
-                           const float* d_rand_coin, uint64_t seed, float* d_prediction, int32_t* d_iters_done, void* stream_) {
-    if (!ctx) { pdp_set_error("pdp_walksat: null context"); return PDP_ERR_ARG; }
-    if (W < 0) { pdp_set_error("pdp_walksat: negative iteration count"); return PDP_ERR_ARG; }
-    if ((d_rand_var == nullptr) != (d_rand_coin == nullptr)) { pdp_set_error("pdp_walksat: rand_var and rand_coin must both be given or both be null"); return PDP_ERR_ARG; }
-    const int rep = batch_replication > 1 ? batch_replication : 1;
-    if (ctx->g.B % rep != 0) { pdp_set_error("pdp_walksat: batch size not divisible by replication"); return PDP_ERR_ARG; }
-    KArgs A = make_args(ctx);
-    WsArgs wa;
-    wa.W = W; wa.epsilon = epsilon; wa.rep = rep; wa.rand_var = d_rand_var; wa.rand_coin = d_rand_coin; wa.seed = seed;
-    wa.prediction = d_prediction; wa.iters_done = d_iters_done;
-    void* args[] = {&A, &wa};
-    int blocks = coop_blocks(ctx, k_walksat);
-    if (blocks < 1) { pdp_set_error("pdp_walksat: occupancy query failed"); return PDP_ERR_CUDA; }
-    PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_walksat, dim3(blocks), dim3(256), args, 0, (cudaStream_t)stream_));
     PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
 }

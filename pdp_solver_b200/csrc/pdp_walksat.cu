@@ -1,0 +1,257 @@
+// pdp_walksat.cu -- WalkSAT post-processing (reference pdp/nn/solver.py:433-467 + 388-399) as one
+// persistent cooperative kernel.
+//
+// The reference recomputes, every iteration and for the whole batch, the clause energies (5 SpMM), the
+// per-variable energy deltas (7 SpMM) and two dense [V,B] arg-max matrices -- to flip ONE variable per
+// unsatisfied problem.  Here the per-clause literal sums, the per-variable break-minus-make deltas and
+// the per-variable "sits in an unsatisfied clause" counts are built once and then maintained
+// incrementally by the thread that flips a problem's variable (integers: exact, order independent), so an
+// iteration costs one streaming selection pass over the variables (12 B per variable) plus O(degree * k)
+// updates per problem.  Selection follows the reference exactly: greedy = first index of the minimum
+// delta over ALL variables of the problem, random = first index of the maximum of fl(fl(x - min x) + 1)
+// with x = [variable in an unsatisfied clause] * r, coin = r_b > epsilon.
+#include "pdp_device.cuh"
+
+namespace {
+
+// Philox-4x32-10 counter based generator: (seed, counter) -> uniform float in [0,1)
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x5eed5eedu;
+#pragma unroll
+    for (int rnd = 0; rnd < 10; ++rnd) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return (float)(x0 >> 8) * (1.0f / 16777216.0f);
+}
+
+struct WsArgs {
+    int32_t W;
+    float epsilon;
+    int32_t rep;
+    const float* rand_var;    // [W,V] or null
+    const float* rand_coin;   // [W,B] or null
+    uint64_t seed;
+    float* prediction;        // [V]
+    int32_t* iters_done;
+};
+
+__device__ __forceinline__ float ws_rand_var(const WsArgs& w, int it, int64_t i, int64_t V) {
+    return w.rand_var ? w.rand_var[(int64_t)it * V + i] : philox_uniform(w.seed, (uint32_t)i, (uint32_t)it, 0x76617231u);
+}
+__device__ __forceinline__ float ws_rand_coin(const WsArgs& w, int it, int64_t b, int64_t B) {
+    return w.rand_coin ? w.rand_coin[(int64_t)it * B + b] : philox_uniform(w.seed, (uint32_t)b, (uint32_t)it, 0x636f696eu);
+}
+
+// per-variable state kept in the closure scratch arrays (idle outside unit propagation)
+#define WS_DELTA(s) ((s).up_cnt)   // [V] energy delta of flipping the variable (break - make)
+#define WS_UVC(s) ((s).up_ev)      // [V] unsatisfied clauses the variable occurs in, times active
+
+// flips variable `ind` of problem b and repairs every quantity that depends on it
+__device__ void ws_flip(const pdp_graph& g, const pdp_state& s, int b, int ind) {
+    const int a_old = (int)s.asg[ind];
+    if (a_old == 0) return;   // inactive variable: flipping 0 is a no-op (solver.py:465)
+    const int vb = g.var_ptr[ind], ve = g.var_ptr[ind + 1];
+    int d_energy = 0;
+    for (int p = vb; p < ve; ++p) {
+        const int c = g.v_cls[p];
+        if (!s.af[c] || (s.single[c] & 2)) continue;   // inactive clause, or clause already handled (duplicate literal)
+        const int cb = g.cl_ptr[c], ce = g.cl_ptr[c + 1];
+        int lsum = 0;
+        for (int e = cb; e < ce; ++e) {
+            const uint32_t w = g.c_var[e];
+            if ((int)(w & PDP_IDX_MASK) == ind) lsum += (w & PDP_SIGN_BIT) ? -a_old : a_old;
+        }
+        const int agg_old = s.ws_true[c], deg = s.ws_deg[c];
+        const int agg_new = agg_old - 2 * lsum;
+        const int u_old = s.single[c] & 1, u_new = (agg_new == -deg) ? 1 : 0;
+        for (int e = cb; e < ce; ++e) {
+            const uint32_t w = g.c_var[e];
+            const int j = (int)(w & PDP_IDX_MASK);
+            if (!s.av[j]) continue;
+            const int aj = (int)s.asg[j];   // still the old value for j == ind
+            const int lit_old = (w & PDP_SIGN_BIT) ? -aj : aj;
+            const int lit_new = (j == ind) ? -lit_old : lit_old;
+            const int c_old = (agg_old - lit_old == 1 - deg) ? lit_old : 0;
+            const int c_new = (agg_new - lit_new == 1 - deg) ? lit_new : 0;
+            if (c_new != c_old) WS_DELTA(s)[j] += c_new - c_old;
+            if (u_new != u_old) WS_UVC(s)[j] += u_new - u_old;
+        }
+        s.ws_true[c] = agg_new;
+        s.single[c] = (uint8_t)(u_new | 2);
+        d_energy += u_new - u_old;
+    }
+    for (int p = vb; p < ve; ++p) s.single[g.v_cls[p]] &= 1;   // clear the visit marks
+    s.asg[ind] = (int8_t)(-a_old);
+    s.energy[b] += d_energy;
+}
+
+__global__ void __launch_bounds__(256) k_walksat(const __grid_constant__ KArgs A, const __grid_constant__ WsArgs wa) {
+    cg::grid_group grid = cg::this_grid();
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int rep = wa.rep > 1 ? wa.rep : 1;
+    const int64_t B0 = g.B / rep;
+    // ---- set-up: assignment (solver.py:436-437), clause sums + energy (486-496), deltas (469-484)
+    WARP_STRIDED(i, g.V) {
+        if (i < g.V) s.asg[i] = s.av[i] ? ((s.sol[i] > 0.5f) ? (int8_t)1 : (int8_t)-1) : (int8_t)0;
+    }
+    WARP_STRIDED(b, g.B) { if (b < g.B) s.energy[b] = 0; }
+    if (gtid() == 0) { s.ctrl[CTRL_WS_UNSAT] = 0; s.ctrl[CTRL_WS_UNSAT + 1] = 0; s.ctrl[CTRL_WS_REDO] = 0; s.ctrl[CTRL_WS_REDO + 1] = 0; }
+    grid.sync();
+    if (wa.W > 0) {
+        KeyedReducer<EnergyAcc> red;
+        WARP_STRIDED(a, g.F) {
+            if (a >= g.F) continue;
+            int agg = 0, deg = 0;
+            for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+                const uint32_t w = g.c_var[c];
+                const int v = (int)(w & PDP_IDX_MASK);
+                const int lit = (int)s.asg[v];
+                agg += (w & PDP_SIGN_BIT) ? -lit : lit;
+                deg += s.av[v];
+            }
+            const bool unsat = (agg == -deg) && s.af[a];
+            s.ws_true[a] = agg; s.ws_deg[a] = deg; s.single[a] = unsat ? 1 : 0;
+            if (unsat) { red.touch(s, g.bfm[a]); red.acc.n += 1; }
+        }
+        red.finish(s);
+    }
+    grid.sync();
+    if (wa.W > 0) {
+        WARP_STRIDED(i, g.V) {
+            if (i >= g.V) continue;
+            const int ai = (int)s.asg[i], avi = s.av[i];
+            int delta = 0, uv = 0;
+            for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) {
+                const int a = g.v_cls[p];
+                const int lit = (g.v_cedge[p] & PDP_SIGN_BIT) ? -ai : ai;
+                if (avi && s.af[a] && (s.ws_true[a] - lit == 1 - s.ws_deg[a])) delta += lit;
+                uv += s.single[a];
+            }
+            WS_DELTA(s)[i] = delta; WS_UVC(s)[i] = uv * avi;
+        }
+        // which problems are still unsatisfied (solver.py:444-451); reset the selection keys
+        WARP_STRIDED(j, B0) {
+            if (j >= B0) continue;
+            bool all_unsat = true;
+            for (int r = 0; r < rep; ++r) if (!(s.energy[(int64_t)r * B0 + j] > 0)) all_unsat = false;
+            if (all_unsat) s.ctrl[CTRL_WS_UNSAT] = 1;
+            for (int r = 0; r < rep; ++r) {
+                const int64_t b = (int64_t)r * B0 + j;
+                s.ws_key[2 * b] = ~0ull; s.ws_key[2 * b + 1] = 0ull; s.ws_best[2 * b] = 0x7f800000u; s.ws_best[2 * b + 1] = 0u;
+            }
+        }
+    }
+    grid.sync();
+    int it = 0;
+    for (; it < wa.W; ++it) {
+        const int slot = it & 1;
+        if (!s.ctrl[CTRL_WS_UNSAT + slot]) break;
+        // ---- candidate selection: one streaming pass over (delta, count, r)
+        {
+            KeyedReducer<PickAcc> red;
+            WARP_STRIDED(i, g.V) {
+                if (i >= g.V) continue;
+                const int b = g.bvm[i];
+                if (!(s.energy[b] > 0)) continue;
+                red.touch(s, b);
+                const int delta = WS_DELTA(s)[i];
+                const float x = ((WS_UVC(s)[i] > 0) ? 1.f : 0.f) * ws_rand_var(wa, it, i, g.V);
+                const unsigned long long kg = ((unsigned long long)(uint32_t)(delta + 0x40000000) << 32) | (uint32_t)i;
+                const unsigned long long kr = ((unsigned long long)f2u(argmax_key(x, 0.f)) << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
+                red.acc.add(kg, kr, f2u(x));
+            }
+            red.finish(s);
+        }
+        if (gtid() == 0) { s.ctrl[CTRL_WS_UNSAT + (slot ^ 1)] = 0; s.ctrl[CTRL_WS_REDO + (slot ^ 1)] = 0; }
+        grid.sync();
+        // min x > 0 (every variable of the problem sits in an unsatisfied clause and drew r > 0): the
+        // reference's key is fl(fl(x - min x) + 1), redo the random pick exactly
+        WARP_STRIDED(b, g.B) {
+            if (b >= g.B) continue;
+            if (s.energy[b] > 0 && s.ws_best[2 * b] != 0u && s.ws_best[2 * b] != 0x7f800000u) {
+                s.ctrl[CTRL_WS_REDO + slot] = 1;
+                s.ws_key[2 * b + 1] = ~0ull;   // becomes an atomicMin over the index
+            }
+        }
+        grid.sync();
+        if (s.ctrl[CTRL_WS_REDO + slot]) {
+            WARP_STRIDED(i, g.V) {
+                if (i >= g.V) continue;
+                const int b = g.bvm[i];
+                if (!(s.energy[b] > 0) || s.ws_best[2 * b] == 0u || s.ws_best[2 * b] == 0x7f800000u) continue;
+                const float m = u2f(s.ws_best[2 * b]);
+                const float kmax = argmax_key(u2f(s.ws_best[2 * b + 1]), m);
+                const float x = ((WS_UVC(s)[i] > 0) ? 1.f : 0.f) * ws_rand_var(wa, it, i, g.V);
+                if (argmax_key(x, m) == kmax) atomicMin(&s.ws_key[2 * b + 1], (unsigned long long)(uint32_t)i);
+            }
+            grid.sync();
+        }
+        // ---- flip one variable per unsatisfied problem (solver.py:460-465) and repair the state
+        WARP_STRIDED(j, B0) {
+            if (j >= B0) continue;
+            bool all_unsat = true;
+            for (int r = 0; r < rep; ++r) {
+                const int64_t b = (int64_t)r * B0 + j;
+                if (s.energy[b] > 0) {
+                    const bool redo = (s.ws_best[2 * b] != 0u && s.ws_best[2 * b] != 0x7f800000u);
+                    const uint32_t gi = (uint32_t)(s.ws_key[2 * b] & 0xffffffffull);
+                    const uint32_t lo = (uint32_t)(s.ws_key[2 * b + 1] & 0xffffffffull);
+                    const uint32_t ri = redo ? lo : (0xffffffffu - lo);
+                    const bool coin = ws_rand_coin(wa, it, b, g.B) > wa.epsilon;
+                    const uint32_t ind = coin ? gi : ri;
+                    if (ind < (uint32_t)g.V) ws_flip(g, s, (int)b, (int)ind);
+                }
+                if (!(s.energy[b] > 0)) all_unsat = false;
+                s.ws_key[2 * b] = ~0ull; s.ws_key[2 * b + 1] = 0ull; s.ws_best[2 * b] = 0x7f800000u; s.ws_best[2 * b + 1] = 0u;
+            }
+            if (all_unsat) s.ctrl[CTRL_WS_UNSAT + (slot ^ 1)] = 1;
+        }
+        grid.sync();
+    }
+    // ---- solver.py:467 + _update_solution (solver.py:388-399)
+    WARP_STRIDED(i, g.V) {
+        if (i >= g.V) continue;
+        const float avf = (float)s.av[i];
+        const float walk = ((float)s.asg[i] + 1.f) / 2.0f;
+        const float merged = avf * walk + (1.0f - avf) * s.sol[i];
+        if (s.av[i]) s.sol[i] = merged;
+        if (wa.prediction) wa.prediction[i] = merged;
+        WS_DELTA(s)[i] = 0; WS_UVC(s)[i] = 0;
+    }
+    WARP_STRIDED(a, g.F) { if (a < g.F) s.single[a] = 0; }
+    WARP_STRIDED(b, g.B) { if (b < g.B) { s.energy[b] = 0; s.dirty[b] = 1; } }
+    if (gtid() == 0) {
+        s.ctrl[CTRL_WS_ITERS] = it; s.ctrl[CTRL_ANY_DIRTY] = 1;
+        if (wa.iters_done) *wa.iters_done = it;
+    }
+}
+
+}  // namespace
+
+extern "C" int pdp_walksat(pdp_ctx* ctx, int32_t W, float epsilon, int32_t batch_replication, const float* d_rand_var,
+                           const float* d_rand_coin, uint64_t seed, float* d_prediction, int32_t* d_iters_done, void* stream_) {
+    if (!ctx) { pdp_set_error("pdp_walksat: null context"); return PDP_ERR_ARG; }
+    if (W < 0) { pdp_set_error("pdp_walksat: negative iteration count"); return PDP_ERR_ARG; }
+    if ((d_rand_var == nullptr) != (d_rand_coin == nullptr)) { pdp_set_error("pdp_walksat: rand_var and rand_coin must both be given or both be null"); return PDP_ERR_ARG; }
+    const int rep = batch_replication > 1 ? batch_replication : 1;
+    if (ctx->g.B % rep != 0) { pdp_set_error("pdp_walksat: batch size not divisible by replication"); return PDP_ERR_ARG; }
+    KArgs A;
+    A.g = ctx->g; A.s = ctx->s; A.trace = nullptr; A.trace_cap = 0;
+    WsArgs wa;
+    wa.W = W; wa.epsilon = epsilon; wa.rep = rep; wa.rand_var = d_rand_var; wa.rand_coin = d_rand_coin; wa.seed = seed;
+    wa.prediction = d_prediction; wa.iters_done = d_iters_done;
+    void* args[] = {&A, &wa};
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walksat, 256, 0) != cudaSuccess || per_sm < 1) {
+        pdp_set_error("pdp_walksat: occupancy query failed"); return PDP_ERR_CUDA;
+    }
+    if (per_sm > 4) per_sm = 4;
+    PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_walksat, dim3(per_sm * ctx->num_sms), dim3(256), args, 0, (cudaStream_t)stream_));
+    PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}

@@ -176,11 +176,11 @@ class PropagatorDecimatorSolverBase(nn.Module):
         self._predictor(decimator_state, sat_problem, True)
         prediction = self._local_search(sat_problem, batch_replication)
         if batch_replication > 1:
-            pred, _ = ctx.deduplicate(batch_replication, prediction)
-            prediction = pred
+            prediction, winner = ctx.deduplicate(batch_replication, prediction)
             # states of the winning replicas (reference solver.py:417-424)
-            propagator_state = decimator_state = None if propagator_state is None else \
-                self._dedup_states(propagator_state, sat_problem, batch_replication, _)
+            if propagator_state is not None:
+                propagator_state = decimator_state = self._dedup_states(propagator_state, sat_problem,
+                                                                        batch_replication, winner)
         return (prediction.unsqueeze(1), None), (propagator_state, decimator_state)
 
     @staticmethod
@@ -219,8 +219,8 @@ class PropagatorDecimatorSolverBase(nn.Module):
             rv = torch.empty(W, V, device=ctx.device)
             rc = torch.empty(W, B, device=ctx.device)
             for it in range(W):
-                rv[it] = torch.rand([V, 1], device=ctx.device).squeeze(1)
-                rc[it] = torch.rand(B, device=ctx.device)
+                torch.rand(V, out=rv[it])
+                torch.rand(B, out=rc[it])
             pred, _ = ctx.walksat(W, self._epsilon, rv, rc, 0, batch_replication)
         else:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if W > 0 else 0
