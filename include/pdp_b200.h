@@ -116,7 +116,7 @@ typedef struct {
     int32_t check_termination;  /* 1 = trainer._check_recurrence_termination semantics  */
     int32_t batch_replication;  /* b of `-b`; problem id of replica r of j is r*B/b + j */
     int32_t full_state;         /* 1 = also keep q_s and q_* (the [E,3] state) exact    */
-    int32_t reserved;
+    int32_t flags;              /* bit 0: use the generic (thread per node) passes, not the blocked ones */
 } pdp_sp_params;
 
 /* PropagatorDecimatorSolverBase._forward_core for the p-d-p model, reference
@@ -151,6 +151,12 @@ int pdp_deduplicate(pdp_ctx* ctx, int32_t batch_replication, const float* d_pred
  * d_trace, at most capacity_events of them; the running count is returned by pdp_trace_length (syncs) */
 int pdp_set_trace_buffer(pdp_ctx* ctx, int32_t* d_trace, int32_t capacity_events);
 int pdp_trace_length(pdp_ctx* ctx, int32_t* host_out, void* stream);
+
+/* self-check of the blocked message layout built by pdp_create (tests): d_errs device int32[8] receives
+ * the number of violated invariants per class (pdp_layout.cu; [6] and [7] must equal E when the
+ * blocked layout is on); host_info int32[5] (nullable) = {blocked, variable blocks, clause blocks,
+ * variable block stride, clause block stride} */
+int pdp_debug_check_layout(pdp_ctx* ctx, int32_t* d_errs, int32_t* host_info, void* stream);
 
 /* counters for bench.py: number of kernels this library launched on behalf of the context */
 int64_t pdp_launch_count(pdp_ctx* ctx);

@@ -22,7 +22,7 @@ F32 = ctypes.c_float
 class SpParams(ctypes.Structure):
     """mirror of pdp_sp_params (include/pdp_b200.h)"""
     _fields_ = [("iterations", I32), ("tolerance", F32), ("t_max", I32), ("pi", F32),
-                ("check_termination", I32), ("batch_replication", I32), ("full_state", I32), ("reserved", I32)]
+                ("check_termination", I32), ("batch_replication", I32), ("full_state", I32), ("flags", I32)]
 
 
 # name -> (restype, argtypes); every symbol include/pdp_b200.h declares
@@ -52,6 +52,7 @@ SIGNATURES = {
     "pdp_deduplicate": (ctypes.c_int, [P, I32, P, P, P, P]),
     "pdp_set_trace_buffer": (ctypes.c_int, [P, P, I32]),
     "pdp_trace_length": (ctypes.c_int, [P, ctypes.POINTER(I32), P]),
+    "pdp_debug_check_layout": (ctypes.c_int, [P, P, ctypes.POINTER(I32 * 5), P]),
     "pdp_launch_count": (I64, [P]),
 }
 
@@ -79,7 +80,7 @@ def load(strict_math=False):
     return lib
 
 
-def check(rc, what=""):
+def check(rc, what="", lib=None):
     if rc != 0:
-        msg = load().pdp_last_error()
+        msg = (lib or load()).pdp_last_error()
         raise PdpError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -2,7 +2,15 @@
 // (pdp_loop.cu) and by the step-wise entry points.  Every phase is a __device__ function executed
 // by ALL threads of a cooperative grid; the caller separates phases with grid.sync().
 //
-// Work distribution: "warp-strided" loops -- warp w of the grid handles nodes [32w, 32w+32), then
+// The SP sweep exists twice:
+//  * blocked passes (blk_clause_pass / blk_var_pass): the product path.  One CTA per block of whole
+//    nodes, messages staged through shared memory, contiguous global reads and piece-wise contiguous
+//    global writes (layout: pdp_common.cuh);
+//  * generic passes (gen_*): thread per node with per-edge indexed global accesses into the same
+//    layout.  They serve what the blocked passes leave out: the full [E,3] state, pi != 0, graphs whose
+//    node degrees do not fit a block, and the problems on the sticky-NaN path.
+//
+// Work distribution of everything else: "warp-strided" loops -- warp w of the grid handles nodes [32w, 32w+32), then
 // jumps by 32 * (warps in the grid).  Loads are coalesced and every lane sees a monotone sequence of
 // problem ids (batches are laid out problem after problem), so per-problem reductions run as lane-local
 // running accumulators that are flushed on a key change and merged warp-wide (__match_any_sync +
@@ -79,6 +87,8 @@ struct KeyedReducer {
             }
         }
         __syncthreads();
+        key = -1;       // everything has been committed: a later touch() starts from scratch
+        acc.reset();
     }
 };
 
@@ -194,127 +204,167 @@ struct PickAcc {
     }
 };
 
+
 // ------------------------------------------------------------------------------------------------
-// SP sweep, clause side: eta'(e) = exp(min(sum_{e' in a(e)} x_e' - x_e, 30)), x = log(max(q_u,1e-40)) * em
-// (pdp_propagate.py:166-175).  Thread per clause; k <= 8 keeps x in registers.
+// activity masks.  The edge mask em(e) = active_variable(i(e)) * active_function(a(e)) of the reference
+// (solver.py:370-371) is kept as one bit per edge in both edge orders (g.vbits / g.cbits), set where a
+// node is de-activated, so that a sweep never gathers the node masks.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sweep_clause_side(const KArgs& A, int r, bool use_mask_global) {
+__device__ __forceinline__ void mask_edge(const pdp_graph& g, int p, int c) {
+    atomicOr(&g.vbits[p >> 4], PDP_VB_MASK << (2 * (p & 15)));
+    atomicOr(&g.cbits[c >> 5], 1u << (c & 31));
+}
+__device__ __forceinline__ void deactivate_variable(const pdp_graph& g, const pdp_state& s, int i) {
+    s.av[i] = 0;
+    for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) mask_edge(g, p, (int)(g.v_cedge[p] & PDP_IDX_MASK));
+}
+__device__ __forceinline__ void deactivate_clause(const pdp_graph& g, const pdp_state& s, int a) {
+    s.af[a] = 0;
+    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) mask_edge(g, g.c_pos[c], c);
+}
+
+// streaming readers of the bit arrays (the words change between passes: read around L1)
+struct VBits {
+    const uint32_t* base; int wi; uint32_t w;
+    __device__ __forceinline__ VBits(const uint32_t* b) : base(b), wi(-1), w(0u) {}
+    __device__ __forceinline__ uint32_t get(int p) {
+        const int i = p >> 4;
+        if (i != wi) { wi = i; w = __ldcg(base + i); }
+        return (w >> ((p & 15) * 2)) & 3u;
+    }
+};
+struct CBits {
+    const uint32_t* base; int wi; uint32_t w;
+    __device__ __forceinline__ CBits(const uint32_t* b) : base(b), wi(-1), w(0u) {}
+    __device__ __forceinline__ bool get(int c) {
+        const int i = c >> 5;
+        if (i != wi) { wi = i; w = __ldcg(base + i); }
+        return (w >> (c & 31)) & 1u;
+    }
+};
+
+// variable side of the SP update with the per-variable part hoisted (pi == 0): for one sign s the terms
+// 0.5(1+s)P + 0.5(1-s)N, opp and exp(opp) do not depend on the edge.  Same operations, same order as
+// sp_var_update_qu.
+__device__ __forceinline__ void sp_var_prepare(float P, float N, float s, float& same_base, float& opp, float& O) {
+    same_base = 0.5f * (1.f + s) * P + 0.5f * (1.f - s) * N;
+    opp = 0.5f * (1.f - s) * P + 0.5f * (1.f + s) * N;
+    opp += 0.f;
+    O = X30(opp);
+}
+__device__ __forceinline__ float sp_var_finish(float same_base, float opp, float O, float y) {
+    float same = same_base - y;
+    same += 0.f;
+    const float dc = X30(same + opp);
+    const float S = X30(same);
+    const float u = S * (1.f - O), v = O * (1.f - S);
+    const float total = u + v + dc;
+    return u / total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic passes: thread per node, indexed global accesses.  MODE selects the problems.
+// ------------------------------------------------------------------------------------------------
+enum { GEN_ALL = 0, GEN_NAN = 1 };
+template <int MODE>
+__device__ __forceinline__ bool gen_take(const pdp_state& s, int b) {
+    if (!s.active[b]) return false;
+    return (MODE == GEN_ALL) ? true : (s.nanflag[b] != 0);
+}
+
+// clause side: eta'(e) = exp(min(sum_{e' in a(e)} x_e' - x_e, 30)), x = log(max(q_u,1e-40)) * em
+// (pdp_propagate.py:166-175).  r = buffer of the previous surveys.
+template <int MODE>
+__device__ __forceinline__ void gen_clause_side(const KArgs& A, int r, bool use_mask) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    const float* __restrict__ qin = s.qu[r];
+    const float* __restrict__ qin = s.qu;
+    const float* __restrict__ eold = s.eta[r];
     float* __restrict__ eout = s.eta[r ^ 1];
     WARP_STRIDED(a, g.F) {
         if (a >= g.F) continue;
         const int b = g.bfm[a];
-        if (!s.active[b]) continue;
-        const bool um = use_mask_global && s.masked[b];
+        if (!gen_take<MODE>(s, b)) continue;
+        const bool um = use_mask && s.masked[b];
         // the reference blends `mask*new + (1-mask)*old` arithmetically, so a NaN message is sticky
-        // (0*NaN); problems that have produced a NaN take the path that re-reads the old value
+        // (0*NaN); problems that have produced a NaN re-read the old value
         const bool sticky = s.nanflag[b] != 0;
-        const float* __restrict__ eold = s.eta[r];
         bool made_nan = false;
         const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
-        const int k = end - beg;
-        const float afa = um ? (float)s.af[a] : 1.f;
-        if (k <= 8) {
-            float x[8]; int pos[8];
-            float tot = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < k) {
-                    const int c = beg + j;
-                    const int p = g.c_pos[c];
-                    float v = L40(qin[p]);
-                    if (um) v = v * ((float)s.av[g.c_var[c] & PDP_IDX_MASK] * afa);
-                    x[j] = v; pos[j] = p;
-                    tot += v;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < k) {
-                    float nv = X30(tot - x[j]);
-                    if (sticky) { const float ov = eold[pos[j]]; if (ov != ov) nv = ov; }
-                    made_nan |= (nv != nv);
-                    eout[pos[j]] = nv;
-                }
-        } else {
-            float tot = 0.f;
-            for (int c = beg; c < end; ++c) {
-                float v = L40(qin[g.c_pos[c]]);
-                if (um) v = v * ((float)s.av[g.c_var[c] & PDP_IDX_MASK] * afa);
-                tot += v;
-            }
-            for (int c = beg; c < end; ++c) {
-                const int p = g.c_pos[c];
-                float v = L40(qin[p]);
-                if (um) v = v * ((float)s.av[g.c_var[c] & PDP_IDX_MASK] * afa);
-                float nv = X30(tot - v);
-                if (sticky) { const float ov = eold[p]; if (ov != ov) nv = ov; }
-                made_nan |= (nv != nv);
-                eout[p] = nv;
-            }
+        CBits cb(g.cbits);
+        float tot = 0.f;
+        for (int c = beg; c < end; ++c) {
+            float v = L40(qin[g.c_qpos[c]]);
+            if (um && cb.get(c)) v = v * 0.f;
+            tot += v;
         }
-        if (made_nan && !sticky) s.nanflag[b] = 1;
+        for (int c = beg; c < end; ++c) {
+            float v = L40(qin[g.c_qpos[c]]);
+            if (um && cb.get(c)) v = v * 0.f;
+            const int pos = g.c_vpos[c];
+            float nv = X30(tot - v);
+            if (sticky) { const float ov = eold[pos]; if (ov != ov) nv = ov; }
+            made_nan |= (nv != nv);
+            eout[pos] = nv;
+        }
+        if (made_nan && !sticky) s.nanpend[b] = 1;
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// SP sweep, variable side (pdp_propagate.py:184-218).  Thread per variable.
-// ------------------------------------------------------------------------------------------------
-template <bool FULL>
-__device__ __forceinline__ void sweep_var_side(const KArgs& A, int r, bool use_mask_global, float pi) {
+// variable side (pdp_propagate.py:184-218): q(t) from eta[r], written in place
+template <int MODE, bool FULL>
+__device__ __forceinline__ void gen_var_side(const KArgs& A, int r, bool use_mask, float pi) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     const float* __restrict__ ein = s.eta[r];
-    float* __restrict__ qout = s.qu[r ^ 1];
     WARP_STRIDED(i, g.V) {
         if (i >= g.V) continue;
         const int b = g.bvm[i];
-        if (!s.active[b]) continue;
-        const bool um = use_mask_global && s.masked[b];
+        if (!gen_take<MODE>(s, b)) continue;
+        const bool um = use_mask && s.masked[b];
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
-        const float avi = um ? (float)s.av[i] : 1.f;
         const bool sticky = s.nanflag[b] != 0;
         bool made_nan = false;
+        VBits vb(g.vbits);
         float P = 0.f, N = 0.f;
         for (int p = beg; p < end; ++p) {
-            float y = L40(1.f - ein[p]);
-            if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
-            const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
+            const uint32_t bits = vb.get(p);
+            float y = L40(1.f - ein[g.p_vpos[p]]);
+            if (um && (bits & PDP_VB_MASK)) y = y * 0.f;
             // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
-            P += (neg ? 0.f : 1.f) * y;
-            N += (neg ? 1.f : 0.f) * y;
+            P += ((bits & PDP_VB_NEG) ? 0.f : 1.f) * y;
+            N += ((bits & PDP_VB_NEG) ? 1.f : 0.f) * y;
         }
         for (int p = beg; p < end; ++p) {
-            float y = L40(1.f - ein[p]);
-            if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
-            const float sg = (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f;
+            const uint32_t bits = vb.get(p);
+            float y = L40(1.f - ein[g.p_vpos[p]]);
+            if (um && (bits & PDP_VB_MASK)) y = y * 0.f;
+            const float sg = (bits & PDP_VB_NEG) ? -1.f : 1.f;
+            const int qp = g.p_qpos[p];
             if (FULL || pi != 0.f) {
                 float u, v, d;
                 sp_var_update(P, N, y, sg, s.ext[p], pi, u, v, d);
                 if (sticky) {
-                    const float ou = s.qu[r][p]; if (ou != ou) u = ou;
-                    if (FULL) { const float ov = s.qs[r][p], od = s.qd[r][p]; if (ov != ov) v = ov; if (od != od) d = od; }
+                    const float ou = s.qu[qp]; if (ou != ou) u = ou;
+                    if (FULL) { const float ov = s.qs[qp], od = s.qd[qp]; if (ov != ov) v = ov; if (od != od) d = od; }
                 }
                 made_nan |= (u != u);
-                qout[p] = u;
-                if (FULL) { s.qs[r ^ 1][p] = v; s.qd[r ^ 1][p] = d; }
+                s.qu[qp] = u;
+                if (FULL) { s.qs[qp] = v; s.qd[qp] = d; }
             } else {
                 float u = sp_var_update_qu(P, N, y, sg);
-                if (sticky) { const float ou = s.qu[r][p]; if (ou != ou) u = ou; }
+                if (sticky) { const float ou = s.qu[qp]; if (ou != ou) u = ou; }
                 made_nan |= (u != u);
-                qout[p] = u;
+                s.qu[qp] = u;
             }
         }
-        if (made_nan && !sticky) s.nanflag[b] = 1;
+        if (made_nan && !sticky) s.nanpend[b] = 1;
     }
 }
 
-// ------------------------------------------------------------------------------------------------
 // decimator statistics (pdp_decimate.py:127-143, util.py:282-286): per variable smooth-max of the new
 // surveys and of |eta_prev - eta_new| * edge_mask, times active_variables; per problem max / min.
 // w = buffer holding the new surveys.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stats_phase(const KArgs& A, int w, bool has_prev, bool em_set) {
+template <int MODE>
+__device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, bool em_set) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     const float* __restrict__ en = s.eta[w];
     const float* __restrict__ eo = s.eta[w ^ 1];
@@ -322,19 +372,21 @@ __device__ __forceinline__ void stats_phase(const KArgs& A, int w, bool has_prev
     WARP_STRIDED(i, g.V) {
         if (i >= g.V) continue;
         const int b = g.bvm[i];
-        if (!s.active[b]) continue;
+        if (!gen_take<MODE>(s, b)) continue;
         red.touch(s, b);
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
         const uint32_t act = s.av[i];
         const bool um = em_set && s.masked[b];
+        VBits vb(g.vbits);
         float n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
         for (int p = beg; p < end; ++p) {
-            const float v = en[p];
+            const int pos = g.p_vpos[p];
+            const float v = en[pos];
             const float c = X30(30.f * v);
             n0 += v * c; d0 += c;
             if (has_prev) {
-                float d = fabsf(eo[p] - v);
-                if (um) d = d * ((float)act * (float)s.af[g.v_cls[p]]);
+                float d = fabsf(eo[pos] - v);
+                if (um && (vb.get(p) & PDP_VB_MASK)) d = d * 0.f;
                 const float cd = X30(30.f * d);
                 n1 += d * cd; d1 += cd;
             }
@@ -347,6 +399,209 @@ __device__ __forceinline__ void stats_phase(const KArgs& A, int w, bool has_prev
 }
 
 // ------------------------------------------------------------------------------------------------
+// blocked passes.  Dynamic shared memory (PDP_SWEEP_SMEM bytes):
+//   [0, 4*PDP_BLK_C)           clause pass: one plane X;  variable pass: planes PA | PB (PDP_BLK_V each)
+//   [4*PDP_BLK_C, +PDP_BLK_C/8) skip bits: slots of nodes the pass leaves alone (frozen / sticky-NaN
+//                               problems inside a block that has work)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool blk_problem_runs(const pdp_state& s, int b) { return s.active[b] && !s.nanflag[b]; }
+
+// true when no problem in [b0, b1] is to be processed by the blocked passes (uniform over the CTA)
+__device__ __forceinline__ bool blk_idle(const pdp_state& s, int b0, int b1) {
+    if (b0 == b1) return !blk_problem_runs(s, b0);
+    int any = 0;
+    for (int b = b0 + (int)threadIdx.x; b <= b1; b += (int)blockDim.x) any |= blk_problem_runs(s, b) ? 1 : 0;
+    return __syncthreads_or(any) == 0;
+}
+
+__device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
+    for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
+}
+
+// write-out: every warp takes pieces; a piece is a run of slots that are adjacent in the destination
+__device__ __forceinline__ void blk_write_out(const int2* __restrict__ piece, int pb, int pe, const uint16_t* __restrict__ src16,
+                                              const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ dst) {
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int k = pb + warp; k < pe; k += nwarp) {
+        const int2 pc = __ldg(&piece[k]);
+        const int len = __ldg(&piece[k + 1].x) - pc.x;
+        const uint16_t* __restrict__ src = src16 + pc.x;
+        float* __restrict__ out = dst + pc.y;
+        for (int t = lane; t < len; t += 32) {
+            const int l = src[t];
+            if (any_skip && ((skip[l >> 5] >> (l & 31)) & 1u)) continue;
+            out[t] = plane[l];
+        }
+    }
+}
+
+// clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
+__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    float* X = reinterpret_cast<float*>(smem);
+    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
+    __shared__ int sm_any_skip;
+    const float* __restrict__ qin = s.qu;
+    float* __restrict__ eout = s.eta[r ^ 1];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int blk = blockIdx.x; blk < g.ncb; blk += gridDim.x) {
+        const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
+        if (a1 <= a0) continue;
+        const int b0 = g.bfm[a0], b1 = g.bfm[a1 - 1];
+        if (blk_idle(s, b0, b1)) continue;
+        const bool multi = (b0 != b1);
+        const int e0 = g.cl_ptr[a0], ne = g.cl_ptr[a1] - e0;
+        for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
+        if (tid == 0) sm_any_skip = 0;
+        // ---- load (contiguous), log, scatter into clause-major order
+        {
+            const float* __restrict__ qsrc = qin + e0;
+            const uint16_t* __restrict__ inv = g.cinv + e0;
+            int x = tid;
+            for (; x + 3 * nthr < ne; x += 4 * nthr) {
+                const float q0 = qsrc[x], q1 = qsrc[x + nthr], q2 = qsrc[x + 2 * nthr], q3 = qsrc[x + 3 * nthr];
+                const int l0 = inv[x], l1 = inv[x + nthr], l2 = inv[x + 2 * nthr], l3 = inv[x + 3 * nthr];
+                X[l0] = L40(q0); X[l1] = L40(q1); X[l2] = L40(q2); X[l3] = L40(q3);
+            }
+            for (; x < ne; x += nthr) X[inv[x]] = L40(qsrc[x]);
+        }
+        __syncthreads();
+        // ---- thread per clause
+        for (int a = a0 + tid; a < a1; a += nthr) {
+            const int cbeg = g.cl_ptr[a], cend = g.cl_ptr[a + 1];
+            const int lo = cbeg - e0, k = cend - cbeg;
+            const int b = multi ? g.bfm[a] : b0;
+            if (multi && !blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); sm_any_skip = 1; continue; }
+            const bool um = use_mask && s.masked[b];
+            bool made_nan = false;
+            if (k <= 8) {
+                float x[8];
+                float tot = 0.f;
+                CBits cb(g.cbits);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < k) {
+                        float v = X[lo + j];
+                        if (um && cb.get(cbeg + j)) v = v * 0.f;
+                        x[j] = v;
+                        tot += v;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < k) {
+                        const float nv = X30(tot - x[j]);
+                        made_nan |= (nv != nv);
+                        X[lo + j] = nv;
+                    }
+                }
+            } else {
+                float tot = 0.f;
+                CBits cb(g.cbits);
+                for (int j = 0; j < k; ++j) {
+                    float v = X[lo + j];
+                    if (um && cb.get(cbeg + j)) v = v * 0.f;
+                    X[lo + j] = v;
+                    tot += v;
+                }
+                for (int j = 0; j < k; ++j) {
+                    const float nv = X30(tot - X[lo + j]);
+                    made_nan |= (nv != nv);
+                    X[lo + j] = nv;
+                }
+            }
+            if (made_nan) s.nanpend[b] = 1;
+        }
+        __syncthreads();
+        blk_write_out(g.cpiece, g.cpiece_ptr[blk], g.cpiece_ptr[blk + 1], g.csrc, X, skip, sm_any_skip != 0, eout);
+        __syncthreads();
+    }
+}
+
+// variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
+// [buffer r], and q(t) [C-layout, in place] from eta(t-1)
+__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
+    float* PB = PA + PDP_BLK_V;                   // eta(t-1), then y
+    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
+    __shared__ int sm_any_skip;
+    const float* __restrict__ en = s.eta[r ^ 1];
+    const float* __restrict__ eo = s.eta[r];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    KeyedReducer<StatAcc> red;
+    for (int blk = blockIdx.x; blk < g.nvb; blk += gridDim.x) {
+        const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
+        if (v1 <= v0) continue;
+        const int b0 = g.bvm[v0], b1 = g.bvm[v1 - 1];
+        if (blk_idle(s, b0, b1)) continue;
+        const bool multi = (b0 != b1);
+        const int e0 = g.var_ptr[v0], ne = g.var_ptr[v1] - e0;
+        for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
+        if (tid == 0) sm_any_skip = 0;
+        // ---- load both survey regions (contiguous), scatter into variable-major order
+        {
+            const float* __restrict__ sn = en + e0;
+            const float* __restrict__ so = eo + e0;
+            const uint16_t* __restrict__ inv = g.vinv + e0;
+            int x = tid;
+            for (; x + nthr < ne; x += 2 * nthr) {
+                const float n0 = sn[x], n1 = sn[x + nthr], o0 = so[x], o1 = so[x + nthr];
+                const int l0 = inv[x], l1 = inv[x + nthr];
+                PA[l0] = n0; PB[l0] = o0; PA[l1] = n1; PB[l1] = o1;
+            }
+            for (; x < ne; x += nthr) { const int l = inv[x]; PA[l] = sn[x]; PB[l] = so[x]; }
+        }
+        __syncthreads();
+        // ---- thread per variable: ordered sums, statistics, update
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            const int pbeg = g.var_ptr[i], pend = g.var_ptr[i + 1];
+            const int lo = pbeg - e0, deg = pend - pbeg;
+            const int b = multi ? g.bvm[i] : b0;
+            if (multi && !blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); sm_any_skip = 1; continue; }
+            const bool umy = use_mask && s.masked[b];
+            const bool umd = em_set && s.masked[b];
+            const uint32_t act = s.av[i];
+            VBits vb(g.vbits);
+            float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
+            for (int j = 0; j < deg; ++j) {
+                const uint32_t bits = vb.get(pbeg + j);
+                const float xn = PA[lo + j], xo = PB[lo + j];
+                float y = L40(1.f - xo);
+                if (umy && (bits & PDP_VB_MASK)) y = y * 0.f;
+                PB[lo + j] = y;
+                P += ((bits & PDP_VB_NEG) ? 0.f : 1.f) * y;
+                N += ((bits & PDP_VB_NEG) ? 1.f : 0.f) * y;
+                const float c = X30(30.f * xn);
+                n0 += xn * c; d0 += c;
+                if (has_prev) {
+                    float d = fabsf(xo - xn);
+                    if (umd && (bits & PDP_VB_MASK)) d = d * 0.f;
+                    const float cd = X30(30.f * d);
+                    n1 += d * cd; d1 += cd;
+                }
+            }
+            red.touch(s, b);
+            red.acc.add((n0 / tmaxf(d0, 1.0f)) * (float)act, (n1 / tmaxf(d1, 1.0f)) * (float)act, has_prev, act);
+            float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
+            sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
+            sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
+            bool made_nan = false;
+            for (int j = 0; j < deg; ++j) {
+                const bool neg = (vb.get(pbeg + j) & PDP_VB_NEG) != 0u;
+                const float u = sp_var_finish(neg ? sb_neg : sb_pos, neg ? opp_neg : opp_pos, neg ? O_neg : O_pos, PB[lo + j]);
+                made_nan |= (u != u);
+                PA[lo + j] = u;
+            }
+            if (made_nan) s.nanpend[b] = 1;
+        }
+        __syncthreads();
+        blk_write_out(g.vpiece, g.vpiece_ptr[blk], g.vpiece_ptr[blk + 1], g.vsrc, PA, skip, sm_any_skip != 0, s.qu);
+        red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SurveyScorer over the converged problems (pdp_predict.py:155-192) + coefficient statistics
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float score_variable(const pdp_graph& g, const pdp_state& s, const float* __restrict__ eta,
@@ -355,7 +610,7 @@ __device__ __forceinline__ float score_variable(const pdp_graph& g, const pdp_st
     float extsum = 0.f, ps = 0.f, ns = 0.f, as = 0.f;
     for (int p = beg; p < end; ++p) {
         extsum += s.ext[p];
-        const float f = L10(1.f - eta[p]) * (float)s.af[g.v_cls[p]];
+        const float f = L10(1.f - eta[g.p_vpos[p]]) * (float)s.af[g.v_cls[p]];
         const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
         ps += (neg ? 0.f : 1.f) * f;
         ns += (neg ? 1.f : 0.f) * f;
@@ -399,11 +654,13 @@ __device__ __forceinline__ void fix_variable(const pdp_graph& g, const pdp_state
     const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
     for (int p = beg; p < end; ++p) {
         const float lit = (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f;
-        if (lit * sg > 0.f) s.af[g.v_cls[p]] = 0;
+        const int a = g.v_cls[p];
+        if (lit * sg > 0.f && s.af[a]) deactivate_clause(g, s, a);
     }
-    s.av[i] = 0;
+    deactivate_variable(g, s, i);
     s.sol[i] = (sg + 1.f) / 2.0f;
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // unit propagation round (solver.py:228-273), split at its data dependencies
@@ -447,11 +704,11 @@ __device__ __forceinline__ void up_apply_conflicts(const KArgs& A) {
     const int64_t n = g.V > g.F ? g.V : g.F;
     WARP_STRIDED(i, n) {
         if (i < g.F) {
-            if (s.single[i]) { s.af[i] = 0; s.single[i] = 0; s.masked[g.bfm[i]] = 1; }
-            else if (s.af[i] && s.conflicts[g.bfm[i]] == 1) s.af[i] = 0;
+            if (s.single[i]) { deactivate_clause(g, s, (int)i); s.single[i] = 0; s.masked[g.bfm[i]] = 1; }
+            else if (s.af[i] && s.conflicts[g.bfm[i]] == 1) deactivate_clause(g, s, (int)i);
         }
         if (i < g.V) {
-            if (s.av[i] && s.conflicts[g.bvm[i]] == 1) s.av[i] = 0;
+            if (s.av[i] && s.conflicts[g.bvm[i]] == 1) deactivate_variable(g, s, (int)i);
         }
         if (i < g.B) {
             if (s.conflicts[i] >= 1) { s.is_sat[i] = 0.f; s.flags[i] |= PDP_FLAG_UP_CONFLICT; s.masked[i] = 1; }
@@ -509,8 +766,11 @@ __device__ __forceinline__ void peel_apply(const KArgs& A) {
         if (!s.pure[i]) continue;
         s.pure[i] = 0;
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
-        for (int p = beg; p < end; ++p) s.af[g.v_cls[p]] = 0;
-        s.av[i] = 0;
+        for (int p = beg; p < end; ++p) {
+            const int a = g.v_cls[p];
+            if (s.af[a]) deactivate_clause(g, s, a);
+        }
+        deactivate_variable(g, s, (int)i);
         s.masked[g.bvm[i]] = 1;
     }
 }

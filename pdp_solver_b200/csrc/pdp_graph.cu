@@ -7,6 +7,8 @@
 
 #include "pdp_common.cuh"
 
+int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps);   // pdp_layout.cu
+
 static thread_local char g_err[512] = "";
 
 void pdp_set_error(const char* fmt, ...) {
@@ -61,12 +63,30 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.v_orig = k.take<int32_t>(E);
     g.bvm = k.take<int32_t>(V);
     g.bfm = k.take<int32_t>(F);
-    for (int i = 0; i < 2; ++i) {
-        s.eta[i] = k.take<float>(E);
-        s.qu[i] = k.take<float>(E);
-        s.qs[i] = k.take<float>(E);
-        s.qd[i] = k.take<float>(E);
-    }
+    g.p_vpos = k.take<int32_t>(E);
+    g.p_qpos = k.take<int32_t>(E);
+    g.c_vpos = k.take<int32_t>(E);
+    g.c_qpos = k.take<int32_t>(E);
+    g.vbits = k.take<uint32_t>(E / 16 + 1);
+    g.cbits = k.take<uint32_t>(E / 32 + 1);
+    // block count <= rounds * SMs + 1 with rounds * SMs <= E / (half a block) + SMs (pdp_layout.cu pick_stride;
+    // nodes of degree above half a block disable the blocked path)
+    const int64_t max_vb = E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2, max_cb = E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2;
+    g.vb_ptr = k.take<int32_t>(max_vb + 1);
+    g.cb_ptr = k.take<int32_t>(max_cb + 1);
+    g.vinv = k.take<uint16_t>(E);
+    g.cinv = k.take<uint16_t>(E);
+    g.vsrc = k.take<uint16_t>(E);
+    g.csrc = k.take<uint16_t>(E);
+    g.vpiece = k.take<int2>(E + 1);
+    g.cpiece = k.take<int2>(E + 1);
+    g.vpiece_ptr = k.take<int32_t>(max_vb + 1);
+    g.cpiece_ptr = k.take<int32_t>(max_cb + 1);
+    s.eta[0] = k.take<float>(E);
+    s.eta[1] = k.take<float>(E);
+    s.qu = k.take<float>(E);
+    s.qs = k.take<float>(E);
+    s.qd = k.take<float>(E);
     s.ext = k.take<float>(E);
     s.av = k.take<uint8_t>(V);
     s.af = k.take<uint8_t>(F);
@@ -80,6 +100,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     s.dirty = k.take<uint8_t>(B);
     s.conv = k.take<uint8_t>(B);
     s.nanflag = k.take<uint8_t>(B);
+    s.nanpend = k.take<uint8_t>(B);
     s.st_max = k.take<uint32_t>(2 * B);
     s.st_min = k.take<uint32_t>(2 * B);
     s.st_nan = k.take<uint32_t>(B);
@@ -127,6 +148,9 @@ __global__ void k_check_maps(const int32_t* __restrict__ bvm, const int32_t* __r
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < V && (bvm[i] < 0 || bvm[i] >= B)) atomicOr(&flags[1], 2);
         if (i < F && (bfm[i] < 0 || bfm[i] >= B)) atomicOr(&flags[1], 2);
+        // the blocked sweep skips whole blocks by the problem range of their first and last node
+        if (i > 0 && i < V && bvm[i - 1] > bvm[i]) atomicOr(&flags[4], 1);
+        if (i > 0 && i < F && bfm[i - 1] > bfm[i]) atomicOr(&flags[4], 1);
     }
 }
 
@@ -174,15 +198,18 @@ __global__ void k_max_degree(const int32_t* __restrict__ ptr, int64_t n, int32_t
 
 }  // namespace
 
-__global__ void k_reset_state(pdp_state s, int64_t V, int64_t F, int64_t B) {
+__global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, int64_t B) {
     int64_t n = V > F ? V : F;
     if (B > n) n = B;
+    if (g.E / 16 + 1 > n) n = g.E / 16 + 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < g.E / 16 + 1) g.vbits[i] &= 0x55555555u;   // keep the sign bits, clear the edge-mask bits
+        if (i < g.E / 32 + 1) g.cbits[i] = 0u;
         if (i < V) { s.av[i] = 1; s.sol[i] = 0.5f; s.up_cnt[i] = 0; s.up_ev[i] = 0; s.pure[i] = 0; s.score[i] = 0.f; s.asg[i] = 0; }
         if (i < F) { s.af[i] = 1; s.single[i] = 0; }
         if (i < B) {
             s.is_sat[i] = 0.5f; s.active[i] = 1; s.counters[i] = 0; s.freeze_iter[i] = -1; s.flags[i] = 0;
-            s.masked[i] = 0; s.dirty[i] = 1; s.conv[i] = 0; s.nanflag[i] = 0; s.n_unsat[i] = 0; s.conflicts[i] = 0;
+            s.masked[i] = 0; s.dirty[i] = 1; s.conv[i] = 0; s.nanflag[i] = 0; s.nanpend[i] = 0; s.n_unsat[i] = 0; s.conflicts[i] = 0;
             s.nav[i] = 0; s.arg_idx[i] = 0x7fffffff; s.energy[i] = 0;
             s.st_max[2 * i] = 0u; s.st_max[2 * i + 1] = 0u; s.st_min[2 * i] = 0x7f800000u; s.st_min[2 * i + 1] = 0x7f800000u;
             s.st_nan[i] = 0u; s.c_max[i] = 0u; s.c_min[i] = 0x7f800000u; s.c_nan[i] = 0u;
@@ -205,8 +232,9 @@ extern "C" int pdp_reset(pdp_ctx* ctx, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int64_t n = ctx->g.V > ctx->g.F ? ctx->g.V : ctx->g.F;
     if (ctx->g.B > n) n = ctx->g.B;
+    if (ctx->g.E / 16 + 1 > n) n = ctx->g.E / 16 + 1;
     if (n < CTRL_SIZE) n = CTRL_SIZE;
-    k_reset_state<<<pdp_grid(n, 256, ctx->num_sms), 256, 0, stream>>>(ctx->s, ctx->g.V, ctx->g.F, ctx->g.B);
+    k_reset_state<<<pdp_grid(n, 256, ctx->num_sms), 256, 0, stream>>>(ctx->g, ctx->s, ctx->g.V, ctx->g.F, ctx->g.B);
     PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
 }
@@ -280,7 +308,7 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
         CK(cub::DeviceScan::InclusiveSum(c->cub_tmp, tb, g.var_ptr, g.var_ptr, (int)(V + 1), stream));
         c->launches++;
     }
-    int32_t hflags[4] = {0, 0, 0, 0};
+    int32_t hflags[5] = {0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     if (hflags[1]) {
@@ -289,14 +317,15 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
         return PDP_ERR_ARG;
     }
     const bool clause_major = (hflags[0] == 0);
+    const bool monotone_maps = (hflags[4] == 0);
 
     if (E > 0) {
         // scratch aliases: message buffers are not live yet
         int32_t* kA = reinterpret_cast<int32_t*>(c->s.eta[0]);
         int32_t* kB = reinterpret_cast<int32_t*>(c->s.eta[1]);
-        int32_t* vA = reinterpret_cast<int32_t*>(c->s.qu[0]);
-        int32_t* vB = reinterpret_cast<int32_t*>(c->s.qu[1]);
-        int32_t* inv = reinterpret_cast<int32_t*>(c->s.qs[0]);
+        int32_t* vA = reinterpret_cast<int32_t*>(c->s.qu);
+        int32_t* vB = reinterpret_cast<int32_t*>(c->s.qs);
+        int32_t* inv = reinterpret_cast<int32_t*>(c->s.qd);
         auto stable_sort = [&](const int32_t* keys, int64_t nkeys, int32_t* out_vals) -> int {
             int bits = 1;
             while (((int64_t)1 << bits) < nkeys && bits < 31) ++bits;
@@ -341,6 +370,10 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
         CK(cudaStreamSynchronize(stream));
         g.max_var_degree = hflags[2];
         g.max_clause_degree = hflags[3];
+    }
+    {
+        int lrc = pdp_build_layout(c, stream, monotone_maps);
+        if (lrc != PDP_OK) { delete c; return lrc; }
     }
     int rc = pdp_reset(c, stream);
     if (rc != PDP_OK) { delete c; return rc; }

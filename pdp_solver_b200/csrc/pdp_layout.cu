@@ -1,0 +1,347 @@
+// pdp_layout.cu -- builds the blocked message layout of the SP sweep (pdp_common.cuh):
+// block partitions of both edge orders, the V-layout / C-layout positions of every edge, the 16-bit
+// local scatter / gather tables of the two passes and their write-out pieces.  Runs once per batch
+// inside pdp_create, entirely on the device (four stable radix sorts on block ids, two scans, two
+// stream compactions); the message arrays are not live yet and serve as scratch.
+#include <cub/cub.cuh>
+#include <stdlib.h>
+
+#include "pdp_common.cuh"
+
+namespace {
+
+#define GS(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// first node of block t: the first node whose first slot is >= t * stride (lower bound over ptr[0..n))
+__global__ void k_block_ptr(const int32_t* __restrict__ ptr, int64_t n, int32_t stride, int32_t nblk, int32_t* blk_ptr) {
+    GS(t, (int64_t)nblk + 1) {
+        if (t == nblk) { blk_ptr[t] = (int32_t)n; continue; }
+        const int64_t target = t * (int64_t)stride;
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ptr[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        blk_ptr[t] = (int32_t)lo;
+    }
+}
+
+// keys of the V-layout sort, in clause-major order: variable block of the edge
+__global__ void k_key_vblock_of_c(pdp_graph g, int32_t* key, int32_t* val) {
+    GS(c, g.E) {
+        const int var = (int)(g.c_var[c] & PDP_IDX_MASK);
+        key[c] = g.var_ptr[var] / g.sv;
+        val[c] = (int32_t)c;
+    }
+}
+// keys of the C-layout sort, in variable-major order: clause block of the edge
+__global__ void k_key_cblock_of_p(pdp_graph g, int32_t* key, int32_t* val) {
+    GS(p, g.E) {
+        key[p] = g.cl_ptr[g.v_cls[p]] / g.sc;
+        val[p] = (int32_t)p;
+    }
+}
+
+// x = V-layout position, lv[x] = clause-major slot stored there, ki[x] = its variable block
+__global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ ki, const int32_t* __restrict__ lv) {
+    GS(x, g.E) {
+        const int c = lv[x];
+        const int p = g.c_pos[c];
+        g.c_vpos[c] = (int32_t)x;
+        g.p_vpos[p] = (int32_t)x;
+        g.vinv[x] = (uint16_t)(p - g.var_ptr[g.vb_ptr[ki[x]]]);
+    }
+}
+// x = C-layout position, lq[x] = variable-major slot stored there, kj[x] = its clause block
+__global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, const int32_t* __restrict__ lq) {
+    GS(x, g.E) {
+        const int p = lq[x];
+        const int c = (int)(g.v_cedge[p] & PDP_IDX_MASK);
+        g.p_qpos[p] = (int32_t)x;
+        g.c_qpos[c] = (int32_t)x;
+        g.cinv[x] = (uint16_t)(c - g.cl_ptr[g.cb_ptr[kj[x]]]);
+    }
+}
+
+// write-out order of the variable blocks: the edges of a block sorted by their C-layout position.
+// Input in C-layout order x (lq[x] = variable-major slot): key = variable block, value = x.
+__global__ void k_key_vblock_of_q(pdp_graph g, const int32_t* __restrict__ lq, int32_t* key, int32_t* val) {
+    GS(x, g.E) {
+        const int p = lq[x];
+        const int var = (int)(g.c_var[g.v_cedge[p] & PDP_IDX_MASK] & PDP_IDX_MASK);
+        key[x] = g.var_ptr[var] / g.sv;
+        val[x] = (int32_t)x;
+    }
+}
+__global__ void k_key_cblock_of_v(pdp_graph g, const int32_t* __restrict__ lv, int32_t* key, int32_t* val) {
+    GS(x, g.E) {
+        const int c = lv[x];
+        key[x] = g.cl_ptr[g.v_cls[g.c_pos[c]]] / g.sc;
+        val[x] = (int32_t)x;
+    }
+}
+
+// w = write-out slot; kb[w] = block, dst[w] = destination position, slot_of_dst[dst] = producer-order slot.
+// src16[w] = local producer-order index; head[w] = (w starts a run of adjacent destinations) ? w : 0
+__global__ void k_fill_writeout(int64_t E, const int32_t* __restrict__ kb, const int32_t* __restrict__ dst,
+                                const int32_t* __restrict__ slot_of_dst, const int32_t* __restrict__ node_ptr,
+                                const int32_t* __restrict__ blk_ptr, uint16_t* src16, int32_t* head) {
+    GS(w, E) {
+        const int b = kb[w], d = dst[w];
+        src16[w] = (uint16_t)(slot_of_dst[d] - node_ptr[blk_ptr[b]]);
+        const bool h = (w == 0) || (kb[w - 1] != b) || (dst[w - 1] + 1 != d);
+        head[w] = h ? (int32_t)w : 0;
+    }
+}
+
+// runstart[w] = start of the run containing w; pieces start every PDP_PIECE elements of a run
+__global__ void k_piece_flags(int64_t E, const int32_t* __restrict__ runstart, int32_t* flag) {
+    GS(w, E) flag[w] = (((int32_t)w - runstart[w]) % PDP_PIECE == 0) ? 1 : 0;
+}
+
+__global__ void k_fill_pieces(int64_t E, const int32_t* __restrict__ piece_w, const int32_t* __restrict__ n_ptr,
+                              const int32_t* __restrict__ dst, int2* piece) {
+    const int32_t n = *n_ptr;
+    GS(k, (int64_t)n + 1) {
+        if (k == n) { piece[k] = make_int2((int32_t)E, 0); continue; }
+        const int w = piece_w[k];
+        piece[k] = make_int2(w, dst[w]);
+    }
+}
+
+// piece_ptr[b] = first piece whose first write-out slot is >= the block's first slot
+__global__ void k_piece_ptr(const int2* __restrict__ piece, const int32_t* __restrict__ n_ptr, const int32_t* __restrict__ node_ptr,
+                            const int32_t* __restrict__ blk_ptr, int32_t nblk, int32_t* piece_ptr) {
+    const int32_t n = *n_ptr;
+    GS(b, (int64_t)nblk + 1) {
+        const int32_t target = node_ptr[blk_ptr[b]];
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (piece[mid].x < target) lo = mid + 1; else hi = mid;
+        }
+        piece_ptr[b] = lo;
+    }
+}
+
+__global__ void k_identity_layout(pdp_graph g) {
+    GS(c, g.E) {
+        const int p = g.c_pos[c];
+        g.p_vpos[p] = p; g.p_qpos[p] = p; g.c_vpos[c] = p; g.c_qpos[c] = p;
+    }
+}
+
+__global__ void k_sign_bits(pdp_graph g) {
+    GS(wi, g.E / 16 + 1) {
+        uint32_t w = 0u;
+        for (int k = 0; k < 16; ++k) {
+            const int64_t p = wi * 16 + k;
+            if (p < g.E && (g.v_cedge[p] & PDP_SIGN_BIT)) w |= PDP_VB_NEG << (2 * k);
+        }
+        g.vbits[wi] = w;
+    }
+    GS(wi, g.E / 32 + 1) g.cbits[wi] = 0u;
+}
+
+struct MaxOp {
+    __host__ __device__ __forceinline__ int32_t operator()(const int32_t& a, const int32_t& b) const { return a > b ? a : b; }
+};
+
+int bits_for(int64_t n) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < n && bits < 31) ++bits;
+    return bits;
+}
+
+}  // namespace
+
+#define LCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { pdp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); return PDP_ERR_CUDA; } } while (0)
+#define LLK() do { c->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { pdp_set_error("%s:%d: launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return PDP_ERR_CUDA; } } while (0)
+#define G1(n) pdp_grid((n), 256, nsm), 256, 0, stream
+
+// block stride: as large as a block allows, shrunk so that the block count is a multiple of the SM count
+static int32_t pick_stride(int64_t E, int32_t blk, int32_t max_degree, int nsm) {
+    const int64_t smax = (int64_t)blk - max_degree + 1;
+    const int64_t rounds = (E + smax * nsm - 1) / (smax * nsm);
+    int64_t s = (E + rounds * nsm - 1) / (rounds * nsm);
+    if (s < 64) s = 64;
+    if (s > smax) s = smax;
+    return (int32_t)s;
+}
+
+int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
+    pdp_graph& g = c->g;
+    const int nsm = c->num_sms;
+    const int64_t E = g.E;
+    g.blocked_ok = 0; g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
+    if (E == 0) return PDP_OK;
+    k_sign_bits<<<G1(E / 16 + 1)>>>(g);
+    LLK();
+    const bool ok = monotone_maps && g.max_var_degree <= PDP_BLK_V / 2 && g.max_clause_degree <= PDP_BLK_C / 2 &&
+                    g.V > 0 && g.F > 0 && getenv("PDP_B200_NO_BLOCKED") == nullptr;
+    if (!ok) {
+        k_identity_layout<<<G1(E)>>>(g);
+        LLK();
+        return PDP_OK;
+    }
+    g.sv = pick_stride(E, PDP_BLK_V, g.max_var_degree, nsm);
+    g.sc = pick_stride(E, PDP_BLK_C, g.max_clause_degree, nsm);
+    g.nvb = (int32_t)(E / g.sv + 1);
+    g.ncb = (int32_t)(E / g.sc + 1);
+    if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2) {
+        pdp_set_error("pdp_create: block tables too small (nvb=%d ncb=%d)", g.nvb, g.ncb);
+        return PDP_ERR_WORKSPACE;
+    }
+    k_block_ptr<<<G1(g.nvb + 1)>>>(g.var_ptr, g.V, g.sv, g.nvb, g.vb_ptr);
+    LLK();
+    k_block_ptr<<<G1(g.ncb + 1)>>>(g.cl_ptr, g.F, g.sc, g.ncb, g.cb_ptr);
+    LLK();
+
+    // scratch: the message arrays
+    int32_t* S0 = reinterpret_cast<int32_t*>(c->s.eta[0]);
+    int32_t* S1 = reinterpret_cast<int32_t*>(c->s.eta[1]);
+    int32_t* S2 = reinterpret_cast<int32_t*>(c->s.qu);
+    int32_t* S3 = reinterpret_cast<int32_t*>(c->s.qs);
+    int32_t* LV = reinterpret_cast<int32_t*>(c->s.qd);    // V-layout position -> clause-major slot
+    int32_t* LQ = reinterpret_cast<int32_t*>(c->s.ext);   // C-layout position -> variable-major slot
+    int32_t* d_count = c->s.ctrl + CTRL_SIZE - 1;
+
+    // stable sort of (key, value) pairs held in S0 / S2; returns the buffers holding the result
+    auto sort_pairs = [&](int nkeys, int32_t** keys_out, int32_t** vals_out, int32_t** keys_free, int32_t** vals_free) -> int {
+        cub::DoubleBuffer<int32_t> dk(S0, S1);
+        cub::DoubleBuffer<int32_t> dv(S2, S3);
+        size_t q = 0;
+        const int bits = bits_for(nkeys);
+        if (cub::DeviceRadixSort::SortPairs(nullptr, q, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: sort scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
+        size_t tb = c->cub_tmp_bytes;
+        if (cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        c->launches++;
+        *keys_out = dk.Current(); *vals_out = dv.Current(); *keys_free = dk.Alternate(); *vals_free = dv.Alternate();
+        return PDP_OK;
+    };
+    int32_t *K, *L, *KF, *LF;
+    int rc;
+
+    // ---- V-layout: edges sorted by (variable block, clause-major slot)
+    k_key_vblock_of_c<<<G1(E)>>>(g, S0, S2);
+    LLK();
+    if ((rc = sort_pairs(g.nvb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+    k_fill_vlayout<<<G1(E)>>>(g, K, L);
+    LLK();
+    LCK(cudaMemcpyAsync(LV, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
+    // ---- C-layout: edges sorted by (clause block, variable-major slot)
+    k_key_cblock_of_p<<<G1(E)>>>(g, S0, S2);
+    LLK();
+    if ((rc = sort_pairs(g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+    k_fill_clayout<<<G1(E)>>>(g, K, L);
+    LLK();
+    LCK(cudaMemcpyAsync(LQ, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
+
+    // ---- write-out orders and pieces
+    for (int side = 0; side < 2; ++side) {
+        const bool var_side = (side == 0);
+        if (var_side) k_key_vblock_of_q<<<G1(E)>>>(g, LQ, S0, S2);
+        else k_key_cblock_of_v<<<G1(E)>>>(g, LV, S0, S2);
+        LLK();
+        if ((rc = sort_pairs(var_side ? g.nvb : g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+        // K[w] = block, L[w] = destination position; KF / LF are free
+        k_fill_writeout<<<G1(E)>>>(E, K, L, var_side ? LQ : LV, var_side ? g.var_ptr : g.cl_ptr,
+                                    var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.vsrc : g.csrc, KF);
+        LLK();
+        {
+            size_t q = 0;
+            LCK(cub::DeviceScan::InclusiveScan(nullptr, q, KF, LF, MaxOp(), (int)E, stream));
+            if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: scan scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
+            size_t tb = c->cub_tmp_bytes;
+            LCK(cub::DeviceScan::InclusiveScan(c->cub_tmp, tb, KF, LF, MaxOp(), (int)E, stream));
+            c->launches++;
+        }
+        k_piece_flags<<<G1(E)>>>(E, LF, KF);   // KF: piece flags
+        LLK();
+        {
+            cub::CountingInputIterator<int32_t> iota(0);
+            size_t q = 0;
+            LCK(cub::DeviceSelect::Flagged(nullptr, q, iota, KF, LF, d_count, (int)E, stream));
+            if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: select scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
+            size_t tb = c->cub_tmp_bytes;
+            LCK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, iota, KF, LF, d_count, (int)E, stream));   // LF: piece starts
+            c->launches++;
+        }
+        int2* piece = var_side ? g.vpiece : g.cpiece;
+        k_fill_pieces<<<G1(E + 1)>>>(E, LF, d_count, L, piece);
+        LLK();
+        k_piece_ptr<<<G1((var_side ? g.nvb : g.ncb) + 1)>>>(piece, d_count, var_side ? g.var_ptr : g.cl_ptr,
+                                                             var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.nvb : g.ncb,
+                                                             var_side ? g.vpiece_ptr : g.cpiece_ptr);
+        LLK();
+    }
+    g.blocked_ok = 1;
+    return PDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-check of the layout tables (tests): counts violated invariants into errs[0..7]
+//   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vinv wrong
+//   2 C-layout position outside its block / cinv wrong           3 variable write-out does not land on p_qpos
+//   4 clause write-out does not land on c_vpos                   5 piece length out of (0, PDP_PIECE]
+//   6 slots covered by the variable pieces (must equal E)        7 slots covered by the clause pieces (must equal E)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_check_layout(pdp_graph g, int32_t* errs) {
+    GS(c, g.E) {
+        const int p = g.c_pos[c];
+        if (g.c_vpos[c] != g.p_vpos[p] || g.c_qpos[c] != g.p_qpos[p] || (int)(g.v_cedge[p] & PDP_IDX_MASK) != (int)c) atomicAdd(&errs[0], 1);
+    }
+    if (!g.blocked_ok) return;
+    GS(blk, g.nvb) {
+        const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
+        const int e0 = g.var_ptr[v0], e1 = g.var_ptr[v1];
+        if (e1 - e0 > PDP_BLK_V) atomicAdd(&errs[1], 1);
+        for (int p = e0; p < e1; ++p) {
+            const int x = g.p_vpos[p];
+            if (x < e0 || x >= e1 || (int)g.vinv[x] != p - e0) atomicAdd(&errs[1], 1);
+        }
+        for (int k = g.vpiece_ptr[blk]; k < g.vpiece_ptr[blk + 1]; ++k) {
+            const int w0 = g.vpiece[k].x, gd = g.vpiece[k].y, len = g.vpiece[k + 1].x - w0;
+            if (len <= 0 || len > PDP_PIECE || w0 < e0 || w0 + len > e1) atomicAdd(&errs[5], 1);
+            for (int t = 0; t < len; ++t) {
+                const int p = e0 + (int)g.vsrc[w0 + t];
+                if (p < e0 || p >= e1 || g.p_qpos[p] != gd + t) atomicAdd(&errs[3], 1);
+            }
+            atomicAdd(&errs[6], len);
+        }
+    }
+    GS(blk, g.ncb) {
+        const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
+        const int e0 = g.cl_ptr[a0], e1 = g.cl_ptr[a1];
+        if (e1 - e0 > PDP_BLK_C) atomicAdd(&errs[2], 1);
+        for (int c = e0; c < e1; ++c) {
+            const int x = g.c_qpos[c];
+            if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
+        }
+        for (int k = g.cpiece_ptr[blk]; k < g.cpiece_ptr[blk + 1]; ++k) {
+            const int w0 = g.cpiece[k].x, gd = g.cpiece[k].y, len = g.cpiece[k + 1].x - w0;
+            if (len <= 0 || len > PDP_PIECE || w0 < e0 || w0 + len > e1) atomicAdd(&errs[5], 1);
+            for (int t = 0; t < len; ++t) {
+                const int c = e0 + (int)g.csrc[w0 + t];
+                if (c < e0 || c >= e1 || g.c_vpos[c] != gd + t) atomicAdd(&errs[4], 1);
+            }
+            atomicAdd(&errs[7], len);
+        }
+    }
+}
+}  // namespace
+
+// d_errs: device int32[8], zeroed here.  host_info (nullable): {blocked_ok, nvb, ncb, sv, sc}
+extern "C" int pdp_debug_check_layout(pdp_ctx* c, int32_t* d_errs, int32_t* host_info, void* stream_) {
+    if (!c || !d_errs) { pdp_set_error("pdp_debug_check_layout: null argument"); return PDP_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nsm = c->num_sms;
+    LCK(cudaMemsetAsync(d_errs, 0, 8 * sizeof(int32_t), stream));
+    int64_t n = c->g.E;
+    if (c->g.nvb > n) n = c->g.nvb;
+    if (n > 0) { k_check_layout<<<G1(n)>>>(c->g, d_errs); LLK(); }
+    if (host_info) { host_info[0] = c->g.blocked_ok; host_info[1] = c->g.nvb; host_info[2] = c->g.ncb; host_info[3] = c->g.sv; host_info[4] = c->g.sc; }
+    return PDP_OK;
+}

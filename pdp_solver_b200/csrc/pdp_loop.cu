@@ -15,6 +15,9 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
     WARP_STRIDED(b, A.g.B) {
         if (b >= A.g.B) continue;
         uint8_t cv = 0;
+        // a NaN produced during this iteration's passes puts the problem on the sticky-NaN path from
+        // the next iteration on (no old NaN existed while it was produced)
+        if (s.nanpend[b]) { s.nanpend[b] = 0; s.nanflag[b] = 1; s.ctrl[CTRL_ANY_NAN] = 1; }
         if (s.active[b]) {
             const uint32_t nanb = s.st_nan[b];
             const uint32_t mx0 = s.st_max[2 * b], mn0 = s.st_min[2 * b];
@@ -100,9 +103,11 @@ __device__ __forceinline__ void termination_phase(const KArgs& A, int iter, int 
     if (gtid() == 0) s.ctrl[CTRL_ANY_DIRTY] = 0;
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(256) k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params prm,
-                                                int32_t* d_iters_done) {
+// FAST: the blocked shared-memory passes (pi == 0, q_u only); otherwise the generic passes
+template <bool FAST, bool FULL>
+__global__ void __launch_bounds__(FAST ? PDP_SWEEP_THREADS : 256, 1)
+k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params prm, int32_t* d_iters_done) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
     cg::grid_group grid = cg::this_grid();
     const pdp_state& s = A.s;
     int iter = s.ctrl[CTRL_ITER];
@@ -115,14 +120,29 @@ __global__ void __launch_bounds__(256) k_sp_run(const __grid_constant__ KArgs A,
     for (int it = 0; it < prm.iterations; ++it) {
         ++iter;
         const int r = (iter - 1) & 1, w = iter & 1;
-        // ---- propagate: both halves read the previous messages (Jacobi), pdp_propagate.py:161-221
-        sweep_clause_side(A, r, use_mask);
-        sweep_var_side<FULL>(A, r, use_mask, prm.pi);
+        // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
+        if (FAST) {
+            blk_clause_pass(A, r, use_mask, smem_dyn);
+            if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
+        } else {
+            gen_clause_side<GEN_ALL>(A, r, use_mask);
+        }
         if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; }
         grid.sync();
-        // ---- decimate: statistics -> decisions -> (score, argmax, fix, simplify)
-        stats_phase(A, w, has_prev, em_set);
+        // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
+        //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
+        if (FAST) {
+            blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
+            if (s.ctrl[CTRL_ANY_NAN]) {
+                gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
+                gen_stats<GEN_NAN>(A, w, has_prev, em_set);
+            }
+        } else {
+            gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
+            gen_stats<GEN_ALL>(A, w, has_prev, em_set);
+        }
         grid.sync();
+        // ---- decimate: decisions -> (score, argmax, fix, simplify)
         decide_phase(A, iter, prm, has_prev);
         grid.sync();
         if (s.ctrl[CTRL_CONV + (iter & 1)]) {
@@ -218,14 +238,24 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
     ctx->full_state_tracked = prm.full_state ? 1 : 0;
     ctx->last_pi = prm.pi;
     void* args[] = {&A, &prm, &d_iters_done};
-    if (prm.full_state) {
-        int blocks = coop_blocks(ctx, k_sp_run<true>);
+    const bool fast = ctx->g.blocked_ok && !prm.full_state && prm.pi == 0.f && !(prm.flags & 1);
+    if (fast) {
+        // one CTA per SM, the whole shared memory: co-residency of the cooperative grid is guaranteed
+        static bool attr_set[64] = {false};
+        if (!attr_set[ctx->device & 63]) {
+            PDP_CUDA_CHECK(cudaFuncSetAttribute(k_sp_run<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PDP_SWEEP_SMEM));
+            attr_set[ctx->device & 63] = true;
+        }
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<true, false>, dim3(ctx->num_sms), dim3(PDP_SWEEP_THREADS), args,
+                                                   PDP_SWEEP_SMEM, stream));
+    } else if (prm.full_state) {
+        int blocks = coop_blocks(ctx, k_sp_run<false, true>);
         if (blocks < 1) { pdp_set_error("pdp_sp_run: occupancy query failed"); return PDP_ERR_CUDA; }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<true>, dim3(blocks), dim3(256), args, 0, stream));
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, true>, dim3(blocks), dim3(256), args, 0, stream));
     } else {
-        int blocks = coop_blocks(ctx, k_sp_run<false>);
+        int blocks = coop_blocks(ctx, k_sp_run<false, false>);
         if (blocks < 1) { pdp_set_error("pdp_sp_run: occupancy query failed"); return PDP_ERR_CUDA; }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false>, dim3(blocks), dim3(256), args, 0, stream));
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, false>, dim3(blocks), dim3(256), args, 0, stream));
     }
     PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;

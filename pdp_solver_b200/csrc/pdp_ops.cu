@@ -159,8 +159,9 @@ __global__ void k_score(pdp_graph g, const float* __restrict__ fs2, const float*
 __global__ void k_load_state(pdp_graph g, pdp_state s, const float* __restrict__ dq3, const float* __restrict__ dfs2, int buf) {
     for (int64_t p = gtid(); p < g.E; p += gthreads()) {
         const int64_t e = g.v_orig[p];
-        s.qu[buf][p] = dq3[3 * e]; s.qs[buf][p] = dq3[3 * e + 1]; s.qd[buf][p] = dq3[3 * e + 2];
-        s.eta[buf][p] = dfs2[2 * e]; s.ext[p] = dfs2[2 * e + 1];
+        const int qp = g.p_qpos[p];
+        s.qu[qp] = dq3[3 * e]; s.qs[qp] = dq3[3 * e + 1]; s.qd[qp] = dq3[3 * e + 2];
+        s.eta[buf][g.p_vpos[p]] = dfs2[2 * e]; s.ext[p] = dfs2[2 * e + 1];
     }
 }
 
@@ -180,7 +181,7 @@ __global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* ou
         const float avi = (float)s.av[i];
         if (rebuild) {
             for (int p = beg; p < end; ++p) {
-                float y = L40(1.f - s.eta[buf ^ 1][p]);
+                float y = L40(1.f - s.eta[buf ^ 1][g.p_vpos[p]]);
                 if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
                 const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
                 P += (neg ? 0.f : 1.f) * y;
@@ -189,15 +190,16 @@ __global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* ou
         }
         for (int p = beg; p < end; ++p) {
             const int64_t e = g.v_orig[p];
-            float u = s.qu[buf][p], v = s.qs[buf][p], d = s.qd[buf][p];
+            const int qp = g.p_qpos[p], vp = g.p_vpos[p];
+            float u = s.qu[qp], v = s.qs[qp], d = s.qd[qp];
             if (rebuild) {
-                float y = L40(1.f - s.eta[buf ^ 1][p]);
+                float y = L40(1.f - s.eta[buf ^ 1][vp]);
                 if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
                 float uu;
                 sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, s.ext[p], pi, uu, v, d);
             }
             if (out_q3) { out_q3[3 * e] = u; out_q3[3 * e + 1] = v; out_q3[3 * e + 2] = d; }
-            if (out_fs2) { out_fs2[2 * e] = s.eta[buf][p]; out_fs2[2 * e + 1] = s.ext[p]; }
+            if (out_fs2) { out_fs2[2 * e] = s.eta[buf][vp]; out_fs2[2 * e + 1] = s.ext[p]; }
         }
     }
 }
@@ -209,6 +211,29 @@ __global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const flo
         if (i < g.F && af) s.af[i] = (af[i] != 0.f) ? 1 : 0;
         if (i < g.B) { s.masked[i] = 1; s.dirty[i] = 1; }
         if (i == 0) s.ctrl[CTRL_ANY_DIRTY] = 1;
+    }
+}
+
+// edge-mask bits from the node masks (after an external pdp_set_masks)
+__global__ void k_rebuild_mask_bits(pdp_graph g, pdp_state s) {
+    for (int64_t wi = gtid(); wi < g.E / 16 + 1; wi += gthreads()) {
+        uint32_t w = g.vbits[wi] & 0x55555555u;
+        for (int k = 0; k < 16; ++k) {
+            const int64_t p = wi * 16 + k;
+            if (p >= g.E) break;
+            const int var = (int)(g.c_var[g.v_cedge[p] & PDP_IDX_MASK] & PDP_IDX_MASK);
+            if (!(s.av[var] && s.af[g.v_cls[p]])) w |= PDP_VB_MASK << (2 * k);
+        }
+        g.vbits[wi] = w;
+    }
+    for (int64_t wi = gtid(); wi < g.E / 32 + 1; wi += gthreads()) {
+        uint32_t w = 0u;
+        for (int k = 0; k < 32; ++k) {
+            const int64_t c = wi * 32 + k;
+            if (c >= g.E) break;
+            if (!(s.av[g.c_var[c] & PDP_IDX_MASK] && s.af[g.v_cls[g.c_pos[c]]])) w |= 1u << k;
+        }
+        g.cbits[wi] = w;
     }
 }
 
@@ -357,6 +382,7 @@ extern "C" int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af,
     const int64_t n = std::max(std::max(ctx->g.V, ctx->g.F), std::max(ctx->g.B, (int64_t)1));
     k_set_masks<<<GRID(n)>>>(ctx->g, ctx->s, d_av, d_af, d_sol);
     PDP_LAUNCH_CHECK(ctx);
+    if (ctx->g.E > 0 && (d_av || d_af)) { k_rebuild_mask_bits<<<GRID(ctx->g.E / 16 + 1)>>>(ctx->g, ctx->s); PDP_LAUNCH_CHECK(ctx); }
     return PDP_OK;
 }
 

@@ -326,3 +326,65 @@ def test_empty_and_degenerate_inputs():
     assert C(m["av"]).sum() == 0
     solved, nun = ctx.cnf_eval(m["sol"])
     assert C(solved).tolist() == [1.0, 1.0, 0.0]
+
+
+# ------------------------------------------------------------------------------------------------
+# blocked message layout (pdp_layout.cu) and the shared-memory passes built on it
+# ------------------------------------------------------------------------------------------------
+LAYOUT_SPECS = [(64, 100, 3, 4.2, 1), (3, 30000, 3, 4.2, 2), (5, 2000, 5, 18.0, 3), (400, 20, 3, 4.0, 4), (1, 200000, 3, 4.2, 5)]
+
+
+@pytest.mark.parametrize("spec", LAYOUT_SPECS, ids=lambda s: "B%d_n%d_k%d" % (s[0], s[1], s[2]))
+def test_blocked_layout_selfcheck(spec):
+    """every invariant of the block tables, position maps, scatter tables and write-out pieces"""
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    Bn, n, k, alpha, seed = spec
+    batch = cnfgen.random_batch(Bn, n, k, alpha, seed)
+    ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
+    errs, info = ctx.check_layout()
+    E = batch[0].shape[1]
+    assert info["blocked"] == 1 and info["nvb"] >= 1 and info["ncb"] >= 1
+    assert errs[:6] == [0] * 6, (errs, info)
+    assert errs[6] == E and errs[7] == E, (errs, info)
+
+
+@pytest.mark.parametrize("path", golden("ops_*.npz") + golden("simplify_*.npz"), ids=name)
+def test_blocked_layout_selfcheck_goldens(path):
+    z = load(path)
+    ctx = make_ctx(z)
+    errs, info = ctx.check_layout()
+    assert errs[:6] == [0] * 6, (errs, info)
+    if info["blocked"]:
+        E = z["graph_map"].shape[1]
+        assert errs[6] == E and errs[7] == E
+
+
+@pytest.mark.parametrize("spec", [(48, 100, 3, 4.2, 150, 21), (2, 20000, 3, 4.1, 60, 22), (6, 500, 5, 17.0, 80, 23)],
+                         ids=lambda s: "B%d_n%d_k%d" % (s[0], s[1], s[2]))
+def test_blocked_equals_generic_bitwise(spec):
+    """the blocked shared-memory passes and the generic thread-per-node passes are the same arithmetic in
+    the same order: messages, masks and decimation sequence must agree bit for bit"""
+    from oracle import pdp_oracle as po
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    Bn, n, k, alpha, Tn, seed = spec
+    batch = cnfgen.random_batch(Bn, n, k, alpha, seed)
+    E = batch[0].shape[1]
+    init = po.init_state(E, randomized=True, rng=np.random.default_rng(seed))
+    outs = []
+    for generic in (False, True):
+        ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
+        ctx.enable_trace()
+        ctx.simplify()
+        ctx.load_state((T(init[0][0]), T(init[0][1])), (T(init[1][0]), T(init[1][1])))
+        done = ctx.sp_run(Tn, 0.02, 25, True, sync=True, generic=generic)
+        q, fs = ctx.store_state()
+        m = ctx.get_masks()
+        tr = C(ctx.trace()).astype(np.int64)
+        tr = tr[np.lexsort((tr[:, 1], tr[:, 0]))]
+        flags, counters, freeze = ctx.problem_flags()
+        outs.append((np.int64(done), C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["af"]), C(m["sol"]), C(m["active"]), tr,
+                     C(flags), C(freeze)))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
