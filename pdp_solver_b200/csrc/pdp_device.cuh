@@ -259,7 +259,7 @@ __device__ __forceinline__ float sp_var_finish(float same_base, float opp, float
     const float S = X30(same);
     const float u = S * (1.f - O), v = O * (1.f - S);
     const float total = u + v + dc;
-    return u / total;
+    return pdp_divf(u, total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,8 +391,8 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
                 n1 += d * cd; d1 += cd;
             }
         }
-        const float sm0 = (n0 / tmaxf(d0, 1.0f)) * (float)act;
-        const float sm1 = (n1 / tmaxf(d1, 1.0f)) * (float)act;
+        const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
+        const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
         red.acc.add(sm0, sm1, has_prev, act);
     }
     red.finish(s);
@@ -418,21 +418,77 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
     for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
 }
 
-// write-out: every warp takes pieces; a piece is a run of slots that are adjacent in the destination
-__device__ __forceinline__ void blk_write_out(const int2* __restrict__ piece, int pb, int pe, const uint16_t* __restrict__ src16,
-                                              const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ dst) {
-    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int k = pb + warp; k < pe; k += nwarp) {
-        const int2 pc = __ldg(&piece[k]);
-        const int len = __ldg(&piece[k + 1].x) - pc.x;
-        const uint16_t* __restrict__ src = src16 + pc.x;
-        float* __restrict__ out = dst + pc.y;
-        for (int t = lane; t < len; t += 32) {
-            const int l = src[t];
-            if (any_skip && ((skip[l >> 5] >> (l & 31)) & 1u)) continue;
-            out[t] = plane[l];
-        }
+// write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
+// consecutive destinations (runs), so a warp's stores coalesce into a few sectors
+template <bool SKIP>
+__device__ __forceinline__ void blk_write_out_t(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
+                                                const float* plane, const uint32_t* skip, float* __restrict__ out) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int w = tid;
+    for (; w + 3 * nthr < ne; w += 4 * nthr) {
+        const int l0 = src[w], l1 = src[w + nthr], l2 = src[w + 2 * nthr], l3 = src[w + 3 * nthr];
+        const int d0 = dst[w], d1 = dst[w + nthr], d2 = dst[w + 2 * nthr], d3 = dst[w + 3 * nthr];
+        const float x0 = plane[l0], x1 = plane[l1], x2 = plane[l2], x3 = plane[l3];
+        if (!SKIP || !((skip[l0 >> 5] >> (l0 & 31)) & 1u)) out[d0] = x0;
+        if (!SKIP || !((skip[l1 >> 5] >> (l1 & 31)) & 1u)) out[d1] = x1;
+        if (!SKIP || !((skip[l2 >> 5] >> (l2 & 31)) & 1u)) out[d2] = x2;
+        if (!SKIP || !((skip[l3 >> 5] >> (l3 & 31)) & 1u)) out[d3] = x3;
     }
+    for (; w < ne; w += nthr) {
+        const int l = src[w];
+        if (!SKIP || !((skip[l >> 5] >> (l & 31)) & 1u)) out[dst[w]] = plane[l];
+    }
+}
+__device__ __forceinline__ void blk_write_out(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
+                                              const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ out) {
+    if (any_skip) blk_write_out_t<true>(src, dst, ne, plane, skip, out);
+    else blk_write_out_t<false>(src, dst, ne, plane, skip, out);
+}
+
+// one clause of K literals held in X[lo .. lo+K): surveys in place.  Returns whether a NaN was produced.
+template <int K>
+__device__ __forceinline__ bool blk_clause_body(float* X, int lo, bool um, const uint32_t* cbits, int cbeg) {
+    float x[K];
+    float tot = 0.f;
+    if (um) {
+        CBits cb(cbits);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            float v = X[lo + j];
+            if (cb.get(cbeg + j)) v = v * 0.f;
+            x[j] = v;
+            tot += v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { x[j] = X[lo + j]; tot += x[j]; }
+    }
+    bool made_nan = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const float nv = X30(tot - x[j]);
+        made_nan |= (nv != nv);
+        X[lo + j] = nv;
+    }
+    return made_nan;
+}
+
+__device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k, bool um, const uint32_t* cbits, int cbeg) {
+    float tot = 0.f;
+    CBits cb(cbits);
+    for (int j = 0; j < k; ++j) {
+        float v = X[lo + j];
+        if (um && cb.get(cbeg + j)) v = v * 0.f;
+        X[lo + j] = v;
+        tot += v;
+    }
+    bool made_nan = false;
+    for (int j = 0; j < k; ++j) {
+        const float nv = X30(tot - X[lo + j]);
+        made_nan |= (nv != nv);
+        X[lo + j] = nv;
+    }
+    return made_nan;
 }
 
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
@@ -451,6 +507,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         if (blk_idle(s, b0, b1)) continue;
         const bool multi = (b0 != b1);
         const int e0 = g.cl_ptr[a0], ne = g.cl_ptr[a1] - e0;
+        const int ku = g.cb_k[blk];
         for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
         // ---- load (contiguous), log, scatter into clause-major order
@@ -467,55 +524,44 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         }
         __syncthreads();
         // ---- thread per clause
+        const bool um0 = use_mask && !multi && s.masked[b0];
         for (int a = a0 + tid; a < a1; a += nthr) {
-            const int cbeg = g.cl_ptr[a], cend = g.cl_ptr[a + 1];
-            const int lo = cbeg - e0, k = cend - cbeg;
-            const int b = multi ? g.bfm[a] : b0;
-            if (multi && !blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); sm_any_skip = 1; continue; }
-            const bool um = use_mask && s.masked[b];
-            bool made_nan = false;
-            if (k <= 8) {
-                float x[8];
-                float tot = 0.f;
-                CBits cb(g.cbits);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < k) {
-                        float v = X[lo + j];
-                        if (um && cb.get(cbeg + j)) v = v * 0.f;
-                        x[j] = v;
-                        tot += v;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < k) {
-                        const float nv = X30(tot - x[j]);
-                        made_nan |= (nv != nv);
-                        X[lo + j] = nv;
-                    }
-                }
-            } else {
-                float tot = 0.f;
-                CBits cb(g.cbits);
-                for (int j = 0; j < k; ++j) {
-                    float v = X[lo + j];
-                    if (um && cb.get(cbeg + j)) v = v * 0.f;
-                    X[lo + j] = v;
-                    tot += v;
-                }
-                for (int j = 0; j < k; ++j) {
-                    const float nv = X30(tot - X[lo + j]);
-                    made_nan |= (nv != nv);
-                    X[lo + j] = nv;
-                }
+            int cbeg, k;
+            if (ku) { k = ku; cbeg = e0 + (a - a0) * ku; }
+            else { cbeg = g.cl_ptr[a]; k = g.cl_ptr[a + 1] - cbeg; }
+            const int lo = cbeg - e0;
+            int b = b0;
+            bool um = um0;
+            if (multi) {
+                b = g.bfm[a];
+                if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); sm_any_skip = 1; continue; }
+                um = use_mask && s.masked[b];
+            }
+            bool made_nan;
+            switch (k) {
+                case 3: made_nan = blk_clause_body<3>(X, lo, um, g.cbits, cbeg); break;
+                case 4: made_nan = blk_clause_body<4>(X, lo, um, g.cbits, cbeg); break;
+                case 5: made_nan = blk_clause_body<5>(X, lo, um, g.cbits, cbeg); break;
+                case 2: made_nan = blk_clause_body<2>(X, lo, um, g.cbits, cbeg); break;
+                default: made_nan = blk_clause_body_any(X, lo, k, um, g.cbits, cbeg); break;
             }
             if (made_nan) s.nanpend[b] = 1;
         }
         __syncthreads();
-        blk_write_out(g.cpiece, g.cpiece_ptr[blk], g.cpiece_ptr[blk + 1], g.csrc, X, skip, sm_any_skip != 0, eout);
+        blk_write_out(g.csrc + e0, g.cdst + e0, ne, X, skip, sm_any_skip != 0, eout);
         __syncthreads();
     }
+}
+
+// statistics of multi-problem blocks: per block-local problem in shared memory
+#define PDP_STAT_SLOTS 64
+struct BlkStats {
+    uint32_t mx0[PDP_STAT_SLOTS], mn0[PDP_STAT_SLOTS], mx1[PDP_STAT_SLOTS], mn1[PDP_STAT_SLOTS], nan[PDP_STAT_SLOTS], nav[PDP_STAT_SLOTS];
+};
+
+// branch-free select (the compiler would otherwise split the update loop into one path per literal sign)
+__device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
+    return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
 }
 
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
@@ -526,6 +572,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     float* PB = PA + PDP_BLK_V;                   // eta(t-1), then y
     uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
     __shared__ int sm_any_skip;
+    __shared__ BlkStats sm_st;
     const float* __restrict__ en = s.eta[r ^ 1];
     const float* __restrict__ eo = s.eta[r];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -536,9 +583,14 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         const int b0 = g.bvm[v0], b1 = g.bvm[v1 - 1];
         if (blk_idle(s, b0, b1)) continue;
         const bool multi = (b0 != b1);
+        const bool local_stats = multi && (b1 - b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
         const int e0 = g.var_ptr[v0], ne = g.var_ptr[v1] - e0;
         for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
+        if (local_stats && tid <= b1 - b0) {
+            sm_st.mx0[tid] = 0u; sm_st.mn0[tid] = 0x7f800000u; sm_st.mx1[tid] = 0u; sm_st.mn1[tid] = 0x7f800000u;
+            sm_st.nan[tid] = 0u; sm_st.nav[tid] = 0u;
+        }
         // ---- load both survey regions (contiguous), scatter into variable-major order
         {
             const float* __restrict__ sn = en + e0;
@@ -553,14 +605,21 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
             for (; x < ne; x += nthr) { const int l = inv[x]; PA[l] = sn[x]; PB[l] = so[x]; }
         }
         __syncthreads();
-        // ---- thread per variable: ordered sums, statistics, update
-        for (int i = v0 + tid; i < v1; i += nthr) {
-            const int pbeg = g.var_ptr[i], pend = g.var_ptr[i + 1];
-            const int lo = pbeg - e0, deg = pend - pbeg;
-            const int b = multi ? g.bvm[i] : b0;
-            if (multi && !blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); sm_any_skip = 1; continue; }
-            const bool umy = use_mask && s.masked[b];
-            const bool umd = em_set && s.masked[b];
+        // ---- thread per variable (descending degree): ordered sums, statistics, update
+        const bool umy0 = use_mask && !multi && s.masked[b0];
+        const bool umd0 = em_set && !multi && s.masked[b0];
+        for (int t = v0 + tid; t < v1; t += nthr) {
+            const int2 ve = __ldg(&g.vsort[t]);
+            const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
+            const int pbeg = e0 + lo;
+            int b = b0;
+            bool umy = umy0, umd = umd0;
+            if (multi) {
+                b = g.bvm[i];
+                if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); sm_any_skip = 1; continue; }
+                umy = use_mask && s.masked[b];
+                umd = em_set && s.masked[b];
+            }
             const uint32_t act = s.av[i];
             VBits vb(g.vbits);
             float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
@@ -570,8 +629,11 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
                 float y = L40(1.f - xo);
                 if (umy && (bits & PDP_VB_MASK)) y = y * 0.f;
                 PB[lo + j] = y;
-                P += ((bits & PDP_VB_NEG) ? 0.f : 1.f) * y;
-                N += ((bits & PDP_VB_NEG) ? 1.f : 0.f) * y;
+                // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
+                const float zy = 0.f * y;
+                const uint32_t negm = 0u - (bits & PDP_VB_NEG);
+                P += fsel(negm, zy, y);
+                N += fsel(negm, y, zy);
                 const float c = X30(30.f * xn);
                 n0 += xn * c; d0 += c;
                 if (has_prev) {
@@ -581,22 +643,45 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
                     n1 += d * cd; d1 += cd;
                 }
             }
-            red.touch(s, b);
-            red.acc.add((n0 / tmaxf(d0, 1.0f)) * (float)act, (n1 / tmaxf(d1, 1.0f)) * (float)act, has_prev, act);
+            const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
+            const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
+            if (!multi) {
+                red.touch(s, b);
+                red.acc.add(sm0, sm1, has_prev, act);
+            } else {
+                StatAcc one;
+                one.reset();
+                one.add(sm0, sm1, has_prev, act);
+                if (local_stats) {
+                    const int lb = b - b0;
+                    atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
+                    if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
+                    if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
+                    if (act) atomicAdd(&sm_st.nav[lb], act);
+                } else {
+                    one.commit(s, b);
+                }
+            }
             float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
             sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
             sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
             bool made_nan = false;
             for (int j = 0; j < deg; ++j) {
-                const bool neg = (vb.get(pbeg + j) & PDP_VB_NEG) != 0u;
-                const float u = sp_var_finish(neg ? sb_neg : sb_pos, neg ? opp_neg : opp_pos, neg ? O_neg : O_pos, PB[lo + j]);
+                const uint32_t negm = 0u - (vb.get(pbeg + j) & PDP_VB_NEG);
+                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), PB[lo + j]);
                 made_nan |= (u != u);
                 PA[lo + j] = u;
             }
             if (made_nan) s.nanpend[b] = 1;
         }
         __syncthreads();
-        blk_write_out(g.vpiece, g.vpiece_ptr[blk], g.vpiece_ptr[blk + 1], g.vsrc, PA, skip, sm_any_skip != 0, s.qu);
+        if (local_stats && tid <= b1 - b0) {
+            StatAcc a;
+            a.mx0 = sm_st.mx0[tid]; a.mn0 = sm_st.mn0[tid]; a.mx1 = sm_st.mx1[tid]; a.mn1 = sm_st.mn1[tid];
+            a.nan = sm_st.nan[tid]; a.nav = sm_st.nav[tid];
+            if (a.mn0 != 0x7f800000u || a.mx0 != 0u || a.nan || a.nav || a.mn1 != 0x7f800000u) a.commit(s, b0 + tid);
+        }
+        blk_write_out(g.vsrc + e0, g.vdst + e0, ne, PA, skip, sm_any_skip != 0, s.qu);
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
     }
 }

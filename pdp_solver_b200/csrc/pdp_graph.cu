@@ -78,10 +78,10 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.cinv = k.take<uint16_t>(E);
     g.vsrc = k.take<uint16_t>(E);
     g.csrc = k.take<uint16_t>(E);
-    g.vpiece = k.take<int2>(E + 1);
-    g.cpiece = k.take<int2>(E + 1);
-    g.vpiece_ptr = k.take<int32_t>(max_vb + 1);
-    g.cpiece_ptr = k.take<int32_t>(max_cb + 1);
+    g.vdst = k.take<int32_t>(E);
+    g.cdst = k.take<int32_t>(E);
+    g.vsort = k.take<int2>(V);
+    g.cb_k = k.take<int32_t>(max_cb + 1);
     s.eta[0] = k.take<float>(E);
     s.eta[1] = k.take<float>(E);
     s.qu = k.take<float>(E);

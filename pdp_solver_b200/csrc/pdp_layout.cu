@@ -82,45 +82,42 @@ __global__ void k_key_cblock_of_v(pdp_graph g, const int32_t* __restrict__ lv, i
 }
 
 // w = write-out slot; kb[w] = block, dst[w] = destination position, slot_of_dst[dst] = producer-order slot.
-// src16[w] = local producer-order index; head[w] = (w starts a run of adjacent destinations) ? w : 0
+// src16[w] = local producer-order index
 __global__ void k_fill_writeout(int64_t E, const int32_t* __restrict__ kb, const int32_t* __restrict__ dst,
                                 const int32_t* __restrict__ slot_of_dst, const int32_t* __restrict__ node_ptr,
-                                const int32_t* __restrict__ blk_ptr, uint16_t* src16, int32_t* head) {
+                                const int32_t* __restrict__ blk_ptr, uint16_t* src16, int32_t* dst_out) {
     GS(w, E) {
-        const int b = kb[w], d = dst[w];
-        src16[w] = (uint16_t)(slot_of_dst[d] - node_ptr[blk_ptr[b]]);
-        const bool h = (w == 0) || (kb[w - 1] != b) || (dst[w - 1] + 1 != d);
-        head[w] = h ? (int32_t)w : 0;
+        const int d = dst[w];
+        src16[w] = (uint16_t)(slot_of_dst[d] - node_ptr[blk_ptr[kb[w]]]);
+        dst_out[w] = d;
     }
 }
 
-// runstart[w] = start of the run containing w; pieces start every PDP_PIECE elements of a run
-__global__ void k_piece_flags(int64_t E, const int32_t* __restrict__ runstart, int32_t* flag) {
-    GS(w, E) flag[w] = (((int32_t)w - runstart[w]) % PDP_PIECE == 0) ? 1 : 0;
+// degree-sorted variable order: key = block << 14 | (16383 - degree)
+__global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
+    GS(v, g.V) {
+        const int deg = g.var_ptr[v + 1] - g.var_ptr[v];
+        key[v] = ((g.var_ptr[v] / g.sv) << 14) | (16383 - (deg > 16383 ? 16383 : deg));
+        val[v] = (int32_t)v;
+    }
 }
-
-__global__ void k_fill_pieces(int64_t E, const int32_t* __restrict__ piece_w, const int32_t* __restrict__ n_ptr,
-                              const int32_t* __restrict__ dst, int2* piece) {
-    const int32_t n = *n_ptr;
-    GS(k, (int64_t)n + 1) {
-        if (k == n) { piece[k] = make_int2((int32_t)E, 0); continue; }
-        const int w = piece_w[k];
-        piece[k] = make_int2(w, dst[w]);
+// order == nullptr: identity
+__global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order) {
+    GS(t, g.V) {
+        const int v = order ? order[t] : (int)t;
+        const int blk = g.var_ptr[v] / g.sv;
+        const int lo = g.var_ptr[v] - g.var_ptr[g.vb_ptr[blk]];
+        const int deg = g.var_ptr[v + 1] - g.var_ptr[v];
+        g.vsort[t] = make_int2(v, lo | (deg << 16));
     }
 }
 
-// piece_ptr[b] = first piece whose first write-out slot is >= the block's first slot
-__global__ void k_piece_ptr(const int2* __restrict__ piece, const int32_t* __restrict__ n_ptr, const int32_t* __restrict__ node_ptr,
-                            const int32_t* __restrict__ blk_ptr, int32_t nblk, int32_t* piece_ptr) {
-    const int32_t n = *n_ptr;
-    GS(b, (int64_t)nblk + 1) {
-        const int32_t target = node_ptr[blk_ptr[b]];
-        int lo = 0, hi = n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (piece[mid].x < target) lo = mid + 1; else hi = mid;
-        }
-        piece_ptr[b] = lo;
+__global__ void k_clause_block_degree(pdp_graph g) {
+    GS(blk, g.ncb) {
+        const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
+        int k = (a1 > a0) ? g.cl_ptr[a0 + 1] - g.cl_ptr[a0] : 0;
+        for (int a = a0; a < a1 && k; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != k) k = 0;
+        g.cb_k[blk] = (k >= 1 && k <= 8) ? k : 0;
     }
 }
 
@@ -142,10 +139,6 @@ __global__ void k_sign_bits(pdp_graph g) {
     }
     GS(wi, g.E / 32 + 1) g.cbits[wi] = 0u;
 }
-
-struct MaxOp {
-    __host__ __device__ __forceinline__ int32_t operator()(const int32_t& a, const int32_t& b) const { return a > b ? a : b; }
-};
 
 int bits_for(int64_t n) {
     int bits = 1;
@@ -204,18 +197,17 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     int32_t* S3 = reinterpret_cast<int32_t*>(c->s.qs);
     int32_t* LV = reinterpret_cast<int32_t*>(c->s.qd);    // V-layout position -> clause-major slot
     int32_t* LQ = reinterpret_cast<int32_t*>(c->s.ext);   // C-layout position -> variable-major slot
-    int32_t* d_count = c->s.ctrl + CTRL_SIZE - 1;
 
     // stable sort of (key, value) pairs held in S0 / S2; returns the buffers holding the result
-    auto sort_pairs = [&](int nkeys, int32_t** keys_out, int32_t** vals_out, int32_t** keys_free, int32_t** vals_free) -> int {
+    auto sort_pairs = [&](int64_t count, int64_t nkeys, int32_t** keys_out, int32_t** vals_out, int32_t** keys_free, int32_t** vals_free) -> int {
         cub::DoubleBuffer<int32_t> dk(S0, S1);
         cub::DoubleBuffer<int32_t> dv(S2, S3);
         size_t q = 0;
         const int bits = bits_for(nkeys);
-        if (cub::DeviceRadixSort::SortPairs(nullptr, q, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        if (cub::DeviceRadixSort::SortPairs(nullptr, q, dk, dv, (int)count, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
         if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: sort scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
         size_t tb = c->cub_tmp_bytes;
-        if (cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        if (cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, dk, dv, (int)count, 0, bits, stream) != cudaSuccess) return PDP_ERR_CUDA;
         c->launches++;
         *keys_out = dk.Current(); *vals_out = dv.Current(); *keys_free = dk.Alternate(); *vals_free = dv.Alternate();
         return PDP_OK;
@@ -226,56 +218,42 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     // ---- V-layout: edges sorted by (variable block, clause-major slot)
     k_key_vblock_of_c<<<G1(E)>>>(g, S0, S2);
     LLK();
-    if ((rc = sort_pairs(g.nvb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+    if ((rc = sort_pairs(E, g.nvb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
     k_fill_vlayout<<<G1(E)>>>(g, K, L);
     LLK();
     LCK(cudaMemcpyAsync(LV, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
     // ---- C-layout: edges sorted by (clause block, variable-major slot)
     k_key_cblock_of_p<<<G1(E)>>>(g, S0, S2);
     LLK();
-    if ((rc = sort_pairs(g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+    if ((rc = sort_pairs(E, g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
     k_fill_clayout<<<G1(E)>>>(g, K, L);
     LLK();
     LCK(cudaMemcpyAsync(LQ, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
 
-    // ---- write-out orders and pieces
+    // ---- write-out orders: the edges of a block sorted by their destination position
     for (int side = 0; side < 2; ++side) {
         const bool var_side = (side == 0);
         if (var_side) k_key_vblock_of_q<<<G1(E)>>>(g, LQ, S0, S2);
         else k_key_cblock_of_v<<<G1(E)>>>(g, LV, S0, S2);
         LLK();
-        if ((rc = sort_pairs(var_side ? g.nvb : g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
-        // K[w] = block, L[w] = destination position; KF / LF are free
+        if ((rc = sort_pairs(E, var_side ? g.nvb : g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+        // K[w] = block, L[w] = destination position
         k_fill_writeout<<<G1(E)>>>(E, K, L, var_side ? LQ : LV, var_side ? g.var_ptr : g.cl_ptr,
-                                    var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.vsrc : g.csrc, KF);
-        LLK();
-        {
-            size_t q = 0;
-            LCK(cub::DeviceScan::InclusiveScan(nullptr, q, KF, LF, MaxOp(), (int)E, stream));
-            if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: scan scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
-            size_t tb = c->cub_tmp_bytes;
-            LCK(cub::DeviceScan::InclusiveScan(c->cub_tmp, tb, KF, LF, MaxOp(), (int)E, stream));
-            c->launches++;
-        }
-        k_piece_flags<<<G1(E)>>>(E, LF, KF);   // KF: piece flags
-        LLK();
-        {
-            cub::CountingInputIterator<int32_t> iota(0);
-            size_t q = 0;
-            LCK(cub::DeviceSelect::Flagged(nullptr, q, iota, KF, LF, d_count, (int)E, stream));
-            if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: select scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
-            size_t tb = c->cub_tmp_bytes;
-            LCK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, iota, KF, LF, d_count, (int)E, stream));   // LF: piece starts
-            c->launches++;
-        }
-        int2* piece = var_side ? g.vpiece : g.cpiece;
-        k_fill_pieces<<<G1(E + 1)>>>(E, LF, d_count, L, piece);
-        LLK();
-        k_piece_ptr<<<G1((var_side ? g.nvb : g.ncb) + 1)>>>(piece, d_count, var_side ? g.var_ptr : g.cl_ptr,
-                                                             var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.nvb : g.ncb,
-                                                             var_side ? g.vpiece_ptr : g.cpiece_ptr);
+                                    var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.vsrc : g.csrc, var_side ? g.vdst : g.cdst);
         LLK();
     }
+    // ---- per block: variables by descending degree (uniform trip counts inside a warp), clause degree
+    if (g.V <= E && g.max_var_degree < 16384 && g.nvb < (1 << 17)) {
+        k_key_vsort<<<G1(g.V)>>>(g, S0, S2);
+        LLK();
+        if ((rc = sort_pairs(g.V, (int64_t)g.nvb << 14, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+        k_fill_vsort<<<G1(g.V)>>>(g, L);
+    } else {
+        k_fill_vsort<<<G1(g.V)>>>(g, nullptr);
+    }
+    LLK();
+    k_clause_block_degree<<<G1(g.ncb)>>>(g);
+    LLK();
     g.blocked_ok = 1;
     return PDP_OK;
 }
@@ -284,16 +262,17 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
 // self-check of the layout tables (tests): counts violated invariants into errs[0..7]
 //   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vinv wrong
 //   2 C-layout position outside its block / cinv wrong           3 variable write-out does not land on p_qpos
-//   4 clause write-out does not land on c_vpos                   5 piece length out of (0, PDP_PIECE]
-//   6 slots covered by the variable pieces (must equal E)        7 slots covered by the clause pieces (must equal E)
+//   4 clause write-out does not land on c_vpos                   5 vsort / cb_k wrong
+//   6 distinct write-out sources of the variable blocks (= E)    7 ... of the clause blocks (= E)
 // ------------------------------------------------------------------------------------------------
 namespace {
-__global__ void k_check_layout(pdp_graph g, int32_t* errs) {
+__global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/32+1] x 2, zeroed */) {
     GS(c, g.E) {
         const int p = g.c_pos[c];
         if (g.c_vpos[c] != g.p_vpos[p] || g.c_qpos[c] != g.p_qpos[p] || (int)(g.v_cedge[p] & PDP_IDX_MASK) != (int)c) atomicAdd(&errs[0], 1);
     }
     if (!g.blocked_ok) return;
+    uint32_t* seen_c = seen + g.E / 32 + 1;
     GS(blk, g.nvb) {
         const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
         const int e0 = g.var_ptr[v0], e1 = g.var_ptr[v1];
@@ -302,15 +281,21 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs) {
             const int x = g.p_vpos[p];
             if (x < e0 || x >= e1 || (int)g.vinv[x] != p - e0) atomicAdd(&errs[1], 1);
         }
-        for (int k = g.vpiece_ptr[blk]; k < g.vpiece_ptr[blk + 1]; ++k) {
-            const int w0 = g.vpiece[k].x, gd = g.vpiece[k].y, len = g.vpiece[k + 1].x - w0;
-            if (len <= 0 || len > PDP_PIECE || w0 < e0 || w0 + len > e1) atomicAdd(&errs[5], 1);
-            for (int t = 0; t < len; ++t) {
-                const int p = e0 + (int)g.vsrc[w0 + t];
-                if (p < e0 || p >= e1 || g.p_qpos[p] != gd + t) atomicAdd(&errs[3], 1);
-            }
-            atomicAdd(&errs[6], len);
+        for (int w = e0; w < e1; ++w) {
+            const int p = e0 + (int)g.vsrc[w];
+            if (p < e0 || p >= e1 || g.p_qpos[p] != g.vdst[w]) { atomicAdd(&errs[3], 1); continue; }
+            if (w > e0 && g.vdst[w] <= g.vdst[w - 1]) atomicAdd(&errs[3], 1);
+            if (!(atomicOr(&seen[p >> 5], 1u << (p & 31)) & (1u << (p & 31)))) atomicAdd(&errs[6], 1);
         }
+        long long sum = 0;
+        for (int t = v0; t < v1; ++t) {
+            const int2 e = g.vsort[t];
+            const int v = e.x, lo = e.y & 0xffff, deg = e.y >> 16;
+            if (v < v0 || v >= v1 || lo != g.var_ptr[v] - e0 || deg != g.var_ptr[v + 1] - g.var_ptr[v]) atomicAdd(&errs[5], 1);
+            if (t > v0 && deg > (g.vsort[t - 1].y >> 16) && g.V <= g.E) atomicAdd(&errs[5], 1);
+            sum += v;
+        }
+        if (sum != ((long long)v0 + v1 - 1) * (v1 - v0) / 2) atomicAdd(&errs[5], 1);
     }
     GS(blk, g.ncb) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
@@ -320,20 +305,23 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs) {
             const int x = g.c_qpos[c];
             if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
         }
-        for (int k = g.cpiece_ptr[blk]; k < g.cpiece_ptr[blk + 1]; ++k) {
-            const int w0 = g.cpiece[k].x, gd = g.cpiece[k].y, len = g.cpiece[k + 1].x - w0;
-            if (len <= 0 || len > PDP_PIECE || w0 < e0 || w0 + len > e1) atomicAdd(&errs[5], 1);
-            for (int t = 0; t < len; ++t) {
-                const int c = e0 + (int)g.csrc[w0 + t];
-                if (c < e0 || c >= e1 || g.c_vpos[c] != gd + t) atomicAdd(&errs[4], 1);
-            }
-            atomicAdd(&errs[7], len);
+        for (int w = e0; w < e1; ++w) {
+            const int c = e0 + (int)g.csrc[w];
+            if (c < e0 || c >= e1 || g.c_vpos[c] != g.cdst[w]) { atomicAdd(&errs[4], 1); continue; }
+            if (w > e0 && g.cdst[w] <= g.cdst[w - 1]) atomicAdd(&errs[4], 1);
+            if (!(atomicOr(&seen_c[c >> 5], 1u << (c & 31)) & (1u << (c & 31)))) atomicAdd(&errs[7], 1);
         }
+        const int k = g.cb_k[blk];
+        bool uni = (a1 > a0);
+        for (int a = a0; a < a1; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != g.cl_ptr[a0 + 1] - g.cl_ptr[a0]) uni = false;
+        const int kk = uni ? g.cl_ptr[a0 + 1] - g.cl_ptr[a0] : 0;
+        if (k != ((kk >= 1 && kk <= 8) ? kk : 0)) atomicAdd(&errs[5], 1);
     }
 }
 }  // namespace
 
-// d_errs: device int32[8], zeroed here.  host_info (nullable): {blocked_ok, nvb, ncb, sv, sc}
+// d_errs: device int32[8], zeroed here.  host_info (nullable): {blocked_ok, nvb, ncb, sv, sc}.
+// Uses the eta[1] message buffer as scratch: call it before pdp_load_state.
 extern "C" int pdp_debug_check_layout(pdp_ctx* c, int32_t* d_errs, int32_t* host_info, void* stream_) {
     if (!c || !d_errs) { pdp_set_error("pdp_debug_check_layout: null argument"); return PDP_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -341,7 +329,13 @@ extern "C" int pdp_debug_check_layout(pdp_ctx* c, int32_t* d_errs, int32_t* host
     LCK(cudaMemsetAsync(d_errs, 0, 8 * sizeof(int32_t), stream));
     int64_t n = c->g.E;
     if (c->g.nvb > n) n = c->g.nvb;
-    if (n > 0) { k_check_layout<<<G1(n)>>>(c->g, d_errs); LLK(); }
+    if (n > 0) {
+        uint32_t* seen = reinterpret_cast<uint32_t*>(c->s.eta[1]);   // 2 * (E/32 + 1) words <= E floats for E >= 3
+        if (c->g.E < 64) seen = reinterpret_cast<uint32_t*>(c->cub_tmp);
+        LCK(cudaMemsetAsync(seen, 0, 2 * (size_t)(c->g.E / 32 + 1) * sizeof(uint32_t), stream));
+        k_check_layout<<<G1(n)>>>(c->g, d_errs, seen);
+        LLK();
+    }
     if (host_info) { host_info[0] = c->g.blocked_ok; host_info[1] = c->g.nvb; host_info[2] = c->g.ncb; host_info[3] = c->g.sv; host_info[4] = c->g.sc; }
     return PDP_OK;
 }
