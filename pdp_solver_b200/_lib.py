@@ -67,7 +67,7 @@ def load(strict_math=False):
     key = bool(strict_math)
     if key in _libs:
         return _libs[key]
-    path = STRICT_LIB_PATH if key else LIB_PATH
+    path = STRICT_LIB_PATH if key else os.environ.get("PDP_B200_LIB", LIB_PATH)   # override: A/B builds of the product library
     if not os.path.exists(path):
         raise PdpError("%s not found -- build it with pdp_solver_b200/csrc/build.sh "
                        "(there is no CPU fallback)" % path)

@@ -207,41 +207,24 @@ struct PickAcc {
 
 // ------------------------------------------------------------------------------------------------
 // activity masks.  The edge mask em(e) = active_variable(i(e)) * active_function(a(e)) of the reference
-// (solver.py:370-371) is kept as one bit per edge in both edge orders (g.vbits / g.cbits), set where a
-// node is de-activated, so that a sweep never gathers the node masks.
+// (solver.py:370-371) is kept as one bit per edge, indexed by the edge's position in each of the two
+// message layouts (g.vmask / g.qmask) and set where a node is de-activated: a pass reads the mask bits
+// of its region with the same contiguous access as the messages and never gathers the node masks.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mask_edge(const pdp_graph& g, int p, int c) {
-    atomicOr(&g.vbits[p >> 4], PDP_VB_MASK << (2 * (p & 15)));
-    atomicOr(&g.cbits[c >> 5], 1u << (c & 31));
+__device__ __forceinline__ void mask_edge(const pdp_graph& g, int vpos, int qpos) {
+    atomicOr(&g.vmask[vpos >> 5], 1u << (vpos & 31));
+    atomicOr(&g.qmask[qpos >> 5], 1u << (qpos & 31));
 }
 __device__ __forceinline__ void deactivate_variable(const pdp_graph& g, const pdp_state& s, int i) {
     s.av[i] = 0;
-    for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) mask_edge(g, p, (int)(g.v_cedge[p] & PDP_IDX_MASK));
+    for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) mask_edge(g, g.p_vpos[p], g.p_qpos[p]);
 }
 __device__ __forceinline__ void deactivate_clause(const pdp_graph& g, const pdp_state& s, int a) {
     s.af[a] = 0;
-    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) mask_edge(g, g.c_pos[c], c);
+    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) mask_edge(g, g.c_vpos[c], g.c_qpos[c]);
 }
-
-// streaming readers of the bit arrays (the words change between passes: read around L1)
-struct VBits {
-    const uint32_t* base; int wi; uint32_t w;
-    __device__ __forceinline__ VBits(const uint32_t* b) : base(b), wi(-1), w(0u) {}
-    __device__ __forceinline__ uint32_t get(int p) {
-        const int i = p >> 4;
-        if (i != wi) { wi = i; w = __ldcg(base + i); }
-        return (w >> ((p & 15) * 2)) & 3u;
-    }
-};
-struct CBits {
-    const uint32_t* base; int wi; uint32_t w;
-    __device__ __forceinline__ CBits(const uint32_t* b) : base(b), wi(-1), w(0u) {}
-    __device__ __forceinline__ bool get(int c) {
-        const int i = c >> 5;
-        if (i != wi) { wi = i; w = __ldcg(base + i); }
-        return (w >> (c & 31)) & 1u;
-    }
-};
+// the words change between passes: read around L1
+__device__ __forceinline__ bool mbit(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 1u; }
 
 // variable side of the SP update with the per-variable part hoisted (pi == 0): for one sign s the terms
 // 0.5(1+s)P + 0.5(1-s)N, opp and exp(opp) do not depend on the edge.  Same operations, same order as
@@ -290,16 +273,17 @@ __device__ __forceinline__ void gen_clause_side(const KArgs& A, int r, bool use_
         const bool sticky = s.nanflag[b] != 0;
         bool made_nan = false;
         const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
-        CBits cb(g.cbits);
         float tot = 0.f;
         for (int c = beg; c < end; ++c) {
-            float v = L40(qin[g.c_qpos[c]]);
-            if (um && cb.get(c)) v = v * 0.f;
+            const int qp = g.c_qpos[c];
+            float v = L40(qin[qp]);
+            if (um && mbit(g.qmask, qp)) v = v * 0.f;
             tot += v;
         }
         for (int c = beg; c < end; ++c) {
-            float v = L40(qin[g.c_qpos[c]]);
-            if (um && cb.get(c)) v = v * 0.f;
+            const int qp = g.c_qpos[c];
+            float v = L40(qin[qp]);
+            if (um && mbit(g.qmask, qp)) v = v * 0.f;
             const int pos = g.c_vpos[c];
             float nv = X30(tot - v);
             if (sticky) { const float ov = eold[pos]; if (ov != ov) nv = ov; }
@@ -323,21 +307,21 @@ __device__ __forceinline__ void gen_var_side(const KArgs& A, int r, bool use_mas
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
         const bool sticky = s.nanflag[b] != 0;
         bool made_nan = false;
-        VBits vb(g.vbits);
         float P = 0.f, N = 0.f;
         for (int p = beg; p < end; ++p) {
-            const uint32_t bits = vb.get(p);
-            float y = L40(1.f - ein[g.p_vpos[p]]);
-            if (um && (bits & PDP_VB_MASK)) y = y * 0.f;
+            const int vp = g.p_vpos[p];
+            const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
+            float y = L40(1.f - ein[vp]);
+            if (um && mbit(g.vmask, vp)) y = y * 0.f;
             // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
-            P += ((bits & PDP_VB_NEG) ? 0.f : 1.f) * y;
-            N += ((bits & PDP_VB_NEG) ? 1.f : 0.f) * y;
+            P += (neg ? 0.f : 1.f) * y;
+            N += (neg ? 1.f : 0.f) * y;
         }
         for (int p = beg; p < end; ++p) {
-            const uint32_t bits = vb.get(p);
-            float y = L40(1.f - ein[g.p_vpos[p]]);
-            if (um && (bits & PDP_VB_MASK)) y = y * 0.f;
-            const float sg = (bits & PDP_VB_NEG) ? -1.f : 1.f;
+            const int vp = g.p_vpos[p];
+            float y = L40(1.f - ein[vp]);
+            if (um && mbit(g.vmask, vp)) y = y * 0.f;
+            const float sg = (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f;
             const int qp = g.p_qpos[p];
             if (FULL || pi != 0.f) {
                 float u, v, d;
@@ -377,7 +361,6 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
         const uint32_t act = s.av[i];
         const bool um = em_set && s.masked[b];
-        VBits vb(g.vbits);
         float n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
         for (int p = beg; p < end; ++p) {
             const int pos = g.p_vpos[p];
@@ -386,7 +369,7 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
             n0 += v * c; d0 += c;
             if (has_prev) {
                 float d = fabsf(eo[pos] - v);
-                if (um && (vb.get(p) & PDP_VB_MASK)) d = d * 0.f;
+                if (um && mbit(g.vmask, pos)) d = d * 0.f;
                 const float cd = X30(30.f * d);
                 n1 += d * cd; d1 += cd;
             }
@@ -418,23 +401,24 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
     for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
 }
 
+#define NT PDP_SWEEP_THREADS   // compile-time stride of the block-wide loops (immediate address offsets)
+
 // write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
 // consecutive destinations (runs), so a warp's stores coalesce into a few sectors
 template <bool SKIP>
 __device__ __forceinline__ void blk_write_out_t(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
                                                 const float* plane, const uint32_t* skip, float* __restrict__ out) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    int w = tid;
-    for (; w + 3 * nthr < ne; w += 4 * nthr) {
-        const int l0 = src[w], l1 = src[w + nthr], l2 = src[w + 2 * nthr], l3 = src[w + 3 * nthr];
-        const int d0 = dst[w], d1 = dst[w + nthr], d2 = dst[w + 2 * nthr], d3 = dst[w + 3 * nthr];
+    int w = threadIdx.x;
+    for (; w + 3 * NT < ne; w += 4 * NT) {
+        const int l0 = src[w], l1 = src[w + NT], l2 = src[w + 2 * NT], l3 = src[w + 3 * NT];
+        const int d0 = dst[w], d1 = dst[w + NT], d2 = dst[w + 2 * NT], d3 = dst[w + 3 * NT];
         const float x0 = plane[l0], x1 = plane[l1], x2 = plane[l2], x3 = plane[l3];
         if (!SKIP || !((skip[l0 >> 5] >> (l0 & 31)) & 1u)) out[d0] = x0;
         if (!SKIP || !((skip[l1 >> 5] >> (l1 & 31)) & 1u)) out[d1] = x1;
         if (!SKIP || !((skip[l2 >> 5] >> (l2 & 31)) & 1u)) out[d2] = x2;
         if (!SKIP || !((skip[l3 >> 5] >> (l3 & 31)) & 1u)) out[d3] = x3;
     }
-    for (; w < ne; w += nthr) {
+    for (; w < ne; w += NT) {
         const int l = src[w];
         if (!SKIP || !((skip[l >> 5] >> (l & 31)) & 1u)) out[dst[w]] = plane[l];
     }
@@ -445,24 +429,38 @@ __device__ __forceinline__ void blk_write_out(const uint16_t* __restrict__ src, 
     else blk_write_out_t<false>(src, dst, ne, plane, skip, out);
 }
 
+// clause pass, load phase: x = log(max(q_u, 1e-40)) * em, scattered into clause-major order.
+// e0 = first C-layout position of the block (the mask bits are indexed by position).
+template <bool MASKED>
+__device__ __forceinline__ void blk_clause_load(const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
+                                                const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
+    int x = threadIdx.x;
+    for (; x + 3 * NT < ne; x += 4 * NT) {
+        const float q0 = qsrc[x], q1 = qsrc[x + NT], q2 = qsrc[x + 2 * NT], q3 = qsrc[x + 3 * NT];
+        const int l0 = inv[x], l1 = inv[x + NT], l2 = inv[x + 2 * NT], l3 = inv[x + 3 * NT];
+        float v0 = L40(q0), v1 = L40(q1), v2 = L40(q2), v3 = L40(q3);
+        if (MASKED) {
+            if (mbit(qmask, e0 + x)) v0 = v0 * 0.f;
+            if (mbit(qmask, e0 + x + NT)) v1 = v1 * 0.f;
+            if (mbit(qmask, e0 + x + 2 * NT)) v2 = v2 * 0.f;
+            if (mbit(qmask, e0 + x + 3 * NT)) v3 = v3 * 0.f;
+        }
+        X[l0] = v0; X[l1] = v1; X[l2] = v2; X[l3] = v3;
+    }
+    for (; x < ne; x += NT) {
+        float v = L40(qsrc[x]);
+        if (MASKED && mbit(qmask, e0 + x)) v = v * 0.f;
+        X[inv[x]] = v;
+    }
+}
+
 // one clause of K literals held in X[lo .. lo+K): surveys in place.  Returns whether a NaN was produced.
 template <int K>
-__device__ __forceinline__ bool blk_clause_body(float* X, int lo, bool um, const uint32_t* cbits, int cbeg) {
+__device__ __forceinline__ bool blk_clause_body(float* X, int lo) {
     float x[K];
     float tot = 0.f;
-    if (um) {
-        CBits cb(cbits);
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            float v = X[lo + j];
-            if (cb.get(cbeg + j)) v = v * 0.f;
-            x[j] = v;
-            tot += v;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; ++j) { x[j] = X[lo + j]; tot += x[j]; }
-    }
+    for (int j = 0; j < K; ++j) { x[j] = X[lo + j]; tot += x[j]; }
     bool made_nan = false;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -472,16 +470,9 @@ __device__ __forceinline__ bool blk_clause_body(float* X, int lo, bool um, const
     }
     return made_nan;
 }
-
-__device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k, bool um, const uint32_t* cbits, int cbeg) {
+__device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k) {
     float tot = 0.f;
-    CBits cb(cbits);
-    for (int j = 0; j < k; ++j) {
-        float v = X[lo + j];
-        if (um && cb.get(cbeg + j)) v = v * 0.f;
-        X[lo + j] = v;
-        tot += v;
-    }
+    for (int j = 0; j < k; ++j) tot += X[lo + j];
     bool made_nan = false;
     for (int j = 0; j < k; ++j) {
         const float nv = X30(tot - X[lo + j]);
@@ -499,7 +490,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     __shared__ int sm_any_skip;
     const float* __restrict__ qin = s.qu;
     float* __restrict__ eout = s.eta[r ^ 1];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x;
     for (int blk = blockIdx.x; blk < g.ncb; blk += gridDim.x) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
         if (a1 <= a0) continue;
@@ -508,42 +499,29 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         const bool multi = (b0 != b1);
         const int e0 = g.cl_ptr[a0], ne = g.cl_ptr[a1] - e0;
         const int ku = g.cb_k[blk];
-        for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
+        for (int i = tid; i < (ne + 31) / 32; i += NT) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
-        // ---- load (contiguous), log, scatter into clause-major order
-        {
-            const float* __restrict__ qsrc = qin + e0;
-            const uint16_t* __restrict__ inv = g.cinv + e0;
-            int x = tid;
-            for (; x + 3 * nthr < ne; x += 4 * nthr) {
-                const float q0 = qsrc[x], q1 = qsrc[x + nthr], q2 = qsrc[x + 2 * nthr], q3 = qsrc[x + 3 * nthr];
-                const int l0 = inv[x], l1 = inv[x + nthr], l2 = inv[x + 2 * nthr], l3 = inv[x + 3 * nthr];
-                X[l0] = L40(q0); X[l1] = L40(q1); X[l2] = L40(q2); X[l3] = L40(q3);
-            }
-            for (; x < ne; x += nthr) X[inv[x]] = L40(qsrc[x]);
-        }
+        // ---- load (contiguous), log, edge mask, scatter into clause-major order
+        if (use_mask && (multi || s.masked[b0])) blk_clause_load<true>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
+        else blk_clause_load<false>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
         __syncthreads();
         // ---- thread per clause
-        const bool um0 = use_mask && !multi && s.masked[b0];
-        for (int a = a0 + tid; a < a1; a += nthr) {
-            int cbeg, k;
-            if (ku) { k = ku; cbeg = e0 + (a - a0) * ku; }
-            else { cbeg = g.cl_ptr[a]; k = g.cl_ptr[a + 1] - cbeg; }
-            const int lo = cbeg - e0;
+        for (int a = a0 + tid; a < a1; a += NT) {
+            int lo, k;
+            if (ku) { k = ku; lo = (a - a0) * ku; }
+            else { lo = g.cl_ptr[a] - e0; k = g.cl_ptr[a + 1] - e0 - lo; }
             int b = b0;
-            bool um = um0;
             if (multi) {
                 b = g.bfm[a];
                 if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); sm_any_skip = 1; continue; }
-                um = use_mask && s.masked[b];
             }
             bool made_nan;
             switch (k) {
-                case 3: made_nan = blk_clause_body<3>(X, lo, um, g.cbits, cbeg); break;
-                case 4: made_nan = blk_clause_body<4>(X, lo, um, g.cbits, cbeg); break;
-                case 5: made_nan = blk_clause_body<5>(X, lo, um, g.cbits, cbeg); break;
-                case 2: made_nan = blk_clause_body<2>(X, lo, um, g.cbits, cbeg); break;
-                default: made_nan = blk_clause_body_any(X, lo, k, um, g.cbits, cbeg); break;
+                case 3: made_nan = blk_clause_body<3>(X, lo); break;
+                case 4: made_nan = blk_clause_body<4>(X, lo); break;
+                case 5: made_nan = blk_clause_body<5>(X, lo); break;
+                case 2: made_nan = blk_clause_body<2>(X, lo); break;
+                default: made_nan = blk_clause_body_any(X, lo, k); break;
             }
             if (made_nan) s.nanpend[b] = 1;
         }
@@ -564,8 +542,35 @@ __device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
     return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
 }
 
+// variable pass, load phase.  The surveys are non-negative, so their sign bits carry the two per-edge
+// flags the variable loops need: PA (new survey) sign = edge masked, PB (old survey) sign = negative literal.
+template <bool MASKED>
+__device__ __forceinline__ void blk_var_load(const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
+                                             const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
+    int x = threadIdx.x;
+    for (; x + NT < ne; x += 2 * NT) {
+        uint32_t n0 = __float_as_uint(sn[x]), n1 = __float_as_uint(sn[x + NT]);
+        const uint32_t o0 = __float_as_uint(so[x]), o1 = __float_as_uint(so[x + NT]);
+        const uint32_t i0 = inv[x], i1 = inv[x + NT];
+        if (MASKED) {
+            n0 |= mbit(vmask, e0 + x) ? 0x80000000u : 0u;
+            n1 |= mbit(vmask, e0 + x + NT) ? 0x80000000u : 0u;
+        }
+        const int l0 = i0 & 0x7fff, l1 = i1 & 0x7fff;
+        PA[l0] = __uint_as_float(n0); PB[l0] = __uint_as_float(o0 ^ ((i0 & PDP_VINV_NEG) << 16));
+        PA[l1] = __uint_as_float(n1); PB[l1] = __uint_as_float(o1 ^ ((i1 & PDP_VINV_NEG) << 16));
+    }
+    for (; x < ne; x += NT) {
+        uint32_t n0 = __float_as_uint(sn[x]);
+        const uint32_t o0 = __float_as_uint(so[x]), i0 = inv[x];
+        if (MASKED) n0 |= mbit(vmask, e0 + x) ? 0x80000000u : 0u;
+        const int l0 = i0 & 0x7fff;
+        PA[l0] = __uint_as_float(n0); PB[l0] = __uint_as_float(o0 ^ ((i0 & PDP_VINV_NEG) << 16));
+    }
+}
+
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
-// [buffer r], and q(t) [C-layout, in place] from eta(t-1)
+// [buffer r], and q(t) [C-layout, in place] from eta(t-1).  Requires eta(t-1) >= +0 or NaN without sign.
 __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
@@ -575,7 +580,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     __shared__ BlkStats sm_st;
     const float* __restrict__ en = s.eta[r ^ 1];
     const float* __restrict__ eo = s.eta[r];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x;
     KeyedReducer<StatAcc> red;
     for (int blk = blockIdx.x; blk < g.nvb; blk += gridDim.x) {
         const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
@@ -585,60 +590,48 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         const bool multi = (b0 != b1);
         const bool local_stats = multi && (b1 - b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
         const int e0 = g.var_ptr[v0], ne = g.var_ptr[v1] - e0;
-        for (int i = tid; i < (ne + 31) / 32; i += nthr) skip[i] = 0u;
+        for (int i = tid; i < (ne + 31) / 32; i += NT) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
         if (local_stats && tid <= b1 - b0) {
             sm_st.mx0[tid] = 0u; sm_st.mn0[tid] = 0x7f800000u; sm_st.mx1[tid] = 0u; sm_st.mn1[tid] = 0x7f800000u;
             sm_st.nan[tid] = 0u; sm_st.nav[tid] = 0u;
         }
         // ---- load both survey regions (contiguous), scatter into variable-major order
-        {
-            const float* __restrict__ sn = en + e0;
-            const float* __restrict__ so = eo + e0;
-            const uint16_t* __restrict__ inv = g.vinv + e0;
-            int x = tid;
-            for (; x + nthr < ne; x += 2 * nthr) {
-                const float n0 = sn[x], n1 = sn[x + nthr], o0 = so[x], o1 = so[x + nthr];
-                const int l0 = inv[x], l1 = inv[x + nthr];
-                PA[l0] = n0; PB[l0] = o0; PA[l1] = n1; PB[l1] = o1;
-            }
-            for (; x < ne; x += nthr) { const int l = inv[x]; PA[l] = sn[x]; PB[l] = so[x]; }
-        }
+        if ((use_mask || em_set) && (multi || s.masked[b0])) blk_var_load<true>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
+        else blk_var_load<false>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
         __syncthreads();
-        // ---- thread per variable (descending degree): ordered sums, statistics, update
-        const bool umy0 = use_mask && !multi && s.masked[b0];
-        const bool umd0 = em_set && !multi && s.masked[b0];
-        for (int t = v0 + tid; t < v1; t += nthr) {
+        // ---- thread per variable (descending degree): ordered sums, statistics, update.
+        // rounds alternate direction over the degree-sorted list: every thread gets high and low degrees
+        for (int base = v0, round = 0; base < v1; base += NT, ++round) {
+            const int t = (round & 1) ? (base + NT - 1 - tid) : (base + tid);
+            if (t >= v1) continue;
             const int2 ve = __ldg(&g.vsort[t]);
             const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
-            const int pbeg = e0 + lo;
             int b = b0;
-            bool umy = umy0, umd = umd0;
             if (multi) {
                 b = g.bvm[i];
                 if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); sm_any_skip = 1; continue; }
-                umy = use_mask && s.masked[b];
-                umd = em_set && s.masked[b];
             }
             const uint32_t act = s.av[i];
-            VBits vb(g.vbits);
             float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
             for (int j = 0; j < deg; ++j) {
-                const uint32_t bits = vb.get(pbeg + j);
-                const float xn = PA[lo + j], xo = PB[lo + j];
+                const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
+                const bool m = (nb >> 31) != 0u;                 // edge masked
+                const uint32_t negm = (uint32_t)((int32_t)ob >> 31);   // all ones: negative literal
+                const float xn = __uint_as_float(nb & 0x7fffffffu), xo = __uint_as_float(ob & 0x7fffffffu);
                 float y = L40(1.f - xo);
-                if (umy && (bits & PDP_VB_MASK)) y = y * 0.f;
-                PB[lo + j] = y;
+                if (use_mask && m) y = y * 0.f;
+                // y <= +0 (or NaN): stored as |y| under the literal's sign bit
+                PB[lo + j] = __uint_as_float((__float_as_uint(y) & 0x7fffffffu) | (ob & 0x80000000u));
                 // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
                 const float zy = 0.f * y;
-                const uint32_t negm = 0u - (bits & PDP_VB_NEG);
                 P += fsel(negm, zy, y);
                 N += fsel(negm, y, zy);
                 const float c = X30(30.f * xn);
                 n0 += xn * c; d0 += c;
                 if (has_prev) {
                     float d = fabsf(xo - xn);
-                    if (umd && (bits & PDP_VB_MASK)) d = d * 0.f;
+                    if (em_set && m) d = d * 0.f;
                     const float cd = X30(30.f * d);
                     n1 += d * cd; d1 += cd;
                 }
@@ -667,8 +660,10 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
             sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
             bool made_nan = false;
             for (int j = 0; j < deg; ++j) {
-                const uint32_t negm = 0u - (vb.get(pbeg + j) & PDP_VB_NEG);
-                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), PB[lo + j]);
+                const uint32_t yb = __float_as_uint(PB[lo + j]);
+                const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
+                const float y = __uint_as_float(yb | 0x80000000u);   // -|y|; -0 for +0 is erased by `same += 0`
+                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
                 made_nan |= (u != u);
                 PA[lo + j] = u;
             }
@@ -685,6 +680,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
     }
 }
+#undef NT
 
 // ------------------------------------------------------------------------------------------------
 // SurveyScorer over the converged problems (pdp_predict.py:155-192) + coefficient statistics

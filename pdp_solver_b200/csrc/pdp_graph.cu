@@ -67,8 +67,8 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.p_qpos = k.take<int32_t>(E);
     g.c_vpos = k.take<int32_t>(E);
     g.c_qpos = k.take<int32_t>(E);
-    g.vbits = k.take<uint32_t>(E / 16 + 1);
-    g.cbits = k.take<uint32_t>(E / 32 + 1);
+    g.vmask = k.take<uint32_t>(E / 32 + 1);
+    g.qmask = k.take<uint32_t>(E / 32 + 1);
     // block count <= rounds * SMs + 1 with rounds * SMs <= E / (half a block) + SMs (pdp_layout.cu pick_stride;
     // nodes of degree above half a block disable the blocked path)
     const int64_t max_vb = E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2, max_cb = E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2;
@@ -201,10 +201,9 @@ __global__ void k_max_degree(const int32_t* __restrict__ ptr, int64_t n, int32_t
 __global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, int64_t B) {
     int64_t n = V > F ? V : F;
     if (B > n) n = B;
-    if (g.E / 16 + 1 > n) n = g.E / 16 + 1;
+    if (g.E / 32 + 1 > n) n = g.E / 32 + 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        if (i < g.E / 16 + 1) g.vbits[i] &= 0x55555555u;   // keep the sign bits, clear the edge-mask bits
-        if (i < g.E / 32 + 1) g.cbits[i] = 0u;
+        if (i < g.E / 32 + 1) { g.vmask[i] = 0u; g.qmask[i] = 0u; }
         if (i < V) { s.av[i] = 1; s.sol[i] = 0.5f; s.up_cnt[i] = 0; s.up_ev[i] = 0; s.pure[i] = 0; s.score[i] = 0.f; s.asg[i] = 0; }
         if (i < F) { s.af[i] = 1; s.single[i] = 0; }
         if (i < B) {
@@ -232,7 +231,7 @@ extern "C" int pdp_reset(pdp_ctx* ctx, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int64_t n = ctx->g.V > ctx->g.F ? ctx->g.V : ctx->g.F;
     if (ctx->g.B > n) n = ctx->g.B;
-    if (ctx->g.E / 16 + 1 > n) n = ctx->g.E / 16 + 1;
+    if (ctx->g.E / 32 + 1 > n) n = ctx->g.E / 32 + 1;
     if (n < CTRL_SIZE) n = CTRL_SIZE;
     k_reset_state<<<pdp_grid(n, 256, ctx->num_sms), 256, 0, stream>>>(ctx->g, ctx->s, ctx->g.V, ctx->g.F, ctx->g.B);
     PDP_LAUNCH_CHECK(ctx);

@@ -49,7 +49,7 @@ __global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ ki, cons
         const int p = g.c_pos[c];
         g.c_vpos[c] = (int32_t)x;
         g.p_vpos[p] = (int32_t)x;
-        g.vinv[x] = (uint16_t)(p - g.var_ptr[g.vb_ptr[ki[x]]]);
+        g.vinv[x] = (uint16_t)((p - g.var_ptr[g.vb_ptr[ki[x]]]) | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
     }
 }
 // x = C-layout position, lq[x] = variable-major slot stored there, kj[x] = its clause block
@@ -128,18 +128,6 @@ __global__ void k_identity_layout(pdp_graph g) {
     }
 }
 
-__global__ void k_sign_bits(pdp_graph g) {
-    GS(wi, g.E / 16 + 1) {
-        uint32_t w = 0u;
-        for (int k = 0; k < 16; ++k) {
-            const int64_t p = wi * 16 + k;
-            if (p < g.E && (g.v_cedge[p] & PDP_SIGN_BIT)) w |= PDP_VB_NEG << (2 * k);
-        }
-        g.vbits[wi] = w;
-    }
-    GS(wi, g.E / 32 + 1) g.cbits[wi] = 0u;
-}
-
 int bits_for(int64_t n) {
     int bits = 1;
     while (((int64_t)1 << bits) < n && bits < 31) ++bits;
@@ -168,8 +156,6 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     const int64_t E = g.E;
     g.blocked_ok = 0; g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
     if (E == 0) return PDP_OK;
-    k_sign_bits<<<G1(E / 16 + 1)>>>(g);
-    LLK();
     const bool ok = monotone_maps && g.max_var_degree <= PDP_BLK_V / 2 && g.max_clause_degree <= PDP_BLK_C / 2 &&
                     g.V > 0 && g.F > 0 && getenv("PDP_B200_NO_BLOCKED") == nullptr;
     if (!ok) {
@@ -177,8 +163,8 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         LLK();
         return PDP_OK;
     }
-    g.sv = pick_stride(E, PDP_BLK_V, g.max_var_degree, nsm);
-    g.sc = pick_stride(E, PDP_BLK_C, g.max_clause_degree, nsm);
+    g.sv = pick_stride(E, PDP_BLK_V, g.max_var_degree, nsm * PDP_SWEEP_CTAS_PER_SM);
+    g.sc = pick_stride(E, PDP_BLK_C, g.max_clause_degree, nsm * PDP_SWEEP_CTAS_PER_SM);
     g.nvb = (int32_t)(E / g.sv + 1);
     g.ncb = (int32_t)(E / g.sc + 1);
     if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2) {
@@ -279,7 +265,8 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
         if (e1 - e0 > PDP_BLK_V) atomicAdd(&errs[1], 1);
         for (int p = e0; p < e1; ++p) {
             const int x = g.p_vpos[p];
-            if (x < e0 || x >= e1 || (int)g.vinv[x] != p - e0) atomicAdd(&errs[1], 1);
+            if (x < e0 || x >= e1 || (int)(g.vinv[x] & 0x7fff) != p - e0 ||
+                ((g.vinv[x] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) atomicAdd(&errs[1], 1);
         }
         for (int w = e0; w < e1; ++w) {
             const int p = e0 + (int)g.vsrc[w];

@@ -105,7 +105,7 @@ __device__ __forceinline__ void termination_phase(const KArgs& A, int iter, int 
 
 // FAST: the blocked shared-memory passes (pi == 0, q_u only); otherwise the generic passes
 template <bool FAST, bool FULL>
-__global__ void __launch_bounds__(FAST ? PDP_SWEEP_THREADS : 256, 1)
+__global__ void __launch_bounds__(FAST ? PDP_SWEEP_THREADS : 256, FAST ? PDP_SWEEP_CTAS_PER_SM : 1)
 k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params prm, int32_t* d_iters_done) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     cg::grid_group grid = cg::this_grid();
@@ -114,14 +114,17 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     bool has_prev = s.ctrl[CTRL_HAS_PREV] != 0;
     bool use_mask = s.ctrl[CTRL_USE_MASK] != 0;
     bool em_set = s.ctrl[CTRL_EM_SET] != 0;
+    int gen_left = FAST ? s.ctrl[CTRL_GEN_ITERS] : 0;
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
     int executed = 0;
     grid.sync();   // everybody has read the control block before anyone may change it
     for (int it = 0; it < prm.iterations; ++it) {
         ++iter;
         const int r = (iter - 1) & 1, w = iter & 1;
+        const bool blocked = FAST && gen_left <= 0;
+        if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
-        if (FAST) {
+        if (blocked) {
             blk_clause_pass(A, r, use_mask, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
@@ -131,7 +134,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         grid.sync();
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
-        if (FAST) {
+        if (blocked) {
             blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
@@ -173,6 +176,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     if (gtid() == 0) {
         s.ctrl[CTRL_ITER] = iter; s.ctrl[CTRL_HAS_PREV] = has_prev; s.ctrl[CTRL_USE_MASK] = use_mask;
         s.ctrl[CTRL_EM_SET] = em_set; s.ctrl[CTRL_ITERS_THIS_RUN] = executed;
+        if (FAST) s.ctrl[CTRL_GEN_ITERS] = gen_left;
         if (d_iters_done) *d_iters_done = executed;
     }
 }
@@ -246,7 +250,7 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
             PDP_CUDA_CHECK(cudaFuncSetAttribute(k_sp_run<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PDP_SWEEP_SMEM));
             attr_set[ctx->device & 63] = true;
         }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<true, false>, dim3(ctx->num_sms), dim3(PDP_SWEEP_THREADS), args,
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<true, false>, dim3(ctx->num_sms * PDP_SWEEP_CTAS_PER_SM), dim3(PDP_SWEEP_THREADS), args,
                                                    PDP_SWEEP_SMEM, stream));
     } else if (prm.full_state) {
         int blocks = coop_blocks(ctx, k_sp_run<false, true>);

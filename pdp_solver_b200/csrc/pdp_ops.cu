@@ -161,7 +161,11 @@ __global__ void k_load_state(pdp_graph g, pdp_state s, const float* __restrict__
         const int64_t e = g.v_orig[p];
         const int qp = g.p_qpos[p];
         s.qu[qp] = dq3[3 * e]; s.qs[qp] = dq3[3 * e + 1]; s.qd[qp] = dq3[3 * e + 2];
-        s.eta[buf][g.p_vpos[p]] = dfs2[2 * e]; s.ext[p] = dfs2[2 * e + 1];
+        const float eta = dfs2[2 * e];
+        s.eta[buf][g.p_vpos[p]] = eta; s.ext[p] = dfs2[2 * e + 1];
+        // the blocked variable pass borrows the sign bit of the old surveys: surveys that arrive with one
+        // (not a probability) go through the generic passes for the one iteration that reads them
+        if (__float_as_uint(eta) >> 31) s.ctrl[CTRL_GEN_ITERS] = 1;
     }
 }
 
@@ -215,25 +219,13 @@ __global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const flo
 }
 
 // edge-mask bits from the node masks (after an external pdp_set_masks)
+__global__ void k_clear_mask_bits(pdp_graph g) {
+    for (int64_t wi = gtid(); wi < g.E / 32 + 1; wi += gthreads()) { g.vmask[wi] = 0u; g.qmask[wi] = 0u; }
+}
 __global__ void k_rebuild_mask_bits(pdp_graph g, pdp_state s) {
-    for (int64_t wi = gtid(); wi < g.E / 16 + 1; wi += gthreads()) {
-        uint32_t w = g.vbits[wi] & 0x55555555u;
-        for (int k = 0; k < 16; ++k) {
-            const int64_t p = wi * 16 + k;
-            if (p >= g.E) break;
-            const int var = (int)(g.c_var[g.v_cedge[p] & PDP_IDX_MASK] & PDP_IDX_MASK);
-            if (!(s.av[var] && s.af[g.v_cls[p]])) w |= PDP_VB_MASK << (2 * k);
-        }
-        g.vbits[wi] = w;
-    }
-    for (int64_t wi = gtid(); wi < g.E / 32 + 1; wi += gthreads()) {
-        uint32_t w = 0u;
-        for (int k = 0; k < 32; ++k) {
-            const int64_t c = wi * 32 + k;
-            if (c >= g.E) break;
-            if (!(s.av[g.c_var[c] & PDP_IDX_MASK] && s.af[g.v_cls[g.c_pos[c]]])) w |= 1u << k;
-        }
-        g.cbits[wi] = w;
+    for (int64_t c = gtid(); c < g.E; c += gthreads()) {
+        const int p = g.c_pos[c];
+        if (!(s.av[g.c_var[c] & PDP_IDX_MASK] && s.af[g.v_cls[p]])) mask_edge(g, g.c_vpos[c], g.c_qpos[c]);
     }
 }
 
@@ -359,6 +351,7 @@ extern "C" int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float*
     (void)d_prop_q3; (void)d_prop_fs2;   // only reachable through the frozen-problem blend; every problem starts active
     NEED(ctx, d_dec_q3 && d_dec_fs2, "pdp_load_state: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
+    PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.ctrl + CTRL_GEN_ITERS, 0, sizeof(int32_t), stream));
     if (ctx->g.E > 0) { k_load_state<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s, d_dec_q3, d_dec_fs2, 0); PDP_LAUNCH_CHECK(ctx); }
     return PDP_OK;
 }
@@ -382,7 +375,12 @@ extern "C" int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af,
     const int64_t n = std::max(std::max(ctx->g.V, ctx->g.F), std::max(ctx->g.B, (int64_t)1));
     k_set_masks<<<GRID(n)>>>(ctx->g, ctx->s, d_av, d_af, d_sol);
     PDP_LAUNCH_CHECK(ctx);
-    if (ctx->g.E > 0 && (d_av || d_af)) { k_rebuild_mask_bits<<<GRID(ctx->g.E / 16 + 1)>>>(ctx->g, ctx->s); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.E > 0 && (d_av || d_af)) {
+        k_clear_mask_bits<<<GRID(ctx->g.E / 32 + 1)>>>(ctx->g);
+        PDP_LAUNCH_CHECK(ctx);
+        k_rebuild_mask_bits<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s);
+        PDP_LAUNCH_CHECK(ctx);
+    }
     return PDP_OK;
 }
 

@@ -388,3 +388,26 @@ def test_blocked_equals_generic_bitwise(spec):
                      C(flags), C(freeze)))
     for a, b in zip(*outs):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_blocked_path_with_signed_input_surveys():
+    """surveys that arrive with a sign bit (not probabilities) must not confuse the blocked variable pass,
+    which borrows that bit: the iteration that reads them runs on the generic passes"""
+    from oracle import pdp_oracle as po
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    batch = cnfgen.random_batch(12, 150, 3, 4.0, 31)
+    E = batch[0].shape[1]
+    init = po.init_state(E, randomized=True, rng=np.random.default_rng(31))
+    init[1][1][::7, 0] *= -1.0    # dec_state function_state[:, 0]
+    outs = []
+    for generic in (False, True):
+        ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
+        ctx.simplify()
+        ctx.load_state((T(init[0][0]), T(init[0][1])), (T(init[1][0]), T(init[1][1])))
+        ctx.sp_run(40, 0.02, 25, True, sync=True, generic=generic)
+        q, fs = ctx.store_state()
+        m = ctx.get_masks()
+        outs.append((C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["sol"])))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
