@@ -402,6 +402,25 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 }
 
 #define NT PDP_SWEEP_THREADS   // compile-time stride of the block-wide loops (immediate address offsets)
+// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in
+// each phase of the blocked passes to the trace buffer: [0..2] clause load / node / write-out, [3..5] variable
+#ifdef PDP_PHASE_TIMING
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_ADD(slot) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot) do {} while (0)
+#endif
+
+// pulls [base, base + bytes) into L2 (one request per 128-byte line).  The per-node phases are issue bound
+// and leave the memory system idle: they start by prefetching what the NEXT block of this CTA will load and
+// the write-out tables of the current one, so that the latency-bound load / write-out phases hit L2.
+__device__ __forceinline__ void blk_prefetch_l2(const void* base, size_t bytes) {
+    const char* p = reinterpret_cast<const char*>(base);
+    const char* end = p + bytes;
+    p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
+    for (p += (size_t)threadIdx.x * 128; p < end; p += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
 // consecutive destinations (runs), so a warp's stores coalesce into a few sectors
@@ -409,14 +428,14 @@ template <bool SKIP>
 __device__ __forceinline__ void blk_write_out_t(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
                                                 const float* plane, const uint32_t* skip, float* __restrict__ out) {
     int w = threadIdx.x;
-    for (; w + 3 * NT < ne; w += 4 * NT) {
-        const int l0 = src[w], l1 = src[w + NT], l2 = src[w + 2 * NT], l3 = src[w + 3 * NT];
-        const int d0 = dst[w], d1 = dst[w + NT], d2 = dst[w + 2 * NT], d3 = dst[w + 3 * NT];
-        const float x0 = plane[l0], x1 = plane[l1], x2 = plane[l2], x3 = plane[l3];
-        if (!SKIP || !((skip[l0 >> 5] >> (l0 & 31)) & 1u)) out[d0] = x0;
-        if (!SKIP || !((skip[l1 >> 5] >> (l1 & 31)) & 1u)) out[d1] = x1;
-        if (!SKIP || !((skip[l2 >> 5] >> (l2 & 31)) & 1u)) out[d2] = x2;
-        if (!SKIP || !((skip[l3 >> 5] >> (l3 & 31)) & 1u)) out[d3] = x3;
+    constexpr int U = 8;
+    for (; w + (U - 1) * NT < ne; w += U * NT) {
+        int l[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { l[u] = src[w + u * NT]; d[u] = dst[w + u * NT]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (!SKIP || !((skip[l[u] >> 5] >> (l[u] & 31)) & 1u)) out[d[u]] = plane[l[u]];
     }
     for (; w < ne; w += NT) {
         const int l = src[w];
@@ -435,17 +454,17 @@ template <bool MASKED>
 __device__ __forceinline__ void blk_clause_load(const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
                                                 const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
     int x = threadIdx.x;
-    for (; x + 3 * NT < ne; x += 4 * NT) {
-        const float q0 = qsrc[x], q1 = qsrc[x + NT], q2 = qsrc[x + 2 * NT], q3 = qsrc[x + 3 * NT];
-        const int l0 = inv[x], l1 = inv[x + NT], l2 = inv[x + 2 * NT], l3 = inv[x + 3 * NT];
-        float v0 = L40(q0), v1 = L40(q1), v2 = L40(q2), v3 = L40(q3);
-        if (MASKED) {
-            if (mbit(qmask, e0 + x)) v0 = v0 * 0.f;
-            if (mbit(qmask, e0 + x + NT)) v1 = v1 * 0.f;
-            if (mbit(qmask, e0 + x + 2 * NT)) v2 = v2 * 0.f;
-            if (mbit(qmask, e0 + x + 3 * NT)) v3 = v3 * 0.f;
+    constexpr int U = 8;
+    for (; x + (U - 1) * NT < ne; x += U * NT) {
+        float q[U]; int l[U]; bool m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { q[u] = qsrc[x + u * NT]; l[u] = inv[x + u * NT]; m[u] = MASKED ? mbit(qmask, e0 + x + u * NT) : false; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float v = L40(q[u]);
+            if (MASKED && m[u]) v = v * 0.f;
+            X[l[u]] = v;
         }
-        X[l0] = v0; X[l1] = v1; X[l2] = v2; X[l3] = v3;
     }
     for (; x < ne; x += NT) {
         float v = L40(qsrc[x]);
@@ -502,9 +521,21 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         for (int i = tid; i < (ne + 31) / 32; i += NT) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
         // ---- load (contiguous), log, edge mask, scatter into clause-major order
+        PHASE_T0();
         if (use_mask && (multi || s.masked[b0])) blk_clause_load<true>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
         else blk_clause_load<false>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
         __syncthreads();
+        PHASE_ADD(0);
+        {   // L2 prefetch: this block's write-out tables, the next block's inputs
+            blk_prefetch_l2(g.csrc + e0, (size_t)ne * 2);
+            blk_prefetch_l2(g.cdst + e0, (size_t)ne * 4);
+            const int nb = blk + gridDim.x;
+            if (nb < g.ncb) {
+                const int n0 = g.cl_ptr[g.cb_ptr[nb]], n1 = g.cl_ptr[g.cb_ptr[nb + 1]];
+                blk_prefetch_l2(qin + n0, (size_t)(n1 - n0) * 4);
+                blk_prefetch_l2(g.cinv + n0, (size_t)(n1 - n0) * 2);
+            }
+        }
         // ---- thread per clause
         for (int a = a0 + tid; a < a1; a += NT) {
             int lo, k;
@@ -526,8 +557,10 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
             if (made_nan) s.nanpend[b] = 1;
         }
         __syncthreads();
+        PHASE_ADD(1);
         blk_write_out(g.csrc + e0, g.cdst + e0, ne, X, skip, sm_any_skip != 0, eout);
         __syncthreads();
+        PHASE_ADD(2);
     }
 }
 
@@ -548,17 +581,19 @@ template <bool MASKED>
 __device__ __forceinline__ void blk_var_load(const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
                                              const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
     int x = threadIdx.x;
-    for (; x + NT < ne; x += 2 * NT) {
-        uint32_t n0 = __float_as_uint(sn[x]), n1 = __float_as_uint(sn[x + NT]);
-        const uint32_t o0 = __float_as_uint(so[x]), o1 = __float_as_uint(so[x + NT]);
-        const uint32_t i0 = inv[x], i1 = inv[x + NT];
-        if (MASKED) {
-            n0 |= mbit(vmask, e0 + x) ? 0x80000000u : 0u;
-            n1 |= mbit(vmask, e0 + x + NT) ? 0x80000000u : 0u;
+    constexpr int U = 6;
+    for (; x + (U - 1) * NT < ne; x += U * NT) {
+        uint32_t n[U], o[U], iv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n[u] = __float_as_uint(sn[x + u * NT]); o[u] = __float_as_uint(so[x + u * NT]); iv[u] = inv[x + u * NT];
+            if (MASKED) n[u] |= mbit(vmask, e0 + x + u * NT) ? 0x80000000u : 0u;
         }
-        const int l0 = i0 & 0x7fff, l1 = i1 & 0x7fff;
-        PA[l0] = __uint_as_float(n0); PB[l0] = __uint_as_float(o0 ^ ((i0 & PDP_VINV_NEG) << 16));
-        PA[l1] = __uint_as_float(n1); PB[l1] = __uint_as_float(o1 ^ ((i1 & PDP_VINV_NEG) << 16));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int l = iv[u] & 0x7fff;
+            PA[l] = __uint_as_float(n[u]); PB[l] = __uint_as_float(o[u] ^ ((iv[u] & PDP_VINV_NEG) << 16));
+        }
     }
     for (; x < ne; x += NT) {
         uint32_t n0 = __float_as_uint(sn[x]);
@@ -597,9 +632,22 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
             sm_st.nan[tid] = 0u; sm_st.nav[tid] = 0u;
         }
         // ---- load both survey regions (contiguous), scatter into variable-major order
+        PHASE_T0();
         if ((use_mask || em_set) && (multi || s.masked[b0])) blk_var_load<true>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
         else blk_var_load<false>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
         __syncthreads();
+        PHASE_ADD(3);
+        {   // L2 prefetch: this block's write-out tables, the next block's inputs
+            blk_prefetch_l2(g.vsrc + e0, (size_t)ne * 2);
+            blk_prefetch_l2(g.vdst + e0, (size_t)ne * 4);
+            const int nb = blk + gridDim.x;
+            if (nb < g.nvb) {
+                const int n0 = g.var_ptr[g.vb_ptr[nb]], n1 = g.var_ptr[g.vb_ptr[nb + 1]];
+                blk_prefetch_l2(en + n0, (size_t)(n1 - n0) * 4);
+                blk_prefetch_l2(eo + n0, (size_t)(n1 - n0) * 4);
+                blk_prefetch_l2(g.vinv + n0, (size_t)(n1 - n0) * 2);
+            }
+        }
         // ---- thread per variable (descending degree): ordered sums, statistics, update.
         // rounds alternate direction over the degree-sorted list: every thread gets high and low degrees
         for (int base = v0, round = 0; base < v1; base += NT, ++round) {
@@ -676,8 +724,10 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
             a.nan = sm_st.nan[tid]; a.nav = sm_st.nav[tid];
             if (a.mn0 != 0x7f800000u || a.mx0 != 0u || a.nan || a.nav || a.mn1 != 0x7f800000u) a.commit(s, b0 + tid);
         }
+        PHASE_ADD(4);
         blk_write_out(g.vsrc + e0, g.vdst + e0, ne, PA, skip, sm_any_skip != 0, s.qu);
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
+        PHASE_ADD(5);
     }
 }
 #undef NT

@@ -117,6 +117,21 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     int gen_left = FAST ? s.ctrl[CTRL_GEN_ITERS] : 0;
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
     int executed = 0;
+#ifdef PDP_PHASE_TIMING
+#define GRID_SYNC() do { const long long _g0 = clock64(); grid.sync(); if (threadIdx.x == 0 && A.trace) atomicAdd(&A.trace[7], (int)((clock64() - _g0) >> 10)); } while (0)
+#else
+#define GRID_SYNC() grid.sync()
+#endif
+#ifdef PDP_PHASE_TIMING
+    const long long _kernel_t0 = clock64();
+#endif
+#ifdef PDP_STAGGER_EXPERIMENT
+    // role = arrival order of this CTA on its SM (trace[32 + smid] must be zero on entry)
+    __shared__ int sm_role_s;
+    if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); sm_role_s = A.trace ? (atomicAdd(&A.trace[32 + smid], 1) & 1) : 0; }
+    __syncthreads();
+    const int sm_role = sm_role_s;
+#endif
     grid.sync();   // everybody has read the control block before anyone may change it
     for (int it = 0; it < prm.iterations; ++it) {
         ++iter;
@@ -125,16 +140,22 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
         if (blocked) {
+#ifdef PDP_STAGGER_EXPERIMENT
+            if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 16) & 0xff) * 1024) __nanosleep(200); }
+#endif
             blk_clause_pass(A, r, use_mask, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
         if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; }
-        grid.sync();
+        GRID_SYNC();
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
+#ifdef PDP_STAGGER_EXPERIMENT
+            if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 8) & 0xff) * 1024) __nanosleep(200); }
+#endif
             blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
@@ -144,17 +165,17 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
             gen_stats<GEN_ALL>(A, w, has_prev, em_set);
         }
-        grid.sync();
+        GRID_SYNC();
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
         decide_phase(A, iter, prm, has_prev);
-        grid.sync();
+        GRID_SYNC();
         if (s.ctrl[CTRL_CONV + (iter & 1)]) {
             score_phase(A, w, prm.pi);
-            grid.sync();
+            GRID_SYNC();
             argmax_phase(A);
-            grid.sync();
+            GRID_SYNC();
             select_and_fix_phase(A, iter);
-            grid.sync();
+            GRID_SYNC();
             if (s.ctrl[CTRL_FIX + (iter & 1)]) closure(A, grid);
         }
         has_prev = true;   // pdp_decimate.py:175
@@ -165,14 +186,17 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (prm.check_termination) {
             if (s.ctrl[CTRL_ANY_DIRTY]) {
                 cnf_count_dirty(A);
-                grid.sync();
+                GRID_SYNC();
                 termination_phase(A, iter, rep);
-                grid.sync();
+                GRID_SYNC();
             }
             if (s.ctrl[CTRL_NUM_ACTIVE] <= 0) break;
         }
     }
-    grid.sync();
+    GRID_SYNC();
+#ifdef PDP_PHASE_TIMING
+    if (threadIdx.x == 0 && A.trace) atomicAdd(&A.trace[6], (int)((clock64() - _kernel_t0) >> 10));
+#endif
     if (gtid() == 0) {
         s.ctrl[CTRL_ITER] = iter; s.ctrl[CTRL_HAS_PREV] = has_prev; s.ctrl[CTRL_USE_MASK] = use_mask;
         s.ctrl[CTRL_EM_SET] = em_set; s.ctrl[CTRL_ITERS_THIS_RUN] = executed;
@@ -292,5 +316,65 @@ extern "C" int pdp_trace_length(pdp_ctx* ctx, int32_t* host_out, void* stream_) 
     cudaStream_t stream = (cudaStream_t)stream_;
     PDP_CUDA_CHECK(cudaMemcpyAsync(host_out, ctx->s.ctrl + CTRL_TRACE_LEN, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     PDP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return PDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling aid: one phase of the blocked passes in isolation over all blocks (read-only on the solver
+// state: outputs go to a caller-supplied scratch array).  phase 0 = variable load, 1 = variable
+// write-out, 2 = clause load, 3 = clause write-out; variant bit 0 = no shared-memory scatter / gather
+// (sequential shared-memory addresses), bit 1 = skip the 16-bit index tables
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(PDP_SWEEP_THREADS, PDP_SWEEP_CTAS_PER_SM)
+k_phase_bench(const __grid_constant__ KArgs A, int phase, int variant, float* scratch) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    float* PA = reinterpret_cast<float*>(smem_dyn);
+    float* PB = PA + PDP_BLK_V;
+    const int tid = threadIdx.x;
+    const bool seq = variant & 1, noidx = variant & 2;
+    const bool var_side = phase < 2;
+    const int nblk = var_side ? g.nvb : g.ncb;
+    float acc = 0.f;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int n0 = var_side ? g.vb_ptr[blk] : g.cb_ptr[blk], n1 = var_side ? g.vb_ptr[blk + 1] : g.cb_ptr[blk + 1];
+        if (n1 <= n0) continue;
+        const int e0 = var_side ? g.var_ptr[n0] : g.cl_ptr[n0];
+        const int ne = (var_side ? g.var_ptr[n1] : g.cl_ptr[n1]) - e0;
+        if (phase == 0) {
+            const float* sn = s.eta[0] + e0; const float* so = s.eta[1] + e0; const uint16_t* inv = g.vinv + e0;
+            for (int x = tid; x < ne; x += PDP_SWEEP_THREADS) {
+                const int l = noidx ? x : (seq ? ((inv[x] & 0) + x) : (inv[x] & 0x7fff));
+                PA[l] = sn[x]; PB[l] = so[x];
+            }
+        } else if (phase == 2) {
+            const float* q = s.qu + e0; const uint16_t* inv = g.cinv + e0;
+            for (int x = tid; x < ne; x += PDP_SWEEP_THREADS) {
+                const int l = noidx ? x : (seq ? ((inv[x] & 0) + x) : inv[x]);
+                PA[l] = q[x];
+            }
+        } else {
+            const uint16_t* src = (phase == 1 ? g.vsrc : g.csrc) + e0;
+            const int32_t* dst = (phase == 1 ? g.vdst : g.cdst) + e0;
+            for (int w = tid; w < ne; w += PDP_SWEEP_THREADS) {
+                const int l = noidx ? w : (seq ? ((src[w] & 0) + w) : src[w]);
+                scratch[dst[w]] = PA[l];
+            }
+        }
+        __syncthreads();
+        acc += PA[tid] + PB[tid];
+        __syncthreads();
+    }
+    if (acc == 123.456f) scratch[0] = acc;
+}
+}  // namespace
+
+extern "C" int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch, void* stream_) {
+    if (!ctx || !d_scratch || !ctx->g.blocked_ok) { pdp_set_error("pdp_debug_phase_bench: needs a blocked layout and a scratch array of E floats"); return PDP_ERR_ARG; }
+    KArgs A = make_args(ctx);
+    PDP_CUDA_CHECK(cudaFuncSetAttribute(k_phase_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, PDP_SWEEP_SMEM));
+    k_phase_bench<<<ctx->num_sms * PDP_SWEEP_CTAS_PER_SM, PDP_SWEEP_THREADS, PDP_SWEEP_SMEM, (cudaStream_t)stream_>>>(A, phase, variant, d_scratch);
+    PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
 }

@@ -109,6 +109,9 @@ class Context(object):
         self._check(self._L.pdp_debug_check_layout(self._h, _ptr(errs), ctypes.byref(info), _stream()), "pdp_debug_check_layout")
         return errs.cpu().tolist(), dict(blocked=int(info[0]), nvb=int(info[1]), ncb=int(info[2]), sv=int(info[3]), sc=int(info[4]))
 
+    def phase_bench(self, phase, variant, scratch):
+        self._check(self._L.pdp_debug_phase_bench(self._h, int(phase), int(variant), _ptr(scratch), _stream()), "pdp_debug_phase_bench")
+
     def launch_count(self):
         return int(self._L.pdp_launch_count(self._h))
 
@@ -212,7 +215,7 @@ class Context(object):
         int32 tensor holding the number of executed iterations (or the int when sync=True).
         generic=True forces the thread-per-node passes (A/B against the blocked shared-memory passes)."""
         prm = SpParams(int(iterations), float(tolerance), int(t_max), float(pi), 1 if check_termination else 0,
-                       int(batch_replication), 1 if full_state else 0, 1 if generic else 0)
+                       int(batch_replication), 1 if full_state else 0, (1 if generic else 0) | int(os.environ.get("PDP_B200_SP_FLAGS", "0"), 0))
         self._timed("sp_run", lambda: self._check(
             self._L.pdp_sp_run(self._h, ctypes.byref(prm), _ptr(self._iters), _stream()), "pdp_sp_run"))
         if sync:
