@@ -63,6 +63,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.v_orig = k.take<int32_t>(E);
     g.bvm = k.take<int32_t>(V);
     g.bfm = k.take<int32_t>(F);
+    g.prob_vptr = k.take<int32_t>(B + 1);
     g.p_vpos = k.take<int32_t>(E);
     g.p_qpos = k.take<int32_t>(E);
     g.c_vpos = k.take<int32_t>(E);
@@ -197,6 +198,18 @@ __global__ void k_max_degree(const int32_t* __restrict__ ptr, int64_t n, int32_t
 }
 
 }  // namespace
+
+// prob_vptr[b] = first variable of problem b (lower bound of b in the non-decreasing batch_variable_map)
+__global__ void k_problem_ptr(const int32_t* __restrict__ bvm, int64_t V, int64_t B, int32_t* prob_vptr) {
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b <= B; b += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = V;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (bvm[mid] < b) lo = mid + 1; else hi = mid;
+        }
+        prob_vptr[b] = (int32_t)lo;
+    }
+}
 
 __global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, int64_t B) {
     int64_t n = V > F ? V : F;
@@ -370,6 +383,9 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
         g.max_var_degree = hflags[2];
         g.max_clause_degree = hflags[3];
     }
+    g.contiguous_problems = monotone_maps ? 1 : 0;
+    k_problem_ptr<<<pdp_grid(B + 1, 256, nsm), 256, 0, stream>>>(g.bvm, V, B, g.prob_vptr);
+    LK();
     {
         int lrc = pdp_build_layout(c, stream, monotone_maps);
         if (lrc != PDP_OK) { delete c; return lrc; }

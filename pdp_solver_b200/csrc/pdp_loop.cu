@@ -249,6 +249,8 @@ extern "C" int pdp_set_trace_buffer(pdp_ctx* ctx, int32_t* d_trace, int32_t capa
     return PDP_OK;
 }
 
+int32_t* pdp_debug_trace_ptr() { return g_trace; }
+
 static KArgs make_args(pdp_ctx* ctx) {
     KArgs A;
     A.g = ctx->g; A.s = ctx->s; A.trace = g_trace; A.trace_cap = g_trace_cap;

@@ -71,3 +71,19 @@ if a.phases:
             ms = e0.elapsed_time(e1)
             b = bytes_per_edge[phase] - (2.0 if variant & 2 else 0.0)
             print("%-16s variant %d: %.3f ms  %.2f TB/s" % (names[phase], variant, ms, b * E / ms / 1e9))
+
+if os.environ.get("PDP_PROF_WALKSAT"):
+    n_act = ctx.count_active_variables()
+    ctx.random_fill(torch.rand(max(n_act, 1), device=dev))
+    for W in (0, 1, 10, 100):
+        for rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pred, it = ctx.walksat(W, 0.5, None, None, seed=7)
+            e1.record()
+            torch.cuda.synchronize()
+        print("walksat W=%d: %.3f ms (iterations done %d)" % (W, e0.elapsed_time(e1), int(it.item())))
+        if os.environ.get("PDP_PHASE_TIMING") and ctx._trace is not None:
+            tr = ctx._trace.reshape(-1)[:8].cpu().numpy().astype(np.float64) * 16.0 / 2 / max(W, 1)
+            print("  CTA0 cycles per iteration: loop-top %.0f, select %.0f, finish %.0f, sync1 %.0f, check+sync2 %.0f, flip %.0f, sync3 %.0f" % tuple(tr[:7]))
+            ctx._trace.zero_()
