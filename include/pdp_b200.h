@@ -95,6 +95,9 @@ int pdp_score(pdp_ctx* ctx, const float* d_fs2, const float* d_af, float pi, flo
  * (reference pdp/nn/solver.py:498-511) into the internal variable-major message arrays */
 int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float* d_prop_fs2,
                    const float* d_dec_q3, const float* d_dec_fs2, void* stream);
+/* the same for a state whose every edge carries the same values, as get_init_state(randomized=False)
+ * returns (reference pdp/nn/pdp_predict.py:203-206: variable_state = 1/3, function_state = [0.5, 0]) */
+int pdp_load_state_const(pdp_ctx* ctx, float qu, float qs, float qd, float eta, float ext, void* stream);
 /* writes the current message state in the caller's edge order: out_q3 [E,3], out_fs2 [E,2] */
 int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* stream);
 /* overwrite / read the SATProblem masks (float 0/1 like the reference's tensors); NULL = skip */

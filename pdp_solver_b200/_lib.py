@@ -39,6 +39,7 @@ SIGNATURES = {
     "pdp_sp_step": (ctypes.c_int, [P, P, P, P, P, P, P, F32, P, P, P]),
     "pdp_score": (ctypes.c_int, [P, P, P, F32, P, P]),
     "pdp_load_state": (ctypes.c_int, [P, P, P, P, P, P]),
+    "pdp_load_state_const": (ctypes.c_int, [P, F32, F32, F32, F32, F32, P]),
     "pdp_store_state": (ctypes.c_int, [P, P, P, P]),
     "pdp_set_masks": (ctypes.c_int, [P, P, P, P, P]),
     "pdp_get_masks": (ctypes.c_int, [P, P, P, P, P, P, P, P]),

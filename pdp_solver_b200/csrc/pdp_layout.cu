@@ -112,12 +112,20 @@ __global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order) {
     }
 }
 
-__global__ void k_clause_block_degree(pdp_graph g) {
+// cb_k[blk] = common degree of the block's clauses (1..8) or 0: seeded with the first clause's degree,
+// cleared by any clause that disagrees
+__global__ void k_clause_block_degree_init(pdp_graph g) {
     GS(blk, g.ncb) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
-        int k = (a1 > a0) ? g.cl_ptr[a0 + 1] - g.cl_ptr[a0] : 0;
-        for (int a = a0; a < a1 && k; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != k) k = 0;
+        const int k = (a1 > a0) ? g.cl_ptr[a0 + 1] - g.cl_ptr[a0] : 0;
         g.cb_k[blk] = (k >= 1 && k <= 8) ? k : 0;
+    }
+}
+__global__ void k_clause_block_degree_check(pdp_graph g) {
+    GS(a, g.F) {
+        const int blk = g.cl_ptr[a] / g.sc;
+        const int k = g.cb_k[blk];
+        if (k != 0 && g.cl_ptr[a + 1] - g.cl_ptr[a] != k) g.cb_k[blk] = 0;
     }
 }
 
@@ -238,7 +246,9 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         k_fill_vsort<<<G1(g.V)>>>(g, nullptr);
     }
     LLK();
-    k_clause_block_degree<<<G1(g.ncb)>>>(g);
+    k_clause_block_degree_init<<<G1(g.ncb)>>>(g);
+    LLK();
+    k_clause_block_degree_check<<<G1(g.F)>>>(g);
     LLK();
     g.blocked_ok = 1;
     return PDP_OK;

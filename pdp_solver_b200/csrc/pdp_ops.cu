@@ -169,6 +169,14 @@ __global__ void k_load_state(pdp_graph g, pdp_state s, const float* __restrict__
     }
 }
 
+// the predict path's initial messages are constants (reference pdp_predict.py:203-206): no gather
+__global__ void k_load_state_const(pdp_graph g, pdp_state s, float qu, float qs, float qd, float eta, float ext, int buf) {
+    for (int64_t p = gtid(); p < g.E; p += gthreads()) {
+        s.qu[p] = qu; s.qs[p] = qs; s.qd[p] = qd; s.eta[buf][p] = eta; s.ext[p] = ext;
+    }
+    if (gtid() == 0 && (__float_as_uint(eta) >> 31)) s.ctrl[CTRL_GEN_ITERS] = 1;
+}
+
 // thread per variable; when the [E,3] state was not tracked every iteration, q_s and q_* are
 // re-derived from the previous surveys with the current masks (materialised once, on exit)
 __global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* out_fs2, int iter, int tracked, float pi) {
@@ -353,6 +361,14 @@ extern "C" int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float*
     cudaStream_t stream = (cudaStream_t)stream_;
     PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.ctrl + CTRL_GEN_ITERS, 0, sizeof(int32_t), stream));
     if (ctx->g.E > 0) { k_load_state<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s, d_dec_q3, d_dec_fs2, 0); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_load_state_const(pdp_ctx* ctx, float qu, float qs, float qd, float eta, float ext, void* stream_) {
+    NEED(ctx, true, "");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.ctrl + CTRL_GEN_ITERS, 0, sizeof(int32_t), stream));
+    if (ctx->g.E > 0) { k_load_state_const<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s, qu, qs, qd, eta, ext, 0); PDP_LAUNCH_CHECK(ctx); }
     return PDP_OK;
 }
 

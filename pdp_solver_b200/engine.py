@@ -156,6 +156,10 @@ class Context(object):
         dq, df = _f32(dec_state[0], self.device), _f32(dec_state[1], self.device)
         self._check(self._L.pdp_load_state(self._h, _ptr(pq), _ptr(pf), _ptr(dq), _ptr(df), _stream()), "pdp_load_state")
 
+    def load_state_const(self, qu, qs, qd, eta, ext):
+        self._check(self._L.pdp_load_state_const(self._h, float(qu), float(qs), float(qd), float(eta), float(ext), _stream()),
+                    "pdp_load_state_const")
+
     def store_state(self):
         q, f = self._new(self.E, 3), self._new(self.E, 2)
         self._check(self._L.pdp_store_state(self._h, _ptr(q), _ptr(f), _stream()), "pdp_store_state")

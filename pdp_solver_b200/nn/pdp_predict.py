@@ -46,7 +46,11 @@ class SurveyScorer(nn.Module):
             function_state = torch.rand(edge_num, 2, dtype=torch.float32, device=self._device)
             function_state[:, 1] = 0
         else:
-            variable_state = torch.ones(edge_num, 3, dtype=torch.float32, device=self._device) / 3.0
-            function_state = 0.5 * torch.ones(edge_num, 2, dtype=torch.float32, device=self._device)
-            function_state[:, 1] = 0
+            variable_state = torch.full((edge_num, 3), 1.0 / 3.0, dtype=torch.float32, device=self._device)
+            function_state = torch.zeros(edge_num, 2, dtype=torch.float32, device=self._device)
+            function_state[:, 0] = 0.5
+            # tag: every row is the same (checked against in-place edits through the version counters), so
+            # the solver can fill its message arrays without gathering 20 bytes per edge
+            variable_state._pdp_const = ((1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0), variable_state._version)
+            function_state._pdp_const = ((0.5, 0.0), function_state._version)
         return (variable_state, function_state)

@@ -104,6 +104,37 @@ class SATProblem(object):
         self._ctx.simplify()
 
 
+def _const_rows(t):
+    """the row every edge shares when `t` is an unmodified constant state of get_init_state, else None"""
+    tag = getattr(t, "_pdp_const", None)
+    if tag is None or tag[1] != t._version:
+        return None
+    return tag[0]
+
+
+class _DeferredState(object):
+    """(variable_state [E,3], function_state [E,2]) of the solver context, materialised in the caller's edge
+    order on first access (pdp_store_state).  Behaves like the tuple the reference returns."""
+
+    def __init__(self, ctx):
+        self._ctx, self._value = ctx, None
+
+    def _get(self):
+        if self._value is None:
+            self._value = tuple(self._ctx.store_state())
+            self._ctx = None
+        return self._value
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return 2
+
+
 def _is_standard_termination(cb):
     """The reference's trainer callback (trainer.py:150-162) -- or anything tagged as equivalent -- is
     evaluated inside the persistent kernel; any other callable is honoured by stepping."""
@@ -160,6 +191,7 @@ class PropagatorDecimatorSolverBase(nn.Module):
         if is_training:
             raise NotImplementedError("training (is_training=True) is outside the accelerated path (SURVEY.md section 8)")
         init_propagator_state, init_decimator_state = init_state
+        self.last_problem = None   # releases the previous batch's workspace before the new one is allocated
         sat_problem = SATProblem((graph_map, batch_variable_map, batch_function_map, edge_feature, meta_data, None),
                                  self._device, batch_replication)
         ctx = sat_problem._ctx
@@ -196,7 +228,12 @@ class PropagatorDecimatorSolverBase(nn.Module):
         termination callback is the trainer's (or None), one launch per iteration otherwise."""
         ctx = sat_problem._ctx
         dec = self._decimator
-        ctx.load_state(init_propagator_state, init_decimator_state[:2])
+        cq = _const_rows(init_decimator_state[0])
+        cf = _const_rows(init_decimator_state[1])
+        if cq is not None and cf is not None:
+            ctx.load_state_const(cq[0], cq[1], cq[2], cf[0], cf[1])
+        else:
+            ctx.load_state(init_propagator_state, init_decimator_state[:2])
         b = sat_problem._batch_replication
         if check_termination is None or _is_standard_termination(check_termination):
             self.last_iterations = ctx.sp_run(iteration_num, dec._tolerance, dec._t_max,
@@ -206,8 +243,9 @@ class PropagatorDecimatorSolverBase(nn.Module):
                 "custom check_termination callbacks are not supported by the fused loop; tag the callable with "
                 "`_pdp_standard_termination = True` if it implements trainer._check_recurrence_termination semantics")
         sat_problem._edge_mask_set = iteration_num > 0
-        q3, fs2 = ctx.store_state()
-        return (q3, fs2), (q3, fs2)
+        # the final message states are exported on first use (the predict path never looks at them)
+        state = _DeferredState(ctx)
+        return state, state
 
     def _local_search(self, sat_problem, batch_replication):
         "WalkSAT post-processing + solution merge (reference solver.py:433-467, 388-399)."
