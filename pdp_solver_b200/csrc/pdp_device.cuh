@@ -38,6 +38,11 @@ __device__ __forceinline__ int64_t gthreads() { return (int64_t)gridDim.x * bloc
 #define WARP_STRIDED(i, N) \
     for (int64_t i##_base = gwarp() * 32, i = i##_base + lane_id(); i##_base < (N); i##_base += gwarps() * 32, i = i##_base + lane_id())
 
+// named barriers (ids 1..15; 0 is __syncthreads): producer / consumer hand-over between warp groups
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void group_sync(int bar_id, int n) { if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, n); }
+
 // ------------------------------------------------------------------------------------------------
 // keyed reduction helper.  ACC needs: void reset(); void merge_shfl(unsigned mask) [warp-reduce over
 // lanes in `mask`, all of which hold the same key]; void commit(const pdp_state&, int key).
@@ -59,12 +64,15 @@ struct KeyedReducer {
     // the same problem merge in registers and hand their partial to a block-level merge in shared
     // memory (one commit per block and problem run: a 1M-variable problem costs ~600 atomics per
     // pass instead of ~10^5); mixed warps commit per lane group.
-    __device__ __forceinline__ void finish(const pdp_state& s) {
+    // bar_id == 0: the whole CTA (__syncthreads); otherwise a named barrier of `gthr` threads whose local
+    // thread index is `t` (a warp group of the pipelined passes)
+    __device__ __forceinline__ void finish(const pdp_state& s, int bar_id = 0, int gthr = 0, int t = -1) {
         __shared__ ACC sm_acc[32];
         __shared__ int sm_key[32];
+        if (bar_id == 0) { gthr = blockDim.x; t = threadIdx.x; }
         const unsigned m = __match_any_sync(0xffffffffu, key);
         const bool uniform = (m == 0xffffffffu);
-        const int warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        const int warp = t >> 5, nwarp = (gthr + 31) >> 5;
         if (uniform) {
             acc.merge_full();
             if (lane_id() == 0) { sm_acc[warp] = acc; sm_key[warp] = key; }
@@ -73,8 +81,8 @@ struct KeyedReducer {
             if (lane_id() == (__ffs(m) - 1) && key >= 0) acc.commit(s, key);
             if (lane_id() == 0) sm_key[warp] = -1;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        group_sync(bar_id, gthr);
+        if (t == 0) {
             int w = 0;
             while (w < nwarp) {
                 const int k = sm_key[w];
@@ -86,7 +94,7 @@ struct KeyedReducer {
                 w = v;
             }
         }
-        __syncthreads();
+        group_sync(bar_id, gthr);
         key = -1;       // everything has been committed: a later touch() starts from scratch
         acc.reset();
     }
@@ -401,64 +409,49 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
     for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
 }
 
-#define NT PDP_SWEEP_THREADS   // compile-time stride of the block-wide loops (immediate address offsets)
-// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in
-// each phase of the blocked passes to the trace buffer: [0..2] clause load / node / write-out, [3..5] variable
-#ifdef PDP_PHASE_TIMING
-#define PHASE_T0() long long _pt = clock64()
-#define PHASE_ADD(slot) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
-#else
-#define PHASE_T0() do {} while (0)
-#define PHASE_ADD(slot) do {} while (0)
-#endif
-
-// pulls [base, base + bytes) into L2 (one request per 128-byte line).  The per-node phases are issue bound
-// and leave the memory system idle: they start by prefetching what the NEXT block of this CTA will load and
-// the write-out tables of the current one, so that the latency-bound load / write-out phases hit L2.
-__device__ __forceinline__ void blk_prefetch_l2(const void* base, size_t bytes) {
-    const char* p = reinterpret_cast<const char*>(base);
-    const char* end = p + bytes;
-    p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
-    for (p += (size_t)threadIdx.x * 128; p < end; p += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+// ================================================================================================
+// phase bodies of the blocked passes, written for a GROUP of G threads with local index t: the whole CTA
+// in the serial passes, one of the two warp groups in the pipelined passes
+// ================================================================================================
 
 // write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
 // consecutive destinations (runs), so a warp's stores coalesce into a few sectors
-template <bool SKIP>
-__device__ __forceinline__ void blk_write_out_t(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                                const float* plane, const uint32_t* skip, float* __restrict__ out) {
-    int w = threadIdx.x;
+template <int G, bool SKIP>
+__device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
+                                               const float* plane, const uint32_t* skip, float* __restrict__ out) {
+    int w = t;
     constexpr int U = 8;
-    for (; w + (U - 1) * NT < ne; w += U * NT) {
+    for (; w + (U - 1) * G < ne; w += U * G) {
         int l[U], d[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = src[w + u * NT]; d[u] = dst[w + u * NT]; }
+        for (int u = 0; u < U; ++u) { l[u] = src[w + u * G]; d[u] = dst[w + u * G]; }
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (!SKIP || !((skip[l[u] >> 5] >> (l[u] & 31)) & 1u)) out[d[u]] = plane[l[u]];
     }
-    for (; w < ne; w += NT) {
+    for (; w < ne; w += G) {
         const int l = src[w];
         if (!SKIP || !((skip[l >> 5] >> (l & 31)) & 1u)) out[dst[w]] = plane[l];
     }
 }
-__device__ __forceinline__ void blk_write_out(const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                              const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ out) {
-    if (any_skip) blk_write_out_t<true>(src, dst, ne, plane, skip, out);
-    else blk_write_out_t<false>(src, dst, ne, plane, skip, out);
+template <int G>
+__device__ __forceinline__ void ph_write_out(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
+                                             const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ out) {
+    if (any_skip) ph_write_out_t<G, true>(t, src, dst, ne, plane, skip, out);
+    else ph_write_out_t<G, false>(t, src, dst, ne, plane, skip, out);
 }
 
 // clause pass, load phase: x = log(max(q_u, 1e-40)) * em, scattered into clause-major order.
 // e0 = first C-layout position of the block (the mask bits are indexed by position).
-template <bool MASKED>
-__device__ __forceinline__ void blk_clause_load(const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
-                                                const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
-    int x = threadIdx.x;
+template <int G, bool MASKED>
+__device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
+                                               const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
+    int x = t;
     constexpr int U = 8;
-    for (; x + (U - 1) * NT < ne; x += U * NT) {
+    for (; x + (U - 1) * G < ne; x += U * G) {
         float q[U]; int l[U]; bool m[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { q[u] = qsrc[x + u * NT]; l[u] = inv[x + u * NT]; m[u] = MASKED ? mbit(qmask, e0 + x + u * NT) : false; }
+        for (int u = 0; u < U; ++u) { q[u] = qsrc[x + u * G]; l[u] = inv[x + u * G]; m[u] = MASKED ? mbit(qmask, e0 + x + u * G) : false; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             float v = L40(q[u]);
@@ -466,7 +459,7 @@ __device__ __forceinline__ void blk_clause_load(const float* __restrict__ qsrc, 
             X[l[u]] = v;
         }
     }
-    for (; x < ne; x += NT) {
+    for (; x < ne; x += G) {
         float v = L40(qsrc[x]);
         if (MASKED && mbit(qmask, e0 + x)) v = v * 0.f;
         X[inv[x]] = v;
@@ -501,66 +494,53 @@ __device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k) {
     return made_nan;
 }
 
-// clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
-__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* X = reinterpret_cast<float*>(smem);
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
-    __shared__ int sm_any_skip;
-    const float* __restrict__ qin = s.qu;
-    float* __restrict__ eout = s.eta[r ^ 1];
-    const int tid = threadIdx.x;
-    for (int blk = blockIdx.x; blk < g.ncb; blk += gridDim.x) {
-        const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
-        if (a1 <= a0) continue;
-        const int b0 = g.bfm[a0], b1 = g.bfm[a1 - 1];
-        if (blk_idle(s, b0, b1)) continue;
-        const bool multi = (b0 != b1);
-        const int e0 = g.cl_ptr[a0], ne = g.cl_ptr[a1] - e0;
-        const int ku = g.cb_k[blk];
-        for (int i = tid; i < (ne + 31) / 32; i += NT) skip[i] = 0u;
-        if (tid == 0) sm_any_skip = 0;
-        // ---- load (contiguous), log, edge mask, scatter into clause-major order
-        PHASE_T0();
-        if (use_mask && (multi || s.masked[b0])) blk_clause_load<true>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
-        else blk_clause_load<false>(qin + e0, g.cinv + e0, g.qmask, e0, ne, X);
-        __syncthreads();
-        PHASE_ADD(0);
-        {   // L2 prefetch: this block's write-out tables, the next block's inputs
-            blk_prefetch_l2(g.csrc + e0, (size_t)ne * 2);
-            blk_prefetch_l2(g.cdst + e0, (size_t)ne * 4);
-            const int nb = blk + gridDim.x;
-            if (nb < g.ncb) {
-                const int n0 = g.cl_ptr[g.cb_ptr[nb]], n1 = g.cl_ptr[g.cb_ptr[nb + 1]];
-                blk_prefetch_l2(qin + n0, (size_t)(n1 - n0) * 4);
-                blk_prefetch_l2(g.cinv + n0, (size_t)(n1 - n0) * 2);
-            }
+// geometry of one block of a pass
+struct BlkGeo {
+    int n0, n1;      // node range
+    int e0, ne;      // first slot / slots
+    int b0, b1;      // problem range
+    __device__ __forceinline__ bool multi() const { return b0 != b1; }
+};
+__device__ __forceinline__ BlkGeo clause_block(const pdp_graph& g, int blk) {
+    BlkGeo B;
+    B.n0 = g.cb_ptr[blk]; B.n1 = g.cb_ptr[blk + 1];
+    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; return B; }
+    B.e0 = g.cl_ptr[B.n0]; B.ne = g.cl_ptr[B.n1] - B.e0;
+    B.b0 = g.bfm[B.n0]; B.b1 = g.bfm[B.n1 - 1];
+    return B;
+}
+__device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) {
+    BlkGeo B;
+    B.n0 = g.vb_ptr[blk]; B.n1 = g.vb_ptr[blk + 1];
+    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; return B; }
+    B.e0 = g.var_ptr[B.n0]; B.ne = g.var_ptr[B.n1] - B.e0;
+    B.b0 = g.bvm[B.n0]; B.b1 = g.bvm[B.n1 - 1];
+    return B;
+}
+
+// clause pass, node phase: thread per clause
+template <int G>
+__device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, int ku,
+                                               float* X, uint32_t* skip, int* any_skip) {
+    const bool multi = B.multi();
+    for (int a = B.n0 + t; a < B.n1; a += G) {
+        int lo, k;
+        if (ku) { k = ku; lo = (a - B.n0) * ku; }
+        else { lo = g.cl_ptr[a] - B.e0; k = g.cl_ptr[a + 1] - B.e0 - lo; }
+        int b = B.b0;
+        if (multi) {
+            b = g.bfm[a];
+            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); *any_skip = 1; continue; }
         }
-        // ---- thread per clause
-        for (int a = a0 + tid; a < a1; a += NT) {
-            int lo, k;
-            if (ku) { k = ku; lo = (a - a0) * ku; }
-            else { lo = g.cl_ptr[a] - e0; k = g.cl_ptr[a + 1] - e0 - lo; }
-            int b = b0;
-            if (multi) {
-                b = g.bfm[a];
-                if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); sm_any_skip = 1; continue; }
-            }
-            bool made_nan;
-            switch (k) {
-                case 3: made_nan = blk_clause_body<3>(X, lo); break;
-                case 4: made_nan = blk_clause_body<4>(X, lo); break;
-                case 5: made_nan = blk_clause_body<5>(X, lo); break;
-                case 2: made_nan = blk_clause_body<2>(X, lo); break;
-                default: made_nan = blk_clause_body_any(X, lo, k); break;
-            }
-            if (made_nan) s.nanpend[b] = 1;
+        bool made_nan;
+        switch (k) {
+            case 3: made_nan = blk_clause_body<3>(X, lo); break;
+            case 4: made_nan = blk_clause_body<4>(X, lo); break;
+            case 5: made_nan = blk_clause_body<5>(X, lo); break;
+            case 2: made_nan = blk_clause_body<2>(X, lo); break;
+            default: made_nan = blk_clause_body_any(X, lo, k); break;
         }
-        __syncthreads();
-        PHASE_ADD(1);
-        blk_write_out(g.csrc + e0, g.cdst + e0, ne, X, skip, sm_any_skip != 0, eout);
-        __syncthreads();
-        PHASE_ADD(2);
+        if (made_nan) s.nanpend[b] = 1;
     }
 }
 
@@ -577,17 +557,17 @@ __device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
 
 // variable pass, load phase.  The surveys are non-negative, so their sign bits carry the two per-edge
 // flags the variable loops need: PA (new survey) sign = edge masked, PB (old survey) sign = negative literal.
-template <bool MASKED>
-__device__ __forceinline__ void blk_var_load(const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
-                                             const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
-    int x = threadIdx.x;
+template <int G, bool MASKED>
+__device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
+                                            const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
+    int x = t;
     constexpr int U = 6;
-    for (; x + (U - 1) * NT < ne; x += U * NT) {
+    for (; x + (U - 1) * G < ne; x += U * G) {
         uint32_t n[U], o[U], iv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            n[u] = __float_as_uint(sn[x + u * NT]); o[u] = __float_as_uint(so[x + u * NT]); iv[u] = inv[x + u * NT];
-            if (MASKED) n[u] |= mbit(vmask, e0 + x + u * NT) ? 0x80000000u : 0u;
+            n[u] = __float_as_uint(sn[x + u * G]); o[u] = __float_as_uint(so[x + u * G]); iv[u] = inv[x + u * G];
+            if (MASKED) n[u] |= mbit(vmask, e0 + x + u * G) ? 0x80000000u : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -595,7 +575,7 @@ __device__ __forceinline__ void blk_var_load(const float* __restrict__ sn, const
             PA[l] = __uint_as_float(n[u]); PB[l] = __uint_as_float(o[u] ^ ((iv[u] & PDP_VINV_NEG) << 16));
         }
     }
-    for (; x < ne; x += NT) {
+    for (; x < ne; x += G) {
         uint32_t n0 = __float_as_uint(sn[x]);
         const uint32_t o0 = __float_as_uint(so[x]), i0 = inv[x];
         if (MASKED) n0 |= mbit(vmask, e0 + x) ? 0x80000000u : 0u;
@@ -604,8 +584,296 @@ __device__ __forceinline__ void blk_var_load(const float* __restrict__ sn, const
     }
 }
 
+// variable pass, node phase: thread per variable (descending degree, rounds alternate direction so that
+// every thread gets high and low degrees): ordered sums, decimator statistics, update.
+// Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
+template <int G>
+__device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
+                                            bool em_set, float* PA, float* PB, uint32_t* skip, int* any_skip,
+                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
+    const bool multi = B.multi();
+    for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
+        const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
+        if (ti >= B.n1) continue;
+        const int2 ve = __ldg(&g.vsort[ti]);
+        const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
+        int b = B.b0;
+        if (multi) {
+            b = g.bvm[i];
+            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); *any_skip = 1; continue; }
+        }
+        const uint32_t act = s.av[i];
+        float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
+        for (int j = 0; j < deg; ++j) {
+            const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
+            const bool m = (nb >> 31) != 0u;                        // edge masked
+            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);    // all ones: negative literal
+            const float xn = __uint_as_float(nb & 0x7fffffffu), xo = __uint_as_float(ob & 0x7fffffffu);
+            float y = L40(1.f - xo);
+            if (use_mask && m) y = y * 0.f;
+            // y <= +0 (or NaN): stored as |y| under the literal's sign bit
+            PB[lo + j] = __uint_as_float((__float_as_uint(y) & 0x7fffffffu) | (ob & 0x80000000u));
+            // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
+            const float zy = 0.f * y;
+            P += fsel(negm, zy, y);
+            N += fsel(negm, y, zy);
+            const float c = X30(30.f * xn);
+            n0 += xn * c; d0 += c;
+            if (has_prev) {
+                float d = fabsf(xo - xn);
+                if (em_set && m) d = d * 0.f;
+                const float cd = X30(30.f * d);
+                n1 += d * cd; d1 += cd;
+            }
+        }
+        const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
+        const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
+        if (!multi) {
+            red.touch(s, b);
+            red.acc.add(sm0, sm1, has_prev, act);
+        } else {
+            StatAcc one;
+            one.reset();
+            one.add(sm0, sm1, has_prev, act);
+            if (local_stats) {
+                const int lb = b - B.b0;
+                atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
+                if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
+                if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
+                if (act) atomicAdd(&sm_st.nav[lb], act);
+            } else {
+                one.commit(s, b);
+            }
+        }
+        float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
+        sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
+        sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
+        bool made_nan = false;
+        for (int j = 0; j < deg; ++j) {
+            const uint32_t yb = __float_as_uint(PB[lo + j]);
+            const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
+            const float y = __uint_as_float(yb | 0x80000000u);   // -|y|; -0 for +0 is erased by `same += 0`
+            const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
+            made_nan |= (u != u);
+            PA[lo + j] = u;
+        }
+        if (made_nan) s.nanpend[b] = 1;
+    }
+}
+
+__device__ __forceinline__ void stats_slots_reset(BlkStats& sm_st, int t, int nprob) {
+    if (t < nprob) {
+        sm_st.mx0[t] = 0u; sm_st.mn0[t] = 0x7f800000u; sm_st.mx1[t] = 0u; sm_st.mn1[t] = 0x7f800000u;
+        sm_st.nan[t] = 0u; sm_st.nav[t] = 0u;
+    }
+}
+__device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats& sm_st, int t, int nprob, int b0) {
+    if (t < nprob) {
+        StatAcc a;
+        a.mx0 = sm_st.mx0[t]; a.mn0 = sm_st.mn0[t]; a.mx1 = sm_st.mx1[t]; a.mn1 = sm_st.mn1[t];
+        a.nan = sm_st.nan[t]; a.nav = sm_st.nav[t];
+        if (a.mn0 != 0x7f800000u || a.mx0 != 0u || a.nan || a.nav || a.mn1 != 0x7f800000u) a.commit(s, b0 + t);
+    }
+}
+
+// ================================================================================================
+// pipelined passes.  The memory phases (load, write-out) are bound by DRAM bandwidth / latency and issue
+// few instructions; the node phases are bound by instruction issue and touch no global memory.  Run back
+// to back by the same threads they add up, so the CTA is split into two warp groups working on two
+// shared-memory slots: the MEMORY group loads block i+1 and writes block i-1 out while the COMPUTE group
+// runs the node phase of block i.  Hand-over through named barriers (bar.arrive / bar.sync):
+//   FULL[slot]  memory -> compute: the slot holds a loaded block
+//   DONE[slot]  compute -> memory: the node phase of the slot's block is finished
+// ================================================================================================
+#define PIPE_MEM_THREADS (32 * PDP_PIPE_MEM_WARPS)
+#define PIPE_CMP_THREADS (PDP_SWEEP_THREADS - PIPE_MEM_THREADS)
+#define PIPE_BAR_FULL 1    // +slot
+#define PIPE_BAR_DONE 3    // +slot
+#define PIPE_BAR_CMP 5     // compute group internal
+#define PIPE_SLOT_BYTES (4 * PDP_BLK_C)
+#define PIPE_MAX_BLOCKS 32 // blocks of one CTA per pass handled per pipeline run
+
+#ifdef PDP_PHASE_TIMING
+#define PT_DECL() long long _pt = clock64()
+#define PT_ADD(slot_) do { if (t == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
+#else
+#define PT_DECL() do {} while (0)
+#define PT_ADD(slot_) do {} while (0)
+#endif
+
+struct PipeSmem {
+    int any_skip[2];
+    int blk[PIPE_MAX_BLOCKS];
+    int nblk;
+};
+
+// the CTA's non-idle blocks of this pass, PIPE_MAX_BLOCKS at a time (uniform over the CTA)
+template <bool VAR>
+__device__ __forceinline__ int pipe_collect(const pdp_graph& g, const pdp_state& s, PipeSmem& ps, int& next_blk) {
+    const int total = VAR ? g.nvb : g.ncb;
+    int n = 0;
+    while (next_blk < total && n < PIPE_MAX_BLOCKS) {
+        const int blk = next_blk;
+        next_blk += gridDim.x;
+        const BlkGeo B = VAR ? var_block(g, blk) : clause_block(g, blk);
+        if (B.n1 <= B.n0) continue;
+        if (blk_idle(s, B.b0, B.b1)) continue;
+        if (threadIdx.x == 0) ps.blk[n] = blk;
+        ++n;
+    }
+    __syncthreads();
+    return n;
+}
+
+__device__ __forceinline__ void pipe_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    __shared__ PipeSmem ps;
+    const float* __restrict__ qin = s.qu;
+    float* __restrict__ eout = s.eta[r ^ 1];
+    const bool is_mem = threadIdx.x < PIPE_MEM_THREADS;
+    const int t = is_mem ? threadIdx.x : (threadIdx.x - PIPE_MEM_THREADS);
+    int next_blk = blockIdx.x;
+    for (;;) {
+        const int n = pipe_collect<false>(g, s, ps, next_blk);
+        if (n == 0) break;
+        PT_DECL();
+        if (is_mem) {
+            for (int i = 0; i < n + 2; ++i) {
+                const int slot = i & 1;
+                float* X = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
+                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
+                if (i >= 2) {   // the slot's previous block: wait for its node phase, write it out
+                    PT_ADD(8);
+                    bar_sync(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
+                    PT_ADD(10);
+                    const BlkGeo B = clause_block(g, ps.blk[i - 2]);
+                    ph_write_out<PIPE_MEM_THREADS>(t, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, ps.any_skip[slot] != 0, eout);
+                    bar_sync(PIPE_BAR_CMP + 1, PIPE_MEM_THREADS);
+                    PT_ADD(9);   // memory group: the slot is free
+                }
+                if (i < n) {
+                    const BlkGeo B = clause_block(g, ps.blk[i]);
+                    for (int w = t; w < (B.ne + 31) / 32; w += PIPE_MEM_THREADS) skip[w] = 0u;
+                    if (t == 0) ps.any_skip[slot] = 0;
+                    if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<PIPE_MEM_THREADS, true>(t, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
+                    else ph_clause_load<PIPE_MEM_THREADS, false>(t, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
+                    __threadfence_block();
+                    bar_arrive(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
+                }
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int slot = i & 1;
+                float* X = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
+                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
+                PT_ADD(11);
+                bar_sync(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
+                PT_ADD(12);
+                const int blk = ps.blk[i];
+                const BlkGeo B = clause_block(g, blk);
+                ph_clause_node<PIPE_CMP_THREADS>(t, g, s, B, g.cb_k[blk], X, skip, &ps.any_skip[slot]);
+                __threadfence_block();
+                bar_arrive(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void pipe_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    __shared__ PipeSmem ps;
+    __shared__ BlkStats sm_st;
+    const float* __restrict__ en = s.eta[r ^ 1];
+    const float* __restrict__ eo = s.eta[r];
+    const bool is_mem = threadIdx.x < PIPE_MEM_THREADS;
+    const int t = is_mem ? threadIdx.x : (threadIdx.x - PIPE_MEM_THREADS);
+    KeyedReducer<StatAcc> red;
+    int next_blk = blockIdx.x;
+    for (;;) {
+        const int n = pipe_collect<true>(g, s, ps, next_blk);
+        if (n == 0) break;
+        PT_DECL();
+        if (is_mem) {
+            for (int i = 0; i < n + 2; ++i) {
+                const int slot = i & 1;
+                float* PA = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
+                float* PB = PA + PDP_BLK_V;
+                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
+                if (i >= 2) {
+                    PT_ADD(16);
+                    bar_sync(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
+                    PT_ADD(18);
+                    const BlkGeo B = var_block(g, ps.blk[i - 2]);
+                    ph_write_out<PIPE_MEM_THREADS>(t, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, ps.any_skip[slot] != 0, s.qu);
+                    bar_sync(PIPE_BAR_CMP + 1, PIPE_MEM_THREADS);
+                    PT_ADD(17);
+                }
+                if (i < n) {
+                    const BlkGeo B = var_block(g, ps.blk[i]);
+                    for (int w = t; w < (B.ne + 31) / 32; w += PIPE_MEM_THREADS) skip[w] = 0u;
+                    if (t == 0) ps.any_skip[slot] = 0;
+                    if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<PIPE_MEM_THREADS, true>(t, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
+                    else ph_var_load<PIPE_MEM_THREADS, false>(t, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
+                    __threadfence_block();
+                    bar_arrive(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
+                }
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int slot = i & 1;
+                float* PA = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
+                float* PB = PA + PDP_BLK_V;
+                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
+                const BlkGeo B = var_block(g, ps.blk[i]);
+                const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);
+                if (local_stats) { stats_slots_reset(sm_st, t, B.b1 - B.b0 + 1); bar_sync(PIPE_BAR_CMP, PIPE_CMP_THREADS); }
+                PT_ADD(19);
+                bar_sync(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
+                PT_ADD(20);
+                ph_var_node<PIPE_CMP_THREADS>(t, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &ps.any_skip[slot], red, sm_st, local_stats);
+                __threadfence_block();
+                bar_arrive(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
+                if (local_stats) { bar_sync(PIPE_BAR_CMP, PIPE_CMP_THREADS); stats_slots_commit(s, sm_st, t, B.b1 - B.b0 + 1, B.b0); }
+                red.finish(s, PIPE_BAR_CMP, PIPE_CMP_THREADS, t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ================================================================================================
+// serial passes: the whole CTA runs load, node phase and write-out of a block back to back
+// ================================================================================================
+#define NT PDP_SWEEP_THREADS
+
+// clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
+__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    float* X = reinterpret_cast<float*>(smem);
+    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
+    __shared__ int sm_any_skip;
+    const float* __restrict__ qin = s.qu;
+    float* __restrict__ eout = s.eta[r ^ 1];
+    const int tid = threadIdx.x;
+    for (int blk = blockIdx.x; blk < g.ncb; blk += gridDim.x) {
+        const BlkGeo B = clause_block(g, blk);
+        if (B.n1 <= B.n0) continue;
+        if (blk_idle(s, B.b0, B.b1)) continue;
+        for (int i = tid; i < (B.ne + 31) / 32; i += NT) skip[i] = 0u;
+        if (tid == 0) sm_any_skip = 0;
+        if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
+        else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
+        __syncthreads();
+        ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip);
+        __syncthreads();
+        ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip != 0, eout);
+        __syncthreads();
+    }
+}
+
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
-// [buffer r], and q(t) [C-layout, in place] from eta(t-1).  Requires eta(t-1) >= +0 or NaN without sign.
+// [buffer r], and q(t) [C-layout, in place] from eta(t-1)
 __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
@@ -618,116 +886,21 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     const int tid = threadIdx.x;
     KeyedReducer<StatAcc> red;
     for (int blk = blockIdx.x; blk < g.nvb; blk += gridDim.x) {
-        const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
-        if (v1 <= v0) continue;
-        const int b0 = g.bvm[v0], b1 = g.bvm[v1 - 1];
-        if (blk_idle(s, b0, b1)) continue;
-        const bool multi = (b0 != b1);
-        const bool local_stats = multi && (b1 - b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
-        const int e0 = g.var_ptr[v0], ne = g.var_ptr[v1] - e0;
-        for (int i = tid; i < (ne + 31) / 32; i += NT) skip[i] = 0u;
+        const BlkGeo B = var_block(g, blk);
+        if (B.n1 <= B.n0) continue;
+        if (blk_idle(s, B.b0, B.b1)) continue;
+        const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
+        for (int i = tid; i < (B.ne + 31) / 32; i += NT) skip[i] = 0u;
         if (tid == 0) sm_any_skip = 0;
-        if (local_stats && tid <= b1 - b0) {
-            sm_st.mx0[tid] = 0u; sm_st.mn0[tid] = 0x7f800000u; sm_st.mx1[tid] = 0u; sm_st.mn1[tid] = 0x7f800000u;
-            sm_st.nan[tid] = 0u; sm_st.nav[tid] = 0u;
-        }
-        // ---- load both survey regions (contiguous), scatter into variable-major order
-        PHASE_T0();
-        if ((use_mask || em_set) && (multi || s.masked[b0])) blk_var_load<true>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
-        else blk_var_load<false>(en + e0, eo + e0, g.vinv + e0, g.vmask, e0, ne, PA, PB);
+        if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
+        if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
+        else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         __syncthreads();
-        PHASE_ADD(3);
-        {   // L2 prefetch: this block's write-out tables, the next block's inputs
-            blk_prefetch_l2(g.vsrc + e0, (size_t)ne * 2);
-            blk_prefetch_l2(g.vdst + e0, (size_t)ne * 4);
-            const int nb = blk + gridDim.x;
-            if (nb < g.nvb) {
-                const int n0 = g.var_ptr[g.vb_ptr[nb]], n1 = g.var_ptr[g.vb_ptr[nb + 1]];
-                blk_prefetch_l2(en + n0, (size_t)(n1 - n0) * 4);
-                blk_prefetch_l2(eo + n0, (size_t)(n1 - n0) * 4);
-                blk_prefetch_l2(g.vinv + n0, (size_t)(n1 - n0) * 2);
-            }
-        }
-        // ---- thread per variable (descending degree): ordered sums, statistics, update.
-        // rounds alternate direction over the degree-sorted list: every thread gets high and low degrees
-        for (int base = v0, round = 0; base < v1; base += NT, ++round) {
-            const int t = (round & 1) ? (base + NT - 1 - tid) : (base + tid);
-            if (t >= v1) continue;
-            const int2 ve = __ldg(&g.vsort[t]);
-            const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
-            int b = b0;
-            if (multi) {
-                b = g.bvm[i];
-                if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); sm_any_skip = 1; continue; }
-            }
-            const uint32_t act = s.av[i];
-            float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
-            for (int j = 0; j < deg; ++j) {
-                const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
-                const bool m = (nb >> 31) != 0u;                 // edge masked
-                const uint32_t negm = (uint32_t)((int32_t)ob >> 31);   // all ones: negative literal
-                const float xn = __uint_as_float(nb & 0x7fffffffu), xo = __uint_as_float(ob & 0x7fffffffu);
-                float y = L40(1.f - xo);
-                if (use_mask && m) y = y * 0.f;
-                // y <= +0 (or NaN): stored as |y| under the literal's sign bit
-                PB[lo + j] = __uint_as_float((__float_as_uint(y) & 0x7fffffffu) | (ob & 0x80000000u));
-                // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
-                const float zy = 0.f * y;
-                P += fsel(negm, zy, y);
-                N += fsel(negm, y, zy);
-                const float c = X30(30.f * xn);
-                n0 += xn * c; d0 += c;
-                if (has_prev) {
-                    float d = fabsf(xo - xn);
-                    if (em_set && m) d = d * 0.f;
-                    const float cd = X30(30.f * d);
-                    n1 += d * cd; d1 += cd;
-                }
-            }
-            const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
-            const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
-            if (!multi) {
-                red.touch(s, b);
-                red.acc.add(sm0, sm1, has_prev, act);
-            } else {
-                StatAcc one;
-                one.reset();
-                one.add(sm0, sm1, has_prev, act);
-                if (local_stats) {
-                    const int lb = b - b0;
-                    atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
-                    if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
-                    if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
-                    if (act) atomicAdd(&sm_st.nav[lb], act);
-                } else {
-                    one.commit(s, b);
-                }
-            }
-            float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
-            sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
-            sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
-            bool made_nan = false;
-            for (int j = 0; j < deg; ++j) {
-                const uint32_t yb = __float_as_uint(PB[lo + j]);
-                const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
-                const float y = __uint_as_float(yb | 0x80000000u);   // -|y|; -0 for +0 is erased by `same += 0`
-                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
-                made_nan |= (u != u);
-                PA[lo + j] = u;
-            }
-            if (made_nan) s.nanpend[b] = 1;
-        }
+        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats);
         __syncthreads();
-        if (local_stats && tid <= b1 - b0) {
-            StatAcc a;
-            a.mx0 = sm_st.mx0[tid]; a.mn0 = sm_st.mn0[tid]; a.mx1 = sm_st.mx1[tid]; a.mn1 = sm_st.mn1[tid];
-            a.nan = sm_st.nan[tid]; a.nav = sm_st.nav[tid];
-            if (a.mn0 != 0x7f800000u || a.mx0 != 0u || a.nan || a.nav || a.mn1 != 0x7f800000u) a.commit(s, b0 + tid);
-        }
-        PHASE_ADD(4);
-        blk_write_out(g.vsrc + e0, g.vdst + e0, ne, PA, skip, sm_any_skip != 0, s.qu);
+        if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
+        ph_write_out<NT>(tid, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, sm_any_skip != 0, s.qu);
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
-        PHASE_ADD(5);
     }
 }
 #undef NT

@@ -143,7 +143,8 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #ifdef PDP_STAGGER_EXPERIMENT
             if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 16) & 0xff) * 1024) __nanosleep(200); }
 #endif
-            blk_clause_pass(A, r, use_mask, smem_dyn);
+            if (PDP_PIPELINE) pipe_clause_pass(A, r, use_mask, smem_dyn);
+            else blk_clause_pass(A, r, use_mask, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
@@ -156,7 +157,8 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #ifdef PDP_STAGGER_EXPERIMENT
             if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 8) & 0xff) * 1024) __nanosleep(200); }
 #endif
-            blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
+            if (PDP_PIPELINE) pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
+            else blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
             if (s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
                 gen_stats<GEN_NAN>(A, w, has_prev, em_set);

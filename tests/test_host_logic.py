@@ -1,0 +1,114 @@
+"""CPU tests of the host side: the C-ABI library exports what include/pdp_b200.h declares (no compute calls
+without a GPU), the product path refuses to run without CUDA, and the multi-GPU sharding logic
+(world_size 2 over gloo) reproduces the unsharded result with the C oracle standing in for the kernels."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "pdp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pdp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_bound_signatures():
+    from pdp_solver_b200 import _lib
+    assert set(_declared_functions()) == set(_lib.SIGNATURES), \
+        set(_declared_functions()) ^ set(_lib.SIGNATURES)
+
+
+@pytest.mark.parametrize("libname", ["libpdp_b200.so", "libpdp_b200_strict.so"])
+def test_library_loads_and_exports_every_symbol(libname):
+    path = os.path.join(ROOT, "pdp_solver_b200", "csrc", libname)
+    if not os.path.exists(path):
+        subprocess.check_call(["bash", os.path.join(ROOT, "pdp_solver_b200", "csrc", "build.sh")])
+    lib = ctypes.CDLL(path)
+    for fn in _declared_functions():
+        assert hasattr(lib, fn), fn
+    lib.pdp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.pdp_version()
+    lib.pdp_workspace_bytes.restype = ctypes.c_size_t
+    lib.pdp_workspace_bytes.argtypes = [ctypes.c_int64] * 4
+    assert lib.pdp_workspace_bytes(1260, 100, 420, 1) > 0
+    assert lib.pdp_workspace_bytes(-1, 0, 0, 0) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    from pdp_solver_b200 import _lib, cnfgen
+    from pdp_solver_b200.engine import Context
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    gm, bvm, bfm, ef = [torch.from_numpy(x) for x in cnfgen.random_batch(2, 20, 3, 4.0, 0)]
+    with pytest.raises(_lib.PdpError):
+        Context(gm, bvm, bfm, ef)
+
+
+def test_lpt_and_extract_roundtrip():
+    from pdp_solver_b200 import cnfgen, sharding
+    batch = cnfgen.mixed_batch([(30, 3, 4.0), (80, 3, 4.2), (10, 3, 3.0), (50, 5, 16.0), (50, 3, 4.1)], 3)
+    nv, nf, ne = sharding.problem_sizes(*batch[:3])
+    assert nv.tolist() == [30, 80, 10, 50, 50] and ne.sum() == batch[0].shape[1]
+    parts = sharding.lpt_assign(ne, 2)
+    assert sorted(parts[0] + parts[1]) == [0, 1, 2, 3, 4]
+    loads = [int(ne[p].sum()) for p in parts]
+    assert max(loads) - min(loads) <= int(ne.max())
+    seen = np.zeros(nv.sum(), dtype=int)
+    for p in parts:
+        sub, vsel = sharding.extract_problems(batch, p)
+        seen[vsel] += 1
+        assert sub[1].max() + 1 == len(p) and sub[0][0].max() < sub[1].size and sub[0][1].max() < sub[2].size
+        # the sub-batch holds exactly the clauses of its problems, literal for literal
+        gm, bvm, bfm, ef = batch
+        esel = np.isin(bvm[gm[0]], p)
+        assert np.array_equal(vsel[sub[0][0]], gm[0][esel]) and np.array_equal(sub[3].reshape(-1), ef.reshape(-1)[esel])
+    assert (seen == 1).all()
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import pdp_oracle as po
+from pdp_solver_b200 import cnfgen, sharding
+
+def solve(sub):
+    o = po.Oracle(*sub, strict=False)
+    o.simplify()
+    o.set_state(*po.init_state(sub[0].shape[1], False))
+    o.run(60, 0.02, 20, True)
+    pred = o.masks()["sol"]
+    solved, _ = o.cnf_eval(pred)
+    return pred, solved
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+batch = cnfgen.mixed_batch([(40, 3, 3.6), (60, 3, 3.8), (25, 3, 3.0), (70, 3, 3.9), (30, 3, 3.5), (55, 3, 3.7)], 11)
+pred, solved = sharding.solve_sharded(batch, solve, rank, world, dist)
+if rank == 0:
+    ref_pred, ref_solved = solve(batch)
+    assert np.array_equal(pred, ref_pred), "sharded prediction differs from the unsharded one"
+    assert np.array_equal(solved, ref_solved)
+    print("SHARDED_OK", int(solved.sum()))
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_equals_unsharded_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SHARDED_OK" in out.stdout

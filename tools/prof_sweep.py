@@ -51,7 +51,9 @@ for rep in range(a.repeat):
         nct = 148 * int(os.environ.get("PDP_PHASE_TIMING"))
         names = ["clause load", "clause node", "clause write-out", "var load", "var node", "var write-out+stats", "kernel total", "grid.sync waits"]
         print("per-CTA mean cycles per iteration: " + ", ".join("%s %.0f" % (n, v / nct / max(done, 1)) for n, v in zip(names, tr)))
-        print("role counters:", ctx._trace.reshape(-1)[32:32 + 8].cpu().tolist())
+        tr2 = ctx._trace.reshape(-1)[:24].cpu().numpy().astype(np.float64) * 1024.0 / nct / max(done, 1)
+        print("pipeline clause: M load+misc %.0f, M write-out %.0f, M wait DONE %.0f | C node+misc %.0f, C wait FULL %.0f" % tuple(tr2[8:13]))
+        print("pipeline var   : M load+misc %.0f, M write-out %.0f, M wait DONE %.0f | C node+misc %.0f, C wait FULL %.0f" % tuple(tr2[16:21]))
         ctx._trace.zero_()
     print("E=%d iterations=%d  %.3f ms  %.3f ms/iter  %.2f G edge-updates/s  %.1f GB/s algorithmic" % (
         E, done, ms, ms / max(done, 1), E * done / ms / 1e6, 20.0 * E * done / ms / 1e6))
