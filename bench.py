@@ -272,9 +272,12 @@ def run_b200_arm(a, rank, world, local_rank):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     loop_s = st["loop_ms"] / 1e3
     achieved = ALG_BYTES_PER_EDGE_UPDATE * st["loop_updates"] / loop_s / 1e9 if loop_s > 0 else None
+    # DRAM traffic of k_sp_run per launch: ncu --set full measured dram__bytes_read.sum + dram__bytes_write.sum per
+    # edge-update on the same workload (profiles/k_sp_run_traffic.json), times the edge-updates of this launch
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_sp_run_traffic.json"))).get("dram_bytes_per_launch")
+        per = json.load(open(os.path.join(ROOT, "profiles", "k_sp_run_traffic.json"))).get("dram_bytes_per_edge_update")
+        traffic = per * st["loop_updates"] / a.steps
     except Exception:
         pass
 

@@ -528,7 +528,11 @@ extern "C" int pdp_walksat(pdp_ctx* ctx, int32_t W, float epsilon, int32_t batch
     WsArgs wa;
     wa.W = W; wa.epsilon = epsilon; wa.rep = rep; wa.rand_var = d_rand_var; wa.rand_coin = d_rand_coin; wa.seed = seed;
     wa.prediction = d_prediction; wa.iters_done = d_iters_done;
-    wa.cta_loop = (rep == 1 && ctx->g.prob_vptr != nullptr && ctx->g.contiguous_problems && getenv("PDP_B200_WS_GRID") == nullptr) ? 1 : 0;
+    // injected draws make the random pick an exact O(n) scan per iteration: one CTA per problem only while
+    // problems are small; large problems with injected draws keep the grid-wide pass
+    const bool small_or_generated = (d_rand_var == nullptr) || (ctx->g.B > 0 && ctx->g.V / ctx->g.B <= 32768);
+    wa.cta_loop = (rep == 1 && ctx->g.prob_vptr != nullptr && ctx->g.contiguous_problems && small_or_generated &&
+                   getenv("PDP_B200_WS_GRID") == nullptr) ? 1 : 0;
     void* args[] = {&A, &wa};
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walksat, 256, 0) != cudaSuccess || per_sm < 1) {

@@ -19,7 +19,7 @@ from . import pdp_decimate, pdp_predict, pdp_propagate, util
 
 # WalkSAT draws are pre-generated with torch.rand in the reference's order when they fit this many
 # floats; above it the kernel's counter-based generator is used (same distribution, other stream).
-TORCH_RNG_DRAW_LIMIT = int(os.environ.get("PDP_TORCH_RNG_DRAW_LIMIT", str(1 << 28)))
+TORCH_RNG_DRAW_LIMIT = int(os.environ.get("PDP_TORCH_RNG_DRAW_LIMIT", str(1 << 24)))
 
 
 class SATProblem(object):
