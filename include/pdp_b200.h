@@ -85,6 +85,20 @@ int pdp_sp_step(pdp_ctx* ctx, const float* d_dec_q3, const float* d_dec_fs2, con
                 const float* d_prop_q3, const float* d_prop_fs2, const uint8_t* d_active, float pi,
                 float* d_out_q3, float* d_out_fs2, void* stream);
 
+/* SurveyPropagator.forward with the neural adaptors applied by the caller (model type p-nd-np), reference
+ * pdp/nn/pdp_propagate.py:139-221 with include_adaptors=True: d_x_log [E] = logsigmoid(function_input_projector(.)),
+ * d_eta_in [E] = sigmoid(variable_input_projector(.)[:,0]), d_ext_in [E] = sign(variable_input_projector(.)[:,1]);
+ * the message arithmetic (edge mask, leave-one-out sums, frozen-problem blend) is the same as pdp_sp_step. */
+int pdp_sp_step_adapted(pdp_ctx* ctx, const float* d_x_log, const float* d_eta_in, const float* d_ext_in,
+                        const float* d_edge_mask, const float* d_prop_q3, const float* d_prop_fs2,
+                        const uint8_t* d_active, float pi, float* d_out_q3, float* d_out_fs2, void* stream);
+
+/* the segmented sums of MessageAggregator.forward, reference pdp/nn/util.py:51-77: d_state [E,channels] ->
+ * d_node_sum [V or F, channels] = torch.mm(mask, state) (ascending edge order inside a node); d_edge_loo (nullable)
+ * [E,channels] = torch.mm(mask_transpose, node_sum) - state (leave one out).  by_variable: 1 = variable_mask, 0 = function_mask */
+int pdp_edge_aggregate(pdp_ctx* ctx, int32_t by_variable, const float* d_state, int32_t channels, float* d_node_sum,
+                       float* d_edge_loo, void* stream);
+
 /* SurveyScorer.forward (adaptors off), reference pdp/nn/pdp_predict.py:155-192.
  * d_fs2 [E,2], d_af [F] -> d_score [V] */
 int pdp_score(pdp_ctx* ctx, const float* d_fs2, const float* d_af, float pi, float* d_score, void* stream);

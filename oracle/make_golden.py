@@ -277,7 +277,69 @@ def gen_traj(name, batch, T_iters, W, epsilon, randomized, seed, **kw):
     save(name, **arrays)
 
 
+# ----------------------------------------------------------------------------------------------
+# neural model types (p-nd-np, np-nd-np): weights + injected initial states + what the reference returns
+# ----------------------------------------------------------------------------------------------
+def gen_neural(name, model_type, batch, T_iters, seed, dims, only=None):
+    """dims = (hidden, mem_hidden, agg_hidden, mem_agg_hidden, classifier).  The reference model is built under
+    torch.manual_seed(seed); its state_dict is stored so that the B200 modules can load it (same keys)."""
+    solver, prop, dec, pred, util, trainer = compat.load_reference()
+    gm, bvm, bfm, ef = tensors(batch)
+    H, MH, AH, MAH, CH = dims
+    torch.manual_seed(seed)
+    clf = trainer.Perceptron(H, CH, 1)
+    if model_type == "p-nd-np":
+        model = solver.NeuralSurveyPropagatorSolver(DEV, "m", edge_dimension=1, meta_data_dimension=0, decimator_dimension=H,
+                                                    mem_hidden_dimension=MH, agg_hidden_dimension=AH, mem_agg_hidden_dimension=MAH,
+                                                    prediction_dimension=1, variable_classifier=clf, function_classifier=None,
+                                                    dropout=0, local_search_iterations=0, epsilon=0.5)
+    else:
+        model = solver.NeuralPropagatorDecimatorSolver(DEV, "m", edge_dimension=1, meta_data_dimension=0, propagator_dimension=H,
+                                                       decimator_dimension=H, mem_hidden_dimension=MH, agg_hidden_dimension=AH,
+                                                       mem_agg_hidden_dimension=MAH, prediction_dimension=1, variable_classifier=clf,
+                                                       function_classifier=None, dropout=0, local_search_iterations=0, epsilon=0.5)
+    model.eval()
+    cb = compat.make_termination_callback(DEV)
+    preds = []
+    orig_pred = model._predictor.forward
+
+    def hook(decimator_state, sat_problem, last_call=False):
+        out = orig_pred(decimator_state, sat_problem, last_call)
+        preds.append(out[0].detach().clone().numpy().reshape(-1))
+        return out
+
+    model._predictor.forward = hook
+    with torch.no_grad():
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=True, batch_replication=1)
+        init_np = [[t.clone().numpy() for t in st] for st in init]
+        (vp, fp), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                                   edge_feature=ef, meta_data=None, is_training=False, iteration_num=T_iters,
+                                   check_termination=cb, simplify=True, batch_replication=1)
+    model._predictor.forward = orig_pred
+    arrays = dict(graph_map=batch[0], bvm=batch[1], bfm=batch[2], ef=batch[3], T=T_iters, dims=np.array(dims),
+                  model_type=np.array(model_type), pred=vp.numpy().reshape(-1), preds=np.stack(preds).astype(np.float32),
+                  init_p0=init_np[0][0], init_p1=init_np[0][1], init_d0=init_np[1][0], init_d1=init_np[1][1],
+                  final_p0=ps[0].numpy(), final_p1=ps[1].numpy(), final_d0=ds[0].numpy(), final_d1=ds[1].numpy())
+    # the reference registers every sub-module twice (attribute + _module_list): store each tensor once
+    seen, alias = {}, []
+    for k, v in model.state_dict().items():
+        key = (v.data_ptr(), tuple(v.shape))
+        if key in seen:
+            alias.append("%s=%s" % (k, seen[key]))
+        else:
+            seen[key] = k
+            arrays["w:" + k] = v.numpy()
+    arrays["w_alias"] = np.array(";".join(alias))
+    save(name, **arrays)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "neural":
+        gen_neural("neural_pndnp_a", "p-nd-np", cnfgen.random_batch(4, 20, 3, 3.8, 51), 12, 5, (24, 16, 16, 8, 8))
+        gen_neural("neural_pndnp_b", "p-nd-np", ragged_batch(52), 8, 6, (20, 12, 12, 6, 6))
+        gen_neural("neural_npndnp_a", "np-nd-np", cnfgen.random_batch(3, 16, 4, 6.5, 53), 10, 7, (24, 16, 16, 8, 8))
+        gen_neural("neural_npndnp_b", "np-nd-np", cnfgen.mixed_batch([(20, 3, 2.0), (12, 5, 8.0), (16, 3, 4.0)], 54), 8, 8, (16, 12, 10, 6, 8))
+        return
     gen_ops("ops_3sat", cnfgen.random_batch(6, 20, 3, 4.0, 11), seed=1, adversarial=False)
     gen_ops("ops_3sat_adv", cnfgen.random_batch(5, 24, 3, 4.2, 12), seed=2, adversarial=True)
     gen_ops("ops_ragged", ragged_batch(13), seed=3, adversarial=True)

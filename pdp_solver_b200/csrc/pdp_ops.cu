@@ -83,32 +83,36 @@ __global__ void k_energy_diff(pdp_graph g, const float* __restrict__ asg, const 
 // ------------------------------------------------------------------------------------------------
 // SurveyPropagator.forward in the caller's edge order (pdp_propagate.py:139-221)
 // ------------------------------------------------------------------------------------------------
+// xlog / ext_in (nullable): the adaptor outputs of the neural variant (pdp_propagate.py:163-164,179-182) --
+// the variable->clause message already in the log domain, the external force column
 __global__ void k_sp_step_clause(pdp_graph g, const float* __restrict__ dq3, const float* __restrict__ em,
                                  const float* __restrict__ pfs2, const float* __restrict__ dfs2,
-                                 const uint8_t* __restrict__ active, float* out_fs2) {
+                                 const uint8_t* __restrict__ active, float* out_fs2,
+                                 const float* __restrict__ xlog, const float* __restrict__ ext_in) {
     WARP_STRIDED(a, g.F) {
         if (a >= g.F) continue;
         const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
         float tot = 0.f;
         for (int c = beg; c < end; ++c) {
             const int e = g.c_orig[c];
-            float v = L40(dq3[3 * (int64_t)e]);
+            float v = xlog ? xlog[e] : L40(dq3[3 * (int64_t)e]);
             if (em) v = v * em[e];
             tot += v;
         }
         for (int c = beg; c < end; ++c) {
             const int e = g.c_orig[c];
-            float v = L40(dq3[3 * (int64_t)e]);
+            float v = xlog ? xlog[e] : L40(dq3[3 * (int64_t)e]);
             if (em) v = v * em[e];
             const float mask = active ? (float)active[g.bvm[g.c_var[c] & PDP_IDX_MASK]] : 1.f;
             out_fs2[2 * (int64_t)e] = mask * X30(tot - v) + (1.f - mask) * pfs2[2 * (int64_t)e];
-            out_fs2[2 * (int64_t)e + 1] = dfs2[2 * (int64_t)e + 1];
+            out_fs2[2 * (int64_t)e + 1] = ext_in ? ext_in[e] : dfs2[2 * (int64_t)e + 1];
         }
     }
 }
 
 __global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const float* __restrict__ em,
-                              const float* __restrict__ pq3, const uint8_t* __restrict__ active, float pi, float* out_q3) {
+                              const float* __restrict__ pq3, const uint8_t* __restrict__ active, float pi, float* out_q3,
+                              const float* __restrict__ eta_in, const float* __restrict__ ext_in) {
     WARP_STRIDED(i, g.V) {
         if (i >= g.V) continue;
         const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
@@ -116,7 +120,7 @@ __global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const
         float P = 0.f, N = 0.f;
         for (int p = beg; p < end; ++p) {
             const int e = g.v_orig[p];
-            float y = L40(1.f - dfs2[2 * (int64_t)e]);
+            float y = L40(1.f - (eta_in ? eta_in[e] : dfs2[2 * (int64_t)e]));
             if (em) y = y * em[e];
             const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
             P += (neg ? 0.f : 1.f) * y;
@@ -124,13 +128,30 @@ __global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const
         }
         for (int p = beg; p < end; ++p) {
             const int64_t e = g.v_orig[p];
-            float y = L40(1.f - dfs2[2 * e]);
+            float y = L40(1.f - (eta_in ? eta_in[e] : dfs2[2 * e]));
             if (em) y = y * em[e];
             float u, v, d;
-            sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, dfs2[2 * e + 1], pi, u, v, d);
+            sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, ext_in ? ext_in[e] : dfs2[2 * e + 1], pi, u, v, d);
             out_q3[3 * e + 0] = mask * u + (1.f - mask) * pq3[3 * e + 0];
             out_q3[3 * e + 1] = mask * v + (1.f - mask) * pq3[3 * e + 1];
             out_q3[3 * e + 2] = mask * d + (1.f - mask) * pq3[3 * e + 2];
+        }
+    }
+}
+
+// node sums of [E,C] edge rows (ascending edge order, fp32) and the leave-one-out gather back to the edges.
+// A warp walks the channels of one node (coalesced rows).
+__global__ void k_edge_aggregate(pdp_graph g, int by_variable, const float* __restrict__ state, int C, float* node_sum, float* edge_loo) {
+    const int64_t nodes = by_variable ? g.V : g.F;
+    const int32_t* ptr = by_variable ? g.var_ptr : g.cl_ptr;
+    const int32_t* orig = by_variable ? g.v_orig : g.c_orig;
+    for (int64_t node = gwarp(); node < nodes; node += gwarps()) {
+        const int beg = ptr[node], end = ptr[node + 1];
+        for (int ch = lane_id(); ch < C; ch += 32) {
+            float acc = 0.f;
+            for (int k = beg; k < end; ++k) acc += state[(int64_t)orig[k] * C + ch];
+            node_sum[node * C + ch] = acc;
+            if (edge_loo) for (int k = beg; k < end; ++k) { const int64_t e = orig[k]; edge_loo[e * C + ch] = acc - state[e * C + ch]; }
         }
     }
 }
@@ -342,8 +363,32 @@ extern "C" int pdp_sp_step(pdp_ctx* ctx, const float* d_dec_q3, const float* d_d
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* pq = d_prop_q3 ? d_prop_q3 : d_dec_q3;
     const float* pf = d_prop_fs2 ? d_prop_fs2 : d_dec_fs2;
-    if (ctx->g.F > 0) { k_sp_step_clause<<<GRID(ctx->g.F)>>>(ctx->g, d_dec_q3, d_edge_mask, pf, d_dec_fs2, d_active, d_out_fs2); PDP_LAUNCH_CHECK(ctx); }
-    if (ctx->g.V > 0) { k_sp_step_var<<<GRID(ctx->g.V)>>>(ctx->g, d_dec_fs2, d_edge_mask, pq, d_active, pi, d_out_q3); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.F > 0) { k_sp_step_clause<<<GRID(ctx->g.F)>>>(ctx->g, d_dec_q3, d_edge_mask, pf, d_dec_fs2, d_active, d_out_fs2, nullptr, nullptr); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.V > 0) { k_sp_step_var<<<GRID(ctx->g.V)>>>(ctx->g, d_dec_fs2, d_edge_mask, pq, d_active, pi, d_out_q3, nullptr, nullptr); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+extern "C" int pdp_sp_step_adapted(pdp_ctx* ctx, const float* d_x_log, const float* d_eta_in, const float* d_ext_in,
+                                   const float* d_edge_mask, const float* d_prop_q3, const float* d_prop_fs2,
+                                   const uint8_t* d_active, float pi, float* d_out_q3, float* d_out_fs2, void* stream_) {
+    NEED(ctx, d_x_log && d_eta_in && d_ext_in && d_prop_q3 && d_prop_fs2 && d_out_q3 && d_out_fs2, "pdp_sp_step_adapted: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.F > 0) { k_sp_step_clause<<<GRID(ctx->g.F)>>>(ctx->g, nullptr, d_edge_mask, d_prop_fs2, nullptr, d_active, d_out_fs2, d_x_log, d_ext_in); PDP_LAUNCH_CHECK(ctx); }
+    if (ctx->g.V > 0) { k_sp_step_var<<<GRID(ctx->g.V)>>>(ctx->g, nullptr, d_edge_mask, d_prop_q3, d_active, pi, d_out_q3, d_eta_in, d_ext_in); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
+// torch.mm(mask[N,E], state[E,C]) of MessageAggregator (util.py:60): per node the sum of its edges' rows in
+// ascending edge order; optionally the gather back to the edges minus the own row (leave one out, util.py:62-68)
+extern "C" int pdp_edge_aggregate(pdp_ctx* ctx, int32_t by_variable, const float* d_state, int32_t channels, float* d_node_sum,
+                                  float* d_edge_loo, void* stream_) {
+    NEED(ctx, d_state && d_node_sum && channels > 0, "pdp_edge_aggregate: bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t nodes = by_variable ? ctx->g.V : ctx->g.F;
+    if (nodes > 0) {
+        k_edge_aggregate<<<GRID(nodes * (int64_t)std::min(channels, 32))>>>(ctx->g, by_variable, d_state, channels, d_node_sum, d_edge_loo);
+        PDP_LAUNCH_CHECK(ctx);
+    }
     return PDP_OK;
 }
 

@@ -144,6 +144,26 @@ class Context(object):
                                   _ptr(oq), _ptr(of), _stream()), "pdp_sp_step")
         return oq, of
 
+    def sp_step_adapted(self, x_log, eta_in, ext_in, edge_mask, prop_q3, prop_fs2, active=None, pi=0.0):
+        x, e, t = (_f32(v, self.device).reshape(-1) for v in (x_log, eta_in, ext_in))
+        pq, pf = _f32(prop_q3, self.device), _f32(prop_fs2, self.device)
+        em = None if edge_mask is None else _f32(edge_mask, self.device).reshape(-1)
+        act = None if active is None else active.to(device=self.device, dtype=torch.uint8).reshape(-1).contiguous()
+        oq, of = self._new(self.E, 3), self._new(self.E, 2)
+        self._check(self._L.pdp_sp_step_adapted(self._h, _ptr(x), _ptr(e), _ptr(t), _ptr(em), _ptr(pq), _ptr(pf), _ptr(act), float(pi),
+                                                _ptr(oq), _ptr(of), _stream()), "pdp_sp_step_adapted")
+        return oq, of
+
+    def edge_aggregate(self, state, by_variable=True, leave_one_out=False):
+        """(node_sum [V|F, C], edge_loo [E, C] or None) of an [E, C] edge tensor (MessageAggregator's segmented sums)"""
+        st = _f32(state, self.device)
+        C = int(st.shape[1])
+        out = self._new(self.V if by_variable else self.F, C)
+        loo = self._new(self.E, C) if leave_one_out else None
+        self._check(self._L.pdp_edge_aggregate(self._h, 1 if by_variable else 0, _ptr(st), C, _ptr(out), _ptr(loo), _stream()),
+                    "pdp_edge_aggregate")
+        return out, loo
+
     def score(self, fs2, af, pi=0.0):
         f, a = _f32(fs2, self.device), _f32(af, self.device).reshape(-1)
         s = self._new(self.V)

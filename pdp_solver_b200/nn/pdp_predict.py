@@ -2,6 +2,65 @@
 import torch
 import torch.nn as nn
 
+from . import util
+
+
+class NeuralPredictor(nn.Module):
+    """The neural predictor (reference pdp_predict.py:20-104): a self-inclusive deep-set aggregator over each
+    variable's edges followed by the classifier.  Same sub-module names (state-dict compatible)."""
+
+    def __init__(self, device, decimator_dimension, prediction_dimension, edge_dimension, meta_data_dimension,
+                 mem_hidden_dimension, agg_hidden_dimension, mem_agg_hidden_dimension, variable_classifier=None,
+                 function_classifier=None):
+        super(NeuralPredictor, self).__init__()
+        self._device = device
+        self._module_list = nn.ModuleList()
+        self._variable_classifier = variable_classifier
+        self._function_classifier = function_classifier
+        self._hidden_dimension = decimator_dimension
+        if variable_classifier is not None:
+            self._variable_aggregator = util.MessageAggregator(
+                device, decimator_dimension + edge_dimension + meta_data_dimension, decimator_dimension, mem_hidden_dimension,
+                mem_agg_hidden_dimension, agg_hidden_dimension, 0, include_self_message=True)
+            self._module_list.append(self._variable_aggregator)
+            self._module_list.append(self._variable_classifier)
+        if function_classifier is not None:
+            self._function_aggregator = util.MessageAggregator(
+                device, decimator_dimension + edge_dimension + meta_data_dimension, decimator_dimension, mem_hidden_dimension,
+                mem_agg_hidden_dimension, agg_hidden_dimension, 0, include_self_message=True)
+            self._module_list.append(self._function_aggregator)
+            self._module_list.append(self._function_classifier)
+
+    def forward(self, decimator_state, sat_problem, last_call=False):
+        if sat_problem._meta_data is not None:
+            raise NotImplementedError("meta_data features are not supported")
+        ctx = sat_problem._ctx
+        if len(decimator_state) == 3:
+            dvs, dfs, edge_mask = decimator_state
+        else:
+            (dvs, dfs), edge_mask = decimator_state, None
+        ef = sat_problem._edge_feature
+        variable_prediction = function_prediction = None
+        if self._variable_classifier is not None:
+            agg = self._variable_aggregator(torch.cat((dvs, ef), 1), None, ctx, True, edge_mask)
+            variable_prediction = self._variable_classifier(agg)
+        if self._function_classifier is not None:
+            agg = self._function_aggregator(torch.cat((dfs, ef), 1), None, ctx, False, edge_mask)
+            function_prediction = self._function_classifier(agg)
+        return variable_prediction, function_prediction
+
+    def get_init_state(self, graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat,
+                       randomized, batch_replication):
+        "reference pdp_predict.py:93-104"
+        edge_num = graph_map.size(1) * batch_replication
+        if randomized:
+            variable_state = 2.0 * torch.rand(edge_num, self._hidden_dimension, dtype=torch.float32, device=self._device) - 1.0
+            function_state = 2.0 * torch.rand(edge_num, self._hidden_dimension, dtype=torch.float32, device=self._device) - 1.0
+        else:
+            variable_state = torch.zeros(edge_num, self._hidden_dimension, dtype=torch.float32, device=self._device)
+            function_state = torch.zeros(edge_num, self._hidden_dimension, dtype=torch.float32, device=self._device)
+        return (variable_state, function_state)
+
 
 class IdentityPredictor(nn.Module):
     """Prediction = the SATProblem's running solution; on the last call undecided variables are filled

@@ -6,7 +6,11 @@ matrices) and the whole propagate -> decimate -> predict loop, the CNF check, un
 peeling and WalkSAT run as hand-written sm_100a kernels behind the C ABI of libpdp_b200.so.
 
 Scope: the classical model types `p-d-p` (SurveyPropagatorSolver) and `walk-sat`
-(WalkSATSolver).  There is no CPU path and no fallback: CPU tensors or a missing library raise.
+(WalkSATSolver) run entirely in the library's kernels (one persistent launch for the whole loop).  The neural
+model types `p-nd-np` (NeuralSurveyPropagatorSolver) and `np-nd-np` (NeuralPropagatorDecimatorSolver) run the
+reference's iteration structure step by step: message arithmetic, segmented sums, CNF check, simplification and
+WalkSAT are the library's kernels, the dense layers (Linear adaptors, GRU cells, MLPs) are library GEMMs through
+torch in fp32.  There is no CPU path and no fallback: CPU tensors or a missing library raise.
 """
 import os
 
@@ -72,6 +76,21 @@ class SATProblem(object):
         ind = torch.stack([x, x % B0])
         mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0))
         return (mask, mask.transpose(0, 1))
+
+    def edge_problem_index(self):
+        "problem id of every edge (int64 [E]), cached"
+        if getattr(self, "_edge_problem", None) is None:
+            self._edge_problem = self._batch_variable_map.long()[self._graph_map[0].long()]
+        return self._edge_problem
+
+    def update_solution(self, variable_prediction):
+        """_update_solution (reference solver.py:388-399): active variables take the prediction, the others keep
+        their solution; returns the merged [V,1] solution"""
+        m = self._ctx.get_masks()
+        av, sol = m["av"], m["sol"]
+        merged = av * variable_prediction.reshape(-1) + (1.0 - av) * sol
+        self._ctx.set_masks(solution=torch.where(av == 1, merged, sol))
+        return merged.unsqueeze(1)
 
     # ---- state views -----------------------------------------------------------------------------
     @property
@@ -201,11 +220,18 @@ class PropagatorDecimatorSolverBase(nn.Module):
 
         propagator_state = decimator_state = None
         if self._propagator is not None and self._decimator is not None:
-            propagator_state, decimator_state = self._forward_core(
-                init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination)
+            if isinstance(self._decimator, pdp_decimate.SequentialDecimator):
+                propagator_state, decimator_state = self._forward_core(
+                    init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination)
+            else:
+                propagator_state, decimator_state = self._forward_core_stepwise(
+                    init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination)
 
-        # predictor, last call: random fill of the undecided variables (pdp_predict.py:121-126)
-        self._predictor(decimator_state, sat_problem, True)
+        # predictor, last call.  IdentityPredictor: random fill of the undecided variables (pdp_predict.py:121-126);
+        # a neural predictor's output becomes the solution of the active variables (solver.py:342,348)
+        last = self._predictor(decimator_state, sat_problem, True)
+        if not isinstance(self._predictor, pdp_predict.IdentityPredictor) and last[0] is not None:
+            sat_problem.update_solution(last[0])
         prediction = self._local_search(sat_problem, batch_replication)
         if batch_replication > 1:
             prediction, winner = ctx.deduplicate(batch_replication, prediction)
@@ -246,6 +272,40 @@ class PropagatorDecimatorSolverBase(nn.Module):
         # the final message states are exported on first use (the predict path never looks at them)
         state = _DeferredState(ctx)
         return state, state
+
+    def _forward_core_stepwise(self, init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination):
+        """reference solver.py:355-386 for the neural compositions, one iteration at a time like the reference
+        (no variable is ever fixed here, so the masks only change in the initial simplify())."""
+        ctx = sat_problem._ctx
+        propagator_state, decimator_state = init_propagator_state, init_decimator_state
+        active_mask = None if check_termination is None else torch.ones(ctx.B, 1, dtype=torch.uint8, device=ctx.device)
+        edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
+        masked = bool((edge_mask.sum() < ctx.E).item())
+        standard = check_termination is not None and _is_standard_termination(check_termination)
+        rep = sat_problem._batch_replication
+        done = 0
+        for _ in range(int(iteration_num)):
+            propagator_state = self._propagator(propagator_state, decimator_state, sat_problem, False, active_mask)
+            decimator_state = self._decimator(decimator_state, propagator_state, sat_problem, False, active_mask)
+            sat_problem._edge_mask_set = True
+            if masked:
+                decimator_state = tuple(decimator_state[:2]) + (edge_mask,)     # solver.py:373-374
+            done += 1
+            if check_termination is not None:
+                prediction = self._predictor(decimator_state, sat_problem)
+                solution = sat_problem.update_solution(prediction[0])
+                if standard:   # trainer._check_recurrence_termination (trainer.py:150-162) on the library's CNF check
+                    solved, _ = ctx.cnf_eval(solution)
+                    ok = solved > 0.5
+                    if rep > 1:  # a solved replica retires every replica of its problem
+                        ok = ok.reshape(rep, -1).any(0).repeat(rep)
+                    active_mask[(active_mask[:, 0] == 1) & ok, 0] = 0
+                else:
+                    check_termination(active_mask, (solution, prediction[1]), sat_problem)
+                if int(active_mask.sum().item()) <= 0:
+                    break
+        self.last_iterations = torch.tensor([done], dtype=torch.int32, device=ctx.device)
+        return propagator_state, decimator_state
 
     def _local_search(self, sat_problem, batch_replication):
         "WalkSAT post-processing + solution merge (reference solver.py:433-467, 388-399)."
@@ -299,7 +359,45 @@ def _out_of_scope(name):
     return _Stub
 
 
-NeuralPropagatorDecimatorSolver = _out_of_scope("NeuralPropagatorDecimatorSolver")
-NeuralSurveyPropagatorSolver = _out_of_scope("NeuralSurveyPropagatorSolver")
+class NeuralPropagatorDecimatorSolver(PropagatorDecimatorSolverBase):
+    "The fully neural PDP solver, model type `np-nd-np` (reference solver.py:517-537)."
+
+    def __init__(self, device, name, edge_dimension, meta_data_dimension, propagator_dimension, decimator_dimension,
+                 mem_hidden_dimension, agg_hidden_dimension, mem_agg_hidden_dimension, prediction_dimension,
+                 variable_classifier=None, function_classifier=None, dropout=0, local_search_iterations=0, epsilon=0.05):
+        super(NeuralPropagatorDecimatorSolver, self).__init__(
+            device=device, name=name,
+            propagator=pdp_propagate.NeuralMessagePasser(device, edge_dimension, decimator_dimension, meta_data_dimension,
+                                                         propagator_dimension, mem_hidden_dimension, mem_agg_hidden_dimension,
+                                                         agg_hidden_dimension, dropout),
+            decimator=pdp_decimate.NeuralDecimator(device, propagator_dimension, meta_data_dimension, decimator_dimension,
+                                                   mem_hidden_dimension, mem_agg_hidden_dimension, agg_hidden_dimension,
+                                                   edge_dimension, dropout),
+            predictor=pdp_predict.NeuralPredictor(device, decimator_dimension, prediction_dimension, edge_dimension,
+                                                  meta_data_dimension, mem_hidden_dimension, agg_hidden_dimension,
+                                                  mem_agg_hidden_dimension, variable_classifier, function_classifier),
+            local_search_iterations=local_search_iterations, epsilon=epsilon)
+        self.to(device)
+
+
+class NeuralSurveyPropagatorSolver(PropagatorDecimatorSolverBase):
+    "SP propagator with neural adaptors + neural decimator, model type `p-nd-np` (reference solver.py:543-561)."
+
+    def __init__(self, device, name, edge_dimension, meta_data_dimension, decimator_dimension, mem_hidden_dimension,
+                 agg_hidden_dimension, mem_agg_hidden_dimension, prediction_dimension, variable_classifier=None,
+                 function_classifier=None, dropout=0, local_search_iterations=0, epsilon=0.05):
+        super(NeuralSurveyPropagatorSolver, self).__init__(
+            device=device, name=name,
+            propagator=pdp_propagate.SurveyPropagator(device, decimator_dimension, include_adaptors=True),
+            decimator=pdp_decimate.NeuralDecimator(device, (3, 1), meta_data_dimension, decimator_dimension,
+                                                   mem_hidden_dimension, mem_agg_hidden_dimension, agg_hidden_dimension,
+                                                   edge_dimension, dropout),
+            predictor=pdp_predict.NeuralPredictor(device, decimator_dimension, prediction_dimension, edge_dimension,
+                                                  meta_data_dimension, mem_hidden_dimension, agg_hidden_dimension,
+                                                  mem_agg_hidden_dimension, variable_classifier, function_classifier),
+            local_search_iterations=local_search_iterations, epsilon=epsilon)
+        self.to(device)
+
+
 ReinforceSurveyPropagatorSolver = _out_of_scope("ReinforceSurveyPropagatorSolver")
 NeuralSequentialDecimatorSolver = _out_of_scope("NeuralSequentialDecimatorSolver")

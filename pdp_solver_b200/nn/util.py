@@ -1,7 +1,65 @@
 """Utilities of the PDP framework, B200-native (reference src/pdp/nn/util.py)."""
+import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..engine import Context
+
+
+class MessageAggregator(nn.Module):
+    """Deep-set message aggregation at variable / function nodes (reference util.py:13-77), same sub-module
+    names and shapes (state-dict compatible).  The dense layers are library GEMMs (cuBLAS through torch, fp32 like
+    the reference); the segmented sum over a node's edges and the leave-one-out gather are the library's
+    pdp_edge_aggregate kernel on the batch's CSR/CSC (ascending edge order) instead of two sparse mm."""
+
+    def __init__(self, device, input_dimension, output_dimension, mem_hidden_dimension,
+                 mem_agg_hidden_dimension, agg_hidden_dimension, feature_dimension, include_self_message):
+        super(MessageAggregator, self).__init__()
+        self._device = device
+        self._include_self_message = include_self_message
+        self._module_list = nn.ModuleList()
+        if mem_hidden_dimension > 0 and mem_agg_hidden_dimension > 0:
+            self._W1_m = nn.Linear(input_dimension, mem_hidden_dimension, bias=True)
+            self._W2_m = nn.Linear(mem_hidden_dimension, mem_agg_hidden_dimension, bias=False)
+            self._module_list.append(self._W1_m)
+            self._module_list.append(self._W2_m)
+        if agg_hidden_dimension > 0 and mem_agg_hidden_dimension > 0:
+            if mem_hidden_dimension <= 0:
+                mem_agg_hidden_dimension = input_dimension
+            self._W1_a = nn.Linear(mem_agg_hidden_dimension + feature_dimension, agg_hidden_dimension, bias=True)
+            self._W2_a = nn.Linear(agg_hidden_dimension, output_dimension, bias=False)
+            self._module_list.append(self._W1_a)
+            self._module_list.append(self._W2_a)
+        self._agg_hidden_dimension = agg_hidden_dimension
+        self._mem_hidden_dimension = mem_hidden_dimension
+        self._mem_agg_hidden_dimension = mem_agg_hidden_dimension
+
+    def forward(self, state, feature, ctx, by_variable, edge_mask=None):
+        """`ctx`, `by_variable` replace the reference's (mask, mask_transpose) sparse matrices: the node side
+        the edges are summed on (reference util.py:51-77)."""
+        if self._mem_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0:
+            state = F.logsigmoid(self._W2_m(F.logsigmoid(self._W1_m(state))))
+        if edge_mask is not None:
+            state = state * edge_mask
+        node_sum, loo = ctx.edge_aggregate(state, by_variable, leave_one_out=not self._include_self_message)
+        aggregated_state = node_sum if self._include_self_message else loo
+        if feature is not None:
+            aggregated_state = torch.cat((aggregated_state, feature), 1)
+        if self._agg_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0:
+            aggregated_state = F.logsigmoid(self._W2_a(F.logsigmoid(self._W1_a(aggregated_state))))
+        return aggregated_state
+
+
+class Perceptron(nn.Module):
+    "The 1-hidden-layer classifier the trainer builds (reference trainer.py:20-29)."
+
+    def __init__(self, input_dimension, hidden_dimension, output_dimension):
+        super(Perceptron, self).__init__()
+        self._layer1 = nn.Linear(input_dimension, hidden_dimension)
+        self._layer2 = nn.Linear(hidden_dimension, output_dimension, bias=False)
+
+    def forward(self, inp):
+        return torch.sigmoid(self._layer2(F.relu(self._layer1(inp))))
 
 
 class SatCNFEvaluator(nn.Module):

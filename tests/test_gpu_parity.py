@@ -411,3 +411,65 @@ def test_blocked_path_with_signed_input_surveys():
         outs.append((C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["sol"])))
     for a, b in zip(*outs):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# neural model types (p-nd-np, np-nd-np) against the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+def _neural_model(z):
+    from pdp_solver_b200.nn import solver as S
+    from pdp_solver_b200.nn import util as U
+    H, MH, AH, MAH, CH = [int(x) for x in z["dims"]]
+    clf = U.Perceptron(H, CH, 1)
+    if str(z["model_type"]) == "p-nd-np":
+        model = S.NeuralSurveyPropagatorSolver(dev(), "m", edge_dimension=1, meta_data_dimension=0, decimator_dimension=H,
+                                               mem_hidden_dimension=MH, agg_hidden_dimension=AH, mem_agg_hidden_dimension=MAH,
+                                               prediction_dimension=1, variable_classifier=clf, function_classifier=None,
+                                               dropout=0, local_search_iterations=0, epsilon=0.5)
+    else:
+        model = S.NeuralPropagatorDecimatorSolver(dev(), "m", edge_dimension=1, meta_data_dimension=0, propagator_dimension=H,
+                                                  decimator_dimension=H, mem_hidden_dimension=MH, agg_hidden_dimension=AH,
+                                                  mem_agg_hidden_dimension=MAH, prediction_dimension=1, variable_classifier=clf,
+                                                  function_classifier=None, dropout=0, local_search_iterations=0, epsilon=0.5)
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    for pair in str(z["w_alias"]).split(";"):
+        if pair:
+            k, src = pair.split("=")
+            sd[k] = sd[src]
+    model.load_state_dict(sd, strict=True)       # same keys and shapes as the reference's state_dict
+    return model.to(dev()).eval()
+
+
+@pytest.mark.parametrize("path", golden("neural_*.npz"), ids=name)
+def test_neural_forward_vs_reference(path):
+    """p-nd-np / np-nd-np forward() with the reference's weights and injected initial states: per-iteration
+    predictions, iteration count, final states and final prediction (dense layers are fp32 library GEMMs whose
+    accumulation order differs from the CPU reference's: 2e-4)."""
+    z = load(path)
+    model = _neural_model(z)
+    gm, bvm, bfm, ef = T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"])
+    init = ((T(z["init_p0"]), T(z["init_p1"])), (T(z["init_d0"]), T(z["init_d1"])))
+    preds = []
+    orig = model._predictor.forward
+
+    def hook(decimator_state, sat_problem, last_call=False):
+        out = orig(decimator_state, sat_problem, last_call)
+        preds.append(C(out[0]).reshape(-1))
+        return out
+
+    model._predictor.forward = hook
+
+    def termination(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+    with torch.no_grad():
+        (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                                  meta_data=None, is_training=False, iteration_num=int(z["T"]), check_termination=termination,
+                                  simplify=True, batch_replication=1)
+    ref = z["preds"]
+    assert len(preds) == ref.shape[0], "iteration count differs"
+    tol = 2e-4
+    assert max(maxdiff(p, r) for p, r in zip(preds, ref)) < tol
+    assert maxdiff(C(vp).reshape(-1), z["pred"]) < tol
+    for ours, key in ((ps[0], "final_p0"), (ps[1], "final_p1"), (ds[0], "final_d0"), (ds[1], "final_d1")):
+        assert maxdiff(C(ours), z[key]) < tol, key
