@@ -333,7 +333,37 @@ def gen_neural(name, model_type, batch, T_iters, seed, dims, only=None):
     save(name, **arrays)
 
 
+# ----------------------------------------------------------------------------------------------
+# batch replication (-b): replicated forward, termination across replicas, WalkSAT, _deduplicate
+# ----------------------------------------------------------------------------------------------
+def gen_replicated(name, batch, T_iters, W, epsilon, seed, b, **kw):
+    r = run_reference_forward(batch, T_iters, W, epsilon, False, seed, b=b, record_iters=False, **kw)
+    gm, bvm, bfm, ef = batch
+    V, B = bvm.shape[0] * b, (int(bvm.max()) + 1) * b
+    draws = r["rec"]["draws"]
+    fill = np.zeros(0, np.float32)
+    rvl, rcl = [], []
+    for j, d in enumerate(draws):
+        if d.ndim == 2:
+            rvl.append(d.reshape(-1))
+        elif j > 0 and draws[j - 1].ndim == 2:
+            rcl.append(d.reshape(-1))
+        else:
+            assert j == 0
+            fill = d.reshape(-1)
+    rv = np.stack(rvl) if rvl else np.zeros((0, V), np.float32)
+    rc = np.stack(rcl) if rcl else np.zeros((0, B), np.float32)
+    ev = np.array(r["rec"]["events"], dtype=np.int64).reshape(-1, 3)
+    save(name, graph_map=gm, bvm=bvm, bfm=bfm, ef=ef, T=T_iters, W=W, epsilon=epsilon, b=b, tol=kw.get("tol", 0.02),
+         t_max=kw.get("t_max", 100), pred=r["pred"], solved=r["solved"], n_unsat=r["n_unsat"], events=ev, fill=fill,
+         rand_var=rv, rand_coin=rc, init_dq=r["init"][1][0], init_df=r["init"][1][1])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "replicated":
+        gen_replicated("rep_b3_a", cnfgen.random_batch(5, 30, 3, 3.7, 61), 120, 25, 0.5, 9, 3, t_max=30)
+        gen_replicated("rep_b2_b", cnfgen.mixed_batch([(30, 3, 3.9), (20, 5, 14.0), (25, 3, 3.0)], 62), 100, 30, 0.4, 10, 2, t_max=25)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "neural":
         gen_neural("neural_pndnp_a", "p-nd-np", cnfgen.random_batch(4, 20, 3, 3.8, 51), 12, 5, (24, 16, 16, 8, 8))
         gen_neural("neural_pndnp_b", "p-nd-np", ragged_batch(52), 8, 6, (20, 12, 12, 6, 6))

@@ -473,3 +473,28 @@ def test_neural_forward_vs_reference(path):
     assert maxdiff(C(vp).reshape(-1), z["pred"]) < tol
     for ours, key in ((ps[0], "final_p0"), (ps[1], "final_p1"), (ds[0], "final_d0"), (ds[1], "final_d1")):
         assert maxdiff(C(ours), z[key]) < tol, key
+
+
+@pytest.mark.parametrize("path", golden("rep_*.npz"), ids=name)
+def test_batch_replication_vs_reference(path):
+    """-b replicas through the CUDA path: replicated batch, fused loop with cross-replica termination
+    (trainer.py:157-160), WalkSAT with the reference's draws, _deduplicate -- final prediction bit exact"""
+    from pdp_solver_b200.engine import Context
+    from tests.test_oracle_golden import _replicate
+    z = load(path)
+    b = int(z["b"])
+    gm, bvm, bfm, ef = _replicate(z)
+    ctx = Context(T(gm), T(bvm), T(bfm), T(ef))
+    ctx.simplify()
+    ctx.load_state((T(z["init_dq"]), T(z["init_df"])), (T(z["init_dq"]), T(z["init_df"])))
+    ctx.sp_run(int(z["T"]), float(z["tol"]), int(z["t_max"]), True, batch_replication=b, sync=True)
+    n_act = ctx.count_active_variables()
+    assert n_act == z["fill"].shape[0]
+    if n_act:
+        ctx.random_fill(T(z["fill"]))
+    pred, _ = ctx.walksat(int(z["W"]), float(z["epsilon"]), T(z["rand_var"]), T(z["rand_coin"]), batch_replication=b, sync=True)
+    out, _ = ctx.deduplicate(b, pred)
+    assert maxdiff(C(out), z["pred"]) == 0
+    o = Context(T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"]))
+    solved, nun = o.cnf_eval(out)
+    assert maxdiff(C(solved), z["solved"]) == 0 and maxdiff(C(nun), z["n_unsat"]) == 0

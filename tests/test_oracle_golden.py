@@ -87,3 +87,31 @@ def test_forward_trajectory(path, strict):
     z = load(path)
     worst = _replay(z, strict)
     assert worst < 1e-3
+
+
+def _replicate(z):
+    """replica r of problem j gets problem id r*B + j (reference solver.py:56-82)"""
+    gm, bvm, bfm, ef, b = z["graph_map"], z["bvm"], z["bfm"], z["ef"], int(z["b"])
+    V, F, B = bvm.shape[0], bfm.shape[0], int(bvm.max()) + 1
+    gmr = np.concatenate([gm + np.array([[r * V], [r * F]], dtype=gm.dtype) for r in range(b)], axis=1)
+    return (gmr.astype(np.int32), np.concatenate([bvm + r * B for r in range(b)]).astype(np.int32),
+            np.concatenate([bfm + r * B for r in range(b)]).astype(np.int32), np.concatenate([ef] * b).astype(np.float32))
+
+
+@pytest.mark.parametrize("path", golden("rep_*.npz"), ids=name)
+def test_batch_replication(path):
+    """-b replicas: termination across replicas, WalkSAT with the recorded draws, _deduplicate (solver.py:401-431)"""
+    from oracle import pdp_oracle as po
+    z = load(path)
+    b = int(z["b"])
+    o = po.Oracle(*_replicate(z), strict=True)
+    o.simplify()
+    o.set_state((z["init_dq"], z["init_df"]), (z["init_dq"], z["init_df"]))
+    o.run(int(z["T"]), float(z["tol"]), int(z["t_max"]), True, b)
+    n_act = o.count_active_variables()
+    assert n_act == z["fill"].shape[0]
+    if n_act:
+        o.random_fill(z["fill"])
+    pred, _ = o.local_search(int(z["W"]), float(z["epsilon"]), z["rand_var"], z["rand_coin"], b)
+    out, _ = o.deduplicate(b, pred)
+    assert maxdiff(out, z["pred"]) == 0
