@@ -693,6 +693,15 @@ __device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats&
 #define PIPE_SLOT_BYTES (4 * PDP_BLK_C)
 #define PIPE_MAX_BLOCKS 32 // blocks of one CTA per pass handled per pipeline run
 
+// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in each
+// phase of the staged passes to the trace buffer: [0..2] clause wait-for-load / node / write-out, [3..5] variable
+#ifdef PDP_PHASE_TIMING
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_ADD(slot_) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot_) do {} while (0)
+#endif
 #ifdef PDP_PHASE_TIMING
 #define PT_DECL() long long _pt = clock64()
 #define PT_ADD(slot_) do { if (t == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
@@ -841,6 +850,350 @@ __device__ __forceinline__ void pipe_var_pass(const KArgs& A, int r, bool use_ma
         __syncthreads();
     }
 }
+
+// ================================================================================================
+// TMA-staged passes.  Everything a block's node phase reads -- the message regions, the 16-bit permutation
+// of the block's slots and the edge-mask words -- is contiguous in global memory, so ONE thread brings it
+// into a shared-memory slot with bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) while
+// the CTA still works on the previous block in the other slot.  The node phases gather through the
+// permutation (slot of the node's j-th edge -> staged position) instead of reading a scattered copy, and
+// leave their results at the same staged positions; the write-out reads them through vsrc2 / csrc2.
+// ================================================================================================
+#if PDP_TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// 16-byte aligned source / destination, size a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// byte offsets inside a slot
+#define TS_VAR_SA 0
+#define TS_VAR_SB ((PDP_BLK_V + 4) * 4)
+#define TS_VAR_PERM (2 * (PDP_BLK_V + 4) * 4)
+#define TS_VAR_MASK (TS_VAR_PERM + (PDP_BLK_V + 8) * 2)
+#define TS_VAR_SKIP (TS_VAR_MASK + (PDP_BLK_V / 32 + 8) * 4)
+#define TS_CL_X 0
+#define TS_CL_PERM ((PDP_BLK_C + 4) * 4)
+#define TS_CL_MASK (TS_CL_PERM + (PDP_BLK_C + 8) * 2)
+#define TS_CL_SKIP (TS_CL_MASK + (PDP_BLK_C / 32 + 8) * 4)
+static_assert(TS_VAR_SKIP + PDP_BLK_V / 8 + 16 <= PDP_TMA_SLOT_BYTES, "variable slot too large");
+static_assert(TS_CL_SKIP + PDP_BLK_C / 8 + 16 <= PDP_TMA_SLOT_BYTES, "clause slot too large");
+static_assert(TS_VAR_SB % 16 == 0 && TS_VAR_PERM % 16 == 0 && TS_VAR_MASK % 16 == 0 && TS_CL_PERM % 16 == 0 && TS_CL_MASK % 16 == 0, "TMA alignment");
+
+struct TmaState {          // per-CTA pipeline state living in registers across the whole kernel
+    uint32_t parity[2];
+};
+struct TmaSmem {
+    uint64_t bar[2];
+    int any_skip[2];
+    int blk[PIPE_MAX_BLOCKS];
+};
+
+// staged geometry of a block: region [base, base + n_st) with base = e0 & ~3
+struct Staged {
+    int base, off, n_st;       // off = e0 - base; n_st = staged floats (multiple of 4)
+    int pbase, poff, n_perm;   // permutation table: 8-element aligned start, staged 16-bit entries (multiple of 8)
+    int wbase, woff, n_w;      // mask words: 4-word aligned start
+};
+__device__ __forceinline__ Staged staged_of(int e0, int ne) {
+    Staged S;
+    S.base = e0 & ~3; S.off = e0 - S.base; S.n_st = (S.off + ne + 3) & ~3;
+    S.pbase = e0 & ~7; S.poff = e0 - S.pbase; S.n_perm = (S.poff + ne + 7) & ~7;
+    const int w0 = S.base >> 5, w1 = (S.base + S.n_st - 1) >> 5;
+    S.wbase = w0 & ~3; S.woff = w0 - S.wbase; S.n_w = (w1 - S.wbase + 1 + 3) & ~3;
+    return S;
+}
+// is the edge at staged position x masked?  (mask words staged from word S.wbase)
+__device__ __forceinline__ bool staged_mbit(const uint32_t* mw, const Staged& S, int x) {
+    const int bitpos = (S.base & 31) + x;
+    return (mw[S.woff + (bitpos >> 5)] >> (bitpos & 31)) & 1u;
+}
+
+__device__ __forceinline__ void tma_issue_clause(const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool masked,
+                                                 unsigned char* slot, uint64_t* bar) {
+    const Staged S = staged_of(B.e0, B.ne);
+    const bool any = B.ne > 0;
+    const uint32_t bytes = any ? ((uint32_t)S.n_st * 4u + (uint32_t)S.n_perm * 2u + (masked ? (uint32_t)S.n_w * 4u : 0u)) : 0u;
+    mbar_expect_tx(bar, bytes);
+    if (!any) return;
+    tma_load_1d(slot + TS_CL_X, s.qu + S.base, (uint32_t)S.n_st * 4u, bar);
+    tma_load_1d(slot + TS_CL_PERM, g.cperm + S.pbase, (uint32_t)S.n_perm * 2u, bar);
+    if (masked) tma_load_1d(slot + TS_CL_MASK, g.qmask + S.wbase, (uint32_t)S.n_w * 4u, bar);
+}
+__device__ __forceinline__ void tma_issue_var(const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool masked, const float* en,
+                                              const float* eo, unsigned char* slot, uint64_t* bar) {
+    const Staged S = staged_of(B.e0, B.ne);
+    const bool any = B.ne > 0;
+    const uint32_t bytes = any ? (2u * (uint32_t)S.n_st * 4u + (uint32_t)S.n_perm * 2u + (masked ? (uint32_t)S.n_w * 4u : 0u)) : 0u;
+    mbar_expect_tx(bar, bytes);
+    if (!any) return;
+    tma_load_1d(slot + TS_VAR_SA, en + S.base, (uint32_t)S.n_st * 4u, bar);
+    tma_load_1d(slot + TS_VAR_SB, eo + S.base, (uint32_t)S.n_st * 4u, bar);
+    tma_load_1d(slot + TS_VAR_PERM, g.vperm + S.pbase, (uint32_t)S.n_perm * 2u, bar);
+    if (masked) tma_load_1d(slot + TS_VAR_MASK, g.vmask + S.wbase, (uint32_t)S.n_w * 4u, bar);
+}
+
+// the CTA's non-idle blocks of this pass into sm.blk (uniform over the CTA)
+template <bool VAR>
+__device__ __forceinline__ int tma_collect(const pdp_graph& g, const pdp_state& s, TmaSmem& sm, int& next_blk) {
+    const int total = VAR ? g.nvb : g.ncb;
+    int n = 0;
+    while (next_blk < total && n < PIPE_MAX_BLOCKS) {
+        const int blk = next_blk;
+        next_blk += gridDim.x;
+        const BlkGeo B = VAR ? var_block(g, blk) : clause_block(g, blk);
+        if (B.n1 <= B.n0) continue;
+        if (blk_idle(s, B.b0, B.b1)) continue;
+        if (threadIdx.x == 0) sm.blk[n] = blk;
+        ++n;
+    }
+    __syncthreads();
+    return n;
+}
+
+#define NT PDP_SWEEP_THREADS
+__device__ __forceinline__ void tma_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, TmaSmem& sm, TmaState& st) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    float* __restrict__ eout = s.eta[r ^ 1];
+    const int tid = threadIdx.x;
+    int next_blk = blockIdx.x;
+    for (;;) {
+        const int n = tma_collect<false>(g, s, sm, next_blk);
+        if (n == 0) break;
+        if (tid == 0) {
+            const BlkGeo B0 = clause_block(g, sm.blk[0]);
+            tma_issue_clause(g, s, B0, use_mask && (B0.multi() || s.masked[B0.b0]), smem, &sm.bar[0]);
+        }
+        for (int i = 0; i < n; ++i) {
+            const int slot = i & 1;
+            unsigned char* base = smem + slot * PDP_TMA_SLOT_BYTES;
+            float* X = reinterpret_cast<float*>(base + TS_CL_X);
+            const uint16_t* perm = reinterpret_cast<const uint16_t*>(base + TS_CL_PERM);
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(base + TS_CL_MASK);
+            uint32_t* skip = reinterpret_cast<uint32_t*>(base + TS_CL_SKIP);
+            const int blk = sm.blk[i];
+            const BlkGeo B = clause_block(g, blk);
+            const Staged S = staged_of(B.e0, B.ne);
+            const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
+            if (i + 1 < n && tid == 0) {   // the other slot is free (its block was written out before the last barrier)
+                const BlkGeo Bn = clause_block(g, sm.blk[i + 1]);
+                tma_issue_clause(g, s, Bn, use_mask && (Bn.multi() || s.masked[Bn.b0]), smem + (slot ^ 1) * PDP_TMA_SLOT_BYTES, &sm.bar[slot ^ 1]);
+            }
+            for (int w = tid; w < (S.n_st + 31) / 32; w += NT) skip[w] = 0u;
+            if (tid == 0) sm.any_skip[slot] = 0;
+            PHASE_T0();
+            mbar_wait(&sm.bar[slot], st.parity[slot]);
+            st.parity[slot] ^= 1u;
+            __syncthreads();
+            PHASE_ADD(0);
+            // ---- thread per clause: x = log(max(q,1e-40)) * em gathered through the permutation
+            const bool multi = B.multi();
+            const int ku = g.cb_k[blk];
+            for (int a = B.n0 + tid; a < B.n1; a += NT) {
+                int lo, k;
+                if (ku) { k = ku; lo = (a - B.n0) * ku; }
+                else { lo = g.cl_ptr[a] - B.e0; k = g.cl_ptr[a + 1] - B.e0 - lo; }
+                int b = B.b0;
+                if (multi) {
+                    b = g.bfm[a];
+                    if (!blk_problem_runs(s, b)) {
+                        for (int j = 0; j < k; ++j) { const int x = perm[S.poff + lo + j]; atomicOr(&skip[x >> 5], 1u << (x & 31)); }
+                        sm.any_skip[slot] = 1;
+                        continue;
+                    }
+                }
+                bool made_nan = false;
+                if (k <= 8) {
+                    float xv[8]; int xs[8];
+                    float tot = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < k) {
+                            const int x = perm[S.poff + lo + j];
+                            float v = L40(X[x]);
+                            if (masked && staged_mbit(mw, S, x)) v = v * 0.f;
+                            xs[j] = x; xv[j] = v; tot += v;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < k) {
+                            const float nv = X30(tot - xv[j]);
+                            made_nan |= (nv != nv);
+                            X[xs[j]] = nv;
+                        }
+                    }
+                } else {
+                    float tot = 0.f;
+                    for (int j = 0; j < k; ++j) {
+                        const int x = perm[S.poff + lo + j];
+                        float v = L40(X[x]);
+                        if (masked && staged_mbit(mw, S, x)) v = v * 0.f;
+                        X[x] = v; tot += v;
+                    }
+                    for (int j = 0; j < k; ++j) {
+                        const int x = perm[S.poff + lo + j];
+                        const float nv = X30(tot - X[x]);
+                        made_nan |= (nv != nv);
+                        X[x] = nv;
+                    }
+                }
+                if (made_nan) s.nanpend[b] = 1;
+            }
+            __syncthreads();
+            PHASE_ADD(1);
+            ph_write_out<NT>(tid, g.csrc2 + B.e0, g.cdst + B.e0, B.ne, X, skip, sm.any_skip[slot] != 0, eout);
+            fence_proxy_async();   // generic-proxy accesses of this slot before the next bulk copy into it
+            __syncthreads();
+            PHASE_ADD(2);
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem,
+                                             TmaSmem& sm, TmaState& st) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    __shared__ BlkStats sm_st;
+    const float* __restrict__ en = s.eta[r ^ 1];
+    const float* __restrict__ eo = s.eta[r];
+    const int tid = threadIdx.x;
+    KeyedReducer<StatAcc> red;
+    int next_blk = blockIdx.x;
+    for (;;) {
+        const int n = tma_collect<true>(g, s, sm, next_blk);
+        if (n == 0) break;
+        if (tid == 0) {
+            const BlkGeo B0 = var_block(g, sm.blk[0]);
+            tma_issue_var(g, s, B0, (use_mask || em_set) && (B0.multi() || s.masked[B0.b0]), en, eo, smem, &sm.bar[0]);
+        }
+        for (int i = 0; i < n; ++i) {
+            const int slot = i & 1;
+            unsigned char* base = smem + slot * PDP_TMA_SLOT_BYTES;
+            float* SA = reinterpret_cast<float*>(base + TS_VAR_SA);   // eta(t), then q(t)
+            float* SB = reinterpret_cast<float*>(base + TS_VAR_SB);   // eta(t-1), then y
+            const uint16_t* perm = reinterpret_cast<const uint16_t*>(base + TS_VAR_PERM);
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(base + TS_VAR_MASK);
+            uint32_t* skip = reinterpret_cast<uint32_t*>(base + TS_VAR_SKIP);
+            const BlkGeo B = var_block(g, sm.blk[i]);
+            const Staged S = staged_of(B.e0, B.ne);
+            const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
+            if (i + 1 < n && tid == 0) {
+                const BlkGeo Bn = var_block(g, sm.blk[i + 1]);
+                tma_issue_var(g, s, Bn, (use_mask || em_set) && (Bn.multi() || s.masked[Bn.b0]), en, eo,
+                              smem + (slot ^ 1) * PDP_TMA_SLOT_BYTES, &sm.bar[slot ^ 1]);
+            }
+            const bool multi = B.multi();
+            const bool local_stats = multi && (B.b1 - B.b0 < PDP_STAT_SLOTS);
+            for (int w = tid; w < (S.n_st + 31) / 32; w += NT) skip[w] = 0u;
+            if (tid == 0) sm.any_skip[slot] = 0;
+            if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
+            PHASE_T0();
+            mbar_wait(&sm.bar[slot], st.parity[slot]);
+            st.parity[slot] ^= 1u;
+            __syncthreads();
+            PHASE_ADD(3);
+            // ---- thread per variable (descending degree, alternating round direction)
+            for (int vbase = B.n0, round = 0; vbase < B.n1; vbase += NT, ++round) {
+                const int ti = (round & 1) ? (vbase + NT - 1 - tid) : (vbase + tid);
+                if (ti >= B.n1) continue;
+                const int2 ve = __ldg(&g.vsort[ti]);
+                const int i_var = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
+                const uint16_t* pj = perm + S.poff + lo;
+                int b = B.b0;
+                if (multi) {
+                    b = g.bvm[i_var];
+                    if (!blk_problem_runs(s, b)) {
+                        for (int j = 0; j < deg; ++j) { const int x = pj[j] & 0x7fff; atomicOr(&skip[x >> 5], 1u << (x & 31)); }
+                        sm.any_skip[slot] = 1;
+                        continue;
+                    }
+                }
+                const uint32_t act = s.av[i_var];
+                float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
+                for (int j = 0; j < deg; ++j) {
+                    const uint32_t pw = pj[j];
+                    const int x = pw & 0x7fff;
+                    const uint32_t negm = 0u - (pw >> 15);     // all ones: negative literal
+                    const bool m = masked && staged_mbit(mw, S, x);
+                    const float xn = SA[x], xo = SB[x];
+                    float y = L40(1.f - xo);
+                    if (use_mask && m) y = y * 0.f;
+                    SB[x] = y;
+                    // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
+                    const float zy = 0.f * y;
+                    P += fsel(negm, zy, y);
+                    N += fsel(negm, y, zy);
+                    const float c = X30(30.f * xn);
+                    n0 += xn * c; d0 += c;
+                    if (has_prev) {
+                        float d = fabsf(xo - xn);
+                        if (em_set && m) d = d * 0.f;
+                        const float cd = X30(30.f * d);
+                        n1 += d * cd; d1 += cd;
+                    }
+                }
+                const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
+                const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
+                if (!multi) {
+                    red.touch(s, b);
+                    red.acc.add(sm0, sm1, has_prev, act);
+                } else {
+                    StatAcc one;
+                    one.reset();
+                    one.add(sm0, sm1, has_prev, act);
+                    if (local_stats) {
+                        const int lb = b - B.b0;
+                        atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
+                        if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
+                        if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
+                        if (act) atomicAdd(&sm_st.nav[lb], act);
+                    } else {
+                        one.commit(s, b);
+                    }
+                }
+                float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
+                sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
+                sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
+                bool made_nan = false;
+                for (int j = 0; j < deg; ++j) {
+                    const uint32_t pw = pj[j];
+                    const int x = pw & 0x7fff;
+                    const uint32_t negm = 0u - (pw >> 15);
+                    const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), SB[x]);
+                    made_nan |= (u != u);
+                    SA[x] = u;
+                }
+                if (made_nan) s.nanpend[b] = 1;
+            }
+            __syncthreads();
+            PHASE_ADD(4);
+            if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
+            ph_write_out<NT>(tid, g.vsrc2 + B.e0, g.vdst + B.e0, B.ne, SA, skip, sm.any_skip[slot] != 0, s.qu);
+            fence_proxy_async();
+            red.finish(s);   // block-level merge of the statistics; its barriers also close the slot
+            PHASE_ADD(5);
+        }
+    }
+}
+#undef NT
+#endif  // PDP_TMA
 
 // ================================================================================================
 // serial passes: the whole CTA runs load, node phase and write-out of a block back to back

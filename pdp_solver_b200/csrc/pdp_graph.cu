@@ -79,6 +79,10 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.cinv = k.take<uint16_t>(E);
     g.vsrc = k.take<uint16_t>(E);
     g.csrc = k.take<uint16_t>(E);
+    g.vperm = k.take<uint16_t>(E + 16);
+    g.cperm = k.take<uint16_t>(E + 16);
+    g.vsrc2 = k.take<uint16_t>(E);
+    g.csrc2 = k.take<uint16_t>(E);
     g.vdst = k.take<int32_t>(E);
     g.cdst = k.take<int32_t>(E);
     g.vsort = k.take<int2>(V);

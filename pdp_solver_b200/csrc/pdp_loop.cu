@@ -117,6 +117,16 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     int gen_left = FAST ? s.ctrl[CTRL_GEN_ITERS] : 0;
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
     int executed = 0;
+#if PDP_TMA
+    __shared__ TmaSmem tma_sm;
+    TmaState tma_st;
+    tma_st.parity[0] = tma_st.parity[1] = 0u;
+    if (FAST) {
+        if (threadIdx.x == 0) { mbar_init(&tma_sm.bar[0], 1); mbar_init(&tma_sm.bar[1], 1); fence_mbar_init(); }
+        fence_proxy_async();
+        __syncthreads();
+    }
+#endif
 #ifdef PDP_PHASE_TIMING
 #define GRID_SYNC() do { const long long _g0 = clock64(); grid.sync(); if (threadIdx.x == 0 && A.trace) atomicAdd(&A.trace[7], (int)((clock64() - _g0) >> 10)); } while (0)
 #else
@@ -143,8 +153,12 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #ifdef PDP_STAGGER_EXPERIMENT
             if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 16) & 0xff) * 1024) __nanosleep(200); }
 #endif
+#if PDP_TMA
+            tma_clause_pass(A, r, use_mask, smem_dyn, tma_sm, tma_st);
+#else
             if (PDP_PIPELINE) pipe_clause_pass(A, r, use_mask, smem_dyn);
             else blk_clause_pass(A, r, use_mask, smem_dyn);
+#endif
             if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
@@ -157,8 +171,12 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #ifdef PDP_STAGGER_EXPERIMENT
             if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 8) & 0xff) * 1024) __nanosleep(200); }
 #endif
+#if PDP_TMA
+            tma_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn, tma_sm, tma_st);
+#else
             if (PDP_PIPELINE) pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
             else blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
+#endif
             if (s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
                 gen_stats<GEN_NAN>(A, w, has_prev, em_set);
