@@ -409,6 +409,16 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
     for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
 }
 
+#ifndef PDP_UNROLL_WO
+#define PDP_UNROLL_WO 8    // elements per thread in flight: write-out (2 loads each)
+#endif
+#ifndef PDP_UNROLL_CL
+#define PDP_UNROLL_CL 8    // clause load (2-3 loads each)
+#endif
+#ifndef PDP_UNROLL_VL
+#define PDP_UNROLL_VL 6    // variable load (3-4 loads each)
+#endif
+
 // ================================================================================================
 // phase bodies of the blocked passes, written for a GROUP of G threads with local index t: the whole CTA
 // in the serial passes, one of the two warp groups in the pipelined passes
@@ -420,7 +430,7 @@ template <int G, bool SKIP>
 __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
                                                const float* plane, const uint32_t* skip, float* __restrict__ out) {
     int w = t;
-    constexpr int U = 8;
+    constexpr int U = PDP_UNROLL_WO;
     for (; w + (U - 1) * G < ne; w += U * G) {
         int l[U], d[U];
 #pragma unroll
@@ -447,7 +457,7 @@ template <int G, bool MASKED>
 __device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
                                                const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
     int x = t;
-    constexpr int U = 8;
+    constexpr int U = PDP_UNROLL_CL;
     for (; x + (U - 1) * G < ne; x += U * G) {
         float q[U]; int l[U]; bool m[U];
 #pragma unroll
@@ -561,7 +571,7 @@ template <int G, bool MASKED>
 __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
                                             const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
     int x = t;
-    constexpr int U = 6;
+    constexpr int U = PDP_UNROLL_VL;
     for (; x + (U - 1) * G < ne; x += U * G) {
         uint32_t n[U], o[U], iv[U];
 #pragma unroll

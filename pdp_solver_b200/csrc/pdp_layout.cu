@@ -93,6 +93,7 @@ __global__ void k_fill_writeout(int64_t E, const int32_t* __restrict__ kb, const
     }
 }
 
+#if PDP_TMA
 // tables of the TMA-staged passes.  A block's region is staged from its 16-byte aligned start
 // (first position & ~3), so a staged position is (layout position) - (first position & ~3).
 __global__ void k_fill_staged_tables(pdp_graph g) {
@@ -110,6 +111,7 @@ __global__ void k_fill_staged_tables(pdp_graph g) {
         g.csrc2[c] = (uint16_t)(g.c_qpos[e0 + g.csrc[c]] - (e0 & ~3));
     }
 }
+#endif
 
 // degree-sorted variable order: key = block << 14 | (16383 - degree)
 __global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
@@ -254,8 +256,10 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
                                     var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.vsrc : g.csrc, var_side ? g.vdst : g.cdst);
         LLK();
     }
+#if PDP_TMA
     k_fill_staged_tables<<<G1(E)>>>(g);
     LLK();
+#endif
     // ---- per block: variables by descending degree (uniform trip counts inside a warp), clause degree
     if (g.V <= E && g.max_var_degree < 16384 && g.nvb < (1 << 17)) {
         k_key_vsort<<<G1(g.V)>>>(g, S0, S2);
@@ -304,11 +308,11 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
             if (w > e0 && g.vdst[w] <= g.vdst[w - 1]) atomicAdd(&errs[3], 1);
             if (!(atomicOr(&seen[p >> 5], 1u << (p & 31)) & (1u << (p & 31)))) atomicAdd(&errs[6], 1);
         }
-        for (int p = e0; p < e1; ++p) {
+        for (int p = e0; p < e1 && PDP_TMA; ++p) {
             const int x = (int)(g.vperm[p] & 0x7fff) + (e0 & ~3);
             if (x != g.p_vpos[p] || ((g.vperm[p] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) atomicAdd(&errs[1], 1);
         }
-        for (int w = e0; w < e1; ++w) {
+        for (int w = e0; w < e1 && PDP_TMA; ++w) {
             const int p = e0 + (int)g.vsrc[w];
             if ((int)g.vsrc2[w] + (e0 & ~3) != g.p_vpos[p]) atomicAdd(&errs[3], 1);
         }
@@ -336,8 +340,8 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
             if (w > e0 && g.cdst[w] <= g.cdst[w - 1]) atomicAdd(&errs[4], 1);
             if (!(atomicOr(&seen_c[c >> 5], 1u << (c & 31)) & (1u << (c & 31)))) atomicAdd(&errs[7], 1);
         }
-        for (int c = e0; c < e1; ++c) if ((int)g.cperm[c] + (e0 & ~3) != g.c_qpos[c]) atomicAdd(&errs[2], 1);
-        for (int w = e0; w < e1; ++w) if ((int)g.csrc2[w] + (e0 & ~3) != g.c_qpos[e0 + (int)g.csrc[w]]) atomicAdd(&errs[4], 1);
+        for (int c = e0; c < e1 && PDP_TMA; ++c) if ((int)g.cperm[c] + (e0 & ~3) != g.c_qpos[c]) atomicAdd(&errs[2], 1);
+        for (int w = e0; w < e1 && PDP_TMA; ++w) if ((int)g.csrc2[w] + (e0 & ~3) != g.c_qpos[e0 + (int)g.csrc[w]]) atomicAdd(&errs[4], 1);
         const int k = g.cb_k[blk];
         bool uni = (a1 > a0);
         for (int a = a0; a < a1; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != g.cl_ptr[a0 + 1] - g.cl_ptr[a0]) uni = false;

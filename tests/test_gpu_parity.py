@@ -498,3 +498,46 @@ def test_batch_replication_vs_reference(path):
     o = Context(T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"]))
     solved, nun = o.cnf_eval(out)
     assert maxdiff(C(solved), z["solved"]) == 0 and maxdiff(C(nun), z["n_unsat"]) == 0
+
+
+def test_full_size_properties():
+    """BASELINE.json's full size (random 3-SAT, n = 1 000 000, alpha = 4.2; the oracle needs ~1 s per iteration
+    there) through size-independent properties: (1) the blocked shared-memory passes and the generic
+    thread-per-node passes agree bit for bit after 6 iterations; (2) the per-problem unsatisfied-clause count of
+    the CNF evaluator equals the energy of the same assignment with every node active (two independent kernels);
+    (3) the verdict is "solved" exactly where no clause is unsatisfied, and the merged prediction is 0/1 valued
+    except for variables that occur in no clause (peeled to 0.5, reference solver.py:180-203)."""
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    batch = cnfgen.random_batch(2, 1000000, 3, 4.2, 99)
+    gm, bvm, bfm, ef = [T(x) for x in batch]
+    E, V, F = gm.shape[1], bvm.shape[0], bfm.shape[0]
+    q3 = torch.full((E, 3), 1.0 / 3.0, device=dev())
+    fs2 = torch.zeros((E, 2), device=dev())
+    fs2[:, 0] = 0.5
+    outs = []
+    for generic in (False, True):
+        ctx = Context(gm, bvm, bfm, ef, batch_size=2)
+        errs, info = ctx.check_layout()
+        assert info["blocked"] == 1 and errs[:6] == [0] * 6 and errs[6] == E and errs[7] == E
+        ctx.simplify()
+        ctx.load_state((q3, fs2), (q3, fs2))
+        assert ctx.sp_run(6, 0.02, 100, True, sync=True, generic=generic) == 6
+        q, fs = ctx.store_state()
+        m = ctx.get_masks()
+        outs.append((q[:, 0].clone(), fs[:, 0].clone(), m["av"].clone(), m["af"].clone()))
+        if generic:
+            break
+        # (2) + (3) on the blocked context
+        n_act = ctx.count_active_variables()
+        ctx.random_fill(torch.rand(max(n_act, 1), device=dev()))
+        pred, _ = ctx.walksat(20, 0.5, None, None, seed=5, sync=True)
+        deg = torch.bincount(gm[0].long(), minlength=V)
+        assert bool(((pred == 0) | (pred == 1) | ((pred == 0.5) & (deg == 0))).all())
+        solved, n_unsat = ctx.cnf_eval(pred)
+        energy, _ = ctx.energy(2 * pred - 1, torch.ones(V, device=dev()), torch.ones(F, device=dev()))
+        assert torch.equal(energy, n_unsat)
+        assert bool(((solved == 1) == (n_unsat == 0)).all())
+        del ctx
+    for a, b in zip(*outs):
+        assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
