@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--t_max", type=int, default=100)
     ap.add_argument("--seed", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config0", action="store_true", help="skip the CNFs-solved/s measurement on BASELINE.json configs[0]")
     ap.add_argument("--cpu-problem-n", type=int, default=0, help="n of the CPU sample problem (default: --n)")
     ap.add_argument("--cpu-iterations", type=int, default=3)
     ap.add_argument("--cpu-walksat", type=int, default=2)
@@ -304,6 +305,8 @@ def run_b200_arm(a, rank, world, local_rank):
                      "edge_updates_per_launch": st["loop_updates"] / a.steps, "launch_ms": st["loop_ms"] / a.steps},
         "clocks": sampler.summary(),
     }
+    if not a.no_config0 and world == 1:
+        line["config0_cnfs_solved"] = config0_solved(dev)
     if not a.no_cpu_baseline and world == 1:
         from oracle import pdp_oracle as po
         po.build()
@@ -315,6 +318,39 @@ def run_b200_arm(a, rank, world, local_rank):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config0_solved(dev):
+    """The "CNFs solved/s" half of the metric on BASELINE.json configs[0] (the n = 1M problems of the main workload are
+    never solved within T = 100): p-d-p on 5000 x random 3-SAT n = 100, m/n = 4.2, T = 1000, + 100 WalkSAT iterations,
+    one whole forward() + CNF check, device-resident inputs, second of two runs."""
+    import torch
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.nn import solver as pdp_solver
+    B, n, T, W = 5000, 100, 1000, 100
+    gm, bvm, bfm, ef = [torch.from_numpy(x).to(dev) for x in cnfgen.random_batch(B, n, 3, 4.2, 1000)]
+    model = pdp_solver.SurveyPropagatorSolver(dev, "p-d-p", tolerance=0.02, t_max=100, local_search_iterations=W, epsilon=0.5)
+
+    def termination(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+    out = None
+    for rep in range(2):
+        torch.manual_seed(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=1)
+        (pred, _), _ = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                             meta_data=None, is_training=False, iteration_num=T, check_termination=termination, batch_replication=1)
+        solved, _ = model.last_problem._ctx.cnf_eval(pred)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        k = int(solved.sum().item())
+        out = {"workload": "p-d-p SP + %d-iteration WalkSAT, random 3-SAT n=%d m/n=4.20, batch %d, T=%d (BASELINE.json configs[0])" % (W, n, B, T),
+               "cnfs_solved": k, "cnfs": B, "ms": ms, "cnfs_solved_per_s": k / (ms / 1e3), "cnfs_per_s": B / (ms / 1e3),
+               "iterations": int(model.last_iterations.item())}
+    return out
 
 
 def main():

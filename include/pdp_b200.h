@@ -133,7 +133,8 @@ typedef struct {
     int32_t check_termination;  /* 1 = trainer._check_recurrence_termination semantics  */
     int32_t batch_replication;  /* b of `-b`; problem id of replica r of j is r*B/b + j */
     int32_t full_state;         /* 1 = also keep q_s and q_* (the [E,3] state) exact    */
-    int32_t flags;              /* bit 0: use the generic (thread per node) passes, not the blocked ones */
+    int32_t flags;              /* bit 0: use the generic (thread per node) passes, not the blocked ones;
+                                   bit 1: grid-wide decimation phases only (no CTA-local decimation)    */
 } pdp_sp_params;
 
 /* PropagatorDecimatorSolverBase._forward_core for the p-d-p model, reference

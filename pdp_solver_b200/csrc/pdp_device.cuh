@@ -1480,6 +1480,179 @@ __device__ __forceinline__ void closure(const KArgs& A, cg::grid_group& grid) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-local decimation.  Everything the decimator does to a converged problem -- scoring, arg-max, fixing
+// the variable, unit propagation and pure-literal peeling to closure, the CNF check and the termination
+// decision -- touches that problem only, so for problems that one CTA can walk (the common case: thousands of
+// n ~ 100 problems per batch) a CTA does all of it with block barriers, where the grid-wide phases above need a
+// few dozen grid barriers per iteration.  Same arithmetic and the same synchronous rounds as the grid-wide
+// phases (which stay for large problems and batch replication).
+// ------------------------------------------------------------------------------------------------
+struct LocSmem {
+    uint32_t cmax, cmin, cnan;
+    int arg, flag, conflicts, nunsat, fixed;
+};
+
+__device__ __forceinline__ bool literal_true(float sgn, float p);
+
+__device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v1, int f0, int f1, LocSmem& ls) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (;;) {   // unit propagation rounds, solver.py:234-273
+        if (tid == 0) { ls.flag = 0; ls.conflicts = 0; }
+        __syncthreads();
+        for (int a = f0 + tid; a < f1; a += nthr) {
+            if (!s.af[a]) continue;
+            int deg = 0; uint32_t hit = 0;
+            for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+                const uint32_t w = g.c_var[c];
+                if (s.av[w & PDP_IDX_MASK]) { ++deg; hit = w; }
+            }
+            if (deg == 1) {
+                s.single[a] = 1;
+                const int j = (int)(hit & PDP_IDX_MASK);
+                atomicAdd(&s.up_cnt[j], 1);
+                atomicAdd(&s.up_ev[j], (hit & PDP_SIGN_BIT) ? -1 : 1);
+                ls.flag = 1;
+            }
+        }
+        __syncthreads();
+        if (!ls.flag) break;
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            const int cnt = s.up_cnt[i];
+            if (cnt > 0 && abs(s.up_ev[i]) != cnt) atomicAdd(&ls.conflicts, 1);
+        }
+        __syncthreads();
+        const int nc = ls.conflicts;   // the `== 1` quirk of solver.py:257,261
+        for (int a = f0 + tid; a < f1; a += nthr) {
+            if (s.single[a]) { deactivate_clause(g, s, a); s.single[a] = 0; s.masked[b] = 1; }
+            else if (s.af[a] && nc == 1) deactivate_clause(g, s, a);
+        }
+        for (int i = v0 + tid; i < v1; i += nthr)
+            if (s.av[i] && nc == 1) deactivate_variable(g, s, i);
+        if (tid == 0 && nc >= 1) { s.is_sat[b] = 0.f; s.flags[b] |= PDP_FLAG_UP_CONFLICT; s.masked[b] = 1; }
+        __syncthreads();
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            const int cnt = s.up_cnt[i];
+            if (cnt > 0) {
+                const int ev = s.up_ev[i];
+                s.up_cnt[i] = 0; s.up_ev[i] = 0;
+                if (s.av[i] && abs(ev) == cnt) fix_variable(g, s, i, ev > 0 ? 1.f : -1.f);
+            }
+        }
+        __syncthreads();
+    }
+    for (;;) {   // pure-literal peeling rounds, solver.py:188-203
+        __syncthreads();
+        if (tid == 0) ls.flag = 0;
+        __syncthreads();
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            if (!s.av[i]) continue;
+            int deg = 0, sdeg = 0;
+            for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p)
+                if (s.af[g.v_cls[p]]) { ++deg; sdeg += (g.v_cedge[p] & PDP_SIGN_BIT) ? -1 : 1; }
+            if (deg == abs(sdeg)) {
+                s.pure[i] = 1;
+                s.sol[i] = ((sdeg > 0 ? 1.f : (sdeg < 0 ? -1.f : 0.f)) + 1.f) / 2.0f;
+                ls.flag = 1;
+            }
+        }
+        __syncthreads();
+        if (!ls.flag) break;
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            if (!s.pure[i]) continue;
+            s.pure[i] = 0;
+            for (int p = g.var_ptr[i]; p < g.var_ptr[i + 1]; ++p) {
+                const int a = g.v_cls[p];
+                if (s.af[a]) deactivate_clause(g, s, a);
+            }
+            deactivate_variable(g, s, i);
+            s.masked[b] = 1;
+        }
+    }
+}
+
+// one converged problem: pdp_decimate.py:152-171 + solver.py:275-285 + trainer.py:150-162
+__device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int iter, int w, float pi, bool check_termination, LocSmem& ls) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int v0 = g.prob_vptr[b], v1 = g.prob_vptr[b + 1], f0 = g.prob_fptr[b], f1 = g.prob_fptr[b + 1];
+    if (tid == 0) { ls.cmax = 0u; ls.cmin = 0x7f800000u; ls.cnan = 0u; ls.arg = 0x7fffffff; ls.fixed = 0; ls.nunsat = 0; }
+    __syncthreads();
+    for (int i = v0 + tid; i < v1; i += nthr) {
+        const float sc = score_variable(g, s, s.eta[w], i, pi);
+        s.score[i] = sc;
+        const float c = fabsf(sc) * (float)s.av[i];
+        if (c != c) ls.cnan = 1u; else { atomicMax(&ls.cmax, f2u(c)); atomicMin(&ls.cmin, f2u(c)); }
+    }
+    __syncthreads();
+    if (!ls.cnan) {   // first index attaining max of fl(fl(c - min) + 1), util.py:257-265
+        const float m = u2f(ls.cmin);
+        const float kmax = argmax_key(u2f(ls.cmax), m);
+        for (int i = v0 + tid; i < v1; i += nthr) {
+            const float c = fabsf(s.score[i]) * (float)s.av[i];
+            if (argmax_key(c, m) == kmax) atomicMin(&ls.arg, i);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && !ls.cnan && u2f(ls.cmax) > 0.f && ls.arg != 0x7fffffff) {
+        const int i = ls.arg;
+        const float sg = sgnf(s.score[i]);
+        if (sg != 0.f && s.av[i]) {
+            fix_variable(g, s, i, sg);
+            s.masked[b] = 1; s.dirty[b] = 1;
+            ls.fixed = 1;
+            if (A.trace) {
+                const int k = atomicAdd(&s.ctrl[CTRL_TRACE_LEN], 1);
+                if (k < A.trace_cap) { A.trace[3 * k] = iter; A.trace[3 * k + 1] = i; A.trace[3 * k + 2] = (int)sg; }
+            }
+        }
+    }
+    __syncthreads();
+    if (ls.fixed) loc_closure(A, b, v0, v1, f0, f1, ls);
+    __syncthreads();
+    if (s.dirty[b]) {
+        if (check_termination) {   // SatCNFEvaluator on _solution over the full formula, then trainer.py:150-162
+            int n = 0;
+            for (int a = f0 + tid; a < f1; a += nthr) {
+                bool sat = false;
+                for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+                    const uint32_t wv = g.c_var[c];
+                    if (literal_true((wv & PDP_SIGN_BIT) ? -1.f : 1.f, s.sol[wv & PDP_IDX_MASK])) { sat = true; break; }
+                }
+                n += sat ? 0 : 1;
+            }
+            n = __reduce_add_sync(0xffffffffu, n);
+            if ((tid & 31) == 0 && n) atomicAdd(&ls.nunsat, n);
+            __syncthreads();
+            if (tid == 0) {
+                if (ls.nunsat == 0) {
+                    if (s.active[b]) { s.active[b] = 0; s.freeze_iter[b] = iter; atomicSub(&s.ctrl[CTRL_NUM_ACTIVE], 1); }
+                    s.flags[b] |= PDP_FLAG_SOLVED;
+                }
+                s.dirty[b] = 0; s.n_unsat[b] = 0;
+            }
+        } else if (tid == 0) {
+            s.ctrl[CTRL_ANY_DIRTY] = 1;
+        }
+    }
+    if (tid == 0) s.conv[b] = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool loc_problem_is_small(const pdp_graph& g, int b) {
+    return (g.prob_vptr[b + 1] - g.prob_vptr[b] <= PDP_LOCAL_MAX_V) && (g.prob_fptr[b + 1] - g.prob_fptr[b] <= PDP_LOCAL_MAX_F);
+}
+
+__device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w, float pi, bool check_termination) {
+    __shared__ LocSmem ls;
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    for (int64_t b = blockIdx.x; b < g.B; b += gridDim.x) {
+        if (!s.conv[b] || !loc_problem_is_small(g, (int)b)) continue;   // uniform over the CTA
+        loc_decimate_problem(A, (int)b, iter, w, pi, check_termination, ls);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // full-formula satisfaction count (SatCNFEvaluator on _solution, util.py:210-236) for dirty problems
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool literal_true(float sgn, float p) {

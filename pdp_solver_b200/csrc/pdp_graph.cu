@@ -64,6 +64,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.bvm = k.take<int32_t>(V);
     g.bfm = k.take<int32_t>(F);
     g.prob_vptr = k.take<int32_t>(B + 1);
+    g.prob_fptr = k.take<int32_t>(B + 1);
     g.p_vpos = k.take<int32_t>(E);
     g.p_qpos = k.take<int32_t>(E);
     g.c_vpos = k.take<int32_t>(E);
@@ -389,6 +390,8 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
     }
     g.contiguous_problems = monotone_maps ? 1 : 0;
     k_problem_ptr<<<pdp_grid(B + 1, 256, nsm), 256, 0, stream>>>(g.bvm, V, B, g.prob_vptr);
+    LK();
+    k_problem_ptr<<<pdp_grid(B + 1, 256, nsm), 256, 0, stream>>>(g.bfm, F, B, g.prob_fptr);
     LK();
     {
         int lrc = pdp_build_layout(c, stream, monotone_maps);

@@ -9,7 +9,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // SequentialDecimator decisions, one thread per problem (pdp_decimate.py:127-150,173)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp_sp_params& prm, bool has_prev) {
+__device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp_sp_params& prm, bool has_prev, bool local_ok) {
     const pdp_state& s = A.s;
     const int slot = CTRL_CONV + (iter & 1);
     WARP_STRIDED(b, A.g.B) {
@@ -50,7 +50,10 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
             s.st_nan[b] = 0u; s.nav[b] = 0;
         }
         s.conv[b] = cv;
-        if (cv) s.ctrl[slot] = 1;
+        if (cv) {
+            s.ctrl[slot] = 1;
+            if (!local_ok || !loc_problem_is_small(A.g, (int)b)) s.ctrl[CTRL_CONVBIG + (iter & 1)] = 1;
+        }
     }
 }
 
@@ -116,6 +119,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     bool em_set = s.ctrl[CTRL_EM_SET] != 0;
     int gen_left = FAST ? s.ctrl[CTRL_GEN_ITERS] : 0;
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
+    const bool local_ok = A.g.contiguous_problems && rep == 1 && !(prm.flags & 2);
     int executed = 0;
 #if PDP_TMA
     __shared__ TmaSmem tma_sm;
@@ -163,7 +167,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
-        if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; }
+        if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_CONVBIG + ((iter + 1) & 1)] = 0; }
         GRID_SYNC();
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
@@ -187,9 +191,14 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         }
         GRID_SYNC();
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
-        decide_phase(A, iter, prm, has_prev);
+        decide_phase(A, iter, prm, has_prev, local_ok);
         GRID_SYNC();
-        if (s.ctrl[CTRL_CONV + (iter & 1)]) {
+        if (local_ok && s.ctrl[CTRL_CONV + (iter & 1)]) {
+            // converged problems one CTA can walk: scoring, arg-max, fix, closure, CNF check, termination, CTA-local
+            loc_decimate_all(A, iter, w, prm.pi, prm.check_termination != 0);
+            GRID_SYNC();
+        }
+        if (s.ctrl[local_ok ? (CTRL_CONVBIG + (iter & 1)) : (CTRL_CONV + (iter & 1))]) {
             score_phase(A, w, prm.pi);
             GRID_SYNC();
             argmax_phase(A);
