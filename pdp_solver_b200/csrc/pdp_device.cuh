@@ -395,7 +395,10 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
 //   [4*PDP_BLK_C, +PDP_BLK_C/8) skip bits: slots of nodes the pass leaves alone (frozen / sticky-NaN
 //                               problems inside a block that has work)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool blk_problem_runs(const pdp_state& s, int b) { return s.active[b] && !s.nanflag[b]; }
+// The serial passes apply the sticky-NaN rule themselves at write-out; the pipelined / TMA variants leave the
+// problems on the sticky-NaN path to the generic passes.
+#define PDP_STICKY_INLINE (!(PDP_PIPELINE || PDP_TMA))
+__device__ __forceinline__ bool blk_problem_runs(const pdp_state& s, int b) { return s.active[b] && (PDP_STICKY_INLINE || !s.nanflag[b]); }
 
 // true when no problem in [b0, b1] is to be processed by the blocked passes (uniform over the CTA)
 __device__ __forceinline__ bool blk_idle(const pdp_state& s, int b0, int b1) {
@@ -426,9 +429,13 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 
 // write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
 // consecutive destinations (runs), so a warp's stores coalesce into a few sectors
-template <int G, bool SKIP>
+// STICKY: 0 = off, 1 = slots flagged in `sticky` bits, 2 = every slot.  A sticky slot keeps a NaN that is already
+// stored at its destination in `old` (the reference blends mask*new + (1-mask)*old arithmetically: 0*NaN = NaN,
+// pdp_propagate.py:175,218).
+template <int G, bool SKIP, int STICKY>
 __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                               const float* plane, const uint32_t* skip, float* __restrict__ out) {
+                                               const float* plane, const uint32_t* skip, const uint32_t* sticky,
+                                               const float* old, float* out) {   // old may alias out (q is updated in place)
     int w = t;
     constexpr int U = PDP_UNROLL_WO;
     for (; w + (U - 1) * G < ne; w += U * G) {
@@ -436,19 +443,37 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) { l[u] = src[w + u * G]; d[u] = dst[w + u * G]; }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (!SKIP || !((skip[l[u] >> 5] >> (l[u] & 31)) & 1u)) out[d[u]] = plane[l[u]];
+        for (int u = 0; u < U; ++u) {
+            if (SKIP && ((skip[l[u] >> 5] >> (l[u] & 31)) & 1u)) continue;
+            float v = plane[l[u]];
+            if (STICKY == 2 || (STICKY == 1 && ((sticky[l[u] >> 5] >> (l[u] & 31)) & 1u))) { const float ov = old[d[u]]; if (ov != ov) v = ov; }
+            out[d[u]] = v;
+        }
     }
     for (; w < ne; w += G) {
         const int l = src[w];
-        if (!SKIP || !((skip[l >> 5] >> (l & 31)) & 1u)) out[dst[w]] = plane[l];
+        if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) continue;
+        float v = plane[l];
+        const int d = dst[w];
+        if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
+        out[d] = v;
     }
 }
+// flags: bit 0 = some slots are skipped, bit 1 = some slots are sticky, bit 2 = every slot is sticky
 template <int G>
 __device__ __forceinline__ void ph_write_out(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                             const float* plane, const uint32_t* skip, bool any_skip, float* __restrict__ out) {
-    if (any_skip) ph_write_out_t<G, true>(t, src, dst, ne, plane, skip, out);
-    else ph_write_out_t<G, false>(t, src, dst, ne, plane, skip, out);
+                                             const float* plane, const uint32_t* skip, int flags, float* out,
+                                             const uint32_t* sticky = nullptr, const float* old = nullptr) {
+    if (flags & 4) {
+        if (flags & 1) ph_write_out_t<G, true, 2>(t, src, dst, ne, plane, skip, sticky, old, out);
+        else ph_write_out_t<G, false, 2>(t, src, dst, ne, plane, skip, sticky, old, out);
+    } else if (flags & 2) {
+        if (flags & 1) ph_write_out_t<G, true, 1>(t, src, dst, ne, plane, skip, sticky, old, out);
+        else ph_write_out_t<G, false, 1>(t, src, dst, ne, plane, skip, sticky, old, out);
+    } else {
+        if (flags & 1) ph_write_out_t<G, true, 0>(t, src, dst, ne, plane, skip, sticky, old, out);
+        else ph_write_out_t<G, false, 0>(t, src, dst, ne, plane, skip, sticky, old, out);
+    }
 }
 
 // clause pass, load phase: x = log(max(q_u, 1e-40)) * em, scattered into clause-major order.
@@ -531,7 +556,7 @@ __device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) {
 // clause pass, node phase: thread per clause
 template <int G>
 __device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, int ku,
-                                               float* X, uint32_t* skip, int* any_skip) {
+                                               float* X, uint32_t* skip, int* any_skip, uint32_t* sticky = nullptr) {
     const bool multi = B.multi();
     for (int a = B.n0 + t; a < B.n1; a += G) {
         int lo, k;
@@ -540,7 +565,8 @@ __device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const 
         int b = B.b0;
         if (multi) {
             b = g.bfm[a];
-            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); *any_skip = 1; continue; }
+            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); atomicOr(any_skip, 1); continue; }
+            if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + k); atomicOr(any_skip, 2); }
         }
         bool made_nan;
         switch (k) {
@@ -600,7 +626,7 @@ __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn,
 template <int G>
 __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
                                             bool em_set, float* PA, float* PB, uint32_t* skip, int* any_skip,
-                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
+                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky = nullptr) {
     const bool multi = B.multi();
     for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
         const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
@@ -610,7 +636,8 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         int b = B.b0;
         if (multi) {
             b = g.bvm[i];
-            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); *any_skip = 1; continue; }
+            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); atomicOr(any_skip, 1); continue; }
+            if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + deg); atomicOr(any_skip, 2); }
         }
         const uint32_t act = s.av[i];
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
@@ -1215,6 +1242,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* X = reinterpret_cast<float*>(smem);
     uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
+    uint32_t* sticky = skip + PDP_BLK_C / 32;
     __shared__ int sm_any_skip;
     const float* __restrict__ qin = s.qu;
     float* __restrict__ eout = s.eta[r ^ 1];
@@ -1223,14 +1251,14 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         const BlkGeo B = clause_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
-        for (int i = tid; i < (B.ne + 31) / 32; i += NT) skip[i] = 0u;
-        if (tid == 0) sm_any_skip = 0;
+        for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
+        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         __syncthreads();
-        ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip);
+        ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip, sticky);
         __syncthreads();
-        ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip != 0, eout);
+        ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip, eout, sticky, s.eta[r]);
         __syncthreads();
     }
 }
@@ -1242,6 +1270,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
     float* PB = PA + PDP_BLK_V;                   // eta(t-1), then y
     uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
+    uint32_t* sticky = skip + PDP_BLK_C / 32;
     __shared__ int sm_any_skip;
     __shared__ BlkStats sm_st;
     const float* __restrict__ en = s.eta[r ^ 1];
@@ -1253,16 +1282,16 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
         const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
-        for (int i = tid; i < (B.ne + 31) / 32; i += NT) skip[i] = 0u;
-        if (tid == 0) sm_any_skip = 0;
+        for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
+        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
         if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         __syncthreads();
-        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats);
+        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
         __syncthreads();
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-        ph_write_out<NT>(tid, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, sm_any_skip != 0, s.qu);
+        ph_write_out<NT>(tid, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, sm_any_skip, s.qu, sticky, s.qu);
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
     }
 }
@@ -1494,12 +1523,12 @@ struct LocSmem {
 
 __device__ __forceinline__ bool literal_true(float sgn, float p);
 
-__device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v1, int f0, int f1, LocSmem& ls) {
+#define LSYNC() bar_sync(bar_id, nthr)
+__device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v1, int f0, int f1, LocSmem& ls, int tid, int nthr, int bar_id) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    const int tid = threadIdx.x, nthr = blockDim.x;
     for (;;) {   // unit propagation rounds, solver.py:234-273
         if (tid == 0) { ls.flag = 0; ls.conflicts = 0; }
-        __syncthreads();
+        LSYNC();
         for (int a = f0 + tid; a < f1; a += nthr) {
             if (!s.af[a]) continue;
             int deg = 0; uint32_t hit = 0;
@@ -1515,13 +1544,13 @@ __device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v
                 ls.flag = 1;
             }
         }
-        __syncthreads();
+        LSYNC();
         if (!ls.flag) break;
         for (int i = v0 + tid; i < v1; i += nthr) {
             const int cnt = s.up_cnt[i];
             if (cnt > 0 && abs(s.up_ev[i]) != cnt) atomicAdd(&ls.conflicts, 1);
         }
-        __syncthreads();
+        LSYNC();
         const int nc = ls.conflicts;   // the `== 1` quirk of solver.py:257,261
         for (int a = f0 + tid; a < f1; a += nthr) {
             if (s.single[a]) { deactivate_clause(g, s, a); s.single[a] = 0; s.masked[b] = 1; }
@@ -1530,7 +1559,7 @@ __device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v
         for (int i = v0 + tid; i < v1; i += nthr)
             if (s.av[i] && nc == 1) deactivate_variable(g, s, i);
         if (tid == 0 && nc >= 1) { s.is_sat[b] = 0.f; s.flags[b] |= PDP_FLAG_UP_CONFLICT; s.masked[b] = 1; }
-        __syncthreads();
+        LSYNC();
         for (int i = v0 + tid; i < v1; i += nthr) {
             const int cnt = s.up_cnt[i];
             if (cnt > 0) {
@@ -1539,12 +1568,12 @@ __device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v
                 if (s.av[i] && abs(ev) == cnt) fix_variable(g, s, i, ev > 0 ? 1.f : -1.f);
             }
         }
-        __syncthreads();
+        LSYNC();
     }
     for (;;) {   // pure-literal peeling rounds, solver.py:188-203
-        __syncthreads();
+        LSYNC();
         if (tid == 0) ls.flag = 0;
-        __syncthreads();
+        LSYNC();
         for (int i = v0 + tid; i < v1; i += nthr) {
             if (!s.av[i]) continue;
             int deg = 0, sdeg = 0;
@@ -1556,7 +1585,7 @@ __device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v
                 ls.flag = 1;
             }
         }
-        __syncthreads();
+        LSYNC();
         if (!ls.flag) break;
         for (int i = v0 + tid; i < v1; i += nthr) {
             if (!s.pure[i]) continue;
@@ -1572,19 +1601,19 @@ __device__ __forceinline__ void loc_closure(const KArgs& A, int b, int v0, int v
 }
 
 // one converged problem: pdp_decimate.py:152-171 + solver.py:275-285 + trainer.py:150-162
-__device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int iter, int w, float pi, bool check_termination, LocSmem& ls) {
+__device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int iter, int w, float pi, bool check_termination, LocSmem& ls,
+                                                     int tid, int nthr, int bar_id) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    const int tid = threadIdx.x, nthr = blockDim.x;
     const int v0 = g.prob_vptr[b], v1 = g.prob_vptr[b + 1], f0 = g.prob_fptr[b], f1 = g.prob_fptr[b + 1];
     if (tid == 0) { ls.cmax = 0u; ls.cmin = 0x7f800000u; ls.cnan = 0u; ls.arg = 0x7fffffff; ls.fixed = 0; ls.nunsat = 0; }
-    __syncthreads();
+    LSYNC();
     for (int i = v0 + tid; i < v1; i += nthr) {
         const float sc = score_variable(g, s, s.eta[w], i, pi);
         s.score[i] = sc;
         const float c = fabsf(sc) * (float)s.av[i];
         if (c != c) ls.cnan = 1u; else { atomicMax(&ls.cmax, f2u(c)); atomicMin(&ls.cmin, f2u(c)); }
     }
-    __syncthreads();
+    LSYNC();
     if (!ls.cnan) {   // first index attaining max of fl(fl(c - min) + 1), util.py:257-265
         const float m = u2f(ls.cmin);
         const float kmax = argmax_key(u2f(ls.cmax), m);
@@ -1593,7 +1622,7 @@ __device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int 
             if (argmax_key(c, m) == kmax) atomicMin(&ls.arg, i);
         }
     }
-    __syncthreads();
+    LSYNC();
     if (tid == 0 && !ls.cnan && u2f(ls.cmax) > 0.f && ls.arg != 0x7fffffff) {
         const int i = ls.arg;
         const float sg = sgnf(s.score[i]);
@@ -1607,9 +1636,9 @@ __device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int 
             }
         }
     }
-    __syncthreads();
-    if (ls.fixed) loc_closure(A, b, v0, v1, f0, f1, ls);
-    __syncthreads();
+    LSYNC();
+    if (ls.fixed) loc_closure(A, b, v0, v1, f0, f1, ls, tid, nthr, bar_id);
+    LSYNC();
     if (s.dirty[b]) {
         if (check_termination) {   // SatCNFEvaluator on _solution over the full formula, then trainer.py:150-162
             int n = 0;
@@ -1623,7 +1652,7 @@ __device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int 
             }
             n = __reduce_add_sync(0xffffffffu, n);
             if ((tid & 31) == 0 && n) atomicAdd(&ls.nunsat, n);
-            __syncthreads();
+            LSYNC();
             if (tid == 0) {
                 if (ls.nunsat == 0) {
                     if (s.active[b]) { s.active[b] = 0; s.freeze_iter[b] = iter; atomicSub(&s.ctrl[CTRL_NUM_ACTIVE], 1); }
@@ -1636,19 +1665,26 @@ __device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int 
         }
     }
     if (tid == 0) s.conv[b] = 0;
-    __syncthreads();
+    LSYNC();
 }
 
 __device__ __forceinline__ bool loc_problem_is_small(const pdp_graph& g, int b) {
     return (g.prob_vptr[b + 1] - g.prob_vptr[b] <= PDP_LOCAL_MAX_V) && (g.prob_fptr[b + 1] - g.prob_fptr[b] <= PDP_LOCAL_MAX_F);
 }
 
+#undef LSYNC
+// groups of PDP_LOCAL_GROUP threads (named barriers 8..15) take one problem each
+#define PDP_LOCAL_GROUP 128
 __device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w, float pi, bool check_termination) {
-    __shared__ LocSmem ls;
+    __shared__ LocSmem ls[8];
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    for (int64_t b = blockIdx.x; b < g.B; b += gridDim.x) {
-        if (!s.conv[b] || !loc_problem_is_small(g, (int)b)) continue;   // uniform over the CTA
-        loc_decimate_problem(A, (int)b, iter, w, pi, check_termination, ls);
+    int ngroups = blockDim.x / PDP_LOCAL_GROUP;
+    if (ngroups > 8) ngroups = 8;
+    const int gthr = blockDim.x / ngroups;           // threads per group (a multiple of 32)
+    const int grp = threadIdx.x / gthr, gt = threadIdx.x % gthr;
+    for (int64_t b = (int64_t)blockIdx.x * ngroups + grp; b < g.B; b += (int64_t)gridDim.x * ngroups) {
+        if (!s.conv[b] || !loc_problem_is_small(g, (int)b)) continue;   // uniform over the group
+        loc_decimate_problem(A, (int)b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
     }
 }
 

@@ -147,9 +147,16 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     const int sm_role = sm_role_s;
 #endif
     grid.sync();   // everybody has read the control block before anyone may change it
+#ifdef PDP_PHASE_TIMING
+    long long _lt = clock64();
+#define LOOP_T(slot_) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _lt) >> 10)); _lt = _n; } } while (0)
+#else
+#define LOOP_T(slot_) do {} while (0)
+#endif
     for (int it = 0; it < prm.iterations; ++it) {
         ++iter;
         const int r = (iter - 1) & 1, w = iter & 1;
+        LOOP_T(23);
         const bool blocked = FAST && gen_left <= 0;
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
@@ -163,12 +170,14 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             if (PDP_PIPELINE) pipe_clause_pass(A, r, use_mask, smem_dyn);
             else blk_clause_pass(A, r, use_mask, smem_dyn);
 #endif
-            if (s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
+            if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
+        LOOP_T(16);
         if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_CONVBIG + ((iter + 1) & 1)] = 0; }
         GRID_SYNC();
+        LOOP_T(17);
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
@@ -181,7 +190,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             if (PDP_PIPELINE) pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
             else blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
 #endif
-            if (s.ctrl[CTRL_ANY_NAN]) {
+            if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
                 gen_stats<GEN_NAN>(A, w, has_prev, em_set);
             }
@@ -189,14 +198,19 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
             gen_stats<GEN_ALL>(A, w, has_prev, em_set);
         }
+        LOOP_T(18);
         GRID_SYNC();
+        LOOP_T(19);
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
         decide_phase(A, iter, prm, has_prev, local_ok);
         GRID_SYNC();
+        LOOP_T(20);
         if (local_ok && s.ctrl[CTRL_CONV + (iter & 1)]) {
             // converged problems one CTA can walk: scoring, arg-max, fix, closure, CNF check, termination, CTA-local
             loc_decimate_all(A, iter, w, prm.pi, prm.check_termination != 0);
+            LOOP_T(21);
             GRID_SYNC();
+            LOOP_T(22);
         }
         if (s.ctrl[local_ok ? (CTRL_CONVBIG + (iter & 1)) : (CTRL_CONV + (iter & 1))]) {
             score_phase(A, w, prm.pi);

@@ -254,6 +254,8 @@ class PropagatorDecimatorSolverBase(nn.Module):
         termination callback is the trainer's (or None), one launch per iteration otherwise."""
         ctx = sat_problem._ctx
         dec = self._decimator
+        if os.environ.get("PDP_PHASE_TIMING"):
+            ctx.enable_trace(256)
         cq = _const_rows(init_decimator_state[0])
         cf = _const_rows(init_decimator_state[1])
         if cq is not None and cf is not None:

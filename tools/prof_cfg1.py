@@ -28,6 +28,9 @@ for rep in range(2):
     ctx = model.last_problem._ctx
     solved, nun = ctx.cnf_eval(pred)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    if os.environ.get("PDP_PHASE_TIMING") and ctx._trace is not None:
+        tr = ctx._trace.reshape(-1)[:32].cpu().numpy().astype(np.float64) * 1024.0 / 148 / max(int(model.last_iterations.item()), 1)
+        print("  cycles/iter/CTA: clause pass %.0f, sync %.0f, var pass %.0f, sync %.0f, decide+sync %.0f, local decimation %.0f, sync %.0f, rest %.0f" % tuple(tr[16:24]))
     flags, counters, freeze = ctx.problem_flags()
     print("rep %d: %.1f ms, iterations %d, solved %d / %d, phases %s, flags: trivial %d solved-in-loop %d contradiction %d" % (
         rep, dt * 1e3, int(model.last_iterations.item()), int(solved.sum().item()), a.problems, ctx.timing,
