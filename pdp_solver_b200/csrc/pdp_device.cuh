@@ -1232,6 +1232,9 @@ __device__ __forceinline__ void tma_var_pass(const KArgs& A, int r, bool use_mas
 #undef NT
 #endif  // PDP_TMA
 
+// (Dynamic block scheduling through a global counter was measured and dropped: with the 2-7 equal-size blocks a CTA
+// gets per pass it evens out nothing, and smaller blocks cost more per edge than they balance.)
+
 // ================================================================================================
 // serial passes: the whole CTA runs load, node phase and write-out of a block back to back
 // ================================================================================================
@@ -1677,14 +1680,20 @@ __device__ __forceinline__ bool loc_problem_is_small(const pdp_graph& g, int b) 
 #define PDP_LOCAL_GROUP 128
 __device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w, float pi, bool check_termination) {
     __shared__ LocSmem ls[8];
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const pdp_state& s = A.s;
     int ngroups = blockDim.x / PDP_LOCAL_GROUP;
     if (ngroups > 8) ngroups = 8;
     const int gthr = blockDim.x / ngroups;           // threads per group (a multiple of 32)
     const int grp = threadIdx.x / gthr, gt = threadIdx.x % gthr;
-    for (int64_t b = (int64_t)blockIdx.x * ngroups + grp; b < g.B; b += (int64_t)gridDim.x * ngroups) {
-        if (!s.conv[b] || !loc_problem_is_small(g, (int)b)) continue;   // uniform over the group
-        loc_decimate_problem(A, (int)b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
+    // the groups drain the queue decide_phase filled (the order is irrelevant: problems do not interact)
+    const int count = s.ctrl[CTRL_LOC_COUNT];
+    for (;;) {
+        if (gt == 0) ls[grp].flag = atomicAdd(&s.ctrl[CTRL_LOC_NEXT], 1);
+        bar_sync(8 + grp, gthr);
+        const int k = ls[grp].flag;
+        bar_sync(8 + grp, gthr);
+        if (k >= count) break;
+        loc_decimate_problem(A, s.loc_list[k], iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
     }
 }
 

@@ -115,6 +115,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     s.c_min = k.take<uint32_t>(B);
     s.c_nan = k.take<uint32_t>(B);
     s.arg_idx = k.take<int32_t>(B);
+    s.loc_list = k.take<int32_t>(B);
     s.n_unsat = k.take<int32_t>(B);
     s.conflicts = k.take<int32_t>(B);
     s.score = k.take<float>(V);

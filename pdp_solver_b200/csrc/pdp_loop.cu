@@ -53,6 +53,7 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
         if (cv) {
             s.ctrl[slot] = 1;
             if (!local_ok || !loc_problem_is_small(A.g, (int)b)) s.ctrl[CTRL_CONVBIG + (iter & 1)] = 1;
+            else s.loc_list[atomicAdd(&s.ctrl[CTRL_LOC_COUNT], 1)] = (int32_t)b;
         }
     }
 }
@@ -121,6 +122,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
     const bool local_ok = A.g.contiguous_problems && rep == 1 && !(prm.flags & 2);
     int executed = 0;
+    if (gtid() == 0) { s.ctrl[CTRL_NEXT_CBLK] = 0; s.ctrl[CTRL_NEXT_VBLK] = 0; s.ctrl[CTRL_LOC_COUNT] = 0; s.ctrl[CTRL_LOC_NEXT] = 0; }
 #if PDP_TMA
     __shared__ TmaSmem tma_sm;
     TmaState tma_st;
@@ -175,6 +177,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
         LOOP_T(16);
+        if (gtid() == 0) { s.ctrl[CTRL_NEXT_VBLK] = 0; s.ctrl[CTRL_LOC_COUNT] = 0; s.ctrl[CTRL_LOC_NEXT] = 0; }
         if (gtid() == 0) { s.ctrl[CTRL_CONV + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_FIX + ((iter + 1) & 1)] = 0; s.ctrl[CTRL_CONVBIG + ((iter + 1) & 1)] = 0; }
         GRID_SYNC();
         LOOP_T(17);
@@ -200,6 +203,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         }
         LOOP_T(18);
         GRID_SYNC();
+        if (gtid() == 0) s.ctrl[CTRL_NEXT_CBLK] = 0;   // the variable pass is over; the next clause pass is a barrier away
         LOOP_T(19);
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
         decide_phase(A, iter, prm, has_prev, local_ok);
