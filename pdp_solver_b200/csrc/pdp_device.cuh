@@ -722,6 +722,7 @@ __device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats&
 //   FULL[slot]  memory -> compute: the slot holds a loaded block
 //   DONE[slot]  compute -> memory: the node phase of the slot's block is finished
 // ================================================================================================
+#if PDP_PIPELINE || PDP_TMA
 #define PIPE_MEM_THREADS (32 * PDP_PIPE_MEM_WARPS)
 #define PIPE_CMP_THREADS (PDP_SWEEP_THREADS - PIPE_MEM_THREADS)
 #define PIPE_BAR_FULL 1    // +slot
@@ -887,6 +888,8 @@ __device__ __forceinline__ void pipe_var_pass(const KArgs& A, int r, bool use_ma
         __syncthreads();
     }
 }
+
+#endif  // PDP_PIPELINE || PDP_TMA
 
 // ================================================================================================
 // TMA-staged passes.  Everything a block's node phase reads -- the message regions, the 16-bit permutation
@@ -1238,14 +1241,15 @@ __device__ __forceinline__ void tma_var_pass(const KArgs& A, int r, bool use_mas
 // ================================================================================================
 // serial passes: the whole CTA runs load, node phase and write-out of a block back to back
 // ================================================================================================
-#define NT PDP_SWEEP_THREADS
 
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
+template <int CTAS>
 __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
+    constexpr int NT = SweepCfg<CTAS>::kThreads, BLK_C = SweepCfg<CTAS>::kBlkC;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* X = reinterpret_cast<float*>(smem);
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
-    uint32_t* sticky = skip + PDP_BLK_C / 32;
+    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
+    uint32_t* sticky = skip + BLK_C / 32;
     __shared__ int sm_any_skip;
     const float* __restrict__ qin = s.qu;
     float* __restrict__ eout = s.eta[r ^ 1];
@@ -1268,12 +1272,14 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
 
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
 // [buffer r], and q(t) [C-layout, in place] from eta(t-1)
+template <int CTAS>
 __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
+    constexpr int NT = SweepCfg<CTAS>::kThreads, BLK_V = SweepCfg<CTAS>::kBlkV, BLK_C = SweepCfg<CTAS>::kBlkC;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
-    float* PB = PA + PDP_BLK_V;                   // eta(t-1), then y
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * PDP_BLK_C);
-    uint32_t* sticky = skip + PDP_BLK_C / 32;
+    float* PB = PA + BLK_V;                       // eta(t-1), then y
+    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
+    uint32_t* sticky = skip + BLK_C / 32;
     __shared__ int sm_any_skip;
     __shared__ BlkStats sm_st;
     const float* __restrict__ en = s.eta[r ^ 1];
@@ -1298,7 +1304,6 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
     }
 }
-#undef NT
 
 // ------------------------------------------------------------------------------------------------
 // SurveyScorer over the converged problems (pdp_predict.py:155-192) + coefficient statistics

@@ -73,7 +73,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.qmask = k.take<uint32_t>(E / 32 + 1);
     // block count <= rounds * SMs + 1 with rounds * SMs <= E / (half a block) + SMs (pdp_layout.cu pick_stride;
     // nodes of degree above half a block disable the blocked path)
-    const int64_t max_vb = E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2, max_cb = E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2;
+    const int64_t max_vb = E / (PDP_BLK_V / 4) + 2 * PDP_MAX_SMS + 2, max_cb = E / (PDP_BLK_C / 4) + 2 * PDP_MAX_SMS + 2;
     g.vb_ptr = k.take<int32_t>(max_vb + 1);
     g.cb_ptr = k.take<int32_t>(max_cb + 1);
     g.vinv = k.take<uint16_t>(E);

@@ -184,18 +184,25 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     const int64_t E = g.E;
     g.blocked_ok = 0; g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
     if (E == 0) return PDP_OK;
-    const bool ok = monotone_maps && g.max_var_degree <= PDP_BLK_V / 2 && g.max_clause_degree <= PDP_BLK_C / 2 &&
+    g.ctas = 1;
+    if (!(PDP_PIPELINE || PDP_TMA)) {
+        const char* forced = getenv("PDP_B200_CTAS");
+        if (forced) g.ctas = (atoi(forced) == 2) ? 2 : 1;
+        else if (g.B > 0 && E / g.B >= PDP_CTAS_EDGES_PER_PROBLEM) g.ctas = 2;
+    }
+    const int blk_v = PDP_BLK_V / g.ctas, blk_c = PDP_BLK_C / g.ctas;
+    const bool ok = monotone_maps && g.max_var_degree <= blk_v / 2 && g.max_clause_degree <= blk_c / 2 &&
                     g.V > 0 && g.F > 0 && getenv("PDP_B200_NO_BLOCKED") == nullptr;
     if (!ok) {
         k_identity_layout<<<G1(E)>>>(g);
         LLK();
         return PDP_OK;
     }
-    g.sv = pick_stride(E, PDP_BLK_V, g.max_var_degree, nsm * PDP_SWEEP_CTAS_PER_SM);
-    g.sc = pick_stride(E, PDP_BLK_C, g.max_clause_degree, nsm * PDP_SWEEP_CTAS_PER_SM);
+    g.sv = pick_stride(E, blk_v, g.max_var_degree, nsm * g.ctas);
+    g.sc = pick_stride(E, blk_c, g.max_clause_degree, nsm * g.ctas);
     g.nvb = (int32_t)(E / g.sv + 1);
     g.ncb = (int32_t)(E / g.sc + 1);
-    if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 2) + PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 2) + PDP_MAX_SMS + 2) {
+    if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 4) + 2 * PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 4) + 2 * PDP_MAX_SMS + 2) {
         pdp_set_error("pdp_create: block tables too small (nvb=%d ncb=%d)", g.nvb, g.ncb);
         return PDP_ERR_WORKSPACE;
     }
@@ -296,7 +303,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
     GS(blk, g.nvb) {
         const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
         const int e0 = g.var_ptr[v0], e1 = g.var_ptr[v1];
-        if (e1 - e0 > PDP_BLK_V) atomicAdd(&errs[1], 1);
+        if (e1 - e0 > PDP_BLK_V / g.ctas) atomicAdd(&errs[1], 1);
         for (int p = e0; p < e1; ++p) {
             const int x = g.p_vpos[p];
             if (x < e0 || x >= e1 || (int)(g.vinv[x] & 0x7fff) != p - e0 ||
@@ -329,7 +336,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
     GS(blk, g.ncb) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
         const int e0 = g.cl_ptr[a0], e1 = g.cl_ptr[a1];
-        if (e1 - e0 > PDP_BLK_C) atomicAdd(&errs[2], 1);
+        if (e1 - e0 > PDP_BLK_C / g.ctas) atomicAdd(&errs[2], 1);
         for (int c = e0; c < e1; ++c) {
             const int x = g.c_qpos[c];
             if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
@@ -367,6 +374,6 @@ extern "C" int pdp_debug_check_layout(pdp_ctx* c, int32_t* d_errs, int32_t* host
         k_check_layout<<<G1(n)>>>(c->g, d_errs, seen);
         LLK();
     }
-    if (host_info) { host_info[0] = c->g.blocked_ok; host_info[1] = c->g.nvb; host_info[2] = c->g.ncb; host_info[3] = c->g.sv; host_info[4] = c->g.sc; }
+    if (host_info) { host_info[0] = c->g.blocked_ok + 16 * c->g.ctas; host_info[1] = c->g.nvb; host_info[2] = c->g.ncb; host_info[3] = c->g.sv; host_info[4] = c->g.sc; }
     return PDP_OK;
 }

@@ -108,8 +108,8 @@ __device__ __forceinline__ void termination_phase(const KArgs& A, int iter, int 
 }
 
 // FAST: the blocked shared-memory passes (pi == 0, q_u only); otherwise the generic passes
-template <bool FAST, bool FULL>
-__global__ void __launch_bounds__(FAST ? PDP_SWEEP_THREADS : 256, FAST ? PDP_SWEEP_CTAS_PER_SM : 1)
+template <bool FAST, bool FULL, int CTAS>
+__global__ void __launch_bounds__(FAST ? SweepCfg<CTAS>::kThreads : 256, FAST ? CTAS : 1)
 k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params prm, int32_t* d_iters_done) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     cg::grid_group grid = cg::this_grid();
@@ -168,9 +168,10 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #endif
 #if PDP_TMA
             tma_clause_pass(A, r, use_mask, smem_dyn, tma_sm, tma_st);
+#elif PDP_PIPELINE
+            pipe_clause_pass(A, r, use_mask, smem_dyn);
 #else
-            if (PDP_PIPELINE) pipe_clause_pass(A, r, use_mask, smem_dyn);
-            else blk_clause_pass(A, r, use_mask, smem_dyn);
+            blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn);
 #endif
             if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
@@ -189,9 +190,10 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #endif
 #if PDP_TMA
             tma_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn, tma_sm, tma_st);
+#elif PDP_PIPELINE
+            pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
 #else
-            if (PDP_PIPELINE) pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
-            else blk_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
+            blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn);
 #endif
             if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) {
                 gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
@@ -317,22 +319,25 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
     void* args[] = {&A, &prm, &d_iters_done};
     const bool fast = ctx->g.blocked_ok && !prm.full_state && prm.pi == 0.f && !(prm.flags & 1);
     if (fast) {
-        // one CTA per SM, the whole shared memory: co-residency of the cooperative grid is guaranteed
-        static bool attr_set[64] = {false};
-        if (!attr_set[ctx->device & 63]) {
-            PDP_CUDA_CHECK(cudaFuncSetAttribute(k_sp_run<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PDP_SWEEP_SMEM));
-            attr_set[ctx->device & 63] = true;
+        // one or two CTAs per SM holding the whole shared memory: co-residency of the cooperative grid is guaranteed
+        static bool attr_set[64][2] = {{false}};
+        const int two = (ctx->g.ctas == 2) ? 1 : 0;
+        void* kern = two ? (void*)k_sp_run<true, false, 2> : (void*)k_sp_run<true, false, 1>;
+        const int smem = (PDP_PIPELINE || PDP_TMA) ? PDP_SWEEP_SMEM : (two ? SweepCfg<2>::kSmem : SweepCfg<1>::kSmem);
+        const int threads = two ? SweepCfg<2>::kThreads : SweepCfg<1>::kThreads;
+        if (!attr_set[ctx->device & 63][two]) {
+            PDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set[ctx->device & 63][two] = true;
         }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<true, false>, dim3(ctx->num_sms * PDP_SWEEP_CTAS_PER_SM), dim3(PDP_SWEEP_THREADS), args,
-                                                   PDP_SWEEP_SMEM, stream));
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(ctx->num_sms * (two ? 2 : 1)), dim3(threads), args, smem, stream));
     } else if (prm.full_state) {
-        int blocks = coop_blocks(ctx, k_sp_run<false, true>);
+        int blocks = coop_blocks(ctx, k_sp_run<false, true, 1>);
         if (blocks < 1) { pdp_set_error("pdp_sp_run: occupancy query failed"); return PDP_ERR_CUDA; }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, true>, dim3(blocks), dim3(256), args, 0, stream));
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, true, 1>, dim3(blocks), dim3(256), args, 0, stream));
     } else {
-        int blocks = coop_blocks(ctx, k_sp_run<false, false>);
+        int blocks = coop_blocks(ctx, k_sp_run<false, false, 1>);
         if (blocks < 1) { pdp_set_error("pdp_sp_run: occupancy query failed"); return PDP_ERR_CUDA; }
-        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, false>, dim3(blocks), dim3(256), args, 0, stream));
+        PDP_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sp_run<false, false, 1>, dim3(blocks), dim3(256), args, 0, stream));
     }
     PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
@@ -422,8 +427,8 @@ k_phase_bench(const __grid_constant__ KArgs A, int phase, int variant, float* sc
 extern "C" int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch, void* stream_) {
     if (!ctx || !d_scratch || !ctx->g.blocked_ok) { pdp_set_error("pdp_debug_phase_bench: needs a blocked layout and a scratch array of E floats"); return PDP_ERR_ARG; }
     KArgs A = make_args(ctx);
-    PDP_CUDA_CHECK(cudaFuncSetAttribute(k_phase_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, PDP_SWEEP_SMEM));
-    k_phase_bench<<<ctx->num_sms * PDP_SWEEP_CTAS_PER_SM, PDP_SWEEP_THREADS, PDP_SWEEP_SMEM, (cudaStream_t)stream_>>>(A, phase, variant, d_scratch);
+    PDP_CUDA_CHECK(cudaFuncSetAttribute(k_phase_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepCfg<1>::kSmem));
+    k_phase_bench<<<ctx->num_sms, PDP_SWEEP_THREADS, SweepCfg<1>::kSmem, (cudaStream_t)stream_>>>(A, phase, variant, d_scratch);
     PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
 }

@@ -107,7 +107,7 @@ class Context(object):
         errs = self._new(8, dtype=torch.int32)
         info = (ctypes.c_int32 * 5)()
         self._check(self._L.pdp_debug_check_layout(self._h, _ptr(errs), ctypes.byref(info), _stream()), "pdp_debug_check_layout")
-        return errs.cpu().tolist(), dict(blocked=int(info[0]), nvb=int(info[1]), ncb=int(info[2]), sv=int(info[3]), sc=int(info[4]))
+        return errs.cpu().tolist(), dict(blocked=int(info[0]) & 15, ctas=int(info[0]) >> 4, nvb=int(info[1]), ncb=int(info[2]), sv=int(info[3]), sc=int(info[4]))
 
     def phase_bench(self, phase, variant, scratch):
         self._check(self._L.pdp_debug_phase_bench(self._h, int(phase), int(variant), _ptr(scratch), _stream()), "pdp_debug_phase_bench")

@@ -572,3 +572,29 @@ def test_local_decimation_equals_grid_decimation(spec):
     assert outs[0][8].shape[0] > 0, "no decimation happened: the test does not exercise anything"
     for a, b in zip(*outs):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("ctas", ["1", "2"])
+def test_both_cta_configurations(ctas, monkeypatch):
+    """the blocked passes exist for one 1024-thread CTA and for two 512-thread CTAs per SM (chosen per batch by
+    problem size); both must reproduce the generic passes bit for bit on the same batch"""
+    from oracle import pdp_oracle as po
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    monkeypatch.setenv("PDP_B200_CTAS", ctas)
+    batch = cnfgen.mixed_batch([(3000, 3, 4.1), (500, 3, 3.9), (800, 5, 16.0), (40000, 3, 4.2), (100, 3, 4.0)], 71)
+    E = batch[0].shape[1]
+    init = po.init_state(E, randomized=True, rng=np.random.default_rng(71))
+    outs = []
+    for generic in (False, True):
+        ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
+        errs, info = ctx.check_layout()
+        assert info["ctas"] == int(ctas) and errs[:6] == [0] * 6 and errs[6] == E and errs[7] == E
+        ctx.simplify()
+        ctx.load_state((T(init[0][0]), T(init[0][1])), (T(init[1][0]), T(init[1][1])))
+        ctx.sp_run(60, 0.02, 25, True, sync=True, generic=generic)
+        q, fs = ctx.store_state()
+        m = ctx.get_masks()
+        outs.append((C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["af"]), C(m["sol"]), C(m["active"])))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
