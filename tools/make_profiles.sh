@@ -9,7 +9,7 @@ tail -c 600 gpurun_out/${tag}_bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err
 # every launch of two steps with its device time (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --problems 2 --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --problems 2 --no-cpu-baseline --no-config0 > gpurun_out/${tag}_bench_under_ncu.log 2>&1
 # the top kernel, full sections, same workload shape as the bench (8 x n=1M), fewer iterations
 ncu --set full --clock-control none --import-source on -k regex:k_sp_run -c 1 -o gpurun_out/${tag}_sp_run \
     python tools/prof_sweep.py --problems 8 --iterations 12 > gpurun_out/${tag}_sp_run.log 2>&1

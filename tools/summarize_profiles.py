@@ -43,7 +43,7 @@ json.dump({"dram_bytes_per_edge_update": per, "dram_bytes_read": gb("dram__bytes
            "source": "ncu --set full --clock-control none, tools/make_profiles.sh, %s_sp_run.ncu-rep" % tag},
           open(os.path.join(P, "k_sp_run_traffic.json"), "w"), indent=1)
 lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep,
-                        os.path.join(ROOT, "pdp_solver_b200", "csrc", "pdp_loop.o"), "k_sp_runILb1ELb0", "30"],
+                        os.path.join(ROOT, "pdp_solver_b200", "csrc", "pdp_loop.o"), "k_sp_runILb1ELb0ELi2", "30"],
                        capture_output=True, text=True).stdout
 with open(os.path.join(P, tag + "_sp_run_ncu.md"), "w") as f:
     f.write("# ncu --set full: k_sp_run<blocked> (persistent SP propagate / decimate loop)\n\n")
