@@ -598,3 +598,38 @@ def test_both_cta_configurations(ctas, monkeypatch):
         outs.append((C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["af"]), C(m["sol"]), C(m["active"])))
     for a, b in zip(*outs):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_interleaved_problems_take_the_generic_paths():
+    """batch maps that are not sorted by problem (nodes of different problems interleaved): no blocked layout, no
+    CTA-local decimation, grid-wide WalkSAT -- the result must equal the sorted batch's, node for node"""
+    from oracle import pdp_oracle as po
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    batch = cnfgen.random_batch(10, 80, 3, 4.0, 81)
+    gm, bvm, bfm, ef = batch
+    V, F, E = bvm.shape[0], bfm.shape[0], gm.shape[1]
+    rng = np.random.default_rng(81)
+    vperm, fperm = rng.permutation(V), rng.permutation(F)        # new index of old node
+    gm2 = np.stack([vperm[gm[0]], fperm[gm[1]]]).astype(np.int32)
+    bvm2 = np.empty_like(bvm); bvm2[vperm] = bvm
+    bfm2 = np.empty_like(bfm); bfm2[fperm] = bfm
+    # keep clause-major edge order with ascending edge index inside a clause (same accumulation order per node)
+    order = np.argsort(gm2[1], kind="stable")
+    init = po.init_state(E, randomized=True, rng=np.random.default_rng(82))
+    res = []
+    for (g_, bv_, bf_, ef_, eord) in ((gm, bvm, bfm, ef, np.arange(E)), (gm2[:, order], bvm2, bfm2, ef[order], order)):
+        ctx = Context(T(g_), T(bv_), T(bf_), T(ef_))
+        errs, info = ctx.check_layout()
+        assert errs[0] == 0
+        ctx.simplify()
+        st = [[x[eord] for x in pair] for pair in init]
+        ctx.load_state((T(st[0][0]), T(st[0][1])), (T(st[1][0]), T(st[1][1])))
+        done = ctx.sp_run(120, 0.02, 25, True, sync=True)
+        m = ctx.get_masks()
+        n_act = ctx.count_active_variables()
+        res.append((info["blocked"], done, C(m["av"]), C(m["af"]), C(m["sol"]), C(m["active"]), n_act))
+    (b1, d1, av1, af1, sol1, act1, n1), (b2, d2, av2, af2, sol2, act2, n2) = res
+    assert b1 == 1 and b2 == 0
+    assert d1 == d2 and n1 == n2 and np.array_equal(act1, act2)
+    assert np.array_equal(av1, av2[vperm]) and np.array_equal(af1, af2[fperm]) and np.array_equal(sol1, sol2[vperm])
