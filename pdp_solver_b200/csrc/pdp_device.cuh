@@ -1235,6 +1235,18 @@ __device__ __forceinline__ void tma_var_pass(const KArgs& A, int r, bool use_mas
 #undef NT
 #endif  // PDP_TMA
 
+// L2 prefetch of [ptr, ptr + bytes) by one bulk instruction (16-byte granularity).  The node phases are issue bound and
+// leave the memory system idle: thread 0 starts them by pulling in what the next block of this CTA will load and the
+// write-out tables of the current block.
+__device__ __forceinline__ void l2_prefetch(const void* ptr, size_t bytes) {
+#if PDP_L2_PREFETCH
+    if (bytes == 0) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)((reinterpret_cast<uintptr_t>(ptr) + bytes - a + 15) & ~(size_t)15);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+#endif
+}
+
 // (Dynamic block scheduling through a global counter was measured and dropped: with the 2-7 equal-size blocks a CTA
 // gets per pass it evens out nothing, and smaller blocks cost more per edge than they balance.)
 
@@ -1263,6 +1275,16 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         __syncthreads();
+        if (tid == 0) {
+            l2_prefetch(g.csrc + B.e0, (size_t)B.ne * 2);
+            l2_prefetch(g.cdst + B.e0, (size_t)B.ne * 4);
+            const int nb = blk + gridDim.x;
+            if (nb < g.ncb) {
+                const BlkGeo Bn = clause_block(g, nb);
+                l2_prefetch(qin + Bn.e0, (size_t)Bn.ne * 4);
+                l2_prefetch(g.cinv + Bn.e0, (size_t)Bn.ne * 2);
+            }
+        }
         ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip, sticky);
         __syncthreads();
         ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip, eout, sticky, s.eta[r]);
@@ -1297,6 +1319,17 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         __syncthreads();
+        if (tid == 0) {
+            l2_prefetch(g.vsrc + B.e0, (size_t)B.ne * 2);
+            l2_prefetch(g.vdst + B.e0, (size_t)B.ne * 4);
+            const int nb = blk + gridDim.x;
+            if (nb < g.nvb) {
+                const BlkGeo Bn = var_block(g, nb);
+                l2_prefetch(en + Bn.e0, (size_t)Bn.ne * 4);
+                l2_prefetch(eo + Bn.e0, (size_t)Bn.ne * 4);
+                l2_prefetch(g.vinv + Bn.e0, (size_t)Bn.ne * 2);
+            }
+        }
         ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
         __syncthreads();
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
