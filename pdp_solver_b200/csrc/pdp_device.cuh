@@ -1709,6 +1709,207 @@ __device__ __forceinline__ void loc_decimate_problem(const KArgs& A, int b, int 
     LSYNC();
 }
 
+// ------------------------------------------------------------------------------------------------
+// shared-memory tier of the CTA-local decimation.  A problem whose masks, adjacency (16-bit local indices) and
+// scratch fit the group's share of the (idle) sweep buffer is decimated entirely in shared memory: the closure
+// is a chain of dozens of dependent rounds, each a couple of microseconds through global memory and tens of
+// nanoseconds here.  Same rounds, same arithmetic as loc_closure; what changed is written back at the end.
+// ------------------------------------------------------------------------------------------------
+struct TinyView {
+    uint8_t *av, *af, *pure, *single;
+    float *sol, *score;
+    int *cnt, *ev;
+    uint16_t *clp, *cvar, *vp, *vcls;   // local CSR / CSC: pointers, (local index | sign << 15)
+};
+__device__ __forceinline__ size_t tiny_bytes(int n, int m, int E) {
+    return (size_t)n * (1 + 1 + 4 + 4 + 4 + 4) + (size_t)m * 2 + (size_t)(m + 1 + n + 1 + 2 * E) * 2 + 64;
+}
+__device__ __forceinline__ TinyView tiny_carve(unsigned char* base, int n, int m, int E) {
+    TinyView t;
+    float* f = reinterpret_cast<float*>(base);
+    t.sol = f; t.score = f + n;
+    t.cnt = reinterpret_cast<int*>(f + 2 * n); t.ev = t.cnt + n;
+    uint16_t* h = reinterpret_cast<uint16_t*>(t.ev + n);
+    t.clp = h; t.vp = t.clp + (m + 1); t.cvar = t.vp + (n + 1); t.vcls = t.cvar + E;
+    uint8_t* q = reinterpret_cast<uint8_t*>(t.vcls + E);
+    t.av = q; t.pure = q + n; t.af = q + 2 * n; t.single = t.af + m;
+    return t;
+}
+
+__device__ __forceinline__ void tiny_fix(const TinyView& t, int i, float sg) {
+    for (int p = t.vp[i]; p < t.vp[i + 1]; ++p) {
+        const uint32_t w = t.vcls[p];
+        const float lit = (w & 0x8000u) ? -1.f : 1.f;
+        if (lit * sg > 0.f) t.af[w & 0x7fffu] = 0;
+    }
+    t.av[i] = 0;
+    t.sol[i] = (sg + 1.f) / 2.0f;
+}
+
+#define LSYNC() bar_sync(bar_id, nthr)
+__device__ __forceinline__ void loc_decimate_tiny(const KArgs& A, int b, int iter, int w, float pi, bool check_termination, LocSmem& ls,
+                                                  int tid, int nthr, int bar_id, unsigned char* area) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int v0 = g.prob_vptr[b], v1 = g.prob_vptr[b + 1], f0 = g.prob_fptr[b], f1 = g.prob_fptr[b + 1];
+    const int n = v1 - v0, m = f1 - f0;
+    const int ec0 = g.cl_ptr[f0], ep0 = g.var_ptr[v0], E = g.cl_ptr[f1] - ec0;
+    const TinyView t = tiny_carve(area, n, m, E);
+    // ---- stage
+    for (int i = tid; i < n; i += nthr) {
+        t.av[i] = s.av[v0 + i]; t.pure[i] = 0; t.sol[i] = s.sol[v0 + i]; t.cnt[i] = 0; t.ev[i] = 0;
+    }
+    for (int i = tid; i <= n; i += nthr) t.vp[i] = (uint16_t)(g.var_ptr[v0 + i] - ep0);
+    for (int a = tid; a < m; a += nthr) { t.af[a] = s.af[f0 + a]; t.single[a] = 0; }
+    for (int a = tid; a <= m; a += nthr) t.clp[a] = (uint16_t)(g.cl_ptr[f0 + a] - ec0);
+    for (int e = tid; e < E; e += nthr) {
+        const uint32_t cw = g.c_var[ec0 + e];
+        t.cvar[e] = (uint16_t)(((cw & PDP_IDX_MASK) - v0) | ((cw & PDP_SIGN_BIT) ? 0x8000u : 0u));
+        t.vcls[e] = (uint16_t)((g.v_cls[ep0 + e] - f0) | ((g.v_cedge[ep0 + e] & PDP_SIGN_BIT) ? 0x8000u : 0u));
+    }
+    if (tid == 0) { ls.cmax = 0u; ls.cmin = 0x7f800000u; ls.cnan = 0u; ls.arg = 0x7fffffff; ls.fixed = 0; ls.nunsat = 0; }
+    LSYNC();
+    // ---- score, arg-max, fix (pdp_decimate.py:152-171)
+    for (int i = tid; i < n; i += nthr) {
+        const float sc = score_variable(g, s, s.eta[w], v0 + i, pi);
+        t.score[i] = sc;
+        const float c = fabsf(sc) * (float)t.av[i];
+        if (c != c) ls.cnan = 1u; else { atomicMax(&ls.cmax, f2u(c)); atomicMin(&ls.cmin, f2u(c)); }
+    }
+    LSYNC();
+    if (!ls.cnan) {
+        const float mn = u2f(ls.cmin);
+        const float kmax = argmax_key(u2f(ls.cmax), mn);
+        for (int i = tid; i < n; i += nthr) {
+            const float c = fabsf(t.score[i]) * (float)t.av[i];
+            if (argmax_key(c, mn) == kmax) atomicMin(&ls.arg, i);
+        }
+    }
+    LSYNC();
+    if (tid == 0 && !ls.cnan && u2f(ls.cmax) > 0.f && ls.arg != 0x7fffffff) {
+        const int i = ls.arg;
+        const float sg = sgnf(t.score[i]);
+        if (sg != 0.f && t.av[i]) {
+            tiny_fix(t, i, sg);
+            s.masked[b] = 1; s.dirty[b] = 1;
+            ls.fixed = 1;
+            if (A.trace) {
+                const int k = atomicAdd(&s.ctrl[CTRL_TRACE_LEN], 1);
+                if (k < A.trace_cap) { A.trace[3 * k] = iter; A.trace[3 * k + 1] = v0 + i; A.trace[3 * k + 2] = (int)sg; }
+            }
+        }
+    }
+    LSYNC();
+    if (ls.fixed) {
+        for (;;) {   // unit propagation rounds, solver.py:234-273
+            if (tid == 0) { ls.flag = 0; ls.conflicts = 0; }
+            LSYNC();
+            for (int a = tid; a < m; a += nthr) {
+                if (!t.af[a]) continue;
+                int deg = 0; uint32_t hit = 0;
+                for (int c = t.clp[a]; c < t.clp[a + 1]; ++c) {
+                    const uint32_t cw = t.cvar[c];
+                    if (t.av[cw & 0x7fffu]) { ++deg; hit = cw; }
+                }
+                if (deg == 1) {
+                    t.single[a] = 1;
+                    const int j = (int)(hit & 0x7fffu);
+                    atomicAdd(&t.cnt[j], 1);
+                    atomicAdd(&t.ev[j], (hit & 0x8000u) ? -1 : 1);
+                    ls.flag = 1;
+                }
+            }
+            LSYNC();
+            if (!ls.flag) break;
+            for (int i = tid; i < n; i += nthr) {
+                const int cnt = t.cnt[i];
+                if (cnt > 0 && abs(t.ev[i]) != cnt) atomicAdd(&ls.conflicts, 1);
+            }
+            LSYNC();
+            const int nc = ls.conflicts;   // the `== 1` quirk of solver.py:257,261
+            for (int a = tid; a < m; a += nthr) {
+                if (t.single[a]) { t.af[a] = 0; t.single[a] = 0; }
+                else if (t.af[a] && nc == 1) t.af[a] = 0;
+            }
+            for (int i = tid; i < n; i += nthr)
+                if (t.av[i] && nc == 1) t.av[i] = 0;
+            if (tid == 0) { s.masked[b] = 1; if (nc >= 1) { s.is_sat[b] = 0.f; s.flags[b] |= PDP_FLAG_UP_CONFLICT; } }
+            LSYNC();
+            for (int i = tid; i < n; i += nthr) {
+                const int cnt = t.cnt[i];
+                if (cnt > 0) {
+                    const int ev = t.ev[i];
+                    t.cnt[i] = 0; t.ev[i] = 0;
+                    if (t.av[i] && abs(ev) == cnt) tiny_fix(t, i, ev > 0 ? 1.f : -1.f);
+                }
+            }
+            LSYNC();
+        }
+        for (;;) {   // pure-literal peeling rounds, solver.py:188-203
+            LSYNC();
+            if (tid == 0) ls.flag = 0;
+            LSYNC();
+            for (int i = tid; i < n; i += nthr) {
+                if (!t.av[i]) continue;
+                int deg = 0, sdeg = 0;
+                for (int p = t.vp[i]; p < t.vp[i + 1]; ++p) {
+                    const uint32_t cw = t.vcls[p];
+                    if (t.af[cw & 0x7fffu]) { ++deg; sdeg += (cw & 0x8000u) ? -1 : 1; }
+                }
+                if (deg == abs(sdeg)) {
+                    t.pure[i] = 1;
+                    t.sol[i] = ((sdeg > 0 ? 1.f : (sdeg < 0 ? -1.f : 0.f)) + 1.f) / 2.0f;
+                    ls.flag = 1;
+                }
+            }
+            LSYNC();
+            if (!ls.flag) break;
+            for (int i = tid; i < n; i += nthr) {
+                if (!t.pure[i]) continue;
+                t.pure[i] = 0;
+                for (int p = t.vp[i]; p < t.vp[i + 1]; ++p) t.af[t.vcls[p] & 0x7fffu] = 0;
+                t.av[i] = 0;
+            }
+            if (tid == 0) s.masked[b] = 1;
+        }
+        // ---- write back what changed: masks (+ edge-mask bits), solutions
+        for (int i = tid; i < n; i += nthr) {
+            if (!t.av[i] && s.av[v0 + i]) deactivate_variable(g, s, v0 + i);
+            s.sol[v0 + i] = t.sol[i];
+        }
+        for (int a = tid; a < m; a += nthr)
+            if (!t.af[a] && s.af[f0 + a]) deactivate_clause(g, s, f0 + a);
+    }
+    LSYNC();
+    if (s.dirty[b]) {
+        if (check_termination) {   // SatCNFEvaluator on _solution over the full formula, then trainer.py:150-162
+            int nun = 0;
+            for (int a = tid; a < m; a += nthr) {
+                bool sat = false;
+                for (int c = t.clp[a]; c < t.clp[a + 1]; ++c) {
+                    const uint32_t cw = t.cvar[c];
+                    if (literal_true((cw & 0x8000u) ? -1.f : 1.f, t.sol[cw & 0x7fffu])) { sat = true; break; }
+                }
+                nun += sat ? 0 : 1;
+            }
+            nun = __reduce_add_sync(0xffffffffu, nun);
+            if ((tid & 31) == 0 && nun) atomicAdd(&ls.nunsat, nun);
+            LSYNC();
+            if (tid == 0) {
+                if (ls.nunsat == 0) {
+                    if (s.active[b]) { s.active[b] = 0; s.freeze_iter[b] = iter; atomicSub(&s.ctrl[CTRL_NUM_ACTIVE], 1); }
+                    s.flags[b] |= PDP_FLAG_SOLVED;
+                }
+                s.dirty[b] = 0; s.n_unsat[b] = 0;
+            }
+        } else if (tid == 0) {
+            s.ctrl[CTRL_ANY_DIRTY] = 1;
+        }
+    }
+    if (tid == 0) s.conv[b] = 0;
+    LSYNC();
+}
+#undef LSYNC
+
 __device__ __forceinline__ bool loc_problem_is_small(const pdp_graph& g, int b) {
     return (g.prob_vptr[b + 1] - g.prob_vptr[b] <= PDP_LOCAL_MAX_V) && (g.prob_fptr[b + 1] - g.prob_fptr[b] <= PDP_LOCAL_MAX_F);
 }
@@ -1716,7 +1917,10 @@ __device__ __forceinline__ bool loc_problem_is_small(const pdp_graph& g, int b) 
 #undef LSYNC
 // groups of PDP_LOCAL_GROUP threads (named barriers 8..15) take one problem each
 #define PDP_LOCAL_GROUP 128
-__device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w, float pi, bool check_termination) {
+// `area` / `area_bytes`: the CTA's dynamic shared memory (the sweep buffer, idle during the decimation), split evenly
+// between the groups; null when the kernel has none
+__device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w, float pi, bool check_termination,
+                                                 unsigned char* area, int area_bytes) {
     __shared__ LocSmem ls[8];
     const pdp_state& s = A.s;
     int ngroups = blockDim.x / PDP_LOCAL_GROUP;
@@ -1731,7 +1935,14 @@ __device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w
         const int k = ls[grp].flag;
         bar_sync(8 + grp, gthr);
         if (k >= count) break;
-        loc_decimate_problem(A, s.loc_list[k], iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
+        const int b = s.loc_list[k];
+        const int share = area ? ((area_bytes / ngroups) & ~15) : 0;
+        const int n = A.g.prob_vptr[b + 1] - A.g.prob_vptr[b], m = A.g.prob_fptr[b + 1] - A.g.prob_fptr[b];
+        const int E = A.g.cl_ptr[A.g.prob_fptr[b + 1]] - A.g.cl_ptr[A.g.prob_fptr[b]];
+        if (n < 32768 && m < 32768 && E < 65536 && tiny_bytes(n, m, E) <= (size_t)share)
+            loc_decimate_tiny(A, b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp, area + (size_t)grp * share);
+        else
+            loc_decimate_problem(A, b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
     }
 }
 

@@ -213,7 +213,8 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         LOOP_T(20);
         if (local_ok && s.ctrl[CTRL_CONV + (iter & 1)]) {
             // converged problems one CTA can walk: scoring, arg-max, fix, closure, CNF check, termination, CTA-local
-            loc_decimate_all(A, iter, w, prm.pi, prm.check_termination != 0);
+            loc_decimate_all(A, iter, w, prm.pi, prm.check_termination != 0, FAST ? smem_dyn : nullptr,
+                             FAST ? ((PDP_PIPELINE || PDP_TMA) ? PDP_SWEEP_SMEM : SweepCfg<CTAS>::kSmem) : 0);
             LOOP_T(21);
             GRID_SYNC();
             LOOP_T(22);
