@@ -1748,12 +1748,20 @@ __device__ __forceinline__ void tiny_fix(const TinyView& t, int i, float sg) {
 
 #define LSYNC() bar_sync(bar_id, nthr)
 __device__ __forceinline__ void loc_decimate_tiny(const KArgs& A, int b, int iter, int w, float pi, bool check_termination, LocSmem& ls,
-                                                  int tid, int nthr, int bar_id, unsigned char* area) {
+                                                  int tid, int nthr, int bar_id, unsigned char* area, int share) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     const int v0 = g.prob_vptr[b], v1 = g.prob_vptr[b + 1], f0 = g.prob_fptr[b], f1 = g.prob_fptr[b + 1];
     const int n = v1 - v0, m = f1 - f0;
     const int ec0 = g.cl_ptr[f0], ep0 = g.var_ptr[v0], E = g.cl_ptr[f1] - ec0;
     const TinyView t = tiny_carve(area, n, m, E);
+    // the surveys of the problem in variable-major order, when they fit too (pi == 0: the external force column drops out)
+    const size_t eta_off = (tiny_bytes(n, m, E) + 15) & ~(size_t)15;
+    const bool stage_eta = (pi == 0.f) && (eta_off + (size_t)E * 4 <= (size_t)share);
+    float* eta_s = reinterpret_cast<float*>(area + eta_off);
+    if (stage_eta) {
+        const float* __restrict__ eta = s.eta[w];
+        for (int e = tid; e < E; e += nthr) eta_s[e] = eta[g.p_vpos[ep0 + e]];
+    }
     // ---- stage
     for (int i = tid; i < n; i += nthr) {
         t.av[i] = s.av[v0 + i]; t.pure[i] = 0; t.sol[i] = s.sol[v0 + i]; t.cnt[i] = 0; t.ev[i] = 0;
@@ -1770,7 +1778,21 @@ __device__ __forceinline__ void loc_decimate_tiny(const KArgs& A, int b, int ite
     LSYNC();
     // ---- score, arg-max, fix (pdp_decimate.py:152-171)
     for (int i = tid; i < n; i += nthr) {
-        const float sc = score_variable(g, s, s.eta[w], v0 + i, pi);
+        float sc;
+        if (stage_eta) {   // score_variable on the staged copies (same order, same operations)
+            float ps = 0.f, ns = 0.f, as = 0.f;
+            for (int p = t.vp[i]; p < t.vp[i + 1]; ++p) {
+                const uint32_t cw = t.vcls[p];
+                const float f = L10(1.f - eta_s[p]) * (float)t.af[cw & 0x7fffu];
+                const bool neg = (cw & 0x8000u) != 0u;
+                ps += (neg ? 0.f : 1.f) * f;
+                ns += (neg ? 1.f : 0.f) * f;
+                as += f;
+            }
+            sc = sp_score_tail(ps, ns, as, 0.f, 0.f);
+        } else {
+            sc = score_variable(g, s, s.eta[w], v0 + i, pi);
+        }
         t.score[i] = sc;
         const float c = fabsf(sc) * (float)t.av[i];
         if (c != c) ls.cnan = 1u; else { atomicMax(&ls.cmax, f2u(c)); atomicMin(&ls.cmin, f2u(c)); }
@@ -1940,7 +1962,7 @@ __device__ __forceinline__ void loc_decimate_all(const KArgs& A, int iter, int w
         const int n = A.g.prob_vptr[b + 1] - A.g.prob_vptr[b], m = A.g.prob_fptr[b + 1] - A.g.prob_fptr[b];
         const int E = A.g.cl_ptr[A.g.prob_fptr[b + 1]] - A.g.cl_ptr[A.g.prob_fptr[b]];
         if (n < 32768 && m < 32768 && E < 65536 && tiny_bytes(n, m, E) <= (size_t)share)
-            loc_decimate_tiny(A, b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp, area + (size_t)grp * share);
+            loc_decimate_tiny(A, b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp, area + (size_t)grp * share, share);
         else
             loc_decimate_problem(A, b, iter, w, pi, check_termination, ls[grp], gt, gthr, 8 + grp);
     }
