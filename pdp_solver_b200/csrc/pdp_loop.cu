@@ -141,13 +141,6 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
 #ifdef PDP_PHASE_TIMING
     const long long _kernel_t0 = clock64();
 #endif
-#ifdef PDP_STAGGER_EXPERIMENT
-    // role = arrival order of this CTA on its SM (trace[32 + smid] must be zero on entry)
-    __shared__ int sm_role_s;
-    if (threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); sm_role_s = A.trace ? (atomicAdd(&A.trace[32 + smid], 1) & 1) : 0; }
-    __syncthreads();
-    const int sm_role = sm_role_s;
-#endif
     grid.sync();   // everybody has read the control block before anyone may change it
 #ifdef PDP_PHASE_TIMING
     long long _lt = clock64();
@@ -163,9 +156,6 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
         if (blocked) {
-#ifdef PDP_STAGGER_EXPERIMENT
-            if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 16) & 0xff) * 1024) __nanosleep(200); }
-#endif
 #if PDP_TMA
             tma_clause_pass(A, r, use_mask, smem_dyn, tma_sm, tma_st);
 #elif PDP_PIPELINE
@@ -185,9 +175,6 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
-#ifdef PDP_STAGGER_EXPERIMENT
-            if (sm_role) { const long long t0 = clock64(); while (clock64() - t0 < (long long)((prm.flags >> 8) & 0xff) * 1024) __nanosleep(200); }
-#endif
 #if PDP_TMA
             tma_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn, tma_sm, tma_st);
 #elif PDP_PIPELINE

@@ -47,13 +47,11 @@ for rep in range(a.repeat):
     ms = e0.elapsed_time(e1)
     done = int(it.item())
     if os.environ.get("PDP_PHASE_TIMING"):
-        tr = ctx._trace.reshape(-1)[:8].cpu().numpy().astype(np.float64) * 1024.0
+        # profiling builds (-DPDP_PHASE_TIMING): thread 0 of every CTA accumulates clock64 cycles >> 10 per phase
         nct = 148 * int(os.environ.get("PDP_PHASE_TIMING"))
-        names = ["clause load", "clause node", "clause write-out", "var load", "var node", "var write-out+stats", "kernel total", "grid.sync waits"]
-        print("per-CTA mean cycles per iteration: " + ", ".join("%s %.0f" % (n, v / nct / max(done, 1)) for n, v in zip(names, tr)))
-        tr2 = ctx._trace.reshape(-1)[:24].cpu().numpy().astype(np.float64) * 1024.0 / nct / max(done, 1)
-        print("pipeline clause: M load+misc %.0f, M write-out %.0f, M wait DONE %.0f | C node+misc %.0f, C wait FULL %.0f" % tuple(tr2[8:13]))
-        print("pipeline var   : M load+misc %.0f, M write-out %.0f, M wait DONE %.0f | C node+misc %.0f, C wait FULL %.0f" % tuple(tr2[16:21]))
+        trl = ctx._trace.reshape(-1)[:32].cpu().numpy().astype(np.float64) * 1024.0 / nct / max(done, 1)
+        print("cycles/iteration/CTA: clause pass %.0f, barrier %.0f, variable pass %.0f, barrier %.0f, decide+barrier %.0f, "
+              "local decimation %.0f, barrier %.0f" % tuple(trl[16:23]))
         ctx._trace.zero_()
     print("E=%d iterations=%d  %.3f ms  %.3f ms/iter  %.2f G edge-updates/s  %.1f GB/s algorithmic" % (
         E, done, ms, ms / max(done, 1), E * done / ms / 1e6, 20.0 * E * done / ms / 1e6))
