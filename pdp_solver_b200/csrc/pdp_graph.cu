@@ -280,14 +280,19 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
     pdp_ctx* c = new pdp_ctx();
     memset(c, 0, sizeof(*c));
     if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; pdp_set_error("pdp_create: no CUDA device"); return PDP_ERR_CUDA; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; pdp_set_error("pdp_create: cudaGetDeviceProperties failed"); return PDP_ERR_CUDA; }
-    if (prop.major < 10) {
+    // cudaGetDeviceProperties costs tens of milliseconds per call; two attributes are all that is needed
+    int cc_major = 0, cc_minor = 0, sm_count = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, c->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, c->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) {
+        delete c; pdp_set_error("pdp_create: cudaDeviceGetAttribute failed"); return PDP_ERR_CUDA;
+    }
+    if (cc_major < 10) {
         delete c;
-        pdp_set_error("pdp_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        pdp_set_error("pdp_create: device is sm_%d%d; this library is built for sm_100a only", cc_major, cc_minor);
         return PDP_ERR_UNSUPPORTED;
     }
-    c->num_sms = prop.multiProcessorCount;
+    c->num_sms = sm_count;
     c->workspace = d_workspace;
     c->workspace_bytes = workspace_bytes;
     c->g.E = E; c->g.V = V; c->g.F = F; c->g.B = B;
