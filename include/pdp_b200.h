@@ -181,6 +181,18 @@ int pdp_debug_check_layout(pdp_ctx* ctx, int32_t* d_errs, int32_t* host_info, vo
  * shared-memory addresses, bit 1 = no 16-bit index tables); d_scratch: E floats */
 int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch, void* stream);
 
+/* ---- host-side ingest helpers (no device work) ---------------------------
+ * pdp_host_parse_ints: scans `text[0..len)` for decimal integers (optional leading '-', any other byte is a
+ * separator) and writes the first `cap` of them to `out`; returns how many the text holds (so a caller may
+ * size with cap = 0 first), -1 on bad arguments, -2 on a value beyond int32.  Replaces json.loads +
+ * np.array(list) of one compact-JSON row (src/pdp/factorgraph/dataset.py:120-136).
+ * pdp_host_parse_dimacs: streaming DIMACS CNF scanner (replaces the dense [m,n] clause matrix of
+ * src/dimacs2json.py:24-50): literals are written to `lits` with their 0 terminators kept; `c` lines and the
+ * `p cnf` line are skipped, `%` ends the file; info[0..3] = declared variables, declared clauses (-1 if no
+ * header), entries written, clauses seen.  PDP_ERR_WORKSPACE if `cap` entries are not enough (info[2] = need). */
+int64_t pdp_host_parse_ints(const char* text, int64_t len, int32_t* out, int64_t cap);
+int pdp_host_parse_dimacs(const char* text, int64_t len, int32_t* lits, int64_t cap, int64_t* info);
+
 /* counters for bench.py: number of kernels this library launched on behalf of the context */
 int64_t pdp_launch_count(pdp_ctx* ctx);
 

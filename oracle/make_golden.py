@@ -358,8 +358,229 @@ def gen_replicated(name, batch, T_iters, W, epsilon, seed, b, **kw):
          t_max=kw.get("t_max", 100), pred=r["pred"], solved=r["solved"], n_unsat=r["n_unsat"], events=ev, fill=fill,
          rand_var=rv, rand_coin=rc, init_dq=r["init"][1][0], init_df=r["init"][1][1])
 
+# ----------------------------------------------------------------------------------------------
+# command-line / input-pipeline fixtures (reference dataset.py, dimacs2json.py, trainer.predict)
+# ----------------------------------------------------------------------------------------------
+def _cli_rows(seed):
+    """a small mixed dataset in the compact row format, python ints only"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = []
+    specs = [(20, 3, 3.4), (35, 3, 3.8), (50, 3, 4.1), (28, 4, 7.5), (60, 3, 3.5), (24, 3, 4.3), (45, 5, 15.0),
+             (32, 3, 3.9), (55, 3, 3.7), (18, 3, 2.5), (40, 3, 4.0), (26, 4, 8.5), (48, 3, 3.6), (30, 3, 4.2)]
+    for j, (n, k, alpha) in enumerate(specs):
+        m = int(n * alpha)
+        lits, cls = [], []
+        for c in range(m):
+            vs = rng.choice(n, size=k, replace=False)
+            sg = rng.integers(0, 2, size=k) * 2 - 1
+            for v, sgn in zip(vs, sg):
+                lits.append(int((v + 1) * sgn))
+                cls.append(c + 1)
+        rows.append([[n, m], lits, cls, float(j % 2), ["prob_%02d.cnf" % j]])
+    return rows
+
+
+_DIMACS = {
+    "alpha_1.cnf": "c a comment line\nc another\np cnf 9 7\n1 -2 3 0\n-1 4 0\n5 -5 6 0\n2 2 -7 0\n-3 -4 -6 0\n9 0\n1 9 -2 0\n",
+    "beta_0.dimacs": "p cnf 12 6\n-12 3 5 0\n3 -5 0\n10 11 -12 0\n-3 0\n5 10 0\n-11 -10 -3 0\n%\n0\n",
+    "gamma.cnf": "c header with unused variables and a short clause count\np cnf 20 9\n4 -8 15 0\n-4 8 0\n15 -16 20 0\n8 16 -20 0\n-15 -4 0\n",
+}
+
+
+def gen_cli():
+    import io
+    import json
+    import yaml
+    _, _, _, _, _, trainer = compat.load_reference()
+    from pdp.factorgraph.dataset import FactorGraphDataset
+    import dimacs2json as ref_d2j
+
+    data_path = os.path.join(OUT, "cli_small.json")
+    rows = _cli_rows(71)
+    with open(data_path, "w") as f:
+        for r in rows:
+            f.write(json.dumps(r) + "\n")
+
+    # --- collate: the reference's dataset + divider, one segment and a forced split ---------------
+    arrays = {}
+    for tag, limit in (("one", 40000000), ("split", 25000)):
+        ds = FactorGraphDataset(input_file=data_path, limit=limit, hidden_dim=3)
+        out = ds.dag_collate_fn([ds[i] for i in range(len(ds))])
+        gm, bvm, bfm, ef, gf, lab, misc = out
+        arrays[tag + "_segments"] = len(gm)
+        arrays[tag + "_limit"] = limit
+        for s in range(len(gm)):
+            arrays["%s_%d_gm" % (tag, s)] = gm[s].numpy()
+            arrays["%s_%d_bvm" % (tag, s)] = bvm[s].numpy()
+            arrays["%s_%d_bfm" % (tag, s)] = bfm[s].numpy()
+            arrays["%s_%d_ef" % (tag, s)] = ef[s].numpy()
+            arrays["%s_%d_label" % (tag, s)] = lab[s].numpy()
+            arrays["%s_%d_ids" % (tag, s)] = np.array([m[0] for m in misc[s]])
+    save("cli_collate", **arrays)
+
+    # --- DIMACS: the reference's CompactDimacs on three small files --------------------------------
+    ddir = os.path.join(OUT, "dimacs")
+    os.makedirs(ddir, exist_ok=True)
+    expected = {}
+    for name, text in _DIMACS.items():
+        path = os.path.join(ddir, name)
+        with open(path, "w") as f:
+            f.write(text)
+        stem = os.path.splitext(path)[0]
+        label = float(stem[-1]) if stem[-1].isdigit() else -1          # dimacs2json.py:111
+        js = ref_d2j.CompactDimacs(path, label, False).to_json()
+        expected[name] = [[int(js[0][0]), int(js[0][1])], [int(x) for x in js[1]], [int(x) for x in js[2]], js[3], js[4]]
+    with open(os.path.join(OUT, "dimacs_expected.json"), "w") as f:
+        json.dump(expected, f)
+
+    # --- whole predict runs of the reference's trainer, two seeds (appendix A, steps 4-6) ----------
+    lines = {}
+    T_iters = 1000
+    for seed in (1, 2):
+        config = {"model_type": "p-d-p", "model_name": "sp", "tolerance": 0.02, "t_max": 100,
+                  "test_path": data_path, "test_recurrence_num": T_iters, "batch_replication": 1, "batch_size": 5000,
+                  "max_cache_size": 100000, "test_batch_limit": 25000, "local_search_iteration": 0, "epsilon": 0.5,
+                  "verbose": False, "cpu_mode": True, "random_seed": seed, "model_path": None, "hidden_dim": 3,
+                  "dropout": 0, "error_dim": 1, "exploration": 0}
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        tr = trainer.SatFactorGraphTrainer(config=config, use_cuda=False, logger=compat._NullLogger())
+        tr._num_cores = 0
+        buf = io.StringIO()
+        tr.predict(test_list=data_path, out_file=buf, import_path_base=None,
+                   post_processor=tr._post_process_predictions, batch_replication=1)
+        lines["seed%d" % seed] = buf.getvalue()
+    with open(os.path.join(OUT, "cli_expected.json"), "w") as f:
+        json.dump({"iterations": T_iters, "test_batch_limit": 25000, "outputs": lines}, f)
+    print("wrote cli fixtures")
+
+# ----------------------------------------------------------------------------------------------
+# the remaining model types: reinforce (pi terms, coin-gated external forces) and np-d-np (neural
+# propagator + sequential decimator with a neural scorer)
+# ----------------------------------------------------------------------------------------------
+def gen_reinforce(name, batch, T_iters, seed, pi, p_dec, randomized):
+    solver, prop, dec, pred, util, trainer = compat.load_reference()
+    gm, bvm, bfm, ef = tensors(batch)
+    torch.manual_seed(seed)
+    model = solver.ReinforceSurveyPropagatorSolver(DEV, "r", pi=pi, decimation_probability=p_dec,
+                                                   local_search_iterations=0, epsilon=0.5)
+    cb0 = compat.make_termination_callback(DEV)
+    preds, actives, coins = [], [], []
+
+    def cb(active, prediction, sat_problem):
+        preds.append(prediction[0].numpy().reshape(-1).copy())
+        cb0(active, prediction, sat_problem)
+        actives.append(active[:, 0].numpy().copy())
+
+    orig_rand = torch.rand
+
+    def rand_hook(*a, **k):
+        r = orig_rand(*a, **k)
+        assert r.numel() == 1
+        coins.append(float(r.reshape(-1)[0]))
+        return r
+
+    with torch.no_grad():
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=randomized, batch_replication=1)
+        init_np = [[t.clone().numpy() for t in st] for st in init]
+        try:
+            torch.rand = rand_hook
+            (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                                      edge_feature=ef, meta_data=None, is_training=False, iteration_num=T_iters,
+                                      check_termination=cb, simplify=True, batch_replication=1)
+        finally:
+            torch.rand = orig_rand
+    save(name, graph_map=batch[0], bvm=batch[1], bfm=batch[2], ef=batch[3], T=T_iters, pi=pi, p_dec=p_dec,
+         coins=np.array(coins, np.float32), preds=np.stack(preds).astype(np.float32), actives=np.stack(actives),
+         pred=vp.numpy().reshape(-1), init_p0=init_np[0][0], init_p1=init_np[0][1], init_d0=init_np[1][0],
+         init_d1=init_np[1][1], final_q=ps[0].numpy(), final_f=ps[1].numpy())
+
+
+def gen_npdnp(name, batch, T_iters, seed, dims, tol, t_max, with_termination):
+    solver, prop, dec, pred, util, trainer = compat.load_reference()
+    gm, bvm, bfm, ef = tensors(batch)
+    H, MH, AH, MAH, CH = dims
+    torch.manual_seed(seed)
+    model = solver.NeuralSequentialDecimatorSolver(DEV, "m", edge_dimension=1, meta_data_dimension=0, propagator_dimension=H,
+                                                   decimator_dimension=H, mem_hidden_dimension=MH, agg_hidden_dimension=AH,
+                                                   mem_agg_hidden_dimension=MAH, classifier_dimension=CH, dropout=0,
+                                                   tolerance=tol, t_max=t_max, local_search_iterations=0, epsilon=0.5)
+    model.eval()
+    cb0 = compat.make_termination_callback(DEV)
+    events, state, actives, draws = [], dict(it=0), [], []
+    orig_dec = model._decimator.forward
+
+    def dec_hook(*a, **k):
+        state["it"] += 1
+        state["problem"] = a[2]
+        return orig_dec(*a, **k)
+
+    model._decimator.forward = dec_hook
+    orig_set = solver.SATProblem.set_variables
+
+    def set_hook(self, assignment):
+        for i in torch.nonzero(assignment[:, 0]).flatten().tolist():
+            events.append((state["it"], i, int(assignment[i, 0].item())))
+        return orig_set(self, assignment)
+
+    def cb(active, prediction, sat_problem):
+        cb0(active, prediction, sat_problem)
+        actives.append(active[:, 0].numpy().copy())
+        state["problem"] = sat_problem
+
+    orig_rand = torch.rand
+
+    def rand_hook(*a, **k):
+        r = orig_rand(*a, **k)
+        draws.append(r.numpy().copy().reshape(-1))
+        return r
+
+    with torch.no_grad():
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=True, batch_replication=1)
+        init_np = [[t.clone().numpy() for t in st] for st in init]
+        try:
+            solver.SATProblem.set_variables = set_hook
+            torch.rand = rand_hook
+            (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                                      edge_feature=ef, meta_data=None, is_training=False, iteration_num=T_iters,
+                                      check_termination=cb if with_termination else None, simplify=True,
+                                      batch_replication=1)
+        finally:
+            torch.rand = orig_rand
+            solver.SATProblem.set_variables = orig_set
+    sp = state["problem"]
+    arrays = dict(graph_map=batch[0], bvm=batch[1], bfm=batch[2], ef=batch[3], T=T_iters, dims=np.array(dims), tol=tol,
+                  t_max=t_max, events=np.array(events, dtype=np.int64).reshape(-1, 3), with_termination=with_termination,
+                  actives=np.stack(actives) if actives else np.zeros((0, 0)),
+                  iterations=state["it"], pred=vp.numpy().reshape(-1), av=sp._active_variables[:, 0].numpy(),
+                  af=sp._active_functions[:, 0].numpy(), fill=np.concatenate(draws) if draws else np.zeros(0, np.float32),
+                  init_p0=init_np[0][0], init_p1=init_np[0][1], init_d0=init_np[1][0], init_d1=init_np[1][1],
+                  final_p0=ps[0].numpy(), final_p1=ps[1].numpy())
+    seen, alias = {}, []
+    for k, v in model.state_dict().items():
+        key = (v.data_ptr(), tuple(v.shape))
+        if key in seen:
+            alias.append("%s=%s" % (k, seen[key]))
+        else:
+            seen[key] = k
+            arrays["w:" + k] = v.numpy()
+    arrays["w_alias"] = np.array(";".join(alias))
+    save(name, **arrays)
+    print("  %d decimation events in %d iterations" % (len(events), state["it"]))
+
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "types":
+        gen_reinforce("reinforce_a", cnfgen.random_batch(1, 40, 3, 3.8, 81), 60, 11, 0.01, 0.5, False)
+        gen_reinforce("reinforce_b", cnfgen.random_batch(5, 30, 3, 3.5, 82), 80, 12, 0.1, 0.5, False)
+        gen_reinforce("reinforce_c", cnfgen.mixed_batch([(30, 3, 4.0), (20, 5, 15.0), (24, 4, 8.0)], 83), 50, 13, 0.05, 0.7, True)
+        gen_npdnp("npdnp_a", cnfgen.random_batch(3, 18, 3, 3.6, 91), 24, 21, (24, 16, 16, 8, 8), 0.02, 3, False)
+        gen_npdnp("npdnp_b", cnfgen.mixed_batch([(16, 3, 3.0), (12, 4, 7.0)], 92), 20, 22, (16, 12, 10, 6, 8), 0.5, 4, False)
+        gen_npdnp("npdnp_c", cnfgen.random_batch(4, 14, 3, 3.2, 93), 12, 23, (16, 12, 10, 6, 8), 0.1, 3, True)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cli":
+        gen_cli()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "replicated":
         gen_replicated("rep_b3_a", cnfgen.random_batch(5, 30, 3, 3.7, 61), 120, 25, 0.5, 9, 3, t_max=30)
         gen_replicated("rep_b2_b", cnfgen.mixed_batch([(30, 3, 3.9), (20, 5, 14.0), (25, 3, 3.0)], 62), 100, 30, 0.4, 10, 2, t_max=25)

@@ -89,6 +89,7 @@ class Oracle(object):
         L = lib()
         gm = np.ascontiguousarray(np.asarray(graph_map, dtype=np.int32))
         self.E = int(gm.shape[1])
+        self.gm = gm
         self.bvm = np.ascontiguousarray(np.asarray(batch_variable_map, dtype=np.int32))
         self.bfm = np.ascontiguousarray(np.asarray(batch_function_map, dtype=np.int32))
         self.V = int(self.bvm.shape[0])
@@ -251,3 +252,67 @@ def init_state(E, randomized=False, rng=None):
     df = rng.random((E, 2), dtype=np.float32)
     df[:, 1] = 0
     return (pq, pf), (dq, df)
+
+
+# ---- model type `reinforce` ------------------------------------------------------------------------
+def _smooth_max_by_variable(o, x):
+    "sparse_smooth_max (reference util.py:282-286): fp32 sums in ascending edge order per variable"
+    x = x.astype(np.float32)
+    w = np.exp(np.minimum(np.float32(30.0) * x, np.float32(30.0))).astype(np.float32)
+    num = np.zeros(o.V, np.float32)
+    den = np.zeros(o.V, np.float32)
+    np.add.at(num, o.gm[0], (x * w).astype(np.float32))
+    np.add.at(den, o.gm[0], w)
+    return (num / np.maximum(den, np.float32(1.0))).astype(np.float32)
+
+
+def _sparse_max(o, x):
+    "sparse_max (reference util.py:267-275): batch-global min, zero floor, fl(fl(max + min) - 1)"
+    x = x.astype(np.float32)
+    mn = np.float32(x.min())
+    mx = np.zeros(o.B, np.float32)
+    np.maximum.at(mx, o.bvm, ((x - mn).astype(np.float32) + np.float32(1.0)).astype(np.float32))
+    return ((mx + mn).astype(np.float32) - np.float32(1.0)).astype(np.float32)
+
+
+def reinforce_run(o, init_prop, init_dec, T, pi, p_dec, coins):
+    """The reference's loop (solver.py:355-386) for ReinforceSurveyPropagatorSolver on the oracle's C operators:
+    SurveyPropagator with pi (pdp_propagate.py:139-221), ReinforceDecimator (pdp_decimate.py:204-233),
+    ReinforcePredictor (pdp_predict.py:221-226), _update_solution (solver.py:388-399) and the trainer's termination
+    (trainer.py:150-162).  Returns (merged prediction per iteration, final q [E,3], final [eta, force] [E,2])."""
+    o.simplify()
+    o.compute_edge_mask()
+    m = o.masks()
+    av, af, sol, em = m["av"], m["af"], m["sol"].copy(), m["em"]
+    var = o.gm[0]
+    active = np.ones(o.B, np.uint8)
+    ps = (np.asarray(init_prop[0], np.float32), np.asarray(init_prop[1], np.float32))
+    ds = (np.asarray(init_dec[0], np.float32), np.asarray(init_dec[1], np.float32))
+    prev, em_attr, merged_all = None, None, []
+    for t in range(int(T)):
+        q, f = o.sp_step(ds[0], ds[1], ds[2] if len(ds) == 3 else None, ps[0], ps[1], active, pi)
+        eta = f[:, 0]
+        if prev is not None and av.sum() > 0:
+            diff = np.abs(prev - eta)
+            if em_attr is not None:
+                diff = diff * em_attr
+            sd = _sparse_max(o, _smooth_max_by_variable(o, diff) * av)
+            active[sd <= 0.01] = 0
+        prev = eta.copy()
+        if coins[t] < p_dec:
+            mask = active[o.bvm[var]].astype(np.float32)
+            score = o.score(f, af, pi)
+            f[:, 1] = mask * np.sign(score)[var] + (1 - mask) * f[:, 1]
+        ps = (q, f)
+        em_attr = em
+        ds = (q, f, em) if em.sum() < o.E else (q, f)
+        force = np.zeros(o.V, np.float32)
+        np.add.at(force, var, f[:, 1])
+        merged = av * (force > 0).astype(np.float32) + (1 - av) * sol
+        sol[av == 1] = merged[av == 1]
+        merged_all.append(merged.copy())
+        solved, _ = o.cnf_eval(merged)
+        active[(active == 1) & (solved > 0.5)] = 0
+        if active.sum() == 0:
+            break
+    return merged_all, ps[0], ps[1]

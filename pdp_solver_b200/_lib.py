@@ -58,6 +58,8 @@ SIGNATURES = {
     "pdp_debug_check_layout": (ctypes.c_int, [P, P, ctypes.POINTER(I32 * 5), P]),
     "pdp_debug_phase_bench": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P]),
     "pdp_launch_count": (I64, [P]),
+    "pdp_host_parse_ints": (I64, [ctypes.c_char_p, I64, P, I64]),
+    "pdp_host_parse_dimacs": (ctypes.c_int, [ctypes.c_char_p, I64, P, I64, ctypes.POINTER(I64 * 4)]),
 }
 
 

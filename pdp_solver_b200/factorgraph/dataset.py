@@ -1,0 +1,171 @@
+"""Input pipeline of the predict path: compact-JSON rows -> batched edge lists (reference
+src/pdp/factorgraph/dataset.py).  Same classes and batching rules as the reference; what changed is how the
+work is done:
+
+* a row is scanned by the library's integer scanner (`pdp_host_parse_ints`) straight into int32 arrays instead of
+  `json.loads` -> Python lists -> `np.array` (dataset.py:120-136);
+* a segment is collated with one concatenate + `np.repeat` of the per-problem offsets instead of the per-problem
+  `np.concatenate` growth loop (dataset.py:166-185, O(B^2) copies), and the cached rows are not modified (the
+  reference adds the offsets into its cached arrays in place, dataset.py:172-173);
+* the tensors come out in pinned memory, ready for an asynchronous host-to-device copy.
+
+Row format (dataset.py:120-136): `[[n, m], [+-(variable+1) per edge], [clause+1 per edge], label, [id]]`.
+"""
+import ctypes
+import json
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class DynamicBatchDivider(object):
+    "The dynamic batching rule of the reference (dataset.py:17-79): segments of at most limit // (E_max * hidden_dim) problems."
+
+    def __init__(self, limit, hidden_dim):
+        self.limit = limit
+        self.hidden_dim = hidden_dim
+
+    def divide_indices(self, edge_num):
+        """index lists of the segments, in the reference's order: one segment in input order when everything fits,
+        otherwise descending edge count (stable), cut greedily"""
+        batch_size = len(edge_num)
+        if batch_size == 0:
+            return []
+        if (self.limit // (max(edge_num) * self.hidden_dim)) >= batch_size:
+            return [list(range(batch_size))]
+        order = sorted(range(batch_size), reverse=True, key=lambda k: edge_num[k])
+        segments, i = [], 0
+        while i < batch_size:
+            allowed = self.limit // (edge_num[order[i]] * self.hidden_dim)
+            if allowed <= 0:
+                raise ValueError("test_batch_limit too small for a problem with %d edges" % edge_num[order[i]])
+            segments.append(order[i:min(i + allowed, batch_size)])
+            i += allowed
+        return segments
+
+    def divide(self, variable_num, function_num, graph_map, edge_feature, graph_feature, label, misc_data):
+        "reference signature (dataset.py:24-79): lists of per-segment lists"
+        cols = (variable_num, function_num, graph_map, edge_feature, label, misc_data)
+        segs = self.divide_indices([len(e) for e in edge_feature])
+        out = [[[c[j] for j in ind] for ind in segs] for c in cols]
+        gf = [[None] if graph_feature[0] is None else [graph_feature[j] for j in ind] for ind in segs]
+        return out[0], out[1], out[2], out[3], gf, out[4], out[5]
+
+
+def parse_row(text):
+    """One compact-JSON row -> (variable_num, function_num, graph_map int32[2,E], edge_feature f32[E], None, label,
+    misc) exactly as the reference's `_convert_line` (dataset.py:120-136)."""
+    if isinstance(text, str):
+        text = text.encode()
+    lib = _lib.load()
+    # the two integer lists are the 2nd and 3rd bracketed groups: "[[n, m], [..], [..], label, [id]]"
+    h1 = text.index(b"]")
+    a0 = text.index(b"[", h1)
+    a1 = text.index(b"]", a0)
+    b0 = text.index(b"[", a1)
+    b1 = text.index(b"]", b0)
+    head = json.loads(text[text.index(b"[") + 1:h1 + 1].decode())
+    variable_num, function_num = int(head[0]), int(head[1])
+    tail = json.loads("[" + text[b1 + 1:].decode().lstrip().lstrip(","))   # label, [id]] -> [label, [id]]
+    label = float(tail[0])
+    misc = tail[1] if len(tail) > 1 else []
+
+    def ints(lo, hi):
+        n_max = (hi - lo) // 2 + 1
+        out = np.empty(n_max, dtype=np.int32)
+        seg = text[lo:hi]
+        n = lib.pdp_host_parse_ints(seg, len(seg), ctypes.c_void_p(out.ctypes.data), n_max)
+        if n < 0 or n > n_max:
+            raise ValueError("malformed integer list in input row")
+        return out[:n]
+
+    lit = ints(a0 + 1, a1)
+    cls = ints(b0 + 1, b1)
+    if lit.shape[0] != cls.shape[0]:
+        raise ValueError("input row: %d literals but %d clause indices" % (lit.shape[0], cls.shape[0]))
+    graph_map = np.stack((np.abs(lit) - 1, np.abs(cls) - 1))
+    edge_feature = np.sign(lit).astype(np.float32)
+    return (variable_num, function_num, graph_map, edge_feature, None, label, misc)
+
+
+def collate_segment(rows, pin=False):
+    """One segment -> (graph_map int32[2,E], batch_variable_map int32[V], batch_function_map int32[F],
+    edge_feature f32[E,1], None, label f32[B,1], misc list) with the reference's numbering
+    (dataset.py:166-185): problem j's variables / clauses are shifted by the totals of problems 0..j-1."""
+    B = len(rows)
+    vn = np.fromiter((r[0] for r in rows), dtype=np.int64, count=B)
+    fn = np.fromiter((r[1] for r in rows), dtype=np.int64, count=B)
+    en = np.fromiter((r[2].shape[1] for r in rows), dtype=np.int64, count=B)
+    E, V, F = int(en.sum()), int(vn.sum()), int(fn.sum())
+    if max(E, V, F) >= 2 ** 31:
+        raise ValueError("segment exceeds int32 indexing")
+    voff = np.concatenate(([0], np.cumsum(vn)[:-1])).astype(np.int32)
+    foff = np.concatenate(([0], np.cumsum(fn)[:-1])).astype(np.int32)
+
+    def buf(shape, dtype):
+        t = torch.empty(shape, dtype=dtype)
+        return t.pin_memory() if pin and torch.cuda.is_available() else t
+
+    gm = buf((2, E), torch.int32)
+    ef = buf((E, 1), torch.float32)
+    g, f = gm.numpy(), ef.numpy()
+    if B:
+        np.concatenate([r[2] for r in rows], axis=1, out=g)
+        g[0] += np.repeat(voff, en)
+        g[1] += np.repeat(foff, en)
+        np.concatenate([r[3] for r in rows], out=f[:, 0])
+    bvm = buf((V,), torch.int32)
+    bfm = buf((F,), torch.int32)
+    pid = np.arange(B, dtype=np.int32)
+    bvm.numpy()[:] = np.repeat(pid, vn)
+    bfm.numpy()[:] = np.repeat(pid, fn)
+    label = torch.from_numpy(np.array([[r[5]] for r in rows], dtype=np.float32).reshape(B, 1))
+    return gm, bvm, bfm, ef, None, label, [r[6] for r in rows]
+
+
+class FactorGraphDataset(object):
+    "Reads CNFs in the compact JSON format (reference dataset.py:85-187), one row per line."
+
+    def __init__(self, input_file, limit, hidden_dim, max_cache_size=100000, generator=None, epoch_size=0,
+                 batch_replication=1, rows=None):
+        self._input_file = input_file
+        self._rows = rows            # already-parsed rows (DIMACS input)
+        self._offsets = None
+        if rows is None:
+            # byte offsets of the lines, one pass (the reference reads the whole file to count rows, dataset.py:96-97)
+            offs, pos = [], 0
+            with open(input_file, "rb") as fh:
+                for line in fh:
+                    if line.strip():
+                        offs.append((pos, len(line)))
+                    pos += len(line)
+            self._offsets = offs
+        self.batch_divider = DynamicBatchDivider(limit // batch_replication, hidden_dim)
+
+    def __len__(self):
+        return len(self._rows) if self._rows is not None else len(self._offsets)
+
+    def __getitem__(self, idx):
+        if self._rows is not None:
+            return self._rows[idx]
+        pos, n = self._offsets[idx]
+        with open(self._input_file, "rb") as fh:
+            fh.seek(pos)
+            return parse_row(fh.read(n))
+
+    _convert_line = staticmethod(parse_row)
+
+    def dag_collate_fn(self, input_data, pin=False):
+        """reference dataset.py:138-187: a list of rows -> per-segment lists
+        (graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat, label, misc_data)"""
+        segs = self.batch_divider.divide_indices([r[2].shape[1] for r in input_data])
+        cols = [collate_segment([input_data[j] for j in ind], pin) for ind in segs]
+        return tuple([c[k] for c in cols] for k in range(7))
+
+    def batches(self, batch_size, pin=False):
+        "what the reference's DataLoader(batch_size, shuffle=False, collate_fn=dag_collate_fn) yields"
+        n = len(self)
+        for lo in range(0, n, batch_size):
+            yield self.dag_collate_fn([self[i] for i in range(lo, min(lo + batch_size, n))], pin)

@@ -113,3 +113,15 @@ class SurveyScorer(nn.Module):
             variable_state._pdp_const = ((1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0), variable_state._version)
             function_state._pdp_const = ((0.5, 0.0), function_state._version)
         return (variable_state, function_state)
+
+
+class ReinforcePredictor(nn.Module):
+    "Prediction of the Reinforce algorithm: a variable is True iff its external forces sum to > 0 (reference pdp_predict.py:214-226)."
+
+    def __init__(self, device):
+        super(ReinforcePredictor, self).__init__()
+        self._device = device
+
+    def forward(self, decimator_state, sat_problem, last_call=False):
+        s, _ = sat_problem._ctx.edge_aggregate(decimator_state[1][:, 1:2].contiguous(), by_variable=True)
+        return (s > 0).float(), None

@@ -220,7 +220,8 @@ class PropagatorDecimatorSolverBase(nn.Module):
 
         propagator_state = decimator_state = None
         if self._propagator is not None and self._decimator is not None:
-            if isinstance(self._decimator, pdp_decimate.SequentialDecimator):
+            if isinstance(self._decimator, pdp_decimate.SequentialDecimator) and \
+                    isinstance(self._decimator._scorer, pdp_predict.SurveyScorer):
                 propagator_state, decimator_state = self._forward_core(
                     init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination)
             else:
@@ -276,8 +277,9 @@ class PropagatorDecimatorSolverBase(nn.Module):
         return state, state
 
     def _forward_core_stepwise(self, init_propagator_state, init_decimator_state, sat_problem, iteration_num, check_termination):
-        """reference solver.py:355-386 for the neural compositions, one iteration at a time like the reference
-        (no variable is ever fixed here, so the masks only change in the initial simplify())."""
+        """reference solver.py:355-386 for the compositions that are not the fused p-d-p loop (p-nd-np, np-nd-np,
+        np-d-np, reinforce), one iteration at a time like the reference.  Only the sequential decimator of np-d-np
+        fixes variables; for the others the masks only change in the initial simplify()."""
         ctx = sat_problem._ctx
         propagator_state, decimator_state = init_propagator_state, init_decimator_state
         active_mask = None if check_termination is None else torch.ones(ctx.B, 1, dtype=torch.uint8, device=ctx.device)
@@ -285,11 +287,15 @@ class PropagatorDecimatorSolverBase(nn.Module):
         masked = bool((edge_mask.sum() < ctx.E).item())
         standard = check_termination is not None and _is_standard_termination(check_termination)
         rep = sat_problem._batch_replication
+        fixes = isinstance(self._decimator, pdp_decimate.SequentialDecimator)
         done = 0
         for _ in range(int(iteration_num)):
             propagator_state = self._propagator(propagator_state, decimator_state, sat_problem, False, active_mask)
             decimator_state = self._decimator(decimator_state, propagator_state, sat_problem, False, active_mask)
             sat_problem._edge_mask_set = True
+            if fixes:
+                edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
+                masked = bool((edge_mask.sum() < ctx.E).item())
             if masked:
                 decimator_state = tuple(decimator_state[:2]) + (edge_mask,)     # solver.py:373-374
             done += 1
@@ -353,14 +359,6 @@ class WalkSATSolver(PropagatorDecimatorSolverBase):
             local_search_iterations=iteration_num, epsilon=epsilon)
 
 
-def _out_of_scope(name):
-    class _Stub(PropagatorDecimatorSolverBase):
-        def __init__(self, *a, **k):
-            raise NotImplementedError("%s is not part of the accelerated path yet (SURVEY.md section 8f)" % name)
-    _Stub.__name__ = name
-    return _Stub
-
-
 class NeuralPropagatorDecimatorSolver(PropagatorDecimatorSolverBase):
     "The fully neural PDP solver, model type `np-nd-np` (reference solver.py:517-537)."
 
@@ -401,5 +399,43 @@ class NeuralSurveyPropagatorSolver(PropagatorDecimatorSolverBase):
         self.to(device)
 
 
-ReinforceSurveyPropagatorSolver = _out_of_scope("ReinforceSurveyPropagatorSolver")
-NeuralSequentialDecimatorSolver = _out_of_scope("NeuralSequentialDecimatorSolver")
+class ReinforceSurveyPropagatorSolver(PropagatorDecimatorSolverBase):
+    """The classical Reinforce solver, model type `reinforce` (reference solver.py:598-610): SP with the pi
+    reinforcement term, external forces set from the SP biases under a batch-global coin, no variable fixing.  Runs
+    step by step on the library's stateless operators (pdp_sp_step, pdp_score, pdp_edge_aggregate, pdp_cnf_eval)."""
+
+    def __init__(self, device, name, pi=0.1, decimation_probability=0.5, local_search_iterations=0, epsilon=0.05):
+        super(ReinforceSurveyPropagatorSolver, self).__init__(
+            device=device, name=name,
+            propagator=pdp_propagate.SurveyPropagator(device, decimator_dimension=1, include_adaptors=False, pi=pi),
+            decimator=pdp_decimate.ReinforceDecimator(
+                device, scorer=pdp_predict.SurveyScorer(device, message_dimension=1, include_adaptors=False, pi=pi),
+                decimation_probability=decimation_probability),
+            predictor=pdp_predict.ReinforcePredictor(device=device),
+            local_search_iterations=local_search_iterations, epsilon=epsilon)
+
+
+class NeuralSequentialDecimatorSolver(PropagatorDecimatorSolverBase):
+    """Neural propagator + sequential decimator with a neural scorer, model type `np-d-np` (reference
+    solver.py:616-637).  Step by step: dense layers through torch, segmented sums / statistics / variable fixing with
+    unit propagation and peeling / CNF check / WalkSAT on the library's kernels."""
+
+    def __init__(self, device, name, edge_dimension, meta_data_dimension, propagator_dimension, decimator_dimension,
+                 mem_hidden_dimension, agg_hidden_dimension, mem_agg_hidden_dimension, classifier_dimension, dropout,
+                 tolerance, t_max, local_search_iterations=0, epsilon=0.05):
+        super(NeuralSequentialDecimatorSolver, self).__init__(
+            device=device, name=name,
+            propagator=pdp_propagate.NeuralMessagePasser(device, edge_dimension, decimator_dimension, meta_data_dimension,
+                                                         propagator_dimension, mem_hidden_dimension, mem_agg_hidden_dimension,
+                                                         agg_hidden_dimension, dropout),
+            decimator=pdp_decimate.SequentialDecimator(
+                device, message_dimension=(3, 1),
+                scorer=pdp_predict.NeuralPredictor(device, decimator_dimension, 1, edge_dimension, meta_data_dimension,
+                                                   mem_hidden_dimension, agg_hidden_dimension, mem_agg_hidden_dimension,
+                                                   variable_classifier=util.PerceptronTanh(decimator_dimension,
+                                                                                           classifier_dimension, 1),
+                                                   function_classifier=None),
+                tolerance=tolerance, t_max=t_max),
+            predictor=pdp_predict.IdentityPredictor(device=device, random_fill=True),
+            local_search_iterations=local_search_iterations, epsilon=epsilon)
+        self.to(device)

@@ -62,6 +62,18 @@ class Perceptron(nn.Module):
         return torch.sigmoid(self._layer2(F.relu(self._layer1(inp))))
 
 
+class PerceptronTanh(nn.Module):
+    "1-hidden-layer perceptron with tanh output, the np-d-np scorer's classifier (reference util.py:240-250)."
+
+    def __init__(self, input_dimension, hidden_dimension, output_dimension):
+        super(PerceptronTanh, self).__init__()
+        self._layer1 = nn.Linear(input_dimension, hidden_dimension)
+        self._layer2 = nn.Linear(hidden_dimension, output_dimension, bias=False)
+
+    def forward(self, inp):
+        return torch.tanh(self._layer2(torch.relu(self._layer1(inp))))
+
+
 class SatCNFEvaluator(nn.Module):
     """Verdict and number of unsatisfied clauses per problem for a variable prediction
     (reference util.py:203-236).  Integer-exact: a literal is true iff s*p + (1-s)/2 > 0.5 in fp32."""

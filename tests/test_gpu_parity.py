@@ -633,3 +633,89 @@ def test_interleaved_problems_take_the_generic_paths():
     assert b1 == 1 and b2 == 0
     assert d1 == d2 and n1 == n2 and np.array_equal(act1, act2)
     assert np.array_equal(av1, av2[vperm]) and np.array_equal(af1, af2[fperm]) and np.array_equal(sol1, sol2[vperm])
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining model types: reinforce and np-d-np against the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+def _standard_termination():
+    def termination(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+    return termination
+
+
+@pytest.mark.parametrize("path", golden("reinforce_*.npz"), ids=name)
+def test_reinforce_forward_vs_reference(path):
+    """model type `reinforce` with the reference's coin draws injected: per-iteration merged predictions and the
+    iteration at which every problem retired are exact, final messages within the survey tolerance"""
+    from pdp_solver_b200.nn import solver as S
+    z = load(path)
+    model = S.ReinforceSurveyPropagatorSolver(dev(), "r", pi=float(z["pi"]), decimation_probability=float(z["p_dec"]),
+                                              local_search_iterations=0, epsilon=0.5)
+    coins = iter(z["coins"].tolist())
+    model._decimator._coin_source = lambda: next(coins)
+    gm, bvm, bfm, ef = T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"])
+    init = ((T(z["init_p0"]), T(z["init_p1"])), (T(z["init_d0"]), T(z["init_d1"])))
+    merged = []
+    orig = S.SATProblem.update_solution
+
+    def hook(self, variable_prediction):
+        out = orig(self, variable_prediction)
+        merged.append(C(out).reshape(-1))
+        return out
+
+    S.SATProblem.update_solution = hook
+    try:
+        with torch.no_grad():
+            (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                                      edge_feature=ef, meta_data=None, is_training=False, iteration_num=int(z["T"]),
+                                      check_termination=_standard_termination(), simplify=True, batch_replication=1)
+    finally:
+        S.SATProblem.update_solution = orig
+    ref = z["preds"]
+    assert int(model.last_iterations.item()) == ref.shape[0] == z["coins"].shape[0], "iteration count differs"
+    assert len(merged) == ref.shape[0] + 1                      # + the final merge of solver.py:342-348
+    for it, (a, b) in enumerate(zip(merged, ref)):
+        assert maxdiff(a, b) == 0, "prediction differs at iteration %d" % (it + 1)
+    assert maxdiff(C(vp).reshape(-1), z["pred"]) == 0
+    assert maxdiff(C(ps[0]), z["final_q"]) < SURVEY_TOL and maxdiff(C(ps[1]), z["final_f"]) < SURVEY_TOL
+    assert ds[1] is ps[1]                                       # the decimator edits the propagator's state in place
+
+
+@pytest.mark.parametrize("path", golden("npdnp_*.npz"), ids=name)
+def test_npdnp_forward_vs_reference(path):
+    """model type `np-d-np` with the reference's weights and injected initial states: identical decimation sequence,
+    final masks, iteration count; final hidden states within the GEMM tolerance"""
+    from pdp_solver_b200.nn import solver as S
+    z = load(path)
+    H, MH, AH, MAH, CH = [int(x) for x in z["dims"]]
+    model = S.NeuralSequentialDecimatorSolver(dev(), "m", edge_dimension=1, meta_data_dimension=0, propagator_dimension=H,
+                                              decimator_dimension=H, mem_hidden_dimension=MH, agg_hidden_dimension=AH,
+                                              mem_agg_hidden_dimension=MAH, classifier_dimension=CH, dropout=0,
+                                              tolerance=float(z["tol"]), t_max=int(z["t_max"]), local_search_iterations=0,
+                                              epsilon=0.5)
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    for pair in str(z["w_alias"]).split(";"):
+        if pair:
+            k, src = pair.split("=")
+            sd[k] = sd[src]
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev()).eval()
+    gm, bvm, bfm, ef = T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"])
+    model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=1)     # resets the decimator
+    init = ((T(z["init_p0"]), T(z["init_p1"])), (T(z["init_d0"]), T(z["init_d1"])))
+    cb = _standard_termination() if bool(z["with_termination"]) else None
+    with torch.no_grad():
+        (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm,
+                                  edge_feature=ef, meta_data=None, is_training=False, iteration_num=int(z["T"]),
+                                  check_termination=cb, simplify=True, batch_replication=1)
+    assert int(model.last_iterations.item()) == int(z["iterations"])
+    ours = [(int(i), int(s)) for idx, sg in model._decimator.decimation_log for i, s in sorted(zip(C(idx).tolist(), C(sg).tolist()))]
+    assert ours == [(int(i), int(s)) for _, i, s in z["events"].tolist()]
+    m = model.last_problem._ctx.get_masks()
+    assert maxdiff(C(m["av"]), z["av"]) == 0 and maxdiff(C(m["af"]), z["af"]) == 0
+    decided = z["av"] == 0
+    assert maxdiff(C(vp).reshape(-1)[decided], z["pred"][decided]) == 0
+    assert int((~decided).sum()) == z["fill"].shape[0]
+    assert maxdiff(C(ps[0]), z["final_p0"]) < 2e-4 and maxdiff(C(ps[1]), z["final_p1"]) < 2e-4

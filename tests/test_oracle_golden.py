@@ -115,3 +115,18 @@ def test_batch_replication(path):
     pred, _ = o.local_search(int(z["W"]), float(z["epsilon"]), z["rand_var"], z["rand_coin"], b)
     out, _ = o.deduplicate(b, pred)
     assert maxdiff(out, z["pred"]) == 0
+
+
+@pytest.mark.parametrize("path", golden("reinforce_*.npz"), ids=name)
+def test_reinforce_vs_reference(path):
+    """model type `reinforce` restated on the oracle's operators (pins the pi terms of SP and of the scorer): merged
+    predictions of every iteration and the stopping iteration exact, final messages to the survey tolerance"""
+    z = load(path)
+    o = po.Oracle(z["graph_map"], z["bvm"], z["bfm"], z["ef"])
+    merged, q, f = po.reinforce_run(o, (z["init_p0"], z["init_p1"]), (z["init_d0"], z["init_d1"]), int(z["T"]),
+                                            float(z["pi"]), float(z["p_dec"]), z["coins"])
+    assert len(merged) == z["preds"].shape[0]
+    for a, b in zip(merged, z["preds"]):
+        assert maxdiff(a, b) == 0
+    assert maxdiff(merged[-1], z["pred"]) == 0
+    assert maxdiff(q, z["final_q"]) < 1e-4 and maxdiff(f, z["final_f"]) < 1e-4
