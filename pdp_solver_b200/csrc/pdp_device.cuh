@@ -421,6 +421,16 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 #ifndef PDP_UNROLL_VL
 #define PDP_UNROLL_VL 6    // variable load (3-4 loads each)
 #endif
+// four-slot groups per thread in flight (PDP_VEC4)
+#ifndef PDP_UNROLL_WO4
+#define PDP_UNROLL_WO4 4
+#endif
+#ifndef PDP_UNROLL_CL4
+#define PDP_UNROLL_CL4 4
+#endif
+#ifndef PDP_UNROLL_VL4
+#define PDP_UNROLL_VL4 3
+#endif
 
 // ================================================================================================
 // phase bodies of the blocked passes, written for a GROUP of G threads with local index t: the whole CTA
@@ -432,10 +442,58 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 // STICKY: 0 = off, 1 = slots flagged in `sticky` bits, 2 = every slot.  A sticky slot keeps a NaN that is already
 // stored at its destination in `old` (the reference blends mask*new + (1-mask)*old arithmetically: 0*NaN = NaN,
 // pdp_propagate.py:175,218).
+// PDP_VEC4 = 1: the memory phases read their contiguous streams four slots per thread and instruction (128-bit loads
+// of the fp32 streams, 64-bit loads of the 16-bit tables).  They are latency-bound (measured, clock64 phase timers):
+// what counts is bytes in flight per thread.  A block's region starts at an arbitrary element of 256-byte aligned
+// arrays, so up to three head and three tail slots go through the scalar path.
+#ifndef PDP_VEC4
+#define PDP_VEC4 1
+#endif
+struct Vec4Range { int head, nvec, tail0; };
+template <typename T>
+__device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32: the region's start in a 4-byte array
+    Vec4Range R;
+    R.head = (int)((16u - ((unsigned)(uintptr_t)p32 & 15u)) & 15u) >> 2;
+    if (R.head > ne) R.head = ne;
+    R.nvec = (ne - R.head) >> 2;
+    R.tail0 = R.head + 4 * R.nvec;
+    return R;
+}
+__device__ __forceinline__ uint32_t mnib(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 15u; }
+
 template <int G, bool SKIP, int STICKY>
 __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
                                                const float* plane, const uint32_t* skip, const uint32_t* sticky,
                                                const float* old, float* out) {   // old may alias out (q is updated in place)
+    auto one = [&](int l, int d) {
+        if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) return;
+        float v = plane[l];
+        if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
+        out[d] = v;
+    };
+#if PDP_VEC4
+    const Vec4Range R = vec4_range(dst, ne);
+    if (t < R.head) one(src[t], dst[t]);
+    if (t < ne - R.tail0) one(src[R.tail0 + t], dst[R.tail0 + t]);
+    const uint2* __restrict__ s4 = reinterpret_cast<const uint2*>(src + R.head);
+    const int4* __restrict__ d4 = reinterpret_cast<const int4*>(dst + R.head);
+    constexpr int U = PDP_UNROLL_WO4;
+    int w = t;
+    for (; w + (U - 1) * G < R.nvec; w += U * G) {
+        uint2 l[U]; int4 d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { l[u] = s4[w + u * G]; d[u] = d4[w + u * G]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            one((int)(l[u].x & 0xffffu), d[u].x); one((int)(l[u].x >> 16), d[u].y);
+            one((int)(l[u].y & 0xffffu), d[u].z); one((int)(l[u].y >> 16), d[u].w);
+        }
+    }
+    for (; w < R.nvec; w += G) {
+        const uint2 l = s4[w]; const int4 d = d4[w];
+        one((int)(l.x & 0xffffu), d.x); one((int)(l.x >> 16), d.y); one((int)(l.y & 0xffffu), d.z); one((int)(l.y >> 16), d.w);
+    }
+#else
     int w = t;
     constexpr int U = PDP_UNROLL_WO;
     for (; w + (U - 1) * G < ne; w += U * G) {
@@ -443,21 +501,10 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) { l[u] = src[w + u * G]; d[u] = dst[w + u * G]; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (SKIP && ((skip[l[u] >> 5] >> (l[u] & 31)) & 1u)) continue;
-            float v = plane[l[u]];
-            if (STICKY == 2 || (STICKY == 1 && ((sticky[l[u] >> 5] >> (l[u] & 31)) & 1u))) { const float ov = old[d[u]]; if (ov != ov) v = ov; }
-            out[d[u]] = v;
-        }
+        for (int u = 0; u < U; ++u) one(l[u], d[u]);
     }
-    for (; w < ne; w += G) {
-        const int l = src[w];
-        if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) continue;
-        float v = plane[l];
-        const int d = dst[w];
-        if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
-        out[d] = v;
-    }
+    for (; w < ne; w += G) one(src[w], dst[w]);
+#endif
 }
 // flags: bit 0 = some slots are skipped, bit 1 = some slots are sticky, bit 2 = every slot is sticky
 template <int G>
@@ -481,6 +528,36 @@ __device__ __forceinline__ void ph_write_out(int t, const uint16_t* __restrict__
 template <int G, bool MASKED>
 __device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
                                                const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
+    auto put = [&](float q, int l, bool m) {
+        float v = L40(q);
+        if (MASKED && m) v = v * 0.f;
+        X[l] = v;
+    };
+#if PDP_VEC4
+    const Vec4Range R = vec4_range(qsrc, ne);
+    if (t < R.head) put(qsrc[t], inv[t], MASKED ? mbit(qmask, e0 + t) : false);
+    if (t < ne - R.tail0) put(qsrc[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(qmask, e0 + R.tail0 + t) : false);
+    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(qsrc + R.head);
+    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
+    const int pos0 = e0 + R.head;     // a multiple of 4: the four mask bits of a group sit in one word
+    constexpr int U = PDP_UNROLL_CL4;
+    int x = t;
+    for (; x + (U - 1) * G < R.nvec; x += U * G) {
+        float4 q[U]; uint2 l[U]; uint32_t m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { q[u] = q4[x + u * G]; l[u] = i4[x + u * G]; m[u] = MASKED ? mnib(qmask, pos0 + 4 * (x + u * G)) : 0u; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            put(q[u].x, (int)(l[u].x & 0xffffu), m[u] & 1u); put(q[u].y, (int)(l[u].x >> 16), m[u] & 2u);
+            put(q[u].z, (int)(l[u].y & 0xffffu), m[u] & 4u); put(q[u].w, (int)(l[u].y >> 16), m[u] & 8u);
+        }
+    }
+    for (; x < R.nvec; x += G) {
+        const float4 q = q4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(qmask, pos0 + 4 * x) : 0u;
+        put(q.x, (int)(l.x & 0xffffu), m & 1u); put(q.y, (int)(l.x >> 16), m & 2u);
+        put(q.z, (int)(l.y & 0xffffu), m & 4u); put(q.w, (int)(l.y >> 16), m & 8u);
+    }
+#else
     int x = t;
     constexpr int U = PDP_UNROLL_CL;
     for (; x + (U - 1) * G < ne; x += U * G) {
@@ -488,17 +565,10 @@ __device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ 
 #pragma unroll
         for (int u = 0; u < U; ++u) { q[u] = qsrc[x + u * G]; l[u] = inv[x + u * G]; m[u] = MASKED ? mbit(qmask, e0 + x + u * G) : false; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float v = L40(q[u]);
-            if (MASKED && m[u]) v = v * 0.f;
-            X[l[u]] = v;
-        }
+        for (int u = 0; u < U; ++u) put(q[u], l[u], m[u]);
     }
-    for (; x < ne; x += G) {
-        float v = L40(qsrc[x]);
-        if (MASKED && mbit(qmask, e0 + x)) v = v * 0.f;
-        X[inv[x]] = v;
-    }
+    for (; x < ne; x += G) put(qsrc[x], inv[x], MASKED ? mbit(qmask, e0 + x) : false);
+#endif
 }
 
 // one clause of K literals held in X[lo .. lo+K): surveys in place.  Returns whether a NaN was produced.
@@ -596,28 +666,54 @@ __device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
 template <int G, bool MASKED>
 __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
                                             const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
+    auto put = [&](float n, float o, uint32_t iv, bool m) {
+        const int l = iv & 0x7fff;
+        PA[l] = __uint_as_float(__float_as_uint(n) | ((MASKED && m) ? 0x80000000u : 0u));
+        PB[l] = __uint_as_float(__float_as_uint(o) ^ ((iv & PDP_VINV_NEG) << 16));
+    };
+#if PDP_VEC4
+    const Vec4Range R = vec4_range(sn, ne);
+    if (t < R.head) put(sn[t], so[t], inv[t], MASKED ? mbit(vmask, e0 + t) : false);
+    if (t < ne - R.tail0) put(sn[R.tail0 + t], so[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(vmask, e0 + R.tail0 + t) : false);
+    const float4* __restrict__ n4 = reinterpret_cast<const float4*>(sn + R.head);
+    const float4* __restrict__ o4 = reinterpret_cast<const float4*>(so + R.head);
+    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
+    const int pos0 = e0 + R.head;
+    constexpr int U = PDP_UNROLL_VL4;
+    int x = t;
+    for (; x + (U - 1) * G < R.nvec; x += U * G) {
+        float4 n[U], o[U]; uint2 l[U]; uint32_t m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n[u] = n4[x + u * G]; o[u] = o4[x + u * G]; l[u] = i4[x + u * G];
+            m[u] = MASKED ? mnib(vmask, pos0 + 4 * (x + u * G)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            put(n[u].x, o[u].x, l[u].x & 0xffffu, m[u] & 1u); put(n[u].y, o[u].y, l[u].x >> 16, m[u] & 2u);
+            put(n[u].z, o[u].z, l[u].y & 0xffffu, m[u] & 4u); put(n[u].w, o[u].w, l[u].y >> 16, m[u] & 8u);
+        }
+    }
+    for (; x < R.nvec; x += G) {
+        const float4 n = n4[x], o = o4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(vmask, pos0 + 4 * x) : 0u;
+        put(n.x, o.x, l.x & 0xffffu, m & 1u); put(n.y, o.y, l.x >> 16, m & 2u);
+        put(n.z, o.z, l.y & 0xffffu, m & 4u); put(n.w, o.w, l.y >> 16, m & 8u);
+    }
+#else
     int x = t;
     constexpr int U = PDP_UNROLL_VL;
     for (; x + (U - 1) * G < ne; x += U * G) {
-        uint32_t n[U], o[U], iv[U];
+        float n[U], o[U]; uint32_t iv[U]; bool m[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            n[u] = __float_as_uint(sn[x + u * G]); o[u] = __float_as_uint(so[x + u * G]); iv[u] = inv[x + u * G];
-            if (MASKED) n[u] |= mbit(vmask, e0 + x + u * G) ? 0x80000000u : 0u;
+            n[u] = sn[x + u * G]; o[u] = so[x + u * G]; iv[u] = inv[x + u * G];
+            m[u] = MASKED ? mbit(vmask, e0 + x + u * G) : false;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int l = iv[u] & 0x7fff;
-            PA[l] = __uint_as_float(n[u]); PB[l] = __uint_as_float(o[u] ^ ((iv[u] & PDP_VINV_NEG) << 16));
-        }
+        for (int u = 0; u < U; ++u) put(n[u], o[u], iv[u], m[u]);
     }
-    for (; x < ne; x += G) {
-        uint32_t n0 = __float_as_uint(sn[x]);
-        const uint32_t o0 = __float_as_uint(so[x]), i0 = inv[x];
-        if (MASKED) n0 |= mbit(vmask, e0 + x) ? 0x80000000u : 0u;
-        const int l0 = i0 & 0x7fff;
-        PA[l0] = __uint_as_float(n0); PB[l0] = __uint_as_float(o0 ^ ((i0 & PDP_VINV_NEG) << 16));
-    }
+    for (; x < ne; x += G) put(sn[x], so[x], inv[x], MASKED ? mbit(vmask, e0 + x) : false);
+#endif
 }
 
 // variable pass, node phase: thread per variable (descending degree, rounds alternate direction so that
@@ -722,6 +818,15 @@ __device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats&
 //   FULL[slot]  memory -> compute: the slot holds a loaded block
 //   DONE[slot]  compute -> memory: the node phase of the slot's block is finished
 // ================================================================================================
+// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in each
+// phase of the blocked passes to the trace buffer: [0..2] clause wait-for-load / node / write-out, [3..5] variable
+#ifdef PDP_PHASE_TIMING
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_ADD(slot_) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot_) do {} while (0)
+#endif
 #if PDP_PIPELINE || PDP_TMA
 #define PIPE_MEM_THREADS (32 * PDP_PIPE_MEM_WARPS)
 #define PIPE_CMP_THREADS (PDP_SWEEP_THREADS - PIPE_MEM_THREADS)
@@ -731,15 +836,6 @@ __device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats&
 #define PIPE_SLOT_BYTES (4 * PDP_BLK_C)
 #define PIPE_MAX_BLOCKS 32 // blocks of one CTA per pass handled per pipeline run
 
-// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in each
-// phase of the staged passes to the trace buffer: [0..2] clause wait-for-load / node / write-out, [3..5] variable
-#ifdef PDP_PHASE_TIMING
-#define PHASE_T0() long long _pt = clock64()
-#define PHASE_ADD(slot_) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
-#else
-#define PHASE_T0() do {} while (0)
-#define PHASE_ADD(slot_) do {} while (0)
-#endif
 #ifdef PDP_PHASE_TIMING
 #define PT_DECL() long long _pt = clock64()
 #define PT_ADD(slot_) do { if (t == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
@@ -1272,9 +1368,11 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         if (blk_idle(s, B.b0, B.b1)) continue;
         for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
         if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
+        PHASE_T0();
         if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
         __syncthreads();
+        PHASE_ADD(0);
         if (tid == 0) {
             l2_prefetch(g.csrc + B.e0, (size_t)B.ne * 2);
             l2_prefetch(g.cdst + B.e0, (size_t)B.ne * 4);
@@ -1287,8 +1385,10 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         }
         ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip, sticky);
         __syncthreads();
+        PHASE_ADD(1);
         ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip, eout, sticky, s.eta[r]);
         __syncthreads();
+        PHASE_ADD(2);
     }
 }
 
@@ -1316,9 +1416,11 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
         if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
+        PHASE_T0();
         if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
         __syncthreads();
+        PHASE_ADD(3);
         if (tid == 0) {
             l2_prefetch(g.vsrc + B.e0, (size_t)B.ne * 2);
             l2_prefetch(g.vdst + B.e0, (size_t)B.ne * 4);
@@ -1332,9 +1434,11 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         }
         ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
         __syncthreads();
+        PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
         ph_write_out<NT>(tid, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, sm_any_skip, s.qu, sticky, s.qu);
         red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
+        PHASE_ADD(5);
     }
 }
 
