@@ -413,7 +413,7 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 }
 
 #ifndef PDP_UNROLL_WO
-#define PDP_UNROLL_WO 8    // elements per thread in flight: write-out (2 loads each)
+#define PDP_UNROLL_WO 6    // elements per thread in flight: write-out (2 loads each)
 #endif
 #ifndef PDP_UNROLL_CL
 #define PDP_UNROLL_CL 8    // clause load (2-3 loads each)
@@ -449,6 +449,11 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 #ifndef PDP_VEC4
 #define PDP_VEC4 1
 #endif
+// the write-out keeps one slot per thread and instruction: with four consecutive slots per thread a warp's stores are
+// strided by four elements and every destination sector is written four times (measured: +30 % on the phase)
+#ifndef PDP_VEC4_WO
+#define PDP_VEC4_WO 0
+#endif
 struct Vec4Range { int head, nvec, tail0; };
 template <typename T>
 __device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32: the region's start in a 4-byte array
@@ -471,7 +476,7 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
         if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
         out[d] = v;
     };
-#if PDP_VEC4
+#if PDP_VEC4_WO
     const Vec4Range R = vec4_range(dst, ne);
     if (t < R.head) one(src[t], dst[t]);
     if (t < ne - R.tail0) one(src[R.tail0 + t], dst[R.tail0 + t]);
@@ -1350,6 +1355,34 @@ __device__ __forceinline__ void l2_prefetch(const void* ptr, size_t bytes) {
 // serial passes: the whole CTA runs load, node phase and write-out of a block back to back
 // ================================================================================================
 
+// Block hand-out of one pass.  Static (block b to CTA b mod grid) when one CTA owns the SM: the CTAs then finish within
+// 1-2 % of each other.  With two CTAs per SM the pair drifts apart, the early one waits at the grid barrier and its
+// partner finishes alone at half the SM's warps (10 % of the iteration, measured), so the blocks after a CTA's first one
+// come from a counter; the next index is fetched while the current block is processed.
+#ifndef PDP_DYN_BLOCKS
+#define PDP_DYN_BLOCKS 1
+#endif
+struct BlkFeed {
+    int* ctr; int nblk; int blk; int par; bool dyn;
+    int* slot;   // two ints of shared memory
+    __device__ __forceinline__ void begin(int* counter, int n, int* sm2, bool dynamic) {
+        ctr = counter; nblk = n; slot = sm2; dyn = dynamic; blk = blockIdx.x; par = 0;
+    }
+    __device__ __forceinline__ bool more() const { return blk < nblk; }
+    // thread 0, at the top of a block: the index of the block after this one (also returned for the L2 prefetch)
+    __device__ __forceinline__ int fetch() {
+        const int nx = dyn ? (int)gridDim.x + atomicAdd(ctr, 1) : blk + (int)gridDim.x;
+        slot[par] = nx;
+        return nx;
+    }
+    // all threads, after the block's last use of shared memory
+    __device__ __forceinline__ void advance() {
+        __syncthreads();
+        blk = slot[par];
+        par ^= 1;
+    }
+};
+
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
 template <int CTAS>
 __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
@@ -1362,7 +1395,13 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     const float* __restrict__ qin = s.qu;
     float* __restrict__ eout = s.eta[r ^ 1];
     const int tid = threadIdx.x;
-    for (int blk = blockIdx.x; blk < g.ncb; blk += gridDim.x) {
+    __shared__ int sm_feed[2];
+    __shared__ int sm_nb;
+    BlkFeed feed;
+    feed.begin(&s.ctrl[CTRL_NEXT_CBLK], g.ncb, sm_feed, PDP_DYN_BLOCKS && CTAS == 2);
+    for (; feed.more(); feed.advance()) {
+        const int blk = feed.blk;
+        if (tid == 0) sm_nb = feed.fetch();
         const BlkGeo B = clause_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
@@ -1376,7 +1415,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         if (tid == 0) {
             l2_prefetch(g.csrc + B.e0, (size_t)B.ne * 2);
             l2_prefetch(g.cdst + B.e0, (size_t)B.ne * 4);
-            const int nb = blk + gridDim.x;
+            const int nb = sm_nb;
             if (nb < g.ncb) {
                 const BlkGeo Bn = clause_block(g, nb);
                 l2_prefetch(qin + Bn.e0, (size_t)Bn.ne * 4);
@@ -1408,7 +1447,13 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     const float* __restrict__ eo = s.eta[r];
     const int tid = threadIdx.x;
     KeyedReducer<StatAcc> red;
-    for (int blk = blockIdx.x; blk < g.nvb; blk += gridDim.x) {
+    __shared__ int sm_feed[2];
+    __shared__ int sm_nb;
+    BlkFeed feed;
+    feed.begin(&s.ctrl[CTRL_NEXT_VBLK], g.nvb, sm_feed, PDP_DYN_BLOCKS && CTAS == 2);
+    for (; feed.more(); feed.advance()) {
+        const int blk = feed.blk;
+        if (tid == 0) sm_nb = feed.fetch();
         const BlkGeo B = var_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
@@ -1424,7 +1469,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         if (tid == 0) {
             l2_prefetch(g.vsrc + B.e0, (size_t)B.ne * 2);
             l2_prefetch(g.vdst + B.e0, (size_t)B.ne * 4);
-            const int nb = blk + gridDim.x;
+            const int nb = sm_nb;
             if (nb < g.nvb) {
                 const BlkGeo Bn = var_block(g, nb);
                 l2_prefetch(en + Bn.e0, (size_t)Bn.ne * 4);
