@@ -412,6 +412,9 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
     for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
 }
 
+#ifndef PDP_VN_UNROLL
+#define PDP_VN_UNROLL 1    // edge loops of the variable node phase
+#endif
 #ifndef PDP_UNROLL_WO
 #define PDP_UNROLL_WO 6    // elements per thread in flight: write-out (2 loads each)
 #endif
@@ -429,7 +432,7 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 #define PDP_UNROLL_CL4 4
 #endif
 #ifndef PDP_UNROLL_VL4
-#define PDP_UNROLL_VL4 3
+#define PDP_UNROLL_VL4 2    // 3 costs a spilled register under the 64-register cap, same speed
 #endif
 
 // ================================================================================================
@@ -726,9 +729,10 @@ __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn,
 // Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
 template <int G>
 __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
-                                            bool em_set, float* PA, float* PB, uint32_t* skip, int* any_skip,
+                                            bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t* skip, int* any_skip,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky = nullptr) {
     const bool multi = B.multi();
+    constexpr int VNU = PDP_VN_UNROLL;
     for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
         const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
         if (ti >= B.n1) continue;
@@ -742,6 +746,7 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         }
         const uint32_t act = s.av[i];
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
+#pragma unroll VNU
         for (int j = 0; j < deg; ++j) {
             const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
             const bool m = (nb >> 31) != 0u;                        // edge masked
@@ -787,6 +792,7 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
         sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
         bool made_nan = false;
+#pragma unroll VNU
         for (int j = 0; j < deg; ++j) {
             const uint32_t yb = __float_as_uint(PB[lo + j]);
             const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
@@ -1362,26 +1368,20 @@ __device__ __forceinline__ void l2_prefetch(const void* ptr, size_t bytes) {
 #ifndef PDP_DYN_BLOCKS
 #define PDP_DYN_BLOCKS 1
 #endif
-struct BlkFeed {
-    int* ctr; int nblk; int blk; int par; bool dyn;
-    int* slot;   // two ints of shared memory
-    __device__ __forceinline__ void begin(int* counter, int n, int* sm2, bool dynamic) {
-        ctr = counter; nblk = n; slot = sm2; dyn = dynamic; blk = blockIdx.x; par = 0;
-    }
-    __device__ __forceinline__ bool more() const { return blk < nblk; }
-    // thread 0, at the top of a block: the index of the block after this one (also returned for the L2 prefetch)
-    __device__ __forceinline__ int fetch() {
-        const int nx = dyn ? (int)gridDim.x + atomicAdd(ctr, 1) : blk + (int)gridDim.x;
-        slot[par] = nx;
-        return nx;
-    }
-    // all threads, after the block's last use of shared memory
-    __device__ __forceinline__ void advance() {
-        __syncthreads();
-        blk = slot[par];
-        par ^= 1;
-    }
-};
+// thread 0, at the top of a block: the index of the block after `blk`, left in slot[par] for feed_advance
+template <bool DYN>
+__device__ __forceinline__ int feed_fetch(int* ctr, int* slot, int par, int blk) {
+    const int nx = DYN ? (int)gridDim.x + atomicAdd(ctr, 1) : blk + (int)gridDim.x;
+    slot[par] = nx;
+    return nx;
+}
+// all threads, after the block's last use of shared memory
+__device__ __forceinline__ int feed_advance(const int* slot, int& par) {
+    __syncthreads();
+    const int nx = slot[par];
+    par ^= 1;
+    return nx;
+}
 
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
 template <int CTAS>
@@ -1397,11 +1397,10 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     const int tid = threadIdx.x;
     __shared__ int sm_feed[2];
     __shared__ int sm_nb;
-    BlkFeed feed;
-    feed.begin(&s.ctrl[CTRL_NEXT_CBLK], g.ncb, sm_feed, PDP_DYN_BLOCKS && CTAS == 2);
-    for (; feed.more(); feed.advance()) {
-        const int blk = feed.blk;
-        if (tid == 0) sm_nb = feed.fetch();
+    constexpr bool DYN = PDP_DYN_BLOCKS && CTAS == 2;
+    int par = 0;
+    for (int blk = blockIdx.x; blk < g.ncb; blk = feed_advance(sm_feed, par)) {
+        if (tid == 0) sm_nb = feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_CBLK], sm_feed, par, blk);
         const BlkGeo B = clause_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
@@ -1449,11 +1448,10 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     KeyedReducer<StatAcc> red;
     __shared__ int sm_feed[2];
     __shared__ int sm_nb;
-    BlkFeed feed;
-    feed.begin(&s.ctrl[CTRL_NEXT_VBLK], g.nvb, sm_feed, PDP_DYN_BLOCKS && CTAS == 2);
-    for (; feed.more(); feed.advance()) {
-        const int blk = feed.blk;
-        if (tid == 0) sm_nb = feed.fetch();
+    constexpr bool DYN = PDP_DYN_BLOCKS && CTAS == 2;
+    int par = 0;
+    for (int blk = blockIdx.x; blk < g.nvb; blk = feed_advance(sm_feed, par)) {
+        if (tid == 0) sm_nb = feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_VBLK], sm_feed, par, blk);
         const BlkGeo B = var_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
