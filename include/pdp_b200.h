@@ -134,7 +134,8 @@ typedef struct {
     int32_t batch_replication;  /* b of `-b`; problem id of replica r of j is r*B/b + j */
     int32_t full_state;         /* 1 = also keep q_s and q_* (the [E,3] state) exact    */
     int32_t flags;              /* bit 0: use the generic (thread per node) passes, not the blocked ones;
-                                   bit 1: grid-wide decimation phases only (no CTA-local decimation)    */
+                                   bit 1: grid-wide decimation phases only (no CTA-local decimation);
+                                   bit 2: full-scan UP / peel closure in those phases (not the frontier lists) */
 } pdp_sp_params;
 
 /* PropagatorDecimatorSolverBase._forward_core for the p-d-p model, reference

@@ -1697,6 +1697,218 @@ __device__ __forceinline__ void closure(const KArgs& A, cg::grid_group& grid) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Frontier closure (large problems, grid-wide).  Once every problem is closed under unit propagation and peeling
+// (after simplify()), fixing a variable can only create unit clauses among the clauses that hold a variable
+// de-activated in the previous round, and pure literals among the variables of clauses de-activated since: the
+// rounds below are the rounds of closure() -- same phases, same synchronous semantics, same helper arithmetic --
+// run over those lists instead of over all F clauses and V variables (8.9 -> ms per decimation iteration at
+// 8 x n = 1 M, where a round's full scan gathers 100 M node flags to find a dozen nodes).
+//   clause list (ping-pong by UP round)   : clauses to test for unit-ness
+//   variable list (ping-pong by peel round): variables to test for purity; filled during the whole UP stage
+//   unit list (by UP round parity)         : variables some unit clause of the round points at
+// List entries are unique per epoch (stamps).  A list that overflows, or a problem wiped by the single-conflict
+// quirk, sends the rest of the closure through the full scans.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fr_push(const pdp_state& s, int list, int32_t* stamp, int id, int epoch) {
+    if (atomicExch(&stamp[id], epoch) == epoch) return;
+    const int k = atomicAdd(&s.ctrl[CTRL_FR_N + list], 1);
+    if (k < PDP_FR_CAP) s.fr_list[list][k] = id; else s.ctrl[CTRL_FR_OVER] = 1;
+}
+__device__ __forceinline__ int fr_len(const pdp_state& s, int slot) {
+    const int n = s.ctrl[slot];
+    return n < PDP_FR_CAP ? n : PDP_FR_CAP;
+}
+// de-activate clause a and queue its still-active variables for the purity test
+__device__ __forceinline__ void fr_deactivate_clause(const pdp_graph& g, const pdp_state& s, int a, int vlist, int epv) {
+    deactivate_clause(g, s, a);
+    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+        const int j = (int)(g.c_var[c] & PDP_IDX_MASK);
+        if (s.av[j]) fr_push(s, vlist, s.stamp_v, j, epv);
+    }
+}
+// fix_variable that also queues: clauses made true -> their variables (purity); the other clauses of i -> unit test
+__device__ __forceinline__ void fr_fix_variable(const pdp_graph& g, const pdp_state& s, int i, float sg, int clist, int epc,
+                                                int vlist, int epv) {
+    const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
+    for (int p = beg; p < end; ++p) {
+        const float lit = (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f;
+        const int a = g.v_cls[p];
+        if (!s.af[a]) continue;
+        if (lit * sg > 0.f) fr_deactivate_clause(g, s, a, vlist, epv);
+        else fr_push(s, clist, s.stamp_c, a, epc);
+    }
+    deactivate_variable(g, s, i);
+    s.sol[i] = (sg + 1.f) / 2.0f;
+}
+
+__device__ __forceinline__ void fr_find_units(const KArgs& A, int clist, int ulist, int flag_slot) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_N + clist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int a = s.fr_list[clist][x];
+        if (!s.af[a]) continue;
+        const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
+        int deg = 0; uint32_t hit = 0;
+        for (int c = beg; c < end; ++c) {
+            const uint32_t w = g.c_var[c];
+            if (s.av[w & PDP_IDX_MASK]) { ++deg; hit = w; }
+        }
+        if (deg == 1) {
+            s.single[a] = 1;
+            const int j = (int)(hit & PDP_IDX_MASK);
+            if (atomicAdd(&s.up_cnt[j], 1) == 0) {
+                const int k = atomicAdd(&s.ctrl[CTRL_FR_NU + ulist], 1);
+                if (k < PDP_FR_CAP) s.fr_unit[ulist][k] = j; else s.ctrl[CTRL_FR_OVER] = 1;
+            }
+            atomicAdd(&s.up_ev[j], (hit & PDP_SIGN_BIT) ? -1 : 1);
+            s.ctrl[flag_slot] = 1;
+        }
+    }
+}
+__device__ __forceinline__ void fr_find_conflicts(const KArgs& A, int ulist) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_NU + ulist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int i = s.fr_unit[ulist][x];
+        const int cnt = s.up_cnt[i];
+        if (cnt > 0 && abs(s.up_ev[i]) != cnt) {
+            if (atomicAdd(&s.conflicts[g.bvm[i]], 1) == 0) s.ctrl[CTRL_FR_WIPE] = 1;   // one conflict may mean a wipe
+        }
+    }
+}
+// up_apply_conflicts over the lists; the wipe of single-conflict problems scans their nodes (rare)
+__device__ __forceinline__ void fr_apply_conflicts(const KArgs& A, int clist, int vlist, int epv) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_N + clist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int a = s.fr_list[clist][x];
+        if (s.single[a]) { fr_deactivate_clause(g, s, a, vlist, epv); s.single[a] = 0; s.masked[g.bfm[a]] = 1; }
+    }
+    if (s.ctrl[CTRL_FR_WIPE]) {
+        const int64_t m = g.V > g.F ? g.V : g.F;
+        WARP_STRIDED(i, m) {
+            if (i < g.F && s.af[i] && !s.single[i] && s.conflicts[g.bfm[i]] == 1) deactivate_clause(g, s, (int)i);
+            if (i < g.V && s.av[i] && s.conflicts[g.bvm[i]] == 1) deactivate_variable(g, s, (int)i);
+        }
+    }
+    WARP_STRIDED(b, g.B) {
+        if (b < g.B && s.conflicts[b] >= 1) { s.is_sat[b] = 0.f; s.flags[b] |= PDP_FLAG_UP_CONFLICT; s.masked[b] = 1; }
+    }
+}
+__device__ __forceinline__ void fr_assign(const KArgs& A, int ulist, int clist_next, int epc, int vlist, int epv) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_NU + ulist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int i = s.fr_unit[ulist][x];
+        const int cnt = s.up_cnt[i];
+        if (cnt > 0) {
+            const int ev = s.up_ev[i];
+            s.up_cnt[i] = 0; s.up_ev[i] = 0;
+            if (s.av[i] && abs(ev) == cnt) fr_fix_variable(g, s, i, ev > 0 ? 1.f : -1.f, clist_next, epc, vlist, epv);
+        }
+    }
+}
+__device__ __forceinline__ void fr_peel_find(const KArgs& A, int vlist, int flag_slot) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_N + vlist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int i = s.fr_list[vlist][x];
+        if (!s.av[i]) continue;
+        const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
+        int deg = 0, sdeg = 0;
+        for (int p = beg; p < end; ++p) {
+            if (s.af[g.v_cls[p]]) { ++deg; sdeg += (g.v_cedge[p] & PDP_SIGN_BIT) ? -1 : 1; }
+        }
+        if (deg == abs(sdeg)) {
+            s.pure[i] = 1;
+            s.sol[i] = ((sdeg > 0 ? 1.f : (sdeg < 0 ? -1.f : 0.f)) + 1.f) / 2.0f;
+            s.ctrl[flag_slot] = 1;
+        }
+    }
+}
+__device__ __forceinline__ void fr_peel_apply(const KArgs& A, int vlist, int vlist_next, int epv) {
+    const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    const int n = fr_len(s, CTRL_FR_N + vlist);
+    WARP_STRIDED(x, n) {
+        if (x >= n) continue;
+        const int i = s.fr_list[vlist][x];
+        if (!s.pure[i]) continue;
+        s.pure[i] = 0;
+        const int beg = g.var_ptr[i], end = g.var_ptr[i + 1];
+        for (int p = beg; p < end; ++p) {
+            const int a = g.v_cls[p];
+            if (s.af[a]) fr_deactivate_clause(g, s, a, vlist_next, epv);
+        }
+        deactivate_variable(g, s, i);
+        s.masked[g.bvm[i]] = 1;
+    }
+}
+
+// Called by ALL threads of the cooperative grid after select_and_fix_phase<frontier> and a grid barrier: clause list 0
+// and variable list 2 hold what the fixes touched (epochs epc0 / epv0, both already stored in the control block).
+__device__ __forceinline__ void closure_frontier(const KArgs& A, cg::grid_group& grid) {
+    const pdp_state& s = A.s;
+    int epc = s.ctrl[CTRL_FR_EPC], epv = s.ctrl[CTRL_FR_EPV];
+    int round = 0, cur = 0;
+    bool fallback = false;
+    for (;;) {   // unit propagation (solver.py:234-273)
+        const int slot = CTRL_FLAG_A + (round & 1), other = CTRL_FLAG_A + ((round + 1) & 1);
+        const int ul = round & 1;
+        if (s.ctrl[CTRL_FR_OVER]) { fallback = true; break; }        // uniform: written before the last barrier
+        fr_find_units(A, cur, ul, slot);
+        if (gtid() == 0) { s.ctrl[other] = 0; s.ctrl[CTRL_FR_N + (cur ^ 1)] = 0; s.ctrl[CTRL_FR_NU + (ul ^ 1)] = 0; }
+        grid.sync();
+        if (!s.ctrl[slot]) break;
+        fr_find_conflicts(A, ul);
+        grid.sync();
+        fr_apply_conflicts(A, cur, 2, epv);
+        grid.sync();
+        ++epc;
+        fr_assign(A, ul, cur ^ 1, epc, 2, epv);
+        up_clear_conflicts(A);
+        if (gtid() == 0) s.ctrl[CTRL_FR_WIPE] = 0;
+        grid.sync();
+        cur ^= 1;
+        ++round;
+    }
+    if (!fallback && s.ctrl[CTRL_FR_OVER]) fallback = true;
+    if (!fallback) {
+        int vc = 2;
+        round = 0;
+        for (;;) {   // peeling (solver.py:188-203)
+            const int slot = CTRL_FLAG_C + (round & 1), other = CTRL_FLAG_C + ((round + 1) & 1);
+            if (s.ctrl[CTRL_FR_OVER]) { fallback = true; break; }
+            fr_peel_find(A, vc, slot);
+            if (gtid() == 0) { s.ctrl[other] = 0; s.ctrl[CTRL_FR_N + (vc ^ 1)] = 0; }
+            grid.sync();
+            if (!s.ctrl[slot]) break;
+            ++epv;
+            fr_peel_apply(A, vc, vc ^ 1, epv);
+            grid.sync();
+            vc ^= 1;
+            ++round;
+        }
+    }
+    grid.sync();
+    if (gtid() == 0) {
+        s.ctrl[CTRL_FR_EPC] = epc + 1; s.ctrl[CTRL_FR_EPV] = epv + 1;
+        for (int i = 0; i < 4; ++i) s.ctrl[CTRL_FR_N + i] = 0;
+        s.ctrl[CTRL_FR_NU] = 0; s.ctrl[CTRL_FR_NU + 1] = 0; s.ctrl[CTRL_FR_OVER] = 0; s.ctrl[CTRL_FR_WIPE] = 0;
+    }
+    if (fallback) {
+        // per-round scratch is clean at a round boundary; the full scans finish the closure from the current masks
+        if (gtid() == 0) { s.ctrl[CTRL_FLAG_A] = 0; s.ctrl[CTRL_FLAG_A + 1] = 0; s.ctrl[CTRL_FLAG_C] = 0; s.ctrl[CTRL_FLAG_C + 1] = 0; }
+        grid.sync();
+        closure(A, grid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-local decimation.  Everything the decimator does to a converged problem -- scoring, arg-max, fixing
 // the variable, unit propagation and pure-literal peeling to closure, the CNF check and the termination
 // decision -- touches that problem only, so for problems that one CTA can walk (the common case: thousands of

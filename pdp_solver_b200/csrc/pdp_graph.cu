@@ -123,6 +123,10 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     s.up_ev = k.take<int32_t>(V);
     s.pure = k.take<uint8_t>(V);
     s.single = k.take<uint8_t>(F);
+    for (int i = 0; i < 4; ++i) s.fr_list[i] = k.take<int32_t>(PDP_FR_CAP);
+    for (int i = 0; i < 2; ++i) s.fr_unit[i] = k.take<int32_t>(PDP_FR_CAP);
+    s.stamp_c = k.take<int32_t>(F);
+    s.stamp_v = k.take<int32_t>(V);
     s.ctrl = k.take<int32_t>(CTRL_SIZE);
     s.asg = k.take<int8_t>(V);
     s.ws_true = k.take<int32_t>(F);
@@ -223,8 +227,8 @@ __global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, in
     if (g.E / 32 + 1 > n) n = g.E / 32 + 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < g.E / 32 + 1) { g.vmask[i] = 0u; g.qmask[i] = 0u; }
-        if (i < V) { s.av[i] = 1; s.sol[i] = 0.5f; s.up_cnt[i] = 0; s.up_ev[i] = 0; s.pure[i] = 0; s.score[i] = 0.f; s.asg[i] = 0; }
-        if (i < F) { s.af[i] = 1; s.single[i] = 0; }
+        if (i < V) { s.av[i] = 1; s.sol[i] = 0.5f; s.up_cnt[i] = 0; s.up_ev[i] = 0; s.pure[i] = 0; s.score[i] = 0.f; s.asg[i] = 0; s.stamp_v[i] = 0; }
+        if (i < F) { s.af[i] = 1; s.single[i] = 0; s.stamp_c[i] = 0; }
         if (i < B) {
             s.is_sat[i] = 0.5f; s.active[i] = 1; s.counters[i] = 0; s.freeze_iter[i] = -1; s.flags[i] = 0;
             s.masked[i] = 0; s.dirty[i] = 1; s.conv[i] = 0; s.nanflag[i] = 0; s.nanpend[i] = 0; s.n_unsat[i] = 0; s.conflicts[i] = 0;
@@ -232,7 +236,8 @@ __global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, in
             s.st_max[2 * i] = 0u; s.st_max[2 * i + 1] = 0u; s.st_min[2 * i] = 0x7f800000u; s.st_min[2 * i + 1] = 0x7f800000u;
             s.st_nan[i] = 0u; s.c_max[i] = 0u; s.c_min[i] = 0x7f800000u; s.c_nan[i] = 0u;
         }
-        if (i < CTRL_SIZE) s.ctrl[i] = (i == CTRL_NUM_ACTIVE) ? (int32_t)B : ((i == CTRL_ANY_DIRTY) ? 1 : 0);
+        if (i < CTRL_SIZE) s.ctrl[i] = (i == CTRL_NUM_ACTIVE) ? (int32_t)B
+                                       : ((i == CTRL_ANY_DIRTY || i == CTRL_FR_EPC || i == CTRL_FR_EPV) ? 1 : 0);
     }
 }
 

@@ -59,9 +59,10 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
 }
 
 // pdp_decimate.py:158-171: fix the arg-max variable of every converged, still active problem
-__device__ __forceinline__ void select_and_fix_phase(const KArgs& A, int iter) {
+__device__ __forceinline__ void select_and_fix_phase(const KArgs& A, int iter, bool frontier) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     const int slot = CTRL_FIX + (iter & 1);
+    const int epc = s.ctrl[CTRL_FR_EPC], epv = s.ctrl[CTRL_FR_EPV];
     WARP_STRIDED(b, g.B) {
         if (b >= g.B) continue;
         if (!s.conv[b]) continue;
@@ -69,7 +70,8 @@ __device__ __forceinline__ void select_and_fix_phase(const KArgs& A, int iter) {
             const int i = s.arg_idx[b];
             const float sg = sgnf(s.score[i]);
             if (sg != 0.f && s.av[i]) {
-                fix_variable(g, s, i, sg);
+                if (frontier) fr_fix_variable(g, s, i, sg, 0, epc, 2, epv);   // + the touched nodes, for closure_frontier
+                else fix_variable(g, s, i, sg);
                 s.masked[b] = 1; s.dirty[b] = 1;
                 s.ctrl[slot] = 1; s.ctrl[CTRL_ANY_DIRTY] = 1;
                 if (A.trace) {
@@ -121,6 +123,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     int gen_left = FAST ? s.ctrl[CTRL_GEN_ITERS] : 0;
     const int rep = prm.batch_replication > 1 ? prm.batch_replication : 1;
     const bool local_ok = A.g.contiguous_problems && rep == 1 && !(prm.flags & 2);
+    const bool frontier = s.ctrl[CTRL_CLOSED] != 0 && !(prm.flags & 4);   // flags bit 2: full-scan closure (A/B, tests)
     int executed = 0;
     if (gtid() == 0) { s.ctrl[CTRL_NEXT_CBLK] = 0; s.ctrl[CTRL_NEXT_VBLK] = 0; s.ctrl[CTRL_LOC_COUNT] = 0; s.ctrl[CTRL_LOC_NEXT] = 0; }
 #if PDP_TMA
@@ -211,9 +214,12 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             GRID_SYNC();
             argmax_phase(A);
             GRID_SYNC();
-            select_and_fix_phase(A, iter);
+            select_and_fix_phase(A, iter, frontier);
             GRID_SYNC();
-            if (s.ctrl[CTRL_FIX + (iter & 1)]) closure(A, grid);
+            if (s.ctrl[CTRL_FIX + (iter & 1)]) {
+                if (frontier) closure_frontier(A, grid);
+                else closure(A, grid);
+            }
         }
         has_prev = true;   // pdp_decimate.py:175
         em_set = true;     // solver.py:370-371
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(256) k_simplify(const __grid_constant__ KArgs 
     if (gtid() == 0) s.ctrl[CTRL_ANY_DIRTY] = 1;
     grid.sync();
     closure(A, grid);
+    if (gtid() == 0) s.ctrl[CTRL_CLOSED] = 1;   // every problem was dirty: all of them are closed now
 }
 
 // SATProblem.set_variables (solver.py:275-279): assignment [V] float in {-1,0,1}
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(256) k_set_variables(const __grid_constant__ K
     }
     grid.sync();
     closure(A, grid);
+    if (gtid() == 0) s.ctrl[CTRL_CLOSED] = 1;
 }
 
 template <typename K>

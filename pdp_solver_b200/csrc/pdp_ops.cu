@@ -243,7 +243,7 @@ __global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const flo
         if (i < g.V) { if (av) s.av[i] = (av[i] != 0.f) ? 1 : 0; if (sol) s.sol[i] = sol[i]; }
         if (i < g.F && af) s.af[i] = (af[i] != 0.f) ? 1 : 0;
         if (i < g.B) { s.masked[i] = 1; s.dirty[i] = 1; }
-        if (i == 0) s.ctrl[CTRL_ANY_DIRTY] = 1;
+        if (i == 0) { s.ctrl[CTRL_ANY_DIRTY] = 1; s.ctrl[CTRL_CLOSED] = 0; }   // masks from outside: closure unknown
     }
 }
 

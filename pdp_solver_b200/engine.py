@@ -234,12 +234,13 @@ class Context(object):
         return self._trace[: n.value].cpu()
 
     def sp_run(self, iterations, tolerance, t_max, check_termination=True, batch_replication=1, pi=0.0,
-               full_state=False, sync=False, generic=False, grid_decimation=False):
+               full_state=False, sync=False, generic=False, grid_decimation=False, full_closure=False):
         """T iterations of propagate/decimate/predict in one persistent kernel.  Returns the device
         int32 tensor holding the number of executed iterations (or the int when sync=True).
-        generic=True forces the thread-per-node passes (A/B against the blocked shared-memory passes)."""
+        generic=True forces the thread-per-node passes (A/B against the blocked shared-memory passes);
+        grid_decimation=True the grid-wide decimation phases; full_closure=True their full-scan UP / peel closure."""
         prm = SpParams(int(iterations), float(tolerance), int(t_max), float(pi), 1 if check_termination else 0,
-                       int(batch_replication), 1 if full_state else 0, (1 if generic else 0) | (2 if grid_decimation else 0) | int(os.environ.get("PDP_B200_SP_FLAGS", "0"), 0))
+                       int(batch_replication), 1 if full_state else 0, (1 if generic else 0) | (2 if grid_decimation else 0) | (4 if full_closure else 0) | int(os.environ.get("PDP_B200_SP_FLAGS", "0"), 0))
         self._timed("sp_run", lambda: self._check(
             self._L.pdp_sp_run(self._h, ctypes.byref(prm), _ptr(self._iters), _stream()), "pdp_sp_run"))
         if sync:

@@ -547,7 +547,8 @@ def test_full_size_properties():
                          ids=lambda s: "B%d_n%d_k%d" % (s[0], s[1], s[2]))
 def test_local_decimation_equals_grid_decimation(spec):
     """the CTA-local decimation (score, arg-max, fix, UP / peel closure, CNF check, termination inside one CTA per
-    problem) against the grid-wide phases: identical decimation sequence, masks, solutions, flags, messages"""
+    problem) against the grid-wide phases, the latter with the frontier closure (lists of touched nodes) and with the
+    full-scan closure: identical decimation sequence, masks, solutions, flags, messages"""
     from oracle import pdp_oracle as po
     from pdp_solver_b200 import cnfgen
     from pdp_solver_b200.engine import Context
@@ -556,12 +557,12 @@ def test_local_decimation_equals_grid_decimation(spec):
     E = batch[0].shape[1]
     init = po.init_state(E, randomized=False)
     outs = []
-    for grid_dec in (False, True):
+    for grid_dec, full_closure in ((False, False), (True, False), (True, True)):
         ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
         ctx.enable_trace()
         ctx.simplify()
         ctx.load_state((T(init[0][0]), T(init[0][1])), (T(init[1][0]), T(init[1][1])))
-        done = ctx.sp_run(Tn, 0.02, 25, True, sync=True, grid_decimation=grid_dec)
+        done = ctx.sp_run(Tn, 0.02, 25, True, sync=True, grid_decimation=grid_dec, full_closure=full_closure)
         q, fs = ctx.store_state()
         m = ctx.get_masks()
         tr = C(ctx.trace()).astype(np.int64)
@@ -570,8 +571,9 @@ def test_local_decimation_equals_grid_decimation(spec):
         outs.append((np.int64(done), C(q[:, 0]), C(fs[:, 0]), C(m["av"]), C(m["af"]), C(m["sol"]), C(m["active"]), C(m["is_sat"]),
                      tr, C(flags), C(freeze)))
     assert outs[0][8].shape[0] > 0, "no decimation happened: the test does not exercise anything"
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b, equal_nan=True)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b, equal_nan=True)
 
 
 @pytest.mark.parametrize("ctas", ["1", "2"])
