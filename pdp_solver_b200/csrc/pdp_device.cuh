@@ -727,7 +727,7 @@ __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn,
 // variable pass, node phase: thread per variable (descending degree, rounds alternate direction so that
 // every thread gets high and low degrees): ordered sums, decimator statistics, update.
 // Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
-template <int G>
+template <int G, bool SCORE = false>
 __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
                                             bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t* skip, int* any_skip,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky = nullptr) {
@@ -745,6 +745,8 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
             if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + deg); atomicOr(any_skip, 2); }
         }
         const uint32_t act = s.av[i];
+        const bool want = SCORE && s.want_score[b];
+        float ps = 0.f, ns = 0.f, as = 0.f;                          // SurveyScorer sums (pdp_predict.py:166-179)
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
 #pragma unroll VNU
         for (int j = 0; j < deg; ++j) {
@@ -762,6 +764,15 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
             N += fsel(negm, y, zy);
             const float c = X30(30.f * xn);
             n0 += xn * c; d0 += c;
+            if (SCORE && want) {
+                // same operations and order as score_variable(); for an active variable the edge mask is the
+                // clause mask the scorer multiplies with (an inactive variable's score is never looked at)
+                const float f = L10(1.f - xn) * (m ? 0.f : 1.f);
+                const float zf = 0.f * f;
+                ps += fsel(negm, zf, f);
+                ns += fsel(negm, f, zf);
+                as += f;
+            }
             if (has_prev) {
                 float d = fabsf(xo - xn);
                 if (em_set && m) d = d * 0.f;
@@ -788,6 +799,7 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
                 one.commit(s, b);
             }
         }
+        if (SCORE && want) s.score[i] = sp_score_tail(ps, ns, as, 0.f, 0.f);   // pi == 0 on this path: ext does not enter
         float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
         sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
         sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
@@ -1475,7 +1487,10 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
                 l2_prefetch(g.vinv + Bn.e0, (size_t)Bn.ne * 2);
             }
         }
-        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
+        if (s.want_score[B.b0] || s.want_score[B.b1])
+            ph_var_node<NT, true>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
+        else
+            ph_var_node<NT, false>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
         __syncthreads();
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
@@ -1511,8 +1526,9 @@ __device__ __forceinline__ void score_phase(const KArgs& A, int w, float pi) {
         const int b = g.bvm[i];
         if (!s.conv[b]) continue;
         red.touch(s, b);
-        const float sc = score_variable(g, s, s.eta[w], (int)i, pi);
-        s.score[i] = sc;
+        float sc;
+        if (s.have_score[b]) sc = s.score[i];     // written by this iteration's variable pass (ph_var_node<SCORE>)
+        else { sc = score_variable(g, s, s.eta[w], (int)i, pi); s.score[i] = sc; }
         red.acc.add(fabsf(sc) * (float)s.av[i]);
     }
     red.finish(s);
@@ -2339,11 +2355,13 @@ __device__ __forceinline__ bool literal_true(float sgn, float p) {
 __device__ __forceinline__ void cnf_count_dirty(const KArgs& A) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     KeyedReducer<CountAcc> red;
+    const bool native = s.ctrl[CTRL_NATIVE] != 0;
     WARP_STRIDED(a, g.F) {
         if (a >= g.F) continue;
         const int b = g.bfm[a];
         if (!s.dirty[b]) continue;
         red.touch(s, b);
+        if (native && s.af[a]) { red.acc.n += 1; continue; }   // an active clause holds no true literal (CTRL_NATIVE)
         const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
         bool sat = false;
         for (int c = beg; c < end; ++c) {

@@ -9,12 +9,14 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // SequentialDecimator decisions, one thread per problem (pdp_decimate.py:127-150,173)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp_sp_params& prm, bool has_prev, bool local_ok) {
+__device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp_sp_params& prm, bool has_prev, bool local_ok,
+                                             bool blocked) {
     const pdp_state& s = A.s;
     const int slot = CTRL_CONV + (iter & 1);
     WARP_STRIDED(b, A.g.B) {
         if (b >= A.g.B) continue;
         uint8_t cv = 0;
+        bool near = false;       // close to the convergence test: worth scoring inside the next variable pass
         // a NaN produced during this iteration's passes puts the problem on the sticky-NaN path from
         // the next iteration on (no old NaN existed while it was produced)
         if (s.nanpend[b]) { s.nanpend[b] = 0; s.nanflag[b] = 1; s.ctrl[CTRL_ANY_NAN] = 1; }
@@ -43,6 +45,7 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
                 if (cnt >= prm.t_max) { c = true; cnt = 0; }        // :147-148
                 cv = (c && act) ? 1 : 0;
                 s.counters[b] = cnt + 1;                            // :173
+                near = act && (c || D < 4.f * prm.tolerance || cnt + 1 >= prm.t_max);
             }
             if (nanb) s.flags[b] |= PDP_FLAG_CONTRADICTION;
             s.st_max[2 * b] = 0u; s.st_max[2 * b + 1] = 0u;
@@ -50,6 +53,9 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
             s.st_nan[b] = 0u; s.nav[b] = 0;
         }
         s.conv[b] = cv;
+        // scores of this iteration's variable pass are valid if it was asked for them and ran blocked
+        s.have_score[b] = (blocked && s.want_score[b]) ? 1 : 0;
+        s.want_score[b] = (near && !s.nanflag[b] && (!local_ok || !loc_problem_is_small(A.g, (int)b))) ? 1 : 0;
         if (cv) {
             s.ctrl[slot] = 1;
             if (!local_ok || !loc_problem_is_small(A.g, (int)b)) s.ctrl[CTRL_CONVBIG + (iter & 1)] = 1;
@@ -198,7 +204,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gtid() == 0) s.ctrl[CTRL_NEXT_CBLK] = 0;   // the variable pass is over; the next clause pass is a barrier away
         LOOP_T(19);
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
-        decide_phase(A, iter, prm, has_prev, local_ok);
+        decide_phase(A, iter, prm, has_prev, local_ok, blocked && PDP_STICKY_INLINE);   // the staged variants do not score
         GRID_SYNC();
         LOOP_T(20);
         if (local_ok && s.ctrl[CTRL_CONV + (iter & 1)]) {
@@ -210,16 +216,20 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
             LOOP_T(22);
         }
         if (s.ctrl[local_ok ? (CTRL_CONVBIG + (iter & 1)) : (CTRL_CONV + (iter & 1))]) {
+            LOOP_T(23);
             score_phase(A, w, prm.pi);
             GRID_SYNC();
+            LOOP_T(24);
             argmax_phase(A);
             GRID_SYNC();
             select_and_fix_phase(A, iter, frontier);
             GRID_SYNC();
+            LOOP_T(25);
             if (s.ctrl[CTRL_FIX + (iter & 1)]) {
                 if (frontier) closure_frontier(A, grid);
                 else closure(A, grid);
             }
+            LOOP_T(26);
         }
         has_prev = true;   // pdp_decimate.py:175
         em_set = true;     // solver.py:370-371
@@ -228,10 +238,13 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         // ---- predict + termination: IdentityPredictor/_update_solution leave _solution as is
         if (prm.check_termination) {
             if (s.ctrl[CTRL_ANY_DIRTY]) {
+                LOOP_T(23);
                 cnf_count_dirty(A);
                 GRID_SYNC();
+                LOOP_T(27);
                 termination_phase(A, iter, rep);
                 GRID_SYNC();
+                LOOP_T(28);
             }
             if (s.ctrl[CTRL_NUM_ACTIVE] <= 0) break;
         }

@@ -243,7 +243,7 @@ __global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const flo
         if (i < g.V) { if (av) s.av[i] = (av[i] != 0.f) ? 1 : 0; if (sol) s.sol[i] = sol[i]; }
         if (i < g.F && af) s.af[i] = (af[i] != 0.f) ? 1 : 0;
         if (i < g.B) { s.masked[i] = 1; s.dirty[i] = 1; }
-        if (i == 0) { s.ctrl[CTRL_ANY_DIRTY] = 1; s.ctrl[CTRL_CLOSED] = 0; }   // masks from outside: closure unknown
+        if (i == 0) { s.ctrl[CTRL_ANY_DIRTY] = 1; s.ctrl[CTRL_CLOSED] = 0; s.ctrl[CTRL_NATIVE] = 0; }   // masks from outside: closure unknown
     }
 }
 
@@ -286,6 +286,7 @@ struct U8ToInt {
 __global__ void k_random_fill(pdp_graph g, pdp_state s, const float* __restrict__ draws) {
     for (int64_t i = gtid(); i < g.V; i += gthreads())
         if (s.av[i]) s.sol[i] = draws[s.scan_tmp[i]];
+    if (gtid() == 0) s.ctrl[CTRL_NATIVE] = 0;   // active variables now carry values: an active clause may be satisfied
 }
 
 // _deduplicate (solver.py:401-431)

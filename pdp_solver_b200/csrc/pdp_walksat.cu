@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) k_walksat(const __grid_constant__ KArgs A
         const float avf = (float)s.av[i];
         const float walk = ((float)s.asg[i] + 1.f) / 2.0f;
         const float merged = avf * walk + (1.0f - avf) * s.sol[i];
-        if (s.av[i]) s.sol[i] = merged;
+        if (s.av[i]) { s.sol[i] = merged; s.ctrl[CTRL_NATIVE] = 0; }
         if (wa.prediction) wa.prediction[i] = merged;
         WS_DELTA(s)[i] = 0; WS_UVC(s)[i] = 0;
     }

@@ -51,9 +51,11 @@ for rep in range(a.repeat):
         nct = 148 * int(os.environ.get("PDP_PHASE_TIMING"))
         trl = ctx._trace.reshape(-1)[:32].cpu().numpy().astype(np.float64) * 1024.0 / nct / max(done, 1)
         print("cycles/iteration/CTA: clause pass %.0f, barrier %.0f, variable pass %.0f, barrier %.0f, decide+barrier %.0f, "
-              "local decimation %.0f, barrier %.0f" % tuple(trl[16:23]))
+              "local decimation %.0f, barrier %.0f, grid decimation + termination %.0f" % tuple(trl[16:24]))
         print("  phases (cycles/iteration/CTA): clause load %.0f, node %.0f, write-out %.0f | variable load %.0f, node %.0f, "
               "write-out %.0f" % tuple(trl[0:6]))
+        print("  grid decimation (cycles/iteration/CTA): score %.0f, arg-max + fix %.0f, closure %.0f | CNF count %.0f, termination %.0f"
+              % tuple(trl[24:29]))
         ctx._trace.zero_()
     print("E=%d iterations=%d  %.3f ms  %.3f ms/iter  %.2f G edge-updates/s  %.1f GB/s algorithmic" % (
         E, done, ms, ms / max(done, 1), E * done / ms / 1e6, 20.0 * E * done / ms / 1e6))
