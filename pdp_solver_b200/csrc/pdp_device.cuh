@@ -1518,9 +1518,35 @@ __device__ __forceinline__ float score_variable(const pdp_graph& g, const pdp_st
     return sp_score_tail(ps, ns, as, sgnf(extsum), pi);
 }
 
+// A batch of a few large problems: the grid walks the node range of each flagged problem (no per-node problem
+// look-up, no dependent loads, one block-level merge per problem) instead of scanning every node of the batch.
+#define PDP_RANGE_SCAN_MAX_B 64
+__device__ __forceinline__ bool range_scans(const pdp_graph& g) { return g.contiguous_problems && g.B <= PDP_RANGE_SCAN_MAX_B; }
+
 __device__ __forceinline__ void score_phase(const KArgs& A, int w, float pi) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     KeyedReducer<CoefAcc> red;
+    if (range_scans(g)) {
+        for (int b = 0; b < (int)g.B; ++b) {
+            if (!s.conv[b]) continue;
+            const int v1 = g.prob_vptr[b + 1];
+            const bool have = s.have_score[b] != 0;
+            red.touch(s, b);
+            if (have) {
+#pragma unroll 4
+                for (int i = g.prob_vptr[b] + (int)gtid(); i < v1; i += (int)gthreads())
+                    red.acc.add(fabsf(s.score[i]) * (float)s.av[i]);
+            } else {
+                for (int i = g.prob_vptr[b] + (int)gtid(); i < v1; i += (int)gthreads()) {
+                    const float sc = score_variable(g, s, s.eta[w], i, pi);
+                    s.score[i] = sc;
+                    red.acc.add(fabsf(sc) * (float)s.av[i]);
+                }
+            }
+            red.finish(s);
+        }
+        return;
+    }
     WARP_STRIDED(i, g.V) {
         if (i >= g.V) continue;
         const int b = g.bvm[i];
@@ -1537,6 +1563,20 @@ __device__ __forceinline__ void score_phase(const KArgs& A, int w, float pi) {
 // first index attaining max of fl(fl(c - min) + 1)  (util.py:257-265)
 __device__ __forceinline__ void argmax_phase(const KArgs& A) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
+    if (range_scans(g)) {
+        for (int b = 0; b < (int)g.B; ++b) {
+            if (!s.conv[b] || s.c_nan[b]) continue;
+            const float m = u2f(s.c_min[b]);
+            const float kmax = argmax_key(u2f(s.c_max[b]), m);
+            const int v1 = g.prob_vptr[b + 1];
+#pragma unroll 4
+            for (int i = g.prob_vptr[b] + (int)gtid(); i < v1; i += (int)gthreads()) {
+                const float c = fabsf(s.score[i]) * (float)s.av[i];
+                if (argmax_key(c, m) == kmax) atomicMin(&s.arg_idx[b], i);
+            }
+        }
+        return;
+    }
     WARP_STRIDED(i, g.V) {
         if (i >= g.V) continue;
         const int b = g.bvm[i];
@@ -2356,6 +2396,24 @@ __device__ __forceinline__ void cnf_count_dirty(const KArgs& A) {
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     KeyedReducer<CountAcc> red;
     const bool native = s.ctrl[CTRL_NATIVE] != 0;
+    if (range_scans(g)) {
+        for (int b = 0; b < (int)g.B; ++b) {
+            if (!s.dirty[b]) continue;
+            const int f1 = g.prob_fptr[b + 1];
+            red.touch(s, b);
+            for (int a = g.prob_fptr[b] + (int)gtid(); a < f1; a += (int)gthreads()) {
+                if (native && s.af[a]) { red.acc.n += 1; continue; }
+                bool sat = false;
+                for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) {
+                    const uint32_t w = g.c_var[c];
+                    if (literal_true((w & PDP_SIGN_BIT) ? -1.f : 1.f, s.sol[w & PDP_IDX_MASK])) { sat = true; break; }
+                }
+                red.acc.n += sat ? 0 : 1;
+            }
+            red.finish(s);
+        }
+        return;
+    }
     WARP_STRIDED(a, g.F) {
         if (a >= g.F) continue;
         const int b = g.bfm[a];
