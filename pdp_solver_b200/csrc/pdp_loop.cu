@@ -69,24 +69,27 @@ __device__ __forceinline__ void select_and_fix_phase(const KArgs& A, int iter, b
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     const int slot = CTRL_FIX + (iter & 1);
     const int epc = s.ctrl[CTRL_FR_EPC], epv = s.ctrl[CTRL_FR_EPV];
-    WARP_STRIDED(b, g.B) {
-        if (b >= g.B) continue;
+    // warp per problem: every lane takes the same decisions, the fix itself is spread over the lanes
+    for (int64_t b = gwarp(); b < g.B; b += gwarps()) {
         if (!s.conv[b]) continue;
         if (!s.c_nan[b] && u2f(s.c_max[b]) > 0.f && s.arg_idx[b] != 0x7fffffff) {
             const int i = s.arg_idx[b];
             const float sg = sgnf(s.score[i]);
             if (sg != 0.f && s.av[i]) {
-                if (frontier) fr_fix_variable(g, s, i, sg, 0, epc, 2, epv);   // + the touched nodes, for closure_frontier
-                else fix_variable(g, s, i, sg);
-                s.masked[b] = 1; s.dirty[b] = 1;
-                s.ctrl[slot] = 1; s.ctrl[CTRL_ANY_DIRTY] = 1;
-                if (A.trace) {
-                    int k = atomicAdd(&s.ctrl[CTRL_TRACE_LEN], 1);
-                    if (k < A.trace_cap) { A.trace[3 * k] = iter; A.trace[3 * k + 1] = i; A.trace[3 * k + 2] = (int)sg; }
+                __syncwarp();     // everybody has read av[i] before lane 0 clears it
+                warp_fix_variable(g, s, i, sg, frontier, epc, epv);   // + the touched nodes, for closure_frontier
+                if (lane_id() == 0) {
+                    s.masked[b] = 1; s.dirty[b] = 1;
+                    s.ctrl[slot] = 1; s.ctrl[CTRL_ANY_DIRTY] = 1;
+                    if (A.trace) {
+                        int k = atomicAdd(&s.ctrl[CTRL_TRACE_LEN], 1);
+                        if (k < A.trace_cap) { A.trace[3 * k] = iter; A.trace[3 * k + 1] = i; A.trace[3 * k + 2] = (int)sg; }
+                    }
                 }
             }
         }
-        s.c_max[b] = 0u; s.c_min[b] = 0x7f800000u; s.c_nan[b] = 0u; s.arg_idx[b] = 0x7fffffff;
+        __syncwarp();             // ... and the per-problem arg-max state before lane 0 resets it
+        if (lane_id() == 0) { s.c_max[b] = 0u; s.c_min[b] = 0x7f800000u; s.c_nan[b] = 0u; s.arg_idx[b] = 0x7fffffff; }
     }
 }
 

@@ -74,7 +74,8 @@ class SATProblem(object):
         B0 = self._batch_size // b
         x = torch.arange(B0 * b, dtype=torch.int64, device=self._graph_map.device)
         ind = torch.stack([x, x % B0])
-        mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0))
+        mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0),
+                                       check_invariants=False)
         return (mask, mask.transpose(0, 1))
 
     def edge_problem_index(self):
