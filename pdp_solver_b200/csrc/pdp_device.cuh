@@ -457,6 +457,15 @@ __device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
 #ifndef PDP_VEC4_WO
 #define PDP_VEC4_WO 0
 #endif
+#ifndef PDP_INPASS_SCORE
+#define PDP_INPASS_SCORE 1
+#endif
+#ifndef PDP_COLD
+#define PDP_COLD __forceinline__
+#endif
+#ifndef PDP_WO_PIPE
+#define PDP_WO_PIPE 0
+#endif
 struct Vec4Range { int head, nvec, tail0; };
 template <typename T>
 __device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32: the region's start in a 4-byte array
@@ -504,6 +513,32 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
 #else
     int w = t;
     constexpr int U = PDP_UNROLL_WO;
+#if PDP_WO_PIPE
+    if (ne <= 0) return;
+    // register double buffer: the index loads of the next batch are in flight while this batch gathers and stores
+    // (the phase waits on exactly these loads: long-scoreboard stalls on the gather, profiles/r1_sp_run_ncu.md)
+    int l[U], d[U];
+    bool have = w + (U - 1) * G < ne;
+    {
+        const int w0 = have ? w : 0;      // (no full batch: the loads below are dummies of valid addresses, ne >= 1 here)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { l[u] = src[have ? w0 + u * G : 0]; d[u] = dst[have ? w0 + u * G : 0]; }
+    }
+    while (have) {
+        const int wn = w + U * G;
+        const bool more = wn + (U - 1) * G < ne;
+        const int wl = more ? wn : w;      // last batch: re-read the current indices (in range, discarded)
+        int ln[U], dn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { ln[u] = src[wl + u * G]; dn[u] = dst[wl + u * G]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(l[u], d[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { l[u] = ln[u]; d[u] = dn[u]; }
+        w = wn;
+        have = more;
+    }
+#else
     for (; w + (U - 1) * G < ne; w += U * G) {
         int l[U], d[U];
 #pragma unroll
@@ -511,6 +546,7 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
 #pragma unroll
         for (int u = 0; u < U; ++u) one(l[u], d[u]);
     }
+#endif
     for (; w < ne; w += G) one(src[w], dst[w]);
 #endif
 }
@@ -724,10 +760,37 @@ __device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn,
 #endif
 }
 
+// variable pass, SurveyScorer (pdp_predict.py:155-192) of the variables whose problem asked for it (want_score): same
+// operations and order as score_variable() on the new surveys held in PA (sign bit = edge masked; for an active variable
+// the edge mask is the clause mask the scorer multiplies with, an inactive variable's score is never looked at) and the
+// literal signs held in PB.  pi == 0 on the blocked path: the external force does not enter.
+template <int G>
+__device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B,
+                                             const float* __restrict__ PA, const float* __restrict__ PB) {
+    for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
+        const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
+        if (ti >= B.n1) continue;
+        const int2 ve = __ldg(&g.vsort[ti]);
+        const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
+        if (!s.want_score[B.multi() ? g.bvm[i] : B.b0]) continue;
+        float ps = 0.f, ns = 0.f, as = 0.f;
+        for (int j = 0; j < deg; ++j) {
+            const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
+            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);
+            const float f = L10(1.f - __uint_as_float(nb & 0x7fffffffu)) * ((nb >> 31) ? 0.f : 1.f);
+            const float zf = 0.f * f;
+            ps += fsel(negm, zf, f);
+            ns += fsel(negm, f, zf);
+            as += f;
+        }
+        s.score[i] = sp_score_tail(ps, ns, as, 0.f, 0.f);
+    }
+}
+
 // variable pass, node phase: thread per variable (descending degree, rounds alternate direction so that
 // every thread gets high and low degrees): ordered sums, decimator statistics, update.
 // Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
-template <int G, bool SCORE = false>
+template <int G>
 __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
                                             bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t* skip, int* any_skip,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky = nullptr) {
@@ -745,8 +808,6 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
             if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + deg); atomicOr(any_skip, 2); }
         }
         const uint32_t act = s.av[i];
-        const bool want = SCORE && s.want_score[b];
-        float ps = 0.f, ns = 0.f, as = 0.f;                          // SurveyScorer sums (pdp_predict.py:166-179)
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
 #pragma unroll VNU
         for (int j = 0; j < deg; ++j) {
@@ -764,15 +825,6 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
             N += fsel(negm, y, zy);
             const float c = X30(30.f * xn);
             n0 += xn * c; d0 += c;
-            if (SCORE && want) {
-                // same operations and order as score_variable(); for an active variable the edge mask is the
-                // clause mask the scorer multiplies with (an inactive variable's score is never looked at)
-                const float f = L10(1.f - xn) * (m ? 0.f : 1.f);
-                const float zf = 0.f * f;
-                ps += fsel(negm, zf, f);
-                ns += fsel(negm, f, zf);
-                as += f;
-            }
             if (has_prev) {
                 float d = fabsf(xo - xn);
                 if (em_set && m) d = d * 0.f;
@@ -799,7 +851,6 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
                 one.commit(s, b);
             }
         }
-        if (SCORE && want) s.score[i] = sp_score_tail(ps, ns, as, 0.f, 0.f);   // pi == 0 on this path: ext does not enter
         float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
         sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
         sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
@@ -1487,10 +1538,10 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
                 l2_prefetch(g.vinv + Bn.e0, (size_t)Bn.ne * 2);
             }
         }
-        if (s.want_score[B.b0] || s.want_score[B.b1])
-            ph_var_node<NT, true>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
-        else
-            ph_var_node<NT, false>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
+        // SurveyScorer of problems about to converge, while the new surveys are still in the planes (the node phase
+        // overwrites them); its own loop, so that the node phase's code is the same with and without it
+        if (PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1])) ph_var_score<NT>(tid, g, s, B, PA, PB);
+        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
         __syncthreads();
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
@@ -1553,7 +1604,7 @@ __device__ __forceinline__ void score_phase(const KArgs& A, int w, float pi) {
         if (!s.conv[b]) continue;
         red.touch(s, b);
         float sc;
-        if (s.have_score[b]) sc = s.score[i];     // written by this iteration's variable pass (ph_var_node<SCORE>)
+        if (s.have_score[b]) sc = s.score[i];     // written by this iteration's variable pass (ph_var_score)
         else { sc = score_variable(g, s, s.eta[w], (int)i, pi); s.score[i] = sc; }
         red.acc.add(fabsf(sc) * (float)s.av[i]);
     }
@@ -1717,7 +1768,7 @@ __device__ __forceinline__ void peel_apply(const KArgs& A) {
 
 // UP closure then peel closure for the dirty problems.  Called by ALL threads of the cooperative grid.
 // Flag slots alternate by round parity so a flag is never reset while it can still be read.
-__device__ __forceinline__ void closure(const KArgs& A, cg::grid_group& grid) {
+__device__ PDP_COLD void closure(const KArgs& A, cg::grid_group& grid) {
     const pdp_state& s = A.s;
     int round = 0;
     for (;;) {   // solver.py:234-273
@@ -1923,7 +1974,7 @@ __device__ __forceinline__ void fr_peel_apply(const KArgs& A, int vlist, int vli
 
 // Called by ALL threads of the cooperative grid after select_and_fix_phase<frontier> and a grid barrier: clause list 0
 // and variable list 2 hold what the fixes touched (epochs epc0 / epv0, both already stored in the control block).
-__device__ __forceinline__ void closure_frontier(const KArgs& A, cg::grid_group& grid) {
+__device__ PDP_COLD void closure_frontier(const KArgs& A, cg::grid_group& grid) {
     const pdp_state& s = A.s;
     int epc = s.ctrl[CTRL_FR_EPC], epv = s.ctrl[CTRL_FR_EPV];
     int round = 0, cur = 0;

@@ -127,6 +127,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     for (int i = 0; i < 2; ++i) s.fr_unit[i] = k.take<int32_t>(PDP_FR_CAP);
     s.want_score = k.take<uint8_t>(B);
     s.have_score = k.take<uint8_t>(B);
+    s.last_d = k.take<float>(B);
     s.stamp_c = k.take<int32_t>(F);
     s.stamp_v = k.take<int32_t>(V);
     s.ctrl = k.take<int32_t>(CTRL_SIZE);
@@ -234,7 +235,7 @@ __global__ void k_reset_state(pdp_graph g, pdp_state s, int64_t V, int64_t F, in
         if (i < B) {
             s.is_sat[i] = 0.5f; s.active[i] = 1; s.counters[i] = 0; s.freeze_iter[i] = -1; s.flags[i] = 0;
             s.masked[i] = 0; s.dirty[i] = 1; s.conv[i] = 0; s.nanflag[i] = 0; s.nanpend[i] = 0; s.n_unsat[i] = 0; s.conflicts[i] = 0;
-            s.nav[i] = 0; s.arg_idx[i] = 0x7fffffff; s.energy[i] = 0; s.want_score[i] = 0; s.have_score[i] = 0;
+            s.nav[i] = 0; s.arg_idx[i] = 0x7fffffff; s.energy[i] = 0; s.want_score[i] = 0; s.have_score[i] = 0; s.last_d[i] = 0.f;
             s.st_max[2 * i] = 0u; s.st_max[2 * i + 1] = 0u; s.st_min[2 * i] = 0x7f800000u; s.st_min[2 * i + 1] = 0x7f800000u;
             s.st_nan[i] = 0u; s.c_max[i] = 0u; s.c_min[i] = 0x7f800000u; s.c_nan[i] = 0u;
         }

@@ -45,7 +45,11 @@ __device__ __forceinline__ void decide_phase(const KArgs& A, int iter, const pdp
                 if (cnt >= prm.t_max) { c = true; cnt = 0; }        // :147-148
                 cv = (c && act) ? 1 : 0;
                 s.counters[b] = cnt + 1;                            // :173
-                near = act && (c || D < 4.f * prm.tolerance || cnt + 1 >= prm.t_max);
+                // will it converge in the NEXT iteration?  It just did (decimation keeps the surveys converged), its counter
+                // runs out, or the statistic, which decays geometrically, extrapolates below the tolerance
+                const float Dp = s.last_d[b];
+                s.last_d[b] = D;
+                near = act && (c || cnt + 1 >= prm.t_max || (Dp > 0.f && D < Dp && D * (D / Dp) < 1.25f * prm.tolerance));
             }
             if (nanb) s.flags[b] |= PDP_FLAG_CONTRADICTION;
             s.st_max[2 * b] = 0u; s.st_max[2 * b + 1] = 0u;
