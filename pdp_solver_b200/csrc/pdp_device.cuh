@@ -1819,11 +1819,11 @@ __device__ PDP_COLD void closure(const KArgs& A, cg::grid_group& grid) {
 __device__ __forceinline__ void fr_push(const pdp_state& s, int list, int32_t* stamp, int id, int epoch) {
     if (atomicExch(&stamp[id], epoch) == epoch) return;
     const int k = atomicAdd(&s.ctrl[CTRL_FR_N + list], 1);
-    if (k < PDP_FR_CAP) s.fr_list[list][k] = id; else s.ctrl[CTRL_FR_OVER] = 1;
+    if (k < s.fr_cap) s.fr_list[list][k] = id; else s.ctrl[CTRL_FR_OVER] = 1;
 }
 __device__ __forceinline__ int fr_len(const pdp_state& s, int slot) {
     const int n = s.ctrl[slot];
-    return n < PDP_FR_CAP ? n : PDP_FR_CAP;
+    return n < s.fr_cap ? n : s.fr_cap;
 }
 // de-activate clause a and queue its still-active variables for the purity test
 __device__ __forceinline__ void fr_deactivate_clause(const pdp_graph& g, const pdp_state& s, int a, int vlist, int epv) {
@@ -1882,7 +1882,7 @@ __device__ __forceinline__ void fr_find_units(const KArgs& A, int clist, int uli
             const int j = (int)(hit & PDP_IDX_MASK);
             if (atomicAdd(&s.up_cnt[j], 1) == 0) {
                 const int k = atomicAdd(&s.ctrl[CTRL_FR_NU + ulist], 1);
-                if (k < PDP_FR_CAP) s.fr_unit[ulist][k] = j; else s.ctrl[CTRL_FR_OVER] = 1;
+                if (k < s.fr_cap) s.fr_unit[ulist][k] = j; else s.ctrl[CTRL_FR_OVER] = 1;
             }
             atomicAdd(&s.up_ev[j], (hit & PDP_SIGN_BIT) ? -1 : 1);
             s.ctrl[flag_slot] = 1;

@@ -125,6 +125,8 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     s.single = k.take<uint8_t>(F);
     for (int i = 0; i < 4; ++i) s.fr_list[i] = k.take<int32_t>(PDP_FR_CAP);
     for (int i = 0; i < 2; ++i) s.fr_unit[i] = k.take<int32_t>(PDP_FR_CAP);
+    s.fr_cap = PDP_FR_CAP;
+    if (const char* cap = getenv("PDP_B200_FR_CAP")) { const int v = atoi(cap); if (v >= 1 && v < PDP_FR_CAP) s.fr_cap = v; }
     s.want_score = k.take<uint8_t>(B);
     s.have_score = k.take<uint8_t>(B);
     s.last_d = k.take<float>(B);

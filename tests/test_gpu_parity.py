@@ -545,7 +545,7 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("spec", [(96, 100, 3, 4.2, 200, 41), (12, 400, 3, 4.0, 150, 42), (40, 60, 3, 3.5, 150, 43)],
                          ids=lambda s: "B%d_n%d_k%d" % (s[0], s[1], s[2]))
-def test_local_decimation_equals_grid_decimation(spec):
+def test_local_decimation_equals_grid_decimation(spec, monkeypatch):
     """the CTA-local decimation (score, arg-max, fix, UP / peel closure, CNF check, termination inside one CTA per
     problem) against the grid-wide phases, the latter with the frontier closure (lists of touched nodes) and with the
     full-scan closure: identical decimation sequence, masks, solutions, flags, messages"""
@@ -557,7 +557,12 @@ def test_local_decimation_equals_grid_decimation(spec):
     E = batch[0].shape[1]
     init = po.init_state(E, randomized=False)
     outs = []
-    for grid_dec, full_closure in ((False, False), (True, False), (True, True)):
+    # last variant: frontier lists of 8 entries -> they overflow and the closure falls back to the full scans mid-way
+    for grid_dec, full_closure, cap in ((False, False, None), (True, False, None), (True, True, None), (True, False, "8")):
+        if cap is None:
+            monkeypatch.delenv("PDP_B200_FR_CAP", raising=False)
+        else:
+            monkeypatch.setenv("PDP_B200_FR_CAP", cap)
         ctx = Context(T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]))
         ctx.enable_trace()
         ctx.simplify()

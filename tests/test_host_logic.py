@@ -112,3 +112,27 @@ def test_sharded_equals_unsharded_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SHARDED_OK" in out.stdout
+
+
+def test_per_problem_max_and_argmax_follow_the_reference_rounding():
+    """problem_max / problem_argmax (np-d-np, reinforce) = util.sparse_max / sparse_argmax (reference util.py:257-275) on a
+    single-problem batch: fl(fl(max fl(fl(x - min) + 1) + min) - 1), zero floor, first index on ties"""
+    import torch
+    from pdp_solver_b200.nn.pdp_decimate import problem_argmax, problem_max
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        n = int(rng.integers(1, 40))
+        x = rng.random(n).astype(np.float32) * np.float32(rng.choice([1e-3, 1.0, 50.0]))
+        if n > 3:
+            x[int(rng.integers(0, n))] = x.max()            # a tie: the first index must win
+        mn = x.min()
+        y = ((x - mn).astype(np.float32) + np.float32(1)).astype(np.float32)
+        want_max = ((max(y.max(), np.float32(0)) + mn).astype(np.float32) - np.float32(1)).astype(np.float32)
+        bvm = torch.zeros(n, dtype=torch.int32)
+        assert problem_max(torch.from_numpy(x), bvm, 1).numpy()[0] == want_max
+        assert int(problem_argmax(torch.from_numpy(x), bvm, 1)[0]) == int(np.argmax(y))
+    # three problems of different sizes in one batch: each behaves as if alone
+    x = torch.tensor([0.2, 0.9, 0.9, 0.0, 0.0, 0.5, 0.1, 0.7], dtype=torch.float32)
+    bvm = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2], dtype=torch.int32)
+    assert problem_argmax(x, bvm, 3).tolist() == [1, 3, 7]
+    assert torch.allclose(problem_max(x, bvm, 3), torch.tensor([0.9, 0.0, 0.7]), atol=1e-6)
