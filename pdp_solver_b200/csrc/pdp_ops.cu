@@ -340,7 +340,7 @@ extern "C" int pdp_cnf_eval(pdp_ctx* ctx, const float* d_pred, float* d_solved, 
 
 extern "C" int pdp_energy(pdp_ctx* ctx, const float* d_asg, const float* d_av, const float* d_af, float* d_energy,
                           float* d_unsat_fn, void* stream_) {
-    NEED(ctx, d_asg && d_av && d_af && d_energy && d_unsat_fn, "pdp_energy: null argument");
+    NEED(ctx, (d_asg && d_av || ctx->g.V == 0) && (d_af && d_unsat_fn || ctx->g.F == 0) && d_energy, "pdp_energy: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     PDP_CUDA_CHECK(cudaMemsetAsync(d_energy, 0, sizeof(float) * (size_t)ctx->g.B, stream));
     if (ctx->g.F > 0) { k_energy<<<GRID(ctx->g.F)>>>(ctx->g, d_asg, d_av, d_af, d_energy, d_unsat_fn, nullptr, nullptr); PDP_LAUNCH_CHECK(ctx); }
@@ -348,7 +348,7 @@ extern "C" int pdp_energy(pdp_ctx* ctx, const float* d_asg, const float* d_av, c
 }
 
 extern "C" int pdp_energy_diff(pdp_ctx* ctx, const float* d_asg, const float* d_av, const float* d_em, float* d_delta, void* stream_) {
-    NEED(ctx, d_asg && d_av && d_em && d_delta, "pdp_energy_diff: null argument");
+    NEED(ctx, (d_asg && d_av && d_delta || ctx->g.V == 0) && (d_em || ctx->g.E == 0), "pdp_energy_diff: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     float* agg = reinterpret_cast<float*>(ctx->s.ws_true);
     float* deg = reinterpret_cast<float*>(ctx->s.ws_deg);
@@ -360,7 +360,7 @@ extern "C" int pdp_energy_diff(pdp_ctx* ctx, const float* d_asg, const float* d_
 extern "C" int pdp_sp_step(pdp_ctx* ctx, const float* d_dec_q3, const float* d_dec_fs2, const float* d_edge_mask,
                            const float* d_prop_q3, const float* d_prop_fs2, const uint8_t* d_active, float pi,
                            float* d_out_q3, float* d_out_fs2, void* stream_) {
-    NEED(ctx, d_dec_q3 && d_dec_fs2 && d_out_q3 && d_out_fs2, "pdp_sp_step: null argument");
+    NEED(ctx, (d_dec_q3 && d_dec_fs2 && d_out_q3 && d_out_fs2) || ctx->g.E == 0, "pdp_sp_step: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* pq = d_prop_q3 ? d_prop_q3 : d_dec_q3;
     const float* pf = d_prop_fs2 ? d_prop_fs2 : d_dec_fs2;
@@ -372,7 +372,7 @@ extern "C" int pdp_sp_step(pdp_ctx* ctx, const float* d_dec_q3, const float* d_d
 extern "C" int pdp_sp_step_adapted(pdp_ctx* ctx, const float* d_x_log, const float* d_eta_in, const float* d_ext_in,
                                    const float* d_edge_mask, const float* d_prop_q3, const float* d_prop_fs2,
                                    const uint8_t* d_active, float pi, float* d_out_q3, float* d_out_fs2, void* stream_) {
-    NEED(ctx, d_x_log && d_eta_in && d_ext_in && d_prop_q3 && d_prop_fs2 && d_out_q3 && d_out_fs2, "pdp_sp_step_adapted: null argument");
+    NEED(ctx, (d_x_log && d_eta_in && d_ext_in && d_prop_q3 && d_prop_fs2 && d_out_q3 && d_out_fs2) || ctx->g.E == 0, "pdp_sp_step_adapted: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (ctx->g.F > 0) { k_sp_step_clause<<<GRID(ctx->g.F)>>>(ctx->g, nullptr, d_edge_mask, d_prop_fs2, nullptr, d_active, d_out_fs2, d_x_log, d_ext_in); PDP_LAUNCH_CHECK(ctx); }
     if (ctx->g.V > 0) { k_sp_step_var<<<GRID(ctx->g.V)>>>(ctx->g, nullptr, d_edge_mask, d_prop_q3, d_active, pi, d_out_q3, d_eta_in, d_ext_in); PDP_LAUNCH_CHECK(ctx); }
@@ -394,7 +394,7 @@ extern "C" int pdp_edge_aggregate(pdp_ctx* ctx, int32_t by_variable, const float
 }
 
 extern "C" int pdp_score(pdp_ctx* ctx, const float* d_fs2, const float* d_af, float pi, float* d_score, void* stream_) {
-    NEED(ctx, d_fs2 && d_af && d_score, "pdp_score: null argument");
+    NEED(ctx, (d_fs2 || ctx->g.E == 0) && (d_af || ctx->g.F == 0) && (d_score || ctx->g.V == 0), "pdp_score: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (ctx->g.V > 0) { k_score<<<GRID(ctx->g.V)>>>(ctx->g, d_fs2, d_af, pi, d_score); PDP_LAUNCH_CHECK(ctx); }
     return PDP_OK;
@@ -403,7 +403,7 @@ extern "C" int pdp_score(pdp_ctx* ctx, const float* d_fs2, const float* d_af, fl
 extern "C" int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float* d_prop_fs2, const float* d_dec_q3,
                               const float* d_dec_fs2, void* stream_) {
     (void)d_prop_q3; (void)d_prop_fs2;   // only reachable through the frozen-problem blend; every problem starts active
-    NEED(ctx, d_dec_q3 && d_dec_fs2, "pdp_load_state: null argument");
+    NEED(ctx, (d_dec_q3 && d_dec_fs2) || ctx->g.E == 0, "pdp_load_state: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.ctrl + CTRL_GEN_ITERS, 0, sizeof(int32_t), stream));
     if (ctx->g.E > 0) { k_load_state<<<GRID(ctx->g.E)>>>(ctx->g, ctx->s, d_dec_q3, d_dec_fs2, 0); PDP_LAUNCH_CHECK(ctx); }
@@ -419,7 +419,7 @@ extern "C" int pdp_load_state_const(pdp_ctx* ctx, float qu, float qs, float qd, 
 }
 
 extern "C" int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* stream_) {
-    NEED(ctx, d_out_q3 || d_out_fs2, "pdp_store_state: null argument");
+    NEED(ctx, d_out_q3 || d_out_fs2 || ctx->g.E == 0, "pdp_store_state: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
     int32_t h[2] = {0, 0};
     PDP_CUDA_CHECK(cudaMemcpyAsync(h, ctx->s.ctrl + CTRL_ITER, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -495,7 +495,7 @@ extern "C" int pdp_random_fill(pdp_ctx* ctx, const float* d_draws, void* stream_
 }
 
 extern "C" int pdp_deduplicate(pdp_ctx* ctx, int32_t rep, const float* d_pred, float* d_out, int32_t* d_winner, void* stream_) {
-    NEED(ctx, d_pred && d_out && d_winner && rep >= 1, "pdp_deduplicate: bad argument");
+    NEED(ctx, (d_pred && d_out || ctx->g.V == 0) && d_winner && rep >= 1, "pdp_deduplicate: bad argument");
     if (ctx->g.B % rep || ctx->g.V % rep) { pdp_set_error("pdp_deduplicate: sizes not divisible by the replication factor"); return PDP_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
     if (ctx->g.F > 0) { k_dedup_energy<<<GRID(ctx->g.F)>>>(ctx->g, ctx->s, d_pred); PDP_LAUNCH_CHECK(ctx); }

@@ -13,6 +13,7 @@ WalkSAT are the library's kernels, the dense layers (Linear adaptors, GRU cells,
 torch in fp32.  There is no CPU path and no fallback: CPU tensors or a missing library raise.
 """
 import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -74,8 +75,9 @@ class SATProblem(object):
         B0 = self._batch_size // b
         x = torch.arange(B0 * b, dtype=torch.int64, device=self._graph_map.device)
         ind = torch.stack([x, x % B0])
-        mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0),
-                                       check_invariants=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)     # "sparse invariant checks are implicitly disabled"
+            mask = torch.sparse_coo_tensor(ind, torch.ones(B0 * b, device=self._graph_map.device), (B0 * b, B0))
         return (mask, mask.transpose(0, 1))
 
     def edge_problem_index(self):

@@ -726,3 +726,46 @@ def test_npdnp_forward_vs_reference(path):
     assert maxdiff(C(vp).reshape(-1)[decided], z["pred"][decided]) == 0
     assert int((~decided).sum()) == z["fill"].shape[0]
     assert maxdiff(C(ps[0]), z["final_p0"]) < 2e-4 and maxdiff(C(ps[1]), z["final_p1"]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# degenerate batches through the module interface
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["no_clauses", "unit", "mixed_with_empty", "contradiction", "replicated"])
+def test_degenerate_batches(case):
+    """problems without clauses (E = 0 for the whole batch, or one empty problem among others), a lone unit clause, a
+    one-variable contradiction, batch replication over an empty problem: shapes, verdicts (against the C oracle's CNF check
+    of the returned prediction) and the values the closure alone decides"""
+    from oracle import pdp_oracle as po
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.nn import solver as S
+    probs, b = {
+        "no_clauses": ([(5, [])], 1),
+        "unit": ([(3, [[2]])], 1),
+        "mixed_with_empty": ([(4, [[1, -2, 3], [-1, 2, 4]]), (3, []), (2, [[1, 2], [-1, -2]])], 1),
+        "contradiction": ([(1, [[1], [-1]])], 1),
+        "replicated": ([(4, [[1, -2, 3]]), (3, [])], 2),
+    }[case]
+    batch = cnfgen.from_clauses(probs)
+    gm, bvm, bfm, ef = [T(x) for x in batch]
+    model = S.SurveyPropagatorSolver(dev(), "x", tolerance=0.02, t_max=10, local_search_iterations=4, epsilon=0.5)
+    init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=b)
+    (pred, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                                meta_data=None, is_training=False, iteration_num=6, check_termination=_standard_termination(),
+                                batch_replication=b)
+    E, V = batch[0].shape[1], batch[1].shape[0]
+    p = C(pred).reshape(-1)
+    assert p.shape == (V,) and tuple(ps[0].shape) == (E, 3) and tuple(ps[1].shape) == (E, 2)
+    assert np.isin(p, [0.0, 0.5, 1.0]).all()
+    from pdp_solver_b200.engine import Context
+    solved, n_unsat = Context(gm, bvm, bfm, ef).cnf_eval(pred)
+    o_solved, o_unsat = po.Oracle(*batch).cnf_eval(p)
+    assert maxdiff(C(solved), o_solved) == 0 and maxdiff(C(n_unsat), o_unsat) == 0
+    if case == "no_clauses":
+        assert (p == 0.5).all() and C(solved).tolist() == [1.0]
+    if case == "unit":
+        assert p.tolist() == [0.5, 1.0, 0.5]
+    if case == "contradiction":
+        assert C(solved).tolist() == [0.0] and p.tolist() == [0.5]
+    if case == "mixed_with_empty":
+        assert C(solved)[:2].tolist() == [1.0, 1.0] and (p[4:7] == 0.5).all()
