@@ -543,6 +543,36 @@ def test_full_size_properties():
         assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
 
 
+def test_full_size_decimation_paths():
+    """the decimation regime at full size (2 x n = 1 000 000, T = 170: the problems converge near iteration 95 and then
+    decimate almost every iteration): the product path (scores from the variable pass, range scans, frontier closure,
+    CNF count without gathers) against the full-scan closure and against the generic passes (scores gathered by
+    score_variable): identical decimation sequence, masks, solution, counters and messages"""
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.engine import Context
+    batch = cnfgen.random_batch(2, 1000000, 3, 4.2, 123)
+    gm, bvm, bfm, ef = [T(x) for x in batch]
+    outs = []
+    for generic, full_closure in ((False, False), (False, True), (True, True)):
+        ctx = Context(gm, bvm, bfm, ef, batch_size=2)
+        ctx.enable_trace()
+        ctx.simplify()
+        ctx.load_state_const(1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0, 0.5, 0.0)
+        done = ctx.sp_run(170, 0.02, 100, True, sync=True, generic=generic, full_closure=full_closure)
+        q, fs = ctx.store_state()
+        m = ctx.get_masks()
+        tr = ctx.trace().to(torch.int64)
+        tr = tr[torch.argsort(tr[:, 0] * (1 << 32) + tr[:, 1])]
+        _, counters, _ = ctx.problem_flags()
+        outs.append((torch.tensor(done), q[:, 0].clone(), fs[:, 0].clone(), m["av"].clone(), m["af"].clone(), m["sol"].clone(),
+                     m["active"].clone(), tr.clone(), counters.clone()))
+        del ctx
+    assert outs[0][7].shape[0] >= 40, "too few decimation steps: the test does not exercise the regime"
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert a.shape == b.shape and (torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all()))
+
+
 @pytest.mark.parametrize("spec", [(96, 100, 3, 4.2, 200, 41), (12, 400, 3, 4.0, 150, 42), (40, 60, 3, 3.5, 150, 43)],
                          ids=lambda s: "B%d_n%d_k%d" % (s[0], s[1], s[2]))
 def test_local_decimation_equals_grid_decimation(spec, monkeypatch):
