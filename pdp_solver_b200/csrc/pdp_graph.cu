@@ -189,14 +189,23 @@ __global__ void k_fill_clause_major(const int32_t* __restrict__ evar, const floa
     }
 }
 
-// v_orig[p] is the original edge index of slot p (stable sort by variable)
-__global__ void k_fill_var_major(const int32_t* __restrict__ ecls, const float* __restrict__ sign,
-                                 const int32_t* __restrict__ v_orig, const int32_t* __restrict__ inv,
+// sort payload of the variable-major order: the original edge index with the literal's sign in bit 31, so that the fill
+// below does not have to gather the sign again (one random 4-byte gather per edge less)
+__global__ void k_iota_signed(const float* __restrict__ sign, uint32_t* out, int64_t E) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = (uint32_t)e | ((sign[e] < 0.f) ? PDP_SIGN_BIT : 0u);
+}
+
+// packed[p] = original edge index | sign of slot p (stable sort by variable); v_orig[p] is written here
+__global__ void k_fill_var_major(const int32_t* __restrict__ ecls, const uint32_t* __restrict__ packed,
+                                 const int32_t* __restrict__ inv, int32_t* v_orig,
                                  uint32_t* v_cedge, int32_t* v_cls, int32_t* c_pos, int64_t E) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x) {
-        int32_t e = v_orig[p];
-        int32_t c = inv ? inv[e] : e;
-        v_cedge[p] = (uint32_t)c | ((sign[e] < 0.f) ? PDP_SIGN_BIT : 0u);
+        const uint32_t w = packed[p];
+        const int32_t e = (int32_t)(w & PDP_IDX_MASK);
+        const int32_t c = inv ? inv[e] : e;
+        v_orig[p] = e;
+        v_cedge[p] = (uint32_t)c | (w & PDP_SIGN_BIT);
         v_cls[p] = ecls[e];
         c_pos[c] = (int32_t)p;
     }
@@ -359,12 +368,15 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
         int32_t* vA = reinterpret_cast<int32_t*>(c->s.qu);
         int32_t* vB = reinterpret_cast<int32_t*>(c->s.qs);
         int32_t* inv = reinterpret_cast<int32_t*>(c->s.qd);
-        auto stable_sort = [&](const int32_t* keys, int64_t nkeys, int32_t* out_vals) -> int {
+        const int32_t* sorted_vals = nullptr;   // where the last stable_sort left its payload
+        // out_vals == nullptr: the payload stays in the scratch buffer (sorted_vals); signed_payload: edge index | sign bit
+        auto stable_sort = [&](const int32_t* keys, int64_t nkeys, int32_t* out_vals, bool signed_payload) -> int {
             int bits = 1;
             while (((int64_t)1 << bits) < nkeys && bits < 31) ++bits;
             cudaError_t e1 = cudaMemcpyAsync(kA, keys, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream);
             if (e1 != cudaSuccess) return -1;
-            k_iota<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(vA, E);
+            if (signed_payload) k_iota_signed<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(d_edge_feature, reinterpret_cast<uint32_t*>(vA), E);
+            else k_iota<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(vA, E);
             c->launches++;
             cub::DoubleBuffer<int32_t> dk(kA, kB);
             cub::DoubleBuffer<int32_t> dv(vA, vB);
@@ -374,27 +386,29 @@ extern "C" int pdp_create(pdp_ctx** out, const int32_t* d_graph_map, const float
             size_t tb = c->cub_tmp_bytes;
             if (cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, dk, dv, (int)E, 0, bits, stream) != cudaSuccess) return -1;
             c->launches++;
-            if (cudaMemcpyAsync(out_vals, dv.Current(), sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
+            sorted_vals = dv.Current();
+            if (out_vals && cudaMemcpyAsync(out_vals, dv.Current(), sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
             return 0;
         };
         if (clause_major) {
             k_iota<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(g.c_orig, E);
             LK();
         } else {
-            int r = stable_sort(ecls, F, g.c_orig);
+            int r = stable_sort(ecls, F, g.c_orig, false);
             if (r != 0) { pdp_set_error("pdp_create: clause sort failed (%d)", r); delete c; return r == -2 ? PDP_ERR_WORKSPACE : PDP_ERR_CUDA; }
         }
         {
-            int r = stable_sort(evar, V, g.v_orig);
+            int r = stable_sort(evar, V, nullptr, true);
             if (r != 0) { pdp_set_error("pdp_create: variable sort failed (%d)", r); delete c; return r == -2 ? PDP_ERR_WORKSPACE : PDP_ERR_CUDA; }
         }
+        const uint32_t* packed = reinterpret_cast<const uint32_t*>(sorted_vals);   // vA or vB: not touched until the fill below
         if (!clause_major) {
             k_invert<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(g.c_orig, inv, E);
             LK();
         }
         k_fill_clause_major<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(evar, d_edge_feature, g.c_orig, g.c_var, E);
         LK();
-        k_fill_var_major<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(ecls, d_edge_feature, g.v_orig, clause_major ? nullptr : inv,
+        k_fill_var_major<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(ecls, packed, clause_major ? nullptr : inv, g.v_orig,
                                                                      g.v_cedge, g.v_cls, g.c_pos, E);
         LK();
         if (V > 0) { k_max_degree<<<pdp_grid(V, 256, nsm), 256, 0, stream>>>(g.var_ptr, V, flags + 2); LK(); }
