@@ -229,7 +229,7 @@ __device__ __forceinline__ void deactivate_variable(const pdp_graph& g, const pd
 }
 __device__ __forceinline__ void deactivate_clause(const pdp_graph& g, const pdp_state& s, int a) {
     s.af[a] = 0;
-    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) mask_edge(g, g.c_vpos[c], g.c_qpos[c]);
+    for (int c = g.cl_ptr[a]; c < g.cl_ptr[a + 1]; ++c) mask_edge(g, cvpos(g, c), cqpos(g, c));
 }
 // the words change between passes: read around L1
 __device__ __forceinline__ bool mbit(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 1u; }
@@ -283,16 +283,16 @@ __device__ __forceinline__ void gen_clause_side(const KArgs& A, int r, bool use_
         const int beg = g.cl_ptr[a], end = g.cl_ptr[a + 1];
         float tot = 0.f;
         for (int c = beg; c < end; ++c) {
-            const int qp = g.c_qpos[c];
+            const int qp = cqpos(g, c);
             float v = L40(qin[qp]);
             if (um && mbit(g.qmask, qp)) v = v * 0.f;
             tot += v;
         }
         for (int c = beg; c < end; ++c) {
-            const int qp = g.c_qpos[c];
+            const int qp = cqpos(g, c);
             float v = L40(qin[qp]);
             if (um && mbit(g.qmask, qp)) v = v * 0.f;
-            const int pos = g.c_vpos[c];
+            const int pos = cvpos(g, c);
             float nv = X30(tot - v);
             if (sticky) { const float ov = eold[pos]; if (ov != ov) nv = ov; }
             made_nan |= (nv != nv);

@@ -67,8 +67,6 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.prob_fptr = k.take<int32_t>(B + 1);
     g.p_vpos = k.take<int32_t>(E);
     g.p_qpos = k.take<int32_t>(E);
-    g.c_vpos = k.take<int32_t>(E);
-    g.c_qpos = k.take<int32_t>(E);
     g.vmask = k.take<uint32_t>(E / 32 + 1);
     g.qmask = k.take<uint32_t>(E / 32 + 1);
     // block count <= rounds * SMs + 1 with rounds * SMs <= E / (half a block) + SMs (pdp_layout.cu pick_stride;

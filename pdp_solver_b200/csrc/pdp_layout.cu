@@ -47,7 +47,6 @@ __global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ ki, cons
     GS(x, g.E) {
         const int c = lv[x];
         const int p = g.c_pos[c];
-        g.c_vpos[c] = (int32_t)x;
         g.p_vpos[p] = (int32_t)x;
         g.vinv[x] = (uint16_t)((p - g.var_ptr[g.vb_ptr[ki[x]]]) | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
     }
@@ -58,7 +57,6 @@ __global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, cons
         const int p = lq[x];
         const int c = (int)(g.v_cedge[p] & PDP_IDX_MASK);
         g.p_qpos[p] = (int32_t)x;
-        g.c_qpos[c] = (int32_t)x;
         g.cinv[x] = (uint16_t)(c - g.cl_ptr[g.cb_ptr[kj[x]]]);
     }
 }
@@ -107,8 +105,8 @@ __global__ void k_fill_staged_tables(pdp_graph g) {
     GS(c, g.E) {   // clause side
         const int cl = g.v_cls[g.c_pos[c]];
         const int e0 = g.cl_ptr[g.cb_ptr[g.cl_ptr[cl] / g.sc]];
-        g.cperm[c] = (uint16_t)(g.c_qpos[c] - (e0 & ~3));
-        g.csrc2[c] = (uint16_t)(g.c_qpos[e0 + g.csrc[c]] - (e0 & ~3));
+        g.cperm[c] = (uint16_t)(cqpos(g, c) - (e0 & ~3));
+        g.csrc2[c] = (uint16_t)(cqpos(g, e0 + g.csrc[c]) - (e0 & ~3));
     }
 }
 #endif
@@ -152,7 +150,7 @@ __global__ void k_clause_block_degree_check(pdp_graph g) {
 __global__ void k_identity_layout(pdp_graph g) {
     GS(c, g.E) {
         const int p = g.c_pos[c];
-        g.p_vpos[p] = p; g.p_qpos[p] = p; g.c_vpos[c] = p; g.c_qpos[c] = p;
+        g.p_vpos[p] = p; g.p_qpos[p] = p;
     }
 }
 
@@ -296,7 +294,7 @@ namespace {
 __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/32+1] x 2, zeroed */) {
     GS(c, g.E) {
         const int p = g.c_pos[c];
-        if (g.c_vpos[c] != g.p_vpos[p] || g.c_qpos[c] != g.p_qpos[p] || (int)(g.v_cedge[p] & PDP_IDX_MASK) != (int)c) atomicAdd(&errs[0], 1);
+        if (cvpos(g, c) != g.p_vpos[p] || cqpos(g, c) != g.p_qpos[p] || (int)(g.v_cedge[p] & PDP_IDX_MASK) != (int)c) atomicAdd(&errs[0], 1);
     }
     if (!g.blocked_ok) return;
     uint32_t* seen_c = seen + g.E / 32 + 1;
@@ -338,17 +336,17 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
         const int e0 = g.cl_ptr[a0], e1 = g.cl_ptr[a1];
         if (e1 - e0 > PDP_BLK_C / g.ctas) atomicAdd(&errs[2], 1);
         for (int c = e0; c < e1; ++c) {
-            const int x = g.c_qpos[c];
+            const int x = cqpos(g, c);
             if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
         }
         for (int w = e0; w < e1; ++w) {
             const int c = e0 + (int)g.csrc[w];
-            if (c < e0 || c >= e1 || g.c_vpos[c] != g.cdst[w]) { atomicAdd(&errs[4], 1); continue; }
+            if (c < e0 || c >= e1 || cvpos(g, c) != g.cdst[w]) { atomicAdd(&errs[4], 1); continue; }
             if (w > e0 && g.cdst[w] <= g.cdst[w - 1]) atomicAdd(&errs[4], 1);
             if (!(atomicOr(&seen_c[c >> 5], 1u << (c & 31)) & (1u << (c & 31)))) atomicAdd(&errs[7], 1);
         }
-        for (int c = e0; c < e1 && PDP_TMA; ++c) if ((int)g.cperm[c] + (e0 & ~3) != g.c_qpos[c]) atomicAdd(&errs[2], 1);
-        for (int w = e0; w < e1 && PDP_TMA; ++w) if ((int)g.csrc2[w] + (e0 & ~3) != g.c_qpos[e0 + (int)g.csrc[w]]) atomicAdd(&errs[4], 1);
+        for (int c = e0; c < e1 && PDP_TMA; ++c) if ((int)g.cperm[c] + (e0 & ~3) != cqpos(g, c)) atomicAdd(&errs[2], 1);
+        for (int w = e0; w < e1 && PDP_TMA; ++w) if ((int)g.csrc2[w] + (e0 & ~3) != cqpos(g, e0 + (int)g.csrc[w])) atomicAdd(&errs[4], 1);
         const int k = g.cb_k[blk];
         bool uni = (a1 > a0);
         for (int a = a0; a < a1; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != g.cl_ptr[a0 + 1] - g.cl_ptr[a0]) uni = false;

@@ -254,7 +254,7 @@ __global__ void k_clear_mask_bits(pdp_graph g) {
 __global__ void k_rebuild_mask_bits(pdp_graph g, pdp_state s) {
     for (int64_t c = gtid(); c < g.E; c += gthreads()) {
         const int p = g.c_pos[c];
-        if (!(s.av[g.c_var[c] & PDP_IDX_MASK] && s.af[g.v_cls[p]])) mask_edge(g, g.c_vpos[c], g.c_qpos[c]);
+        if (!(s.av[g.c_var[c] & PDP_IDX_MASK] && s.af[g.v_cls[p]])) mask_edge(g, cvpos(g, c), cqpos(g, c));
     }
 }
 
