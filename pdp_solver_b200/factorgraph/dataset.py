@@ -167,5 +167,14 @@ class FactorGraphDataset(object):
     def batches(self, batch_size, pin=False):
         "what the reference's DataLoader(batch_size, shuffle=False, collate_fn=dag_collate_fn) yields"
         n = len(self)
-        for lo in range(0, n, batch_size):
-            yield self.dag_collate_fn([self[i] for i in range(lo, min(lo + batch_size, n))], pin)
+        if self._rows is not None:
+            for lo in range(0, n, batch_size):
+                yield self.dag_collate_fn(self._rows[lo:lo + batch_size], pin)
+            return
+        with open(self._input_file, "rb") as fh:          # one handle for the whole pass
+            for lo in range(0, n, batch_size):
+                rows = []
+                for pos, size in self._offsets[lo:lo + batch_size]:
+                    fh.seek(pos)
+                    rows.append(parse_row(fh.read(size)))
+                yield self.dag_collate_fn(rows, pin)
