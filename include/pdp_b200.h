@@ -192,6 +192,12 @@ int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch
  * `p cnf` line are skipped, `%` ends the file; info[0..3] = declared variables, declared clauses (-1 if no
  * header), entries written, clauses seen.  PDP_ERR_WORKSPACE if `cap` entries are not enough (info[2] = need). */
 int64_t pdp_host_parse_ints(const char* text, int64_t len, int32_t* out, int64_t cap);
+/* pdp_host_parse_rows: a whole compact-JSON file (one `[[n, m], [literals], [clauses], label, [id]]` row per line,
+ * src/pdp/factorgraph/dataset.py:120-136) in one pass: the two integer lists of every row back to back in lits / cls
+ * (row r = [row_ptr[r], row_ptr[r+1])), nm[2r..] = n, m, label[r], tail[2r..] = byte range of the id list for the caller to
+ * decode.  Returns the row count, -(line number) of the first malformed row, or -2^62 when a capacity is too small. */
+int64_t pdp_host_parse_rows(const char* text, int64_t len, int32_t* lits, int32_t* cls, int64_t int_cap,
+                            int64_t* row_ptr, int32_t* nm, double* label, int64_t* tail, int64_t row_cap);
 int pdp_host_parse_dimacs(const char* text, int64_t len, int32_t* lits, int64_t cap, int64_t* info);
 
 /* counters for bench.py: number of kernels this library launched on behalf of the context */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "pdp_debug_phase_bench": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P]),
     "pdp_launch_count": (I64, [P]),
     "pdp_host_parse_ints": (I64, [ctypes.c_char_p, I64, P, I64]),
+    "pdp_host_parse_rows": (I64, [ctypes.c_char_p, I64, P, P, I64, P, P, P, P, I64]),
     "pdp_host_parse_dimacs": (ctypes.c_int, [ctypes.c_char_p, I64, P, I64, ctypes.POINTER(I64 * 4)]),
 }
 

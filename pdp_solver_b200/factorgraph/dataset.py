@@ -90,6 +90,42 @@ def parse_row(text):
     return (variable_num, function_num, graph_map, edge_feature, None, label, misc)
 
 
+def parse_file(path):
+    """Every row of a compact-JSON file in one pass of the library's scanner (`pdp_host_parse_rows`): a list of the tuples
+    `parse_row` returns.  The per-row arrays are views into four file-wide arrays (no per-row allocation)."""
+    lib = _lib.load()
+    with open(path, "rb") as fh:
+        data = fh.read()
+    int_cap = len(data) // 2 + 1
+    row_cap = len(data) // 16 + 2          # the shortest row has 19 bytes
+    lits = np.empty(int_cap, dtype=np.int32)
+    cls = np.empty(int_cap, dtype=np.int32)
+    row_ptr = np.empty(row_cap + 1, dtype=np.int64)
+    nm = np.empty(2 * row_cap, dtype=np.int32)
+    label = np.empty(row_cap, dtype=np.float64)
+    tail = np.empty(2 * row_cap, dtype=np.int64)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)      # noqa: E731
+    n = lib.pdp_host_parse_rows(data, len(data), P(lits), P(cls), int_cap, P(row_ptr), P(nm), P(label), P(tail), row_cap)
+    if n < 0:
+        raise ValueError("%s: malformed row at line %d" % (path, -n) if n > -(1 << 61) else "%s: parser capacity" % path)
+    total = int(row_ptr[n])
+    lits, cls = lits[:total], cls[:total]
+    gm = np.empty((2, total), dtype=np.int32)
+    np.abs(lits, out=gm[0])
+    gm[0] -= 1
+    np.abs(cls, out=gm[1])
+    gm[1] -= 1
+    ef = np.sign(lits).astype(np.float32)
+    rows = []
+    for r in range(n):
+        a, b = int(row_ptr[r]), int(row_ptr[r + 1])
+        t = data[int(tail[2 * r]):int(tail[2 * r + 1])].strip()
+        t = t[:-1].strip() if t.endswith(b"]") else t              # the row's own closing bracket
+        misc = json.loads(t.decode()) if t else []
+        rows.append((int(nm[2 * r]), int(nm[2 * r + 1]), gm[:, a:b], ef[a:b], None, float(label[r]), misc))
+    return rows
+
+
 def collate_segment(rows, pin=False):
     """One segment -> (graph_map int32[2,E], batch_variable_map int32[V], batch_function_map int32[F],
     edge_feature f32[E,1], None, label f32[B,1], misc list) with the reference's numbering
@@ -131,17 +167,10 @@ class FactorGraphDataset(object):
     def __init__(self, input_file, limit, hidden_dim, max_cache_size=100000, generator=None, epoch_size=0,
                  batch_replication=1, rows=None):
         self._input_file = input_file
-        self._rows = rows            # already-parsed rows (DIMACS input)
+        # already-parsed rows (DIMACS input), or the whole file scanned once (the reference reads the whole file just to
+        # count its rows, dataset.py:96-97, then parses each row with json.loads)
+        self._rows = rows if rows is not None else parse_file(input_file)
         self._offsets = None
-        if rows is None:
-            # byte offsets of the lines, one pass (the reference reads the whole file to count rows, dataset.py:96-97)
-            offs, pos = [], 0
-            with open(input_file, "rb") as fh:
-                for line in fh:
-                    if line.strip():
-                        offs.append((pos, len(line)))
-                    pos += len(line)
-            self._offsets = offs
         self.batch_divider = DynamicBatchDivider(limit // batch_replication, hidden_dim)
 
     def __len__(self):

@@ -120,3 +120,27 @@ def test_cli_parser_and_config_merge():
     assert cfg["model_type"] == "walk-sat" and cfg["local_search_iteration"] == 77 and cfg["hidden_dim"] == 3
     assert cfg["batch_replication"] == 4 and cfg["epsilon"] == 0.3 and cfg["model_path"] is None
     assert cfg["batch_size"] == 5000 and cfg["test_batch_limit"] == 40000000 and cfg["dropout"] == 0
+
+
+def test_parse_file_equals_parse_row(tmp_path):
+    "the one-pass file scanner (pdp_host_parse_rows) against the per-row path on the fixture file and on odd rows"
+    from pdp_solver_b200.factorgraph.dataset import parse_file, parse_row
+    path = os.path.join(GOLD, "cli_small.json")
+    rows = parse_file(path)
+    lines = [l for l in open(path) if l.strip()]
+    assert len(rows) == len(lines)
+    for r, line in zip(rows, lines):
+        q = parse_row(line)
+        assert r[0] == q[0] and r[1] == q[1] and r[5] == q[5] and r[6] == q[6] and r[4] is None
+        assert np.array_equal(r[2], q[2]) and np.array_equal(r[3], q[3])
+        assert r[2].dtype == np.int32 and r[3].dtype == np.float32
+    odd = tmp_path / "odd.json"
+    odd.write_text('[[3,2],[1,-2,3,-1],[1,1,2,2],1]\n\n  [[2, 0], [], [], -1, ["empty", 7]]\n[[1,1],[ -1 ],[1],0.0,[]]')
+    rows = parse_file(str(odd))
+    assert [(r[0], r[1], r[5], r[6]) for r in rows] == [(3, 2, 1.0, []), (2, 0, -1.0, ["empty", 7]), (1, 1, 0.0, [])]
+    assert rows[0][2].tolist() == [[0, 1, 2, 0], [0, 0, 1, 1]] and rows[0][3].tolist() == [1, -1, 1, -1]
+    assert rows[1][2].shape == (2, 0) and rows[2][2].tolist() == [[0], [0]] and rows[2][3].tolist() == [-1]
+    bad = tmp_path / "bad.json"
+    bad.write_text('[[3,2],[1,-2,3,-1],[1,1,2,2],1]\n[[3,2],[1,-2,3],[1,1],1]\n')
+    with pytest.raises(ValueError, match="line 2"):
+        parse_file(str(bad))
