@@ -73,12 +73,12 @@ class FactorGraphTrainerBase(object):
     def predict(self, test_list, out_file, import_path_base=None, post_processor=None, batch_replication=1, rows=None):
         """Produces predictions.  `rows`: already-parsed problems (the DIMACS input of satyr.py -d) instead of a
         JSON file."""
+        start_time = time.time()      # the input is scanned when the dataset is built: part of the time reported
         dataset = FactorGraphDataset(
             input_file=test_list, limit=self._config["test_batch_limit"], hidden_dim=self._config["hidden_dim"],
             max_cache_size=self._config.get("max_cache_size", 100000), batch_replication=batch_replication, rows=rows)
         if import_path_base is not None:
             self._load(import_path_base)
-        start_time = time.time()
         self._predict_epoch(dataset.batches(self._config["batch_size"], pin=True), post_processor, batch_replication,
                             out_file)
         torch.cuda.synchronize(self._device)
