@@ -63,18 +63,23 @@ __global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, cons
 
 // write-out order of the variable blocks: the edges of a block sorted by their C-layout position.
 // Input in C-layout order x (lq[x] = variable-major slot): key = variable block, value = x.
+// block of a slot of the node-major order: the stride region the slot lies in, or an earlier one when the slot's node
+// started before that region (block t begins at the first node whose first slot is >= t * stride, k_block_ptr).  Two
+// loads from the small block tables instead of three dependent random gathers through the adjacency.
+__device__ __forceinline__ int block_of_slot(const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ blk_ptr, int stride, int slot) {
+    int b = slot / stride;
+    while (b > 0 && slot < node_ptr[blk_ptr[b]]) --b;
+    return b;
+}
 __global__ void k_key_vblock_of_q(pdp_graph g, const int32_t* __restrict__ lq, int32_t* key, int32_t* val) {
     GS(x, g.E) {
-        const int p = lq[x];
-        const int var = (int)(g.c_var[g.v_cedge[p] & PDP_IDX_MASK] & PDP_IDX_MASK);
-        key[x] = g.var_ptr[var] / g.sv;
+        key[x] = block_of_slot(g.var_ptr, g.vb_ptr, g.sv, lq[x]);
         val[x] = (int32_t)x;
     }
 }
 __global__ void k_key_cblock_of_v(pdp_graph g, const int32_t* __restrict__ lv, int32_t* key, int32_t* val) {
     GS(x, g.E) {
-        const int c = lv[x];
-        key[x] = g.cl_ptr[g.v_cls[g.c_pos[c]]] / g.sc;
+        key[x] = block_of_slot(g.cl_ptr, g.cb_ptr, g.sc, lv[x]);
         val[x] = (int32_t)x;
     }
 }
