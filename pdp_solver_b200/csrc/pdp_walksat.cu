@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_walksat(const __grid_constant__ KArgs A
                 const int v = (int)(w & PDP_IDX_MASK);
                 const int lit = (int)s.asg[v];
                 agg += (w & PDP_SIGN_BIT) ? -lit : lit;
-                deg += s.av[v];
+                deg += (lit != 0) ? 1 : 0;      // asg is 0 exactly for the inactive variables: no second gather of av
             }
             const bool unsat = (agg == -deg) && s.af[a];
             s.ws_true[a] = agg; s.ws_deg[a] = deg; s.single[a] = unsat ? 1 : 0;
