@@ -144,3 +144,18 @@ def test_parse_file_equals_parse_row(tmp_path):
     bad.write_text('[[3,2],[1,-2,3,-1],[1,1,2,2],1]\n[[3,2],[1,-2,3],[1,1],1]\n')
     with pytest.raises(ValueError, match="line 2"):
         parse_file(str(bad))
+
+
+def test_dimacs_directory_to_json_roundtrip(tmp_path):
+    "convert_directory writes rows that the file scanner reads back identically to the direct DIMACS conversion"
+    from pdp_solver_b200 import dimacs2json
+    from pdp_solver_b200.factorgraph.dataset import parse_file
+    out = tmp_path / "rows.json"
+    ddir = os.path.join(GOLD, "dimacs")
+    dimacs2json.convert_directory(ddir, str(out))
+    rows = parse_file(str(out))
+    direct = [dimacs2json.convert_one(p) for p in dimacs2json.dimacs_files(ddir)]
+    assert len(rows) == len(direct) == 3
+    for a, b in zip(rows, direct):
+        assert a[0] == b[0] and a[1] == b[1] and a[5] == b[5] and a[6] == b[6]
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
