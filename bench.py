@@ -16,8 +16,12 @@ WalkSAT, solution merge.  Weak scaling: every rank owns its own problems, no dat
 `e2e`    : the same through the public API with HOST (pinned) batch tensors; H2D of the batch and D2H
            of the prediction + verdicts are inside the timed region.
 `roofline`: the persistent SP kernel (k_sp_run) timed alone with CUDA events on its stream.
-`--impl reference`: the reference algorithm on the host cores (the C oracle port, OpenMP, all
-           threads; the Python reference cannot travel to the GPU box) on a bounded sample.
+`--impl reference`: the UNMODIFIED reference (baseline/_ref or /root/reference, loaded through oracle/compat.py) on
+           the host cores: its own `model(...)` forward with use_cuda=False (== satyr.py --cpu_mode,
+           src/pdp/factorgraph/base.py:280-305), torch threads = cpu_count as the reference sets them, on a
+           bounded sample of the workload (one smaller problem, few iterations; set-up, loop and WalkSAT timed
+           separately and the whole-step figure rebuilt for the workload's T and W).  The C oracle port is the
+           fallback when the reference tree is absent (`kind: "port"`).
 """
 import argparse
 import json
@@ -53,10 +57,23 @@ def parse():
     ap.add_argument("--seed", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config0", action="store_true", help="skip the CNFs-solved/s measurement on BASELINE.json configs[0]")
-    ap.add_argument("--cpu-problem-n", type=int, default=0, help="n of the CPU sample problem (default: --n)")
+    ap.add_argument("--cpu-problem-n", type=int, default=100000, help="n of the CPU sample problem (0: --n)")
     ap.add_argument("--cpu-iterations", type=int, default=3)
     ap.add_argument("--cpu-walksat", type=int, default=2)
+    ap.add_argument("--cpu-port", action="store_true", help="time the C oracle port even when the reference is present")
     return ap.parse_args()
+
+
+def config_of(a):
+    """the `config` object of the JSON line: a function of the arguments only, identical in both arms"""
+    m = int(a.n * a.alpha)
+    E, V, F = a.k * m * a.problems, a.n * a.problems, m * a.problems
+    from pdp_solver_b200.nn import solver as pdp_solver
+    return {"workload": workload_name(a), "model_type": "p-d-p", "edges_per_gpu": E, "variables_per_gpu": V,
+            "clauses_per_gpu": F, "init": "deterministic (predict path)",
+            "rng": "torch" if a.walksat * (V + a.problems) <= pdp_solver.TORCH_RNG_DRAW_LIMIT else "philox",
+            "l2": "inputs larger than L2 (%.1f GB message+topology working set per GPU)" % (E * 48 / 1e9),
+            "sharding": "problems sharded across ranks, no per-iteration collective"}
 
 
 def workload_name(a):
@@ -102,10 +119,10 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores
+# CPU arm: the reference itself (oracle/ref_timing.py) or, when its tree is absent, the C oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_forward(batch, T, W, tol, t_max, eps, seed):
-    """one forward() of the reference algorithm on the CPU; returns (seconds, edge_updates, solved)"""
+def port_forward(batch, T, W, tol, t_max, eps, seed):
+    """one forward() of the C oracle port; returns dict like ref_timing.timed_forward"""
     from oracle import pdp_oracle as po
     gm, bvm, bfm, ef = batch
     E = gm.shape[1]
@@ -114,47 +131,111 @@ def cpu_forward(batch, T, W, tol, t_max, eps, seed):
     o = po.Oracle(gm, bvm, bfm, ef, strict=False)
     o.simplify()
     o.set_state(*po.init_state(E, False))
+    t1 = time.perf_counter()
     done = o.run(T, tol, t_max, True)
+    t2 = time.perf_counter()
     n_act = o.count_active_variables()
     if n_act:
         o.random_fill(rng.random(n_act, dtype=np.float32))
     rv = rng.random((max(W, 1), o.V), dtype=np.float32)
     rc = rng.random((max(W, 1), o.B), dtype=np.float32)
+    t3 = time.perf_counter()
     pred, _ = o.local_search(W, eps, rv, rc)
+    t4 = time.perf_counter()
     solved, _ = o.cnf_eval(pred)
-    dt = time.perf_counter() - t0
-    return dt, float(done) * E, int(solved.sum())
+    t5 = time.perf_counter()
+    return {"total_s": t5 - t0, "loop_s": t2 - t1, "walksat_s": t4 - t3, "setup_s": (t1 - t0) + (t3 - t2) + (t5 - t4),
+            "iterations": int(done), "solved": int(solved.sum()), "edges": int(E)}
 
 
-def cpu_sample(a):
-    from pdp_solver_b200 import cnfgen
-    n = a.cpu_problem_n or a.n
-    return cnfgen.random_batch(1, n, a.k, a.alpha, a.seed + 999), n
+class CpuArm(object):
+    """the reference's CPU path on a bounded sample of the workload"""
+
+    def __init__(self, a):
+        import torch
+        from pdp_solver_b200 import cnfgen
+        from oracle import ref_timing
+        self.a = a
+        self.n = a.cpu_problem_n or a.n
+        self.batch = cnfgen.random_batch(1, self.n, a.k, a.alpha, a.seed + 999)
+        self.kind = "reference" if (ref_timing.available() and not a.cpu_port) else "port"
+        if self.kind == "reference":
+            self.cores = ref_timing.pin_threads()
+            self.model = ref_timing.build_model("p-d-p", torch.device("cpu"), a.cpu_walksat, a.epsilon, a.tolerance, a.t_max)
+        else:
+            from oracle import pdp_oracle as po
+            po.build()
+            po.set_num_threads(os.cpu_count() or 1)
+            self.cores = po.num_threads()
+        self.sample = ("1 problem of n=%d (workload: n=%d), T=%d SP iterations + %d WalkSAT iterations per step; set-up / "
+                       "loop / WalkSAT timed separately; `value` = whole-step rate rebuilt for the workload's T=%d, W=%d "
+                       "from the measured per-iteration costs") % (self.n, a.n, a.cpu_iterations, a.cpu_walksat, a.iterations, a.walksat)
+
+    def step(self, seed):
+        if self.kind == "reference":
+            import torch
+            from oracle import ref_timing
+            return ref_timing.timed_forward(self.model, self.batch, self.a.cpu_iterations, torch.device("cpu"), seed=seed)
+        a = self.a
+        return port_forward(self.batch, a.cpu_iterations, a.cpu_walksat, a.tolerance, a.t_max, a.epsilon, seed)
+
+    def summarize(self, runs):
+        """per-iteration costs of the sample and the whole-step rate they give at the workload's T and W"""
+        a = self.a
+        E = runs[0]["edges"]
+        it = sum(r["iterations"] for r in runs)
+        loop = sum(r["loop_s"] for r in runs)
+        s_it = loop / max(it, 1)
+        s_ws = sum(r["walksat_s"] for r in runs) / max(a.cpu_walksat * len(runs), 1)
+        setup = sum(r["setup_s"] for r in runs) / len(runs)
+        step_s = setup + a.iterations * s_it + a.walksat * s_ws
+        return {"value": E * a.iterations / step_s, "unit": "edge-updates/s", "cores": self.cores, "kind": self.kind,
+                "sample": self.sample, "loop_edge_updates_per_s": E / s_it if s_it > 0 else None,
+                "s_per_sp_iteration": s_it, "s_per_walksat_iteration": s_ws, "setup_s": setup,
+                "sample_edges": E, "measured_step_s": sum(r["total_s"] for r in runs) / len(runs)}
+
+
+def reference_gpu_probe(a):
+    """second comparator: the reference's own CUDA branch (torch sparse on the same B200), one small forward"""
+    try:
+        import torch
+        from oracle import ref_timing
+        from pdp_solver_b200 import cnfgen
+        if not (torch.cuda.is_available() and ref_timing.available()):
+            return {"unavailable": "no CUDA device or no reference tree"}
+        dev = torch.device("cuda", 0)
+        n = a.cpu_problem_n or a.n
+        batch = cnfgen.random_batch(1, n, a.k, a.alpha, a.seed + 999)
+        model = ref_timing.build_model("p-d-p", dev, a.cpu_walksat, a.epsilon, a.tolerance, a.t_max)
+        T = 10
+        ref_timing.timed_forward(model, batch, 2, dev)
+        r = ref_timing.timed_forward(model, batch, T, dev)
+        s_it = r["loop_s"] / max(r["iterations"], 1)
+        return {"what": "reference CUDA branch (torch sparse) on cuda:0, 1 problem n=%d, T=%d" % (n, T),
+                "s_per_sp_iteration": s_it, "loop_edge_updates_per_s": r["edges"] / s_it if s_it > 0 else None,
+                "setup_s": r["setup_s"], "s_per_walksat_iteration": r["walksat_s"] / max(a.cpu_walksat, 1)}
+    except Exception as e:   # the reference's legacy sparse constructors may not survive this torch
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 def run_reference_arm(a, rank, world):
     if rank != 0:
         return
-    from oracle import pdp_oracle as po
-    po.build()
-    batch, n = cpu_sample(a)
-    sample = "1 problem n=%d, T=%d SP iterations + %d WalkSAT iterations per step (bounded sample of the workload)" % (
-        n, a.cpu_iterations, a.cpu_walksat)
-    for _ in range(min(a.warmup, 1)):
-        cpu_forward(batch, 1, 1, a.tolerance, a.t_max, a.epsilon, a.seed)
-    tot_t, tot_u = 0.0, 0.0
+    arm = CpuArm(a)
+    for s in range(min(a.warmup, 1)):
+        arm.step(a.seed)
+    runs = []
+    t0 = time.perf_counter()
     for s in range(a.steps):
-        dt, upd, _ = cpu_forward(batch, a.cpu_iterations, a.cpu_walksat, a.tolerance, a.t_max, a.epsilon, a.seed + s)
-        tot_t += dt
-        tot_u += upd
-    val = tot_u / tot_t
-    line = {"impl": "reference", "metric": "sp_edge_updates_per_s", "value": val, "unit": "edge-updates/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(a.steps, 1),
+        runs.append(arm.step(a.seed + s))
+    wall = time.perf_counter() - t0
+    cb = arm.summarize(runs)
+    line = {"impl": "reference", "metric": "sp_edge_updates_per_s", "value": cb["value"], "unit": "edge-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a)},
-            "cpu_baseline": {"value": val, "unit": "edge-updates/s", "cores": po.num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "config": config_of(a), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "reference_gpu": reference_gpu_probe(a)}
     print(json.dumps(line))
 
 
@@ -286,10 +367,7 @@ def run_b200_arm(a, rank, world, local_rank):
         "metric": "sp_edge_updates_per_s", "value": upd / (ms / 1e3), "unit": "edge-updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "model_type": "p-d-p", "edges_per_gpu": E, "variables_per_gpu": V,
-                   "clauses_per_gpu": F, "init": "deterministic (predict path)", "rng": "torch" if a.walksat * (V + B) <= pdp_solver.TORCH_RNG_DRAW_LIMIT else "philox",
-                   "l2": "inputs larger than L2 (%.1f GB message+topology working set per GPU)" % (E * 48 / 1e9),
-                   "sharding": "problems sharded across ranks, no per-iteration collective"},
+        "config": config_of(a),
         "cnfs_solved_per_s": solved / (ms / 1e3), "cnfs_per_s": world * B * a.steps / (ms / 1e3),
         "sp_loop_edge_updates_per_s_rank0": st["loop_updates"] / loop_s if loop_s > 0 else None,
         "phase_ms_per_step_rank0": {"sp_loop": st["loop_ms"] / a.steps, "walksat": st["ws_ms"] / a.steps,
@@ -307,14 +385,9 @@ def run_b200_arm(a, rank, world, local_rank):
     }
     if not a.no_config0 and world == 1:
         line["config0_cnfs_solved"] = config0_solved(dev)
-    if not a.no_cpu_baseline and world == 1:
-        from oracle import pdp_oracle as po
-        po.build()
-        cb, n = cpu_sample(a)
-        dt, u, _ = cpu_forward(cb, a.cpu_iterations, a.cpu_walksat, a.tolerance, a.t_max, a.epsilon, a.seed)
-        line["cpu_baseline"] = {"value": u / dt, "unit": "edge-updates/s", "cores": po.num_threads(), "kind": "port",
-                                "sample": "1 problem n=%d, T=%d SP iterations + %d WalkSAT iterations (%.1f s)" % (
-                                    n, a.cpu_iterations, a.cpu_walksat, dt)}
+    if not a.no_cpu_baseline:
+        arm = CpuArm(a)
+        line["cpu_baseline"] = arm.summarize([arm.step(a.seed)])
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

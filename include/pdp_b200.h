@@ -177,11 +177,6 @@ int pdp_trace_length(pdp_ctx* ctx, int32_t* host_out, void* stream);
  * variable block stride, clause block stride} */
 int pdp_debug_check_layout(pdp_ctx* ctx, int32_t* d_errs, int32_t* host_info, void* stream);
 
-/* profiling aid: runs ONE phase of the blocked SP passes over all blocks without touching the solver
- * state (phase 0/1 = variable load / write-out, 2/3 = clause load / write-out; variant bit 0 = sequential
- * shared-memory addresses, bit 1 = no 16-bit index tables); d_scratch: E floats */
-int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch, void* stream);
-
 /* ---- host-side ingest helpers (no device work) ---------------------------
  * pdp_host_parse_ints: scans `text[0..len)` for decimal integers (optional leading '-', any other byte is a
  * separator) and writes the first `cap` of them to `out`; returns how many the text holds (so a caller may

@@ -9,21 +9,38 @@ are monkey-patched in place:
   S2  pdp/nn/solver.py:420,424 float division inside view() when batch_replication > 1
   S3  pdp/nn/solver.py:555     p-nd-np builds GRUCell(1+1, H) but SP returns 2 columns
 
-The reference only exists at /root/reference in the authoring container; it does not
-travel to the GPU box.  Everything here is therefore used by `oracle/make_golden.py`
-(fixture generation) and by CPU-side oracle validation tests that skip when the tree
-is absent.
+The reference is looked up at /root/reference (authoring container) and at baseline/_ref (the pip
+--target install of the unmodified reference, which travels to the GPU box).  Used by
+`oracle/make_golden.py` (fixture generation), by CPU-side oracle validation tests that skip when the
+tree is absent, and by `bench.py --impl reference` / the `cpu_baseline` leg (timing the reference's
+own `--cpu_mode` forward).
 """
 import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("PDP_REFERENCE_ROOT", "/root/reference")
-REF_SRC = os.path.join(REF_ROOT, "src")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """directory holding the reference's `pdp` package: $PDP_REFERENCE_ROOT/src, /root/reference/src (authoring
+    container) or baseline/_ref (the unmodified reference installed with `pip install --no-deps --target baseline/_ref`,
+    git-ignored; it travels to the GPU box with the snapshot)"""
+    cands = []
+    if os.environ.get("PDP_REFERENCE_ROOT"):
+        cands += [os.path.join(os.environ["PDP_REFERENCE_ROOT"], "src"), os.environ["PDP_REFERENCE_ROOT"]]
+    cands += ["/root/reference/src", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if os.path.isdir(os.path.join(c, "pdp", "nn")):
+            return c
+    return cands[-1]
+
+
+REF_SRC = _find_reference()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_SRC, "pdp"))
+    return os.path.isdir(os.path.join(REF_SRC, "pdp", "nn"))
 
 
 _patched = False

@@ -818,3 +818,12 @@ int ora_num_threads(void) {
     return 1;
 #endif
 }
+
+/* pins the OpenMP team size (torchrun exports OMP_NUM_THREADS=1 into every rank) */
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -235,6 +235,13 @@ def num_threads():
     return int(lib().ora_num_threads())
 
 
+def set_num_threads(n):
+    """pins the OpenMP team size: torchrun exports OMP_NUM_THREADS=1 into every rank"""
+    L = lib()
+    L.ora_set_num_threads.argtypes = [ctypes.c_int]
+    L.ora_set_num_threads(int(n))
+
+
 def init_state(E, randomized=False, rng=None):
     """(propagator_state, decimator_state) as SurveyPropagatorSolver.get_init_state builds them
     (reference pdp_propagate.py:223-237 and pdp_predict.py:194-208); the random variant takes a numpy

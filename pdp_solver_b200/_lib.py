@@ -56,7 +56,6 @@ SIGNATURES = {
     "pdp_set_trace_buffer": (ctypes.c_int, [P, P, I32]),
     "pdp_trace_length": (ctypes.c_int, [P, ctypes.POINTER(I32), P]),
     "pdp_debug_check_layout": (ctypes.c_int, [P, P, ctypes.POINTER(I32 * 5), P]),
-    "pdp_debug_phase_bench": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P]),
     "pdp_launch_count": (I64, [P]),
     "pdp_host_parse_ints": (I64, [ctypes.c_char_p, I64, P, I64]),
     "pdp_host_parse_rows": (I64, [ctypes.c_char_p, I64, P, P, I64, P, P, P, P, I64]),

@@ -239,15 +239,13 @@ __device__ __forceinline__ bool mbit(const uint32_t* words, int pos) { return (_
 // sp_var_update_qu.
 __device__ __forceinline__ void sp_var_prepare(float P, float N, float s, float& same_base, float& opp, float& O) {
     same_base = 0.5f * (1.f + s) * P + 0.5f * (1.f - s) * N;
-    opp = 0.5f * (1.f - s) * P + 0.5f * (1.f + s) * N;
-    opp += 0.f;
+    opp = 0.5f * (1.f - s) * P + 0.5f * (1.f + s) * N;   // (the reference's `+ log(1 - 0)` = +0 only turns a -0 into +0: exp is blind to it)
     O = X30(opp);
 }
 __device__ __forceinline__ float sp_var_finish(float same_base, float opp, float O, float y) {
-    float same = same_base - y;
-    same += 0.f;
-    const float dc = X30(same + opp);
+    const float same = same_base - y;
     const float S = X30(same);
+    const float dc = X30(same + opp);
     const float u = S * (1.f - O), v = O * (1.f - S);
     const float total = u + v + dc;
     return pdp_divf(u, total);
@@ -319,7 +317,7 @@ __device__ __forceinline__ void gen_var_side(const KArgs& A, int r, bool use_mas
         for (int p = beg; p < end; ++p) {
             const int vp = g.p_vpos[p];
             const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
-            float y = L40(1.f - ein[vp]);
+            float y = L40_1m(ein[vp]);
             if (um && mbit(g.vmask, vp)) y = y * 0.f;
             // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
             P += (neg ? 0.f : 1.f) * y;
@@ -327,7 +325,7 @@ __device__ __forceinline__ void gen_var_side(const KArgs& A, int r, bool use_mas
         }
         for (int p = beg; p < end; ++p) {
             const int vp = g.p_vpos[p];
-            float y = L40(1.f - ein[vp]);
+            float y = L40_1m(ein[vp]);
             if (um && mbit(g.vmask, vp)) y = y * 0.f;
             const float sg = (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f;
             const int qp = g.p_qpos[p];
@@ -373,12 +371,12 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
         for (int p = beg; p < end; ++p) {
             const int pos = g.p_vpos[p];
             const float v = en[pos];
-            const float c = X30(30.f * v);
+            const float c = X30S(v);
             n0 += v * c; d0 += c;
             if (has_prev) {
                 float d = fabsf(eo[pos] - v);
                 if (um && mbit(g.vmask, pos)) d = d * 0.f;
-                const float cd = X30(30.f * d);
+                const float cd = X30S(d);
                 n1 += d * cd; d1 += cd;
             }
         }
@@ -389,1167 +387,7 @@ __device__ __forceinline__ void gen_stats(const KArgs& A, int w, bool has_prev, 
     red.finish(s);
 }
 
-// ------------------------------------------------------------------------------------------------
-// blocked passes.  Dynamic shared memory (PDP_SWEEP_SMEM bytes):
-//   [0, 4*PDP_BLK_C)           clause pass: one plane X;  variable pass: planes PA | PB (PDP_BLK_V each)
-//   [4*PDP_BLK_C, +PDP_BLK_C/8) skip bits: slots of nodes the pass leaves alone (frozen / sticky-NaN
-//                               problems inside a block that has work)
-// ------------------------------------------------------------------------------------------------
-// The serial passes apply the sticky-NaN rule themselves at write-out; the pipelined / TMA variants leave the
-// problems on the sticky-NaN path to the generic passes.
-#define PDP_STICKY_INLINE (!(PDP_PIPELINE || PDP_TMA))
-__device__ __forceinline__ bool blk_problem_runs(const pdp_state& s, int b) { return s.active[b] && (PDP_STICKY_INLINE || !s.nanflag[b]); }
-
-// true when no problem in [b0, b1] is to be processed by the blocked passes (uniform over the CTA)
-__device__ __forceinline__ bool blk_idle(const pdp_state& s, int b0, int b1) {
-    if (b0 == b1) return !blk_problem_runs(s, b0);
-    int any = 0;
-    for (int b = b0 + (int)threadIdx.x; b <= b1; b += (int)blockDim.x) any |= blk_problem_runs(s, b) ? 1 : 0;
-    return __syncthreads_or(any) == 0;
-}
-
-__device__ __forceinline__ void blk_mark_skip(uint32_t* skip, int lo, int hi) {
-    for (int l = lo; l < hi; ++l) atomicOr(&skip[l >> 5], 1u << (l & 31));
-}
-
-#ifndef PDP_VN_UNROLL
-#define PDP_VN_UNROLL 1    // edge loops of the variable node phase
-#endif
-#ifndef PDP_UNROLL_WO
-#define PDP_UNROLL_WO 6    // elements per thread in flight: write-out (2 loads each)
-#endif
-#ifndef PDP_UNROLL_CL
-#define PDP_UNROLL_CL 8    // clause load (2-3 loads each)
-#endif
-#ifndef PDP_UNROLL_VL
-#define PDP_UNROLL_VL 6    // variable load (3-4 loads each)
-#endif
-// four-slot groups per thread in flight (PDP_VEC4)
-#ifndef PDP_UNROLL_WO4
-#define PDP_UNROLL_WO4 4
-#endif
-#ifndef PDP_UNROLL_CL4
-#define PDP_UNROLL_CL4 4
-#endif
-#ifndef PDP_UNROLL_VL4
-#define PDP_UNROLL_VL4 2    // 3 costs a spilled register under the 64-register cap, same speed
-#endif
-
-// ================================================================================================
-// phase bodies of the blocked passes, written for a GROUP of G threads with local index t: the whole CTA
-// in the serial passes, one of the two warp groups in the pipelined passes
-// ================================================================================================
-
-// write-out: slots [0, ne) of the block in ascending destination order; consecutive slots mostly hit
-// consecutive destinations (runs), so a warp's stores coalesce into a few sectors
-// STICKY: 0 = off, 1 = slots flagged in `sticky` bits, 2 = every slot.  A sticky slot keeps a NaN that is already
-// stored at its destination in `old` (the reference blends mask*new + (1-mask)*old arithmetically: 0*NaN = NaN,
-// pdp_propagate.py:175,218).
-// PDP_VEC4 = 1: the memory phases read their contiguous streams four slots per thread and instruction (128-bit loads
-// of the fp32 streams, 64-bit loads of the 16-bit tables).  They are latency-bound (measured, clock64 phase timers):
-// what counts is bytes in flight per thread.  A block's region starts at an arbitrary element of 256-byte aligned
-// arrays, so up to three head and three tail slots go through the scalar path.
-#ifndef PDP_VEC4
-#define PDP_VEC4 1
-#endif
-// the write-out keeps one slot per thread and instruction: with four consecutive slots per thread a warp's stores are
-// strided by four elements and every destination sector is written four times (measured: +30 % on the phase)
-#ifndef PDP_VEC4_WO
-#define PDP_VEC4_WO 0
-#endif
-#ifndef PDP_INPASS_SCORE
-#define PDP_INPASS_SCORE 1
-#endif
-#ifndef PDP_COLD
-#define PDP_COLD __forceinline__
-#endif
-#ifndef PDP_WO_PIPE
-#define PDP_WO_PIPE 0
-#endif
-struct Vec4Range { int head, nvec, tail0; };
-template <typename T>
-__device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32: the region's start in a 4-byte array
-    Vec4Range R;
-    R.head = (int)((16u - ((unsigned)(uintptr_t)p32 & 15u)) & 15u) >> 2;
-    if (R.head > ne) R.head = ne;
-    R.nvec = (ne - R.head) >> 2;
-    R.tail0 = R.head + 4 * R.nvec;
-    return R;
-}
-__device__ __forceinline__ uint32_t mnib(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 15u; }
-
-template <int G, bool SKIP, int STICKY>
-__device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                               const float* plane, const uint32_t* skip, const uint32_t* sticky,
-                                               const float* old, float* out) {   // old may alias out (q is updated in place)
-    auto one = [&](int l, int d) {
-        if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) return;
-        float v = plane[l];
-        if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
-        out[d] = v;
-    };
-#if PDP_VEC4_WO
-    const Vec4Range R = vec4_range(dst, ne);
-    if (t < R.head) one(src[t], dst[t]);
-    if (t < ne - R.tail0) one(src[R.tail0 + t], dst[R.tail0 + t]);
-    const uint2* __restrict__ s4 = reinterpret_cast<const uint2*>(src + R.head);
-    const int4* __restrict__ d4 = reinterpret_cast<const int4*>(dst + R.head);
-    constexpr int U = PDP_UNROLL_WO4;
-    int w = t;
-    for (; w + (U - 1) * G < R.nvec; w += U * G) {
-        uint2 l[U]; int4 d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = s4[w + u * G]; d[u] = d4[w + u * G]; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            one((int)(l[u].x & 0xffffu), d[u].x); one((int)(l[u].x >> 16), d[u].y);
-            one((int)(l[u].y & 0xffffu), d[u].z); one((int)(l[u].y >> 16), d[u].w);
-        }
-    }
-    for (; w < R.nvec; w += G) {
-        const uint2 l = s4[w]; const int4 d = d4[w];
-        one((int)(l.x & 0xffffu), d.x); one((int)(l.x >> 16), d.y); one((int)(l.y & 0xffffu), d.z); one((int)(l.y >> 16), d.w);
-    }
-#else
-    int w = t;
-    constexpr int U = PDP_UNROLL_WO;
-#if PDP_WO_PIPE
-    if (ne <= 0) return;
-    // register double buffer: the index loads of the next batch are in flight while this batch gathers and stores
-    // (the phase waits on exactly these loads: long-scoreboard stalls on the gather, profiles/r1_sp_run_ncu.md)
-    int l[U], d[U];
-    bool have = w + (U - 1) * G < ne;
-    {
-        const int w0 = have ? w : 0;      // (no full batch: the loads below are dummies of valid addresses, ne >= 1 here)
-#pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = src[have ? w0 + u * G : 0]; d[u] = dst[have ? w0 + u * G : 0]; }
-    }
-    while (have) {
-        const int wn = w + U * G;
-        const bool more = wn + (U - 1) * G < ne;
-        const int wl = more ? wn : w;      // last batch: re-read the current indices (in range, discarded)
-        int ln[U], dn[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { ln[u] = src[wl + u * G]; dn[u] = dst[wl + u * G]; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) one(l[u], d[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = ln[u]; d[u] = dn[u]; }
-        w = wn;
-        have = more;
-    }
-#else
-    for (; w + (U - 1) * G < ne; w += U * G) {
-        int l[U], d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = src[w + u * G]; d[u] = dst[w + u * G]; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) one(l[u], d[u]);
-    }
-#endif
-    for (; w < ne; w += G) one(src[w], dst[w]);
-#endif
-}
-// flags: bit 0 = some slots are skipped, bit 1 = some slots are sticky, bit 2 = every slot is sticky
-template <int G>
-__device__ __forceinline__ void ph_write_out(int t, const uint16_t* __restrict__ src, const int32_t* __restrict__ dst, int ne,
-                                             const float* plane, const uint32_t* skip, int flags, float* out,
-                                             const uint32_t* sticky = nullptr, const float* old = nullptr) {
-    if (flags & 4) {
-        if (flags & 1) ph_write_out_t<G, true, 2>(t, src, dst, ne, plane, skip, sticky, old, out);
-        else ph_write_out_t<G, false, 2>(t, src, dst, ne, plane, skip, sticky, old, out);
-    } else if (flags & 2) {
-        if (flags & 1) ph_write_out_t<G, true, 1>(t, src, dst, ne, plane, skip, sticky, old, out);
-        else ph_write_out_t<G, false, 1>(t, src, dst, ne, plane, skip, sticky, old, out);
-    } else {
-        if (flags & 1) ph_write_out_t<G, true, 0>(t, src, dst, ne, plane, skip, sticky, old, out);
-        else ph_write_out_t<G, false, 0>(t, src, dst, ne, plane, skip, sticky, old, out);
-    }
-}
-
-// clause pass, load phase: x = log(max(q_u, 1e-40)) * em, scattered into clause-major order.
-// e0 = first C-layout position of the block (the mask bits are indexed by position).
-template <int G, bool MASKED>
-__device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
-                                               const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
-    auto put = [&](float q, int l, bool m) {
-        float v = L40(q);
-        if (MASKED && m) v = v * 0.f;
-        X[l] = v;
-    };
-#if PDP_VEC4
-    const Vec4Range R = vec4_range(qsrc, ne);
-    if (t < R.head) put(qsrc[t], inv[t], MASKED ? mbit(qmask, e0 + t) : false);
-    if (t < ne - R.tail0) put(qsrc[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(qmask, e0 + R.tail0 + t) : false);
-    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(qsrc + R.head);
-    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
-    const int pos0 = e0 + R.head;     // a multiple of 4: the four mask bits of a group sit in one word
-    constexpr int U = PDP_UNROLL_CL4;
-    int x = t;
-    for (; x + (U - 1) * G < R.nvec; x += U * G) {
-        float4 q[U]; uint2 l[U]; uint32_t m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { q[u] = q4[x + u * G]; l[u] = i4[x + u * G]; m[u] = MASKED ? mnib(qmask, pos0 + 4 * (x + u * G)) : 0u; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            put(q[u].x, (int)(l[u].x & 0xffffu), m[u] & 1u); put(q[u].y, (int)(l[u].x >> 16), m[u] & 2u);
-            put(q[u].z, (int)(l[u].y & 0xffffu), m[u] & 4u); put(q[u].w, (int)(l[u].y >> 16), m[u] & 8u);
-        }
-    }
-    for (; x < R.nvec; x += G) {
-        const float4 q = q4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(qmask, pos0 + 4 * x) : 0u;
-        put(q.x, (int)(l.x & 0xffffu), m & 1u); put(q.y, (int)(l.x >> 16), m & 2u);
-        put(q.z, (int)(l.y & 0xffffu), m & 4u); put(q.w, (int)(l.y >> 16), m & 8u);
-    }
-#else
-    int x = t;
-    constexpr int U = PDP_UNROLL_CL;
-    for (; x + (U - 1) * G < ne; x += U * G) {
-        float q[U]; int l[U]; bool m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { q[u] = qsrc[x + u * G]; l[u] = inv[x + u * G]; m[u] = MASKED ? mbit(qmask, e0 + x + u * G) : false; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) put(q[u], l[u], m[u]);
-    }
-    for (; x < ne; x += G) put(qsrc[x], inv[x], MASKED ? mbit(qmask, e0 + x) : false);
-#endif
-}
-
-// one clause of K literals held in X[lo .. lo+K): surveys in place.  Returns whether a NaN was produced.
-template <int K>
-__device__ __forceinline__ bool blk_clause_body(float* X, int lo) {
-    float x[K];
-    float tot = 0.f;
-#pragma unroll
-    for (int j = 0; j < K; ++j) { x[j] = X[lo + j]; tot += x[j]; }
-    bool made_nan = false;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const float nv = X30(tot - x[j]);
-        made_nan |= (nv != nv);
-        X[lo + j] = nv;
-    }
-    return made_nan;
-}
-__device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k) {
-    float tot = 0.f;
-    for (int j = 0; j < k; ++j) tot += X[lo + j];
-    bool made_nan = false;
-    for (int j = 0; j < k; ++j) {
-        const float nv = X30(tot - X[lo + j]);
-        made_nan |= (nv != nv);
-        X[lo + j] = nv;
-    }
-    return made_nan;
-}
-
-// geometry of one block of a pass
-struct BlkGeo {
-    int n0, n1;      // node range
-    int e0, ne;      // first slot / slots
-    int b0, b1;      // problem range
-    __device__ __forceinline__ bool multi() const { return b0 != b1; }
-};
-__device__ __forceinline__ BlkGeo clause_block(const pdp_graph& g, int blk) {
-    BlkGeo B;
-    B.n0 = g.cb_ptr[blk]; B.n1 = g.cb_ptr[blk + 1];
-    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; return B; }
-    B.e0 = g.cl_ptr[B.n0]; B.ne = g.cl_ptr[B.n1] - B.e0;
-    B.b0 = g.bfm[B.n0]; B.b1 = g.bfm[B.n1 - 1];
-    return B;
-}
-__device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) {
-    BlkGeo B;
-    B.n0 = g.vb_ptr[blk]; B.n1 = g.vb_ptr[blk + 1];
-    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; return B; }
-    B.e0 = g.var_ptr[B.n0]; B.ne = g.var_ptr[B.n1] - B.e0;
-    B.b0 = g.bvm[B.n0]; B.b1 = g.bvm[B.n1 - 1];
-    return B;
-}
-
-// clause pass, node phase: thread per clause
-template <int G>
-__device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, int ku,
-                                               float* X, uint32_t* skip, int* any_skip, uint32_t* sticky = nullptr) {
-    const bool multi = B.multi();
-    for (int a = B.n0 + t; a < B.n1; a += G) {
-        int lo, k;
-        if (ku) { k = ku; lo = (a - B.n0) * ku; }
-        else { lo = g.cl_ptr[a] - B.e0; k = g.cl_ptr[a + 1] - B.e0 - lo; }
-        int b = B.b0;
-        if (multi) {
-            b = g.bfm[a];
-            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); atomicOr(any_skip, 1); continue; }
-            if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + k); atomicOr(any_skip, 2); }
-        }
-        bool made_nan;
-        switch (k) {
-            case 3: made_nan = blk_clause_body<3>(X, lo); break;
-            case 4: made_nan = blk_clause_body<4>(X, lo); break;
-            case 5: made_nan = blk_clause_body<5>(X, lo); break;
-            case 2: made_nan = blk_clause_body<2>(X, lo); break;
-            default: made_nan = blk_clause_body_any(X, lo, k); break;
-        }
-        if (made_nan) s.nanpend[b] = 1;
-    }
-}
-
-// statistics of multi-problem blocks: per block-local problem in shared memory
-#define PDP_STAT_SLOTS 64
-struct BlkStats {
-    uint32_t mx0[PDP_STAT_SLOTS], mn0[PDP_STAT_SLOTS], mx1[PDP_STAT_SLOTS], mn1[PDP_STAT_SLOTS], nan[PDP_STAT_SLOTS], nav[PDP_STAT_SLOTS];
-};
-
-// branch-free select (the compiler would otherwise split the update loop into one path per literal sign)
-__device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
-    return __uint_as_float((__float_as_uint(a) & mask) | (__float_as_uint(b) & ~mask));
-}
-
-// variable pass, load phase.  The surveys are non-negative, so their sign bits carry the two per-edge
-// flags the variable loops need: PA (new survey) sign = edge masked, PB (old survey) sign = negative literal.
-template <int G, bool MASKED>
-__device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
-                                            const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
-    auto put = [&](float n, float o, uint32_t iv, bool m) {
-        const int l = iv & 0x7fff;
-        PA[l] = __uint_as_float(__float_as_uint(n) | ((MASKED && m) ? 0x80000000u : 0u));
-        PB[l] = __uint_as_float(__float_as_uint(o) ^ ((iv & PDP_VINV_NEG) << 16));
-    };
-#if PDP_VEC4
-    const Vec4Range R = vec4_range(sn, ne);
-    if (t < R.head) put(sn[t], so[t], inv[t], MASKED ? mbit(vmask, e0 + t) : false);
-    if (t < ne - R.tail0) put(sn[R.tail0 + t], so[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(vmask, e0 + R.tail0 + t) : false);
-    const float4* __restrict__ n4 = reinterpret_cast<const float4*>(sn + R.head);
-    const float4* __restrict__ o4 = reinterpret_cast<const float4*>(so + R.head);
-    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
-    const int pos0 = e0 + R.head;
-    constexpr int U = PDP_UNROLL_VL4;
-    int x = t;
-    for (; x + (U - 1) * G < R.nvec; x += U * G) {
-        float4 n[U], o[U]; uint2 l[U]; uint32_t m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            n[u] = n4[x + u * G]; o[u] = o4[x + u * G]; l[u] = i4[x + u * G];
-            m[u] = MASKED ? mnib(vmask, pos0 + 4 * (x + u * G)) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            put(n[u].x, o[u].x, l[u].x & 0xffffu, m[u] & 1u); put(n[u].y, o[u].y, l[u].x >> 16, m[u] & 2u);
-            put(n[u].z, o[u].z, l[u].y & 0xffffu, m[u] & 4u); put(n[u].w, o[u].w, l[u].y >> 16, m[u] & 8u);
-        }
-    }
-    for (; x < R.nvec; x += G) {
-        const float4 n = n4[x], o = o4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(vmask, pos0 + 4 * x) : 0u;
-        put(n.x, o.x, l.x & 0xffffu, m & 1u); put(n.y, o.y, l.x >> 16, m & 2u);
-        put(n.z, o.z, l.y & 0xffffu, m & 4u); put(n.w, o.w, l.y >> 16, m & 8u);
-    }
-#else
-    int x = t;
-    constexpr int U = PDP_UNROLL_VL;
-    for (; x + (U - 1) * G < ne; x += U * G) {
-        float n[U], o[U]; uint32_t iv[U]; bool m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            n[u] = sn[x + u * G]; o[u] = so[x + u * G]; iv[u] = inv[x + u * G];
-            m[u] = MASKED ? mbit(vmask, e0 + x + u * G) : false;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) put(n[u], o[u], iv[u], m[u]);
-    }
-    for (; x < ne; x += G) put(sn[x], so[x], inv[x], MASKED ? mbit(vmask, e0 + x) : false);
-#endif
-}
-
-// variable pass, SurveyScorer (pdp_predict.py:155-192) of the variables whose problem asked for it (want_score): same
-// operations and order as score_variable() on the new surveys held in PA (sign bit = edge masked; for an active variable
-// the edge mask is the clause mask the scorer multiplies with, an inactive variable's score is never looked at) and the
-// literal signs held in PB.  pi == 0 on the blocked path: the external force does not enter.
-template <int G>
-__device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B,
-                                             const float* __restrict__ PA, const float* __restrict__ PB) {
-    for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
-        const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
-        if (ti >= B.n1) continue;
-        const int2 ve = __ldg(&g.vsort[ti]);
-        const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
-        if (!s.want_score[B.multi() ? g.bvm[i] : B.b0]) continue;
-        float ps = 0.f, ns = 0.f, as = 0.f;
-        for (int j = 0; j < deg; ++j) {
-            const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
-            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);
-            const float f = L10(1.f - __uint_as_float(nb & 0x7fffffffu)) * ((nb >> 31) ? 0.f : 1.f);
-            const float zf = 0.f * f;
-            ps += fsel(negm, zf, f);
-            ns += fsel(negm, f, zf);
-            as += f;
-        }
-        s.score[i] = sp_score_tail(ps, ns, as, 0.f, 0.f);
-    }
-}
-
-// variable pass, node phase: thread per variable (descending degree, rounds alternate direction so that
-// every thread gets high and low degrees): ordered sums, decimator statistics, update.
-// Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
-template <int G>
-__device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask, bool has_prev,
-                                            bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t* skip, int* any_skip,
-                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky = nullptr) {
-    const bool multi = B.multi();
-    constexpr int VNU = PDP_VN_UNROLL;
-    for (int base = B.n0, round = 0; base < B.n1; base += G, ++round) {
-        const int ti = (round & 1) ? (base + G - 1 - t) : (base + t);
-        if (ti >= B.n1) continue;
-        const int2 ve = __ldg(&g.vsort[ti]);
-        const int i = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
-        int b = B.b0;
-        if (multi) {
-            b = g.bvm[i];
-            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + deg); atomicOr(any_skip, 1); continue; }
-            if (PDP_STICKY_INLINE && sticky && s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + deg); atomicOr(any_skip, 2); }
-        }
-        const uint32_t act = s.av[i];
-        float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
-#pragma unroll VNU
-        for (int j = 0; j < deg; ++j) {
-            const uint32_t nb = __float_as_uint(PA[lo + j]), ob = __float_as_uint(PB[lo + j]);
-            const bool m = (nb >> 31) != 0u;                        // edge masked
-            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);    // all ones: negative literal
-            const float xn = __uint_as_float(nb & 0x7fffffffu), xo = __uint_as_float(ob & 0x7fffffffu);
-            float y = L40(1.f - xo);
-            if (use_mask && m) y = y * 0.f;
-            // y <= +0 (or NaN): stored as |y| under the literal's sign bit
-            PB[lo + j] = __uint_as_float((__float_as_uint(y) & 0x7fffffffu) | (ob & 0x80000000u));
-            // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
-            const float zy = 0.f * y;
-            P += fsel(negm, zy, y);
-            N += fsel(negm, y, zy);
-            const float c = X30(30.f * xn);
-            n0 += xn * c; d0 += c;
-            if (has_prev) {
-                float d = fabsf(xo - xn);
-                if (em_set && m) d = d * 0.f;
-                const float cd = X30(30.f * d);
-                n1 += d * cd; d1 += cd;
-            }
-        }
-        const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
-        const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
-        if (!multi) {
-            red.touch(s, b);
-            red.acc.add(sm0, sm1, has_prev, act);
-        } else {
-            StatAcc one;
-            one.reset();
-            one.add(sm0, sm1, has_prev, act);
-            if (local_stats) {
-                const int lb = b - B.b0;
-                atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
-                if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
-                if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
-                if (act) atomicAdd(&sm_st.nav[lb], act);
-            } else {
-                one.commit(s, b);
-            }
-        }
-        float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
-        sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
-        sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
-        bool made_nan = false;
-#pragma unroll VNU
-        for (int j = 0; j < deg; ++j) {
-            const uint32_t yb = __float_as_uint(PB[lo + j]);
-            const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
-            const float y = __uint_as_float(yb | 0x80000000u);   // -|y|; -0 for +0 is erased by `same += 0`
-            const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
-            made_nan |= (u != u);
-            PA[lo + j] = u;
-        }
-        if (made_nan) s.nanpend[b] = 1;
-    }
-}
-
-__device__ __forceinline__ void stats_slots_reset(BlkStats& sm_st, int t, int nprob) {
-    if (t < nprob) {
-        sm_st.mx0[t] = 0u; sm_st.mn0[t] = 0x7f800000u; sm_st.mx1[t] = 0u; sm_st.mn1[t] = 0x7f800000u;
-        sm_st.nan[t] = 0u; sm_st.nav[t] = 0u;
-    }
-}
-__device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats& sm_st, int t, int nprob, int b0) {
-    if (t < nprob) {
-        StatAcc a;
-        a.mx0 = sm_st.mx0[t]; a.mn0 = sm_st.mn0[t]; a.mx1 = sm_st.mx1[t]; a.mn1 = sm_st.mn1[t];
-        a.nan = sm_st.nan[t]; a.nav = sm_st.nav[t];
-        if (a.mn0 != 0x7f800000u || a.mx0 != 0u || a.nan || a.nav || a.mn1 != 0x7f800000u) a.commit(s, b0 + t);
-    }
-}
-
-// ================================================================================================
-// pipelined passes.  The memory phases (load, write-out) are bound by DRAM bandwidth / latency and issue
-// few instructions; the node phases are bound by instruction issue and touch no global memory.  Run back
-// to back by the same threads they add up, so the CTA is split into two warp groups working on two
-// shared-memory slots: the MEMORY group loads block i+1 and writes block i-1 out while the COMPUTE group
-// runs the node phase of block i.  Hand-over through named barriers (bar.arrive / bar.sync):
-//   FULL[slot]  memory -> compute: the slot holds a loaded block
-//   DONE[slot]  compute -> memory: the node phase of the slot's block is finished
-// ================================================================================================
-// PDP_PHASE_TIMING (profiling builds only): thread 0 of every CTA adds the clock cycles (>> 10) it spent in each
-// phase of the blocked passes to the trace buffer: [0..2] clause wait-for-load / node / write-out, [3..5] variable
-#ifdef PDP_PHASE_TIMING
-#define PHASE_T0() long long _pt = clock64()
-#define PHASE_ADD(slot_) do { if (threadIdx.x == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
-#else
-#define PHASE_T0() do {} while (0)
-#define PHASE_ADD(slot_) do {} while (0)
-#endif
-#if PDP_PIPELINE || PDP_TMA
-#define PIPE_MEM_THREADS (32 * PDP_PIPE_MEM_WARPS)
-#define PIPE_CMP_THREADS (PDP_SWEEP_THREADS - PIPE_MEM_THREADS)
-#define PIPE_BAR_FULL 1    // +slot
-#define PIPE_BAR_DONE 3    // +slot
-#define PIPE_BAR_CMP 5     // compute group internal
-#define PIPE_SLOT_BYTES (4 * PDP_BLK_C)
-#define PIPE_MAX_BLOCKS 32 // blocks of one CTA per pass handled per pipeline run
-
-#ifdef PDP_PHASE_TIMING
-#define PT_DECL() long long _pt = clock64()
-#define PT_ADD(slot_) do { if (t == 0 && A.trace) { const long long _n = clock64(); atomicAdd(&A.trace[slot_], (int)((_n - _pt) >> 10)); _pt = _n; } } while (0)
-#else
-#define PT_DECL() do {} while (0)
-#define PT_ADD(slot_) do {} while (0)
-#endif
-
-struct PipeSmem {
-    int any_skip[2];
-    int blk[PIPE_MAX_BLOCKS];
-    int nblk;
-};
-
-// the CTA's non-idle blocks of this pass, PIPE_MAX_BLOCKS at a time (uniform over the CTA)
-template <bool VAR>
-__device__ __forceinline__ int pipe_collect(const pdp_graph& g, const pdp_state& s, PipeSmem& ps, int& next_blk) {
-    const int total = VAR ? g.nvb : g.ncb;
-    int n = 0;
-    while (next_blk < total && n < PIPE_MAX_BLOCKS) {
-        const int blk = next_blk;
-        next_blk += gridDim.x;
-        const BlkGeo B = VAR ? var_block(g, blk) : clause_block(g, blk);
-        if (B.n1 <= B.n0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
-        if (threadIdx.x == 0) ps.blk[n] = blk;
-        ++n;
-    }
-    __syncthreads();
-    return n;
-}
-
-__device__ __forceinline__ void pipe_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    __shared__ PipeSmem ps;
-    const float* __restrict__ qin = s.qu;
-    float* __restrict__ eout = s.eta[r ^ 1];
-    const bool is_mem = threadIdx.x < PIPE_MEM_THREADS;
-    const int t = is_mem ? threadIdx.x : (threadIdx.x - PIPE_MEM_THREADS);
-    int next_blk = blockIdx.x;
-    for (;;) {
-        const int n = pipe_collect<false>(g, s, ps, next_blk);
-        if (n == 0) break;
-        PT_DECL();
-        if (is_mem) {
-            for (int i = 0; i < n + 2; ++i) {
-                const int slot = i & 1;
-                float* X = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
-                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
-                if (i >= 2) {   // the slot's previous block: wait for its node phase, write it out
-                    PT_ADD(8);
-                    bar_sync(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
-                    PT_ADD(10);
-                    const BlkGeo B = clause_block(g, ps.blk[i - 2]);
-                    ph_write_out<PIPE_MEM_THREADS>(t, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, ps.any_skip[slot] != 0, eout);
-                    bar_sync(PIPE_BAR_CMP + 1, PIPE_MEM_THREADS);
-                    PT_ADD(9);   // memory group: the slot is free
-                }
-                if (i < n) {
-                    const BlkGeo B = clause_block(g, ps.blk[i]);
-                    for (int w = t; w < (B.ne + 31) / 32; w += PIPE_MEM_THREADS) skip[w] = 0u;
-                    if (t == 0) ps.any_skip[slot] = 0;
-                    if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<PIPE_MEM_THREADS, true>(t, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-                    else ph_clause_load<PIPE_MEM_THREADS, false>(t, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-                    __threadfence_block();
-                    bar_arrive(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
-                }
-            }
-        } else {
-            for (int i = 0; i < n; ++i) {
-                const int slot = i & 1;
-                float* X = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
-                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
-                PT_ADD(11);
-                bar_sync(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
-                PT_ADD(12);
-                const int blk = ps.blk[i];
-                const BlkGeo B = clause_block(g, blk);
-                ph_clause_node<PIPE_CMP_THREADS>(t, g, s, B, g.cb_k[blk], X, skip, &ps.any_skip[slot]);
-                __threadfence_block();
-                bar_arrive(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void pipe_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    __shared__ PipeSmem ps;
-    __shared__ BlkStats sm_st;
-    const float* __restrict__ en = s.eta[r ^ 1];
-    const float* __restrict__ eo = s.eta[r];
-    const bool is_mem = threadIdx.x < PIPE_MEM_THREADS;
-    const int t = is_mem ? threadIdx.x : (threadIdx.x - PIPE_MEM_THREADS);
-    KeyedReducer<StatAcc> red;
-    int next_blk = blockIdx.x;
-    for (;;) {
-        const int n = pipe_collect<true>(g, s, ps, next_blk);
-        if (n == 0) break;
-        PT_DECL();
-        if (is_mem) {
-            for (int i = 0; i < n + 2; ++i) {
-                const int slot = i & 1;
-                float* PA = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
-                float* PB = PA + PDP_BLK_V;
-                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
-                if (i >= 2) {
-                    PT_ADD(16);
-                    bar_sync(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
-                    PT_ADD(18);
-                    const BlkGeo B = var_block(g, ps.blk[i - 2]);
-                    ph_write_out<PIPE_MEM_THREADS>(t, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, ps.any_skip[slot] != 0, s.qu);
-                    bar_sync(PIPE_BAR_CMP + 1, PIPE_MEM_THREADS);
-                    PT_ADD(17);
-                }
-                if (i < n) {
-                    const BlkGeo B = var_block(g, ps.blk[i]);
-                    for (int w = t; w < (B.ne + 31) / 32; w += PIPE_MEM_THREADS) skip[w] = 0u;
-                    if (t == 0) ps.any_skip[slot] = 0;
-                    if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<PIPE_MEM_THREADS, true>(t, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-                    else ph_var_load<PIPE_MEM_THREADS, false>(t, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-                    __threadfence_block();
-                    bar_arrive(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
-                }
-            }
-        } else {
-            for (int i = 0; i < n; ++i) {
-                const int slot = i & 1;
-                float* PA = reinterpret_cast<float*>(smem + slot * PIPE_SLOT_BYTES);
-                float* PB = PA + PDP_BLK_V;
-                uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 2 * PIPE_SLOT_BYTES + slot * (PDP_BLK_C / 8));
-                const BlkGeo B = var_block(g, ps.blk[i]);
-                const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);
-                if (local_stats) { stats_slots_reset(sm_st, t, B.b1 - B.b0 + 1); bar_sync(PIPE_BAR_CMP, PIPE_CMP_THREADS); }
-                PT_ADD(19);
-                bar_sync(PIPE_BAR_FULL + slot, PDP_SWEEP_THREADS);
-                PT_ADD(20);
-                ph_var_node<PIPE_CMP_THREADS>(t, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &ps.any_skip[slot], red, sm_st, local_stats);
-                __threadfence_block();
-                bar_arrive(PIPE_BAR_DONE + slot, PDP_SWEEP_THREADS);
-                if (local_stats) { bar_sync(PIPE_BAR_CMP, PIPE_CMP_THREADS); stats_slots_commit(s, sm_st, t, B.b1 - B.b0 + 1, B.b0); }
-                red.finish(s, PIPE_BAR_CMP, PIPE_CMP_THREADS, t);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-#endif  // PDP_PIPELINE || PDP_TMA
-
-// ================================================================================================
-// TMA-staged passes.  Everything a block's node phase reads -- the message regions, the 16-bit permutation
-// of the block's slots and the edge-mask words -- is contiguous in global memory, so ONE thread brings it
-// into a shared-memory slot with bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) while
-// the CTA still works on the previous block in the other slot.  The node phases gather through the
-// permutation (slot of the node's j-th edge -> staged position) instead of reading a scattered copy, and
-// leave their results at the same staged positions; the write-out reads them through vsrc2 / csrc2.
-// ================================================================================================
-#if PDP_TMA
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-// 16-byte aligned source / destination, size a multiple of 16
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// byte offsets inside a slot
-#define TS_VAR_SA 0
-#define TS_VAR_SB ((PDP_BLK_V + 4) * 4)
-#define TS_VAR_PERM (2 * (PDP_BLK_V + 4) * 4)
-#define TS_VAR_MASK (TS_VAR_PERM + (PDP_BLK_V + 8) * 2)
-#define TS_VAR_SKIP (TS_VAR_MASK + (PDP_BLK_V / 32 + 8) * 4)
-#define TS_CL_X 0
-#define TS_CL_PERM ((PDP_BLK_C + 4) * 4)
-#define TS_CL_MASK (TS_CL_PERM + (PDP_BLK_C + 8) * 2)
-#define TS_CL_SKIP (TS_CL_MASK + (PDP_BLK_C / 32 + 8) * 4)
-static_assert(TS_VAR_SKIP + PDP_BLK_V / 8 + 16 <= PDP_TMA_SLOT_BYTES, "variable slot too large");
-static_assert(TS_CL_SKIP + PDP_BLK_C / 8 + 16 <= PDP_TMA_SLOT_BYTES, "clause slot too large");
-static_assert(TS_VAR_SB % 16 == 0 && TS_VAR_PERM % 16 == 0 && TS_VAR_MASK % 16 == 0 && TS_CL_PERM % 16 == 0 && TS_CL_MASK % 16 == 0, "TMA alignment");
-
-struct TmaState {          // per-CTA pipeline state living in registers across the whole kernel
-    uint32_t parity[2];
-};
-struct TmaSmem {
-    uint64_t bar[2];
-    int any_skip[2];
-    int blk[PIPE_MAX_BLOCKS];
-};
-
-// staged geometry of a block: region [base, base + n_st) with base = e0 & ~3
-struct Staged {
-    int base, off, n_st;       // off = e0 - base; n_st = staged floats (multiple of 4)
-    int pbase, poff, n_perm;   // permutation table: 8-element aligned start, staged 16-bit entries (multiple of 8)
-    int wbase, woff, n_w;      // mask words: 4-word aligned start
-};
-__device__ __forceinline__ Staged staged_of(int e0, int ne) {
-    Staged S;
-    S.base = e0 & ~3; S.off = e0 - S.base; S.n_st = (S.off + ne + 3) & ~3;
-    S.pbase = e0 & ~7; S.poff = e0 - S.pbase; S.n_perm = (S.poff + ne + 7) & ~7;
-    const int w0 = S.base >> 5, w1 = (S.base + S.n_st - 1) >> 5;
-    S.wbase = w0 & ~3; S.woff = w0 - S.wbase; S.n_w = (w1 - S.wbase + 1 + 3) & ~3;
-    return S;
-}
-// is the edge at staged position x masked?  (mask words staged from word S.wbase)
-__device__ __forceinline__ bool staged_mbit(const uint32_t* mw, const Staged& S, int x) {
-    const int bitpos = (S.base & 31) + x;
-    return (mw[S.woff + (bitpos >> 5)] >> (bitpos & 31)) & 1u;
-}
-
-__device__ __forceinline__ void tma_issue_clause(const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool masked,
-                                                 unsigned char* slot, uint64_t* bar) {
-    const Staged S = staged_of(B.e0, B.ne);
-    const bool any = B.ne > 0;
-    const uint32_t bytes = any ? ((uint32_t)S.n_st * 4u + (uint32_t)S.n_perm * 2u + (masked ? (uint32_t)S.n_w * 4u : 0u)) : 0u;
-    mbar_expect_tx(bar, bytes);
-    if (!any) return;
-    tma_load_1d(slot + TS_CL_X, s.qu + S.base, (uint32_t)S.n_st * 4u, bar);
-    tma_load_1d(slot + TS_CL_PERM, g.cperm + S.pbase, (uint32_t)S.n_perm * 2u, bar);
-    if (masked) tma_load_1d(slot + TS_CL_MASK, g.qmask + S.wbase, (uint32_t)S.n_w * 4u, bar);
-}
-__device__ __forceinline__ void tma_issue_var(const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool masked, const float* en,
-                                              const float* eo, unsigned char* slot, uint64_t* bar) {
-    const Staged S = staged_of(B.e0, B.ne);
-    const bool any = B.ne > 0;
-    const uint32_t bytes = any ? (2u * (uint32_t)S.n_st * 4u + (uint32_t)S.n_perm * 2u + (masked ? (uint32_t)S.n_w * 4u : 0u)) : 0u;
-    mbar_expect_tx(bar, bytes);
-    if (!any) return;
-    tma_load_1d(slot + TS_VAR_SA, en + S.base, (uint32_t)S.n_st * 4u, bar);
-    tma_load_1d(slot + TS_VAR_SB, eo + S.base, (uint32_t)S.n_st * 4u, bar);
-    tma_load_1d(slot + TS_VAR_PERM, g.vperm + S.pbase, (uint32_t)S.n_perm * 2u, bar);
-    if (masked) tma_load_1d(slot + TS_VAR_MASK, g.vmask + S.wbase, (uint32_t)S.n_w * 4u, bar);
-}
-
-// the CTA's non-idle blocks of this pass into sm.blk (uniform over the CTA)
-template <bool VAR>
-__device__ __forceinline__ int tma_collect(const pdp_graph& g, const pdp_state& s, TmaSmem& sm, int& next_blk) {
-    const int total = VAR ? g.nvb : g.ncb;
-    int n = 0;
-    while (next_blk < total && n < PIPE_MAX_BLOCKS) {
-        const int blk = next_blk;
-        next_blk += gridDim.x;
-        const BlkGeo B = VAR ? var_block(g, blk) : clause_block(g, blk);
-        if (B.n1 <= B.n0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
-        if (threadIdx.x == 0) sm.blk[n] = blk;
-        ++n;
-    }
-    __syncthreads();
-    return n;
-}
-
-#define NT PDP_SWEEP_THREADS
-__device__ __forceinline__ void tma_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, TmaSmem& sm, TmaState& st) {
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* __restrict__ eout = s.eta[r ^ 1];
-    const int tid = threadIdx.x;
-    int next_blk = blockIdx.x;
-    for (;;) {
-        const int n = tma_collect<false>(g, s, sm, next_blk);
-        if (n == 0) break;
-        if (tid == 0) {
-            const BlkGeo B0 = clause_block(g, sm.blk[0]);
-            tma_issue_clause(g, s, B0, use_mask && (B0.multi() || s.masked[B0.b0]), smem, &sm.bar[0]);
-        }
-        for (int i = 0; i < n; ++i) {
-            const int slot = i & 1;
-            unsigned char* base = smem + slot * PDP_TMA_SLOT_BYTES;
-            float* X = reinterpret_cast<float*>(base + TS_CL_X);
-            const uint16_t* perm = reinterpret_cast<const uint16_t*>(base + TS_CL_PERM);
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>(base + TS_CL_MASK);
-            uint32_t* skip = reinterpret_cast<uint32_t*>(base + TS_CL_SKIP);
-            const int blk = sm.blk[i];
-            const BlkGeo B = clause_block(g, blk);
-            const Staged S = staged_of(B.e0, B.ne);
-            const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
-            if (i + 1 < n && tid == 0) {   // the other slot is free (its block was written out before the last barrier)
-                const BlkGeo Bn = clause_block(g, sm.blk[i + 1]);
-                tma_issue_clause(g, s, Bn, use_mask && (Bn.multi() || s.masked[Bn.b0]), smem + (slot ^ 1) * PDP_TMA_SLOT_BYTES, &sm.bar[slot ^ 1]);
-            }
-            for (int w = tid; w < (S.n_st + 31) / 32; w += NT) skip[w] = 0u;
-            if (tid == 0) sm.any_skip[slot] = 0;
-            PHASE_T0();
-            mbar_wait(&sm.bar[slot], st.parity[slot]);
-            st.parity[slot] ^= 1u;
-            __syncthreads();
-            PHASE_ADD(0);
-            // ---- thread per clause: x = log(max(q,1e-40)) * em gathered through the permutation
-            const bool multi = B.multi();
-            const int ku = g.cb_k[blk];
-            for (int a = B.n0 + tid; a < B.n1; a += NT) {
-                int lo, k;
-                if (ku) { k = ku; lo = (a - B.n0) * ku; }
-                else { lo = g.cl_ptr[a] - B.e0; k = g.cl_ptr[a + 1] - B.e0 - lo; }
-                int b = B.b0;
-                if (multi) {
-                    b = g.bfm[a];
-                    if (!blk_problem_runs(s, b)) {
-                        for (int j = 0; j < k; ++j) { const int x = perm[S.poff + lo + j]; atomicOr(&skip[x >> 5], 1u << (x & 31)); }
-                        sm.any_skip[slot] = 1;
-                        continue;
-                    }
-                }
-                bool made_nan = false;
-                if (k <= 8) {
-                    float xv[8]; int xs[8];
-                    float tot = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j < k) {
-                            const int x = perm[S.poff + lo + j];
-                            float v = L40(X[x]);
-                            if (masked && staged_mbit(mw, S, x)) v = v * 0.f;
-                            xs[j] = x; xv[j] = v; tot += v;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j < k) {
-                            const float nv = X30(tot - xv[j]);
-                            made_nan |= (nv != nv);
-                            X[xs[j]] = nv;
-                        }
-                    }
-                } else {
-                    float tot = 0.f;
-                    for (int j = 0; j < k; ++j) {
-                        const int x = perm[S.poff + lo + j];
-                        float v = L40(X[x]);
-                        if (masked && staged_mbit(mw, S, x)) v = v * 0.f;
-                        X[x] = v; tot += v;
-                    }
-                    for (int j = 0; j < k; ++j) {
-                        const int x = perm[S.poff + lo + j];
-                        const float nv = X30(tot - X[x]);
-                        made_nan |= (nv != nv);
-                        X[x] = nv;
-                    }
-                }
-                if (made_nan) s.nanpend[b] = 1;
-            }
-            __syncthreads();
-            PHASE_ADD(1);
-            ph_write_out<NT>(tid, g.csrc2 + B.e0, g.cdst + B.e0, B.ne, X, skip, sm.any_skip[slot] != 0, eout);
-            fence_proxy_async();   // generic-proxy accesses of this slot before the next bulk copy into it
-            __syncthreads();
-            PHASE_ADD(2);
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem,
-                                             TmaSmem& sm, TmaState& st) {
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    __shared__ BlkStats sm_st;
-    const float* __restrict__ en = s.eta[r ^ 1];
-    const float* __restrict__ eo = s.eta[r];
-    const int tid = threadIdx.x;
-    KeyedReducer<StatAcc> red;
-    int next_blk = blockIdx.x;
-    for (;;) {
-        const int n = tma_collect<true>(g, s, sm, next_blk);
-        if (n == 0) break;
-        if (tid == 0) {
-            const BlkGeo B0 = var_block(g, sm.blk[0]);
-            tma_issue_var(g, s, B0, (use_mask || em_set) && (B0.multi() || s.masked[B0.b0]), en, eo, smem, &sm.bar[0]);
-        }
-        for (int i = 0; i < n; ++i) {
-            const int slot = i & 1;
-            unsigned char* base = smem + slot * PDP_TMA_SLOT_BYTES;
-            float* SA = reinterpret_cast<float*>(base + TS_VAR_SA);   // eta(t), then q(t)
-            float* SB = reinterpret_cast<float*>(base + TS_VAR_SB);   // eta(t-1), then y
-            const uint16_t* perm = reinterpret_cast<const uint16_t*>(base + TS_VAR_PERM);
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>(base + TS_VAR_MASK);
-            uint32_t* skip = reinterpret_cast<uint32_t*>(base + TS_VAR_SKIP);
-            const BlkGeo B = var_block(g, sm.blk[i]);
-            const Staged S = staged_of(B.e0, B.ne);
-            const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
-            if (i + 1 < n && tid == 0) {
-                const BlkGeo Bn = var_block(g, sm.blk[i + 1]);
-                tma_issue_var(g, s, Bn, (use_mask || em_set) && (Bn.multi() || s.masked[Bn.b0]), en, eo,
-                              smem + (slot ^ 1) * PDP_TMA_SLOT_BYTES, &sm.bar[slot ^ 1]);
-            }
-            const bool multi = B.multi();
-            const bool local_stats = multi && (B.b1 - B.b0 < PDP_STAT_SLOTS);
-            for (int w = tid; w < (S.n_st + 31) / 32; w += NT) skip[w] = 0u;
-            if (tid == 0) sm.any_skip[slot] = 0;
-            if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
-            PHASE_T0();
-            mbar_wait(&sm.bar[slot], st.parity[slot]);
-            st.parity[slot] ^= 1u;
-            __syncthreads();
-            PHASE_ADD(3);
-            // ---- thread per variable (descending degree, alternating round direction)
-            for (int vbase = B.n0, round = 0; vbase < B.n1; vbase += NT, ++round) {
-                const int ti = (round & 1) ? (vbase + NT - 1 - tid) : (vbase + tid);
-                if (ti >= B.n1) continue;
-                const int2 ve = __ldg(&g.vsort[ti]);
-                const int i_var = ve.x, lo = ve.y & 0xffff, deg = ve.y >> 16;
-                const uint16_t* pj = perm + S.poff + lo;
-                int b = B.b0;
-                if (multi) {
-                    b = g.bvm[i_var];
-                    if (!blk_problem_runs(s, b)) {
-                        for (int j = 0; j < deg; ++j) { const int x = pj[j] & 0x7fff; atomicOr(&skip[x >> 5], 1u << (x & 31)); }
-                        sm.any_skip[slot] = 1;
-                        continue;
-                    }
-                }
-                const uint32_t act = s.av[i_var];
-                float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
-                for (int j = 0; j < deg; ++j) {
-                    const uint32_t pw = pj[j];
-                    const int x = pw & 0x7fff;
-                    const uint32_t negm = 0u - (pw >> 15);     // all ones: negative literal
-                    const bool m = masked && staged_mbit(mw, S, x);
-                    const float xn = SA[x], xo = SB[x];
-                    float y = L40(1.f - xo);
-                    if (use_mask && m) y = y * 0.f;
-                    SB[x] = y;
-                    // the reference's pos/neg incidence matrices hold explicit zeros: 0*y keeps NaN alive
-                    const float zy = 0.f * y;
-                    P += fsel(negm, zy, y);
-                    N += fsel(negm, y, zy);
-                    const float c = X30(30.f * xn);
-                    n0 += xn * c; d0 += c;
-                    if (has_prev) {
-                        float d = fabsf(xo - xn);
-                        if (em_set && m) d = d * 0.f;
-                        const float cd = X30(30.f * d);
-                        n1 += d * cd; d1 += cd;
-                    }
-                }
-                const float sm0 = pdp_divs(n0, tmaxf(d0, 1.0f)) * (float)act;
-                const float sm1 = pdp_divs(n1, tmaxf(d1, 1.0f)) * (float)act;
-                if (!multi) {
-                    red.touch(s, b);
-                    red.acc.add(sm0, sm1, has_prev, act);
-                } else {
-                    StatAcc one;
-                    one.reset();
-                    one.add(sm0, sm1, has_prev, act);
-                    if (local_stats) {
-                        const int lb = b - B.b0;
-                        atomicMax(&sm_st.mx0[lb], one.mx0); atomicMin(&sm_st.mn0[lb], one.mn0);
-                        if (has_prev) { atomicMax(&sm_st.mx1[lb], one.mx1); atomicMin(&sm_st.mn1[lb], one.mn1); }
-                        if (one.nan) atomicOr(&sm_st.nan[lb], one.nan);
-                        if (act) atomicAdd(&sm_st.nav[lb], act);
-                    } else {
-                        one.commit(s, b);
-                    }
-                }
-                float sb_pos, opp_pos, O_pos, sb_neg, opp_neg, O_neg;
-                sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
-                sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
-                bool made_nan = false;
-                for (int j = 0; j < deg; ++j) {
-                    const uint32_t pw = pj[j];
-                    const int x = pw & 0x7fff;
-                    const uint32_t negm = 0u - (pw >> 15);
-                    const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), SB[x]);
-                    made_nan |= (u != u);
-                    SA[x] = u;
-                }
-                if (made_nan) s.nanpend[b] = 1;
-            }
-            __syncthreads();
-            PHASE_ADD(4);
-            if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-            ph_write_out<NT>(tid, g.vsrc2 + B.e0, g.vdst + B.e0, B.ne, SA, skip, sm.any_skip[slot] != 0, s.qu);
-            fence_proxy_async();
-            red.finish(s);   // block-level merge of the statistics; its barriers also close the slot
-            PHASE_ADD(5);
-        }
-    }
-}
-#undef NT
-#endif  // PDP_TMA
-
-// L2 prefetch of [ptr, ptr + bytes) by one bulk instruction (16-byte granularity).  The node phases are issue bound and
-// leave the memory system idle: thread 0 starts them by pulling in what the next block of this CTA will load and the
-// write-out tables of the current block.
-__device__ __forceinline__ void l2_prefetch(const void* ptr, size_t bytes) {
-#if PDP_L2_PREFETCH
-    if (bytes == 0) return;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)15;
-    const uint32_t n = (uint32_t)((reinterpret_cast<uintptr_t>(ptr) + bytes - a + 15) & ~(size_t)15);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
-#endif
-}
-
-// (Dynamic block scheduling through a global counter was measured and dropped: with the 2-7 equal-size blocks a CTA
-// gets per pass it evens out nothing, and smaller blocks cost more per edge than they balance.)
-
-// ================================================================================================
-// serial passes: the whole CTA runs load, node phase and write-out of a block back to back
-// ================================================================================================
-
-// Block hand-out of one pass.  Static (block b to CTA b mod grid) when one CTA owns the SM: the CTAs then finish within
-// 1-2 % of each other.  With two CTAs per SM the pair drifts apart, the early one waits at the grid barrier and its
-// partner finishes alone at half the SM's warps (10 % of the iteration, measured), so the blocks after a CTA's first one
-// come from a counter; the next index is fetched while the current block is processed.
-#ifndef PDP_DYN_BLOCKS
-#define PDP_DYN_BLOCKS 1
-#endif
-// thread 0, at the top of a block: the index of the block after `blk`, left in slot[par] for feed_advance
-template <bool DYN>
-__device__ __forceinline__ int feed_fetch(int* ctr, int* slot, int par, int blk) {
-    const int nx = DYN ? (int)gridDim.x + atomicAdd(ctr, 1) : blk + (int)gridDim.x;
-    slot[par] = nx;
-    return nx;
-}
-// all threads, after the block's last use of shared memory
-__device__ __forceinline__ int feed_advance(const int* slot, int& par) {
-    __syncthreads();
-    const int nx = slot[par];
-    par ^= 1;
-    return nx;
-}
-
-// clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
-template <int CTAS>
-__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
-    constexpr int NT = SweepCfg<CTAS>::kThreads, BLK_C = SweepCfg<CTAS>::kBlkC;
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* X = reinterpret_cast<float*>(smem);
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
-    uint32_t* sticky = skip + BLK_C / 32;
-    __shared__ int sm_any_skip;
-    const float* __restrict__ qin = s.qu;
-    float* __restrict__ eout = s.eta[r ^ 1];
-    const int tid = threadIdx.x;
-    __shared__ int sm_feed[2];
-    __shared__ int sm_nb;
-    constexpr bool DYN = PDP_DYN_BLOCKS && CTAS == 2;
-    int par = 0;
-    for (int blk = blockIdx.x; blk < g.ncb; blk = feed_advance(sm_feed, par)) {
-        if (tid == 0) sm_nb = feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_CBLK], sm_feed, par, blk);
-        const BlkGeo B = clause_block(g, blk);
-        if (B.n1 <= B.n0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
-        for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
-        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
-        PHASE_T0();
-        if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-        else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-        __syncthreads();
-        PHASE_ADD(0);
-        if (tid == 0) {
-            l2_prefetch(g.csrc + B.e0, (size_t)B.ne * 2);
-            l2_prefetch(g.cdst + B.e0, (size_t)B.ne * 4);
-            const int nb = sm_nb;
-            if (nb < g.ncb) {
-                const BlkGeo Bn = clause_block(g, nb);
-                l2_prefetch(qin + Bn.e0, (size_t)Bn.ne * 4);
-                l2_prefetch(g.cinv + Bn.e0, (size_t)Bn.ne * 2);
-            }
-        }
-        ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip, sticky);
-        __syncthreads();
-        PHASE_ADD(1);
-        ph_write_out<NT>(tid, g.csrc + B.e0, g.cdst + B.e0, B.ne, X, skip, sm_any_skip, eout, sticky, s.eta[r]);
-        __syncthreads();
-        PHASE_ADD(2);
-    }
-}
-
-// variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
-// [buffer r], and q(t) [C-layout, in place] from eta(t-1)
-template <int CTAS>
-__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
-    constexpr int NT = SweepCfg<CTAS>::kThreads, BLK_V = SweepCfg<CTAS>::kBlkV, BLK_C = SweepCfg<CTAS>::kBlkC;
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
-    float* PB = PA + BLK_V;                       // eta(t-1), then y
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
-    uint32_t* sticky = skip + BLK_C / 32;
-    __shared__ int sm_any_skip;
-    __shared__ BlkStats sm_st;
-    const float* __restrict__ en = s.eta[r ^ 1];
-    const float* __restrict__ eo = s.eta[r];
-    const int tid = threadIdx.x;
-    KeyedReducer<StatAcc> red;
-    __shared__ int sm_feed[2];
-    __shared__ int sm_nb;
-    constexpr bool DYN = PDP_DYN_BLOCKS && CTAS == 2;
-    int par = 0;
-    for (int blk = blockIdx.x; blk < g.nvb; blk = feed_advance(sm_feed, par)) {
-        if (tid == 0) sm_nb = feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_VBLK], sm_feed, par, blk);
-        const BlkGeo B = var_block(g, blk);
-        if (B.n1 <= B.n0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
-        const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
-        for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
-        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
-        if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
-        PHASE_T0();
-        if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-        else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-        __syncthreads();
-        PHASE_ADD(3);
-        if (tid == 0) {
-            l2_prefetch(g.vsrc + B.e0, (size_t)B.ne * 2);
-            l2_prefetch(g.vdst + B.e0, (size_t)B.ne * 4);
-            const int nb = sm_nb;
-            if (nb < g.nvb) {
-                const BlkGeo Bn = var_block(g, nb);
-                l2_prefetch(en + Bn.e0, (size_t)Bn.ne * 4);
-                l2_prefetch(eo + Bn.e0, (size_t)Bn.ne * 4);
-                l2_prefetch(g.vinv + Bn.e0, (size_t)Bn.ne * 2);
-            }
-        }
-        // SurveyScorer of problems about to converge, while the new surveys are still in the planes (the node phase
-        // overwrites them); its own loop, so that the node phase's code is the same with and without it
-        if (PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1])) ph_var_score<NT>(tid, g, s, B, PA, PB);
-        ph_var_node<NT>(tid, g, s, B, use_mask, has_prev, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky);
-        __syncthreads();
-        PHASE_ADD(4);
-        if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-        ph_write_out<NT>(tid, g.vsrc + B.e0, g.vdst + B.e0, B.ne, PA, skip, sm_any_skip, s.qu, sticky, s.qu);
-        red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
-        PHASE_ADD(5);
-    }
-}
+#include "pdp_sweep.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // SurveyScorer over the converged problems (pdp_predict.py:155-192) + coefficient statistics

@@ -76,14 +76,11 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.cb_ptr = k.take<int32_t>(max_cb + 1);
     g.vinv = k.take<uint16_t>(E);
     g.cinv = k.take<uint16_t>(E);
-    g.vsrc = k.take<uint16_t>(E);
-    g.csrc = k.take<uint16_t>(E);
-    g.vperm = k.take<uint16_t>(E + 16);
-    g.cperm = k.take<uint16_t>(E + 16);
-    g.vsrc2 = k.take<uint16_t>(E);
-    g.csrc2 = k.take<uint16_t>(E);
-    g.vdst = k.take<int32_t>(E);
-    g.cdst = k.take<int32_t>(E);
+    g.v_wrun = k.take<uint2>(E / 32 + 2);
+    g.c_wrun = k.take<uint2>(E / 32 + 2);
+    g.v_wadj = k.take<int32_t>(E);
+    g.c_wadj = k.take<int32_t>(E);
+    g.wo_tmp = k.take<int32_t>(3 * (E / 32 + 2));
     g.vsort = k.take<int2>(V);
     g.cb_k = k.take<int32_t>(max_cb + 1);
     s.eta[0] = k.take<float>(E);

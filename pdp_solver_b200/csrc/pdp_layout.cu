@@ -1,8 +1,8 @@
 // pdp_layout.cu -- builds the blocked message layout of the SP sweep (pdp_common.cuh):
 // block partitions of both edge orders, the V-layout / C-layout positions of every edge, the 16-bit
-// local scatter / gather tables of the two passes and their write-out pieces.  Runs once per batch
-// inside pdp_create, entirely on the device (four stable radix sorts on block ids, two scans, two
-// stream compactions); the message arrays are not live yet and serve as scratch.
+// local scatter / gather tables of the two passes (variable blocks: transposed by warp groups, pdp_sweep.cuh) and the
+// run-length coded destinations of their write-outs.  Runs once per batch inside pdp_create, entirely on the
+// device (five stable radix sorts, three scans); the message arrays are not live yet and serve as scratch.
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
@@ -34,35 +34,6 @@ __global__ void k_key_vblock_of_c(pdp_graph g, int32_t* key, int32_t* val) {
         val[c] = (int32_t)c;
     }
 }
-// keys of the C-layout sort, in variable-major order: clause block of the edge
-__global__ void k_key_cblock_of_p(pdp_graph g, int32_t* key, int32_t* val) {
-    GS(p, g.E) {
-        key[p] = g.cl_ptr[g.v_cls[p]] / g.sc;
-        val[p] = (int32_t)p;
-    }
-}
-
-// x = V-layout position, lv[x] = clause-major slot stored there, ki[x] = its variable block
-__global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ ki, const int32_t* __restrict__ lv) {
-    GS(x, g.E) {
-        const int c = lv[x];
-        const int p = g.c_pos[c];
-        g.p_vpos[p] = (int32_t)x;
-        g.vinv[x] = (uint16_t)((p - g.var_ptr[g.vb_ptr[ki[x]]]) | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
-    }
-}
-// x = C-layout position, lq[x] = variable-major slot stored there, kj[x] = its clause block
-__global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, const int32_t* __restrict__ lq) {
-    GS(x, g.E) {
-        const int p = lq[x];
-        const int c = (int)(g.v_cedge[p] & PDP_IDX_MASK);
-        g.p_qpos[p] = (int32_t)x;
-        g.cinv[x] = (uint16_t)(c - g.cl_ptr[g.cb_ptr[kj[x]]]);
-    }
-}
-
-// write-out order of the variable blocks: the edges of a block sorted by their C-layout position.
-// Input in C-layout order x (lq[x] = variable-major slot): key = variable block, value = x.
 // block of a slot of the node-major order: the stride region the slot lies in, or an earlier one when the slot's node
 // started before that region (block t begins at the first node whose first slot is >= t * stride, k_block_ptr).  Two
 // loads from the small block tables instead of three dependent random gathers through the adjacency.
@@ -71,50 +42,80 @@ __device__ __forceinline__ int block_of_slot(const int32_t* __restrict__ node_pt
     while (b > 0 && slot < node_ptr[blk_ptr[b]]) --b;
     return b;
 }
-__global__ void k_key_vblock_of_q(pdp_graph g, const int32_t* __restrict__ lq, int32_t* key, int32_t* val) {
+
+// x = V-layout position, lv[x] = clause-major slot stored there
+// tslot[p] = local (transposed) slot of variable-major slot p inside its variable block
+__global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ lv, const uint16_t* __restrict__ tslot) {
     GS(x, g.E) {
-        key[x] = block_of_slot(g.var_ptr, g.vb_ptr, g.sv, lq[x]);
-        val[x] = (int32_t)x;
+        const int c = lv[x];
+        const int p = g.c_pos[c];
+        g.p_vpos[p] = (int32_t)x;
+        g.vinv[x] = (uint16_t)(tslot[p] | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
     }
 }
+// keys of the C-layout sort, taken in V-layout order (variable block, clause-major slot): the clause block of the
+// edge.  The stable sort leaves every clause block's edges ordered by (variable block, clause-major slot): the edges
+// between one clause block and one variable block -- a RUN -- appear in the same order in both layouts.
 __global__ void k_key_cblock_of_v(pdp_graph g, const int32_t* __restrict__ lv, int32_t* key, int32_t* val) {
     GS(x, g.E) {
         key[x] = block_of_slot(g.cl_ptr, g.cb_ptr, g.sc, lv[x]);
-        val[x] = (int32_t)x;
+        val[x] = lv[x];
+    }
+}
+// x = C-layout position, lq[x] = clause-major slot stored there, kj[x] = its clause block
+__global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, const int32_t* __restrict__ lq) {
+    GS(x, g.E) {
+        const int c = lq[x];
+        g.p_qpos[g.c_pos[c]] = (int32_t)x;
+        g.cinv[x] = (uint16_t)(c - g.cl_ptr[g.cb_ptr[kj[x]]]);
+    }
+}
+// Write-out order = load order: a pass writes the result of the edge it loaded from position x of its own layout to
+// that edge's position in the other layout, which ascends with x inside a block.  dst[x], and the block of x.
+__global__ void k_wo_seq_var(pdp_graph g, const int32_t* __restrict__ lv, int32_t* dst, int32_t* blk) {
+    GS(x, g.E) {
+        const int p = g.c_pos[lv[x]];
+        dst[x] = g.p_qpos[p];
+        blk[x] = block_of_slot(g.var_ptr, g.vb_ptr, g.sv, p);
+    }
+}
+__global__ void k_wo_seq_clause(pdp_graph g, const int32_t* __restrict__ lq, const int32_t* __restrict__ kj, int32_t* dst, int32_t* blk) {
+    GS(x, g.E) {
+        dst[x] = g.p_vpos[g.c_pos[lq[x]]];
+        blk[x] = kj[x];
     }
 }
 
-// w = write-out slot; kb[w] = block, dst[w] = destination position, slot_of_dst[dst] = producer-order slot.
-// src16[w] = local producer-order index
-__global__ void k_fill_writeout(int64_t E, const int32_t* __restrict__ kb, const int32_t* __restrict__ dst,
-                                const int32_t* __restrict__ slot_of_dst, const int32_t* __restrict__ node_ptr,
-                                const int32_t* __restrict__ blk_ptr, uint16_t* src16, int32_t* dst_out) {
-    GS(w, E) {
-        const int d = dst[w];
-        src16[w] = (uint16_t)(slot_of_dst[d] - node_ptr[blk_ptr[kb[w]]]);
-        dst_out[w] = d;
+// run-length coding of the destinations: slot w starts a run unless it continues the previous slot's block and
+// destination.  One thread per 32 slots: bits[word], cnt[word] = popc(bits).
+__global__ void k_wo_bits(int64_t E, const int32_t* __restrict__ kb, const int32_t* __restrict__ dst, int64_t nwords,
+                          uint32_t* bits, int32_t* cnt) {
+    GS(word, nwords) {
+        uint32_t b = 0u;
+        const int64_t w0 = word * 32;
+        for (int i = 0; i < 32 && w0 + i < E; ++i) {
+            const int64_t w = w0 + i;
+            if (w == 0 || kb[w] != kb[w - 1] || dst[w] != dst[w - 1] + 1) b |= 1u << i;
+        }
+        bits[word] = b;
+        cnt[word] = __popc(b);
     }
 }
-
-#if PDP_TMA
-// tables of the TMA-staged passes.  A block's region is staged from its 16-byte aligned start
-// (first position & ~3), so a staged position is (layout position) - (first position & ~3).
-__global__ void k_fill_staged_tables(pdp_graph g) {
-    GS(p, g.E) {   // variable side
-        const int var = (int)(g.c_var[g.v_cedge[p] & PDP_IDX_MASK] & PDP_IDX_MASK);
-        const int e0 = g.var_ptr[g.vb_ptr[g.var_ptr[var] / g.sv]];
-        g.vperm[p] = (uint16_t)((g.p_vpos[p] - (e0 & ~3)) | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
-        // write-out slot w = p ranges over the same block: its source is the edge at local index vsrc[w]
-        g.vsrc2[p] = (uint16_t)(g.p_vpos[e0 + g.vsrc[p]] - (e0 & ~3));
-    }
-    GS(c, g.E) {   // clause side
-        const int cl = g.v_cls[g.c_pos[c]];
-        const int e0 = g.cl_ptr[g.cb_ptr[g.cl_ptr[cl] / g.sc]];
-        g.cperm[c] = (uint16_t)(cqpos(g, c) - (e0 & ~3));
-        g.csrc2[c] = (uint16_t)(cqpos(g, e0 + g.csrc[c]) - (e0 & ~3));
+// rank[word] = run starts before the word (exclusive scan of cnt): wrun[word] = {bits, rank - 1}, wadj[run] = dst - slot
+__global__ void k_wo_pack(int64_t E, const int32_t* __restrict__ dst, int64_t nwords, const uint32_t* __restrict__ bits,
+                          const int32_t* __restrict__ rank, uint2* wrun, int32_t* wadj) {
+    GS(word, nwords) {
+        uint32_t b = bits[word];
+        int r = rank[word];
+        wrun[word] = make_uint2(b, (uint32_t)(r - 1));
+        while (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const int64_t w = word * 32 + i;
+            wadj[r++] = dst[w] - (int32_t)w;
+        }
     }
 }
-#endif
 
 // degree-sorted variable order: key = block << 14 | (16383 - degree)
 __global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
@@ -124,14 +125,38 @@ __global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
         val[v] = (int32_t)v;
     }
 }
-// order == nullptr: identity
-__global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order) {
+// pad[t] = slots of the group that starts at rank t (32 x the degree of its first, largest member), 0 for other ranks.
+// Ranks are cut into groups of 32 from the first rank of every block.
+__global__ void k_group_slots(pdp_graph g, const int32_t* __restrict__ order, int32_t* pad) {
     GS(t, g.V) {
-        const int v = order ? order[t] : (int)t;
+        const int v = order[t];
+        const int t0 = g.vb_ptr[g.var_ptr[v] / g.sv];
+        pad[t] = ((((int)t - t0) & 31) == 0) ? 32 * (g.var_ptr[v + 1] - g.var_ptr[v]) : 0;
+    }
+}
+// psum = exclusive scan of pad: psum[first rank of a group] - psum[first rank of its block] is the group's base slot
+__global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order, const int32_t* __restrict__ psum, int32_t* max_slots) {
+    int worst = 0;
+    GS(t, g.V) {
+        const int v = order[t];
         const int blk = g.var_ptr[v] / g.sv;
-        const int lo = g.var_ptr[v] - g.var_ptr[g.vb_ptr[blk]];
+        const int t0 = g.vb_ptr[blk];
+        const int tg = t0 + (((int)t - t0) & ~31);
         const int deg = g.var_ptr[v + 1] - g.var_ptr[v];
-        g.vsort[t] = make_int2(v, lo | (deg << 16));
+        const int base = psum[tg] - psum[t0];
+        g.vsort[t] = make_int2(v, (base & 0xffff) | (deg << 16));
+        if (tg == (int)t) worst = max(worst, base + 32 * deg);     // end of this group's slots = padded size so far
+    }
+    if (worst) atomicMax(max_slots, worst);
+}
+// padded transposed slots: lane l = rank within the group, row j = the j-th edge (pdp_sweep.cuh var_group)
+__global__ void k_fill_tslot(pdp_graph g, uint16_t* tslot) {
+    GS(t, g.V) {
+        const int2 e = g.vsort[t];
+        const int v = e.x, base = e.y & 0xffff, deg = (int)((unsigned)e.y >> 16);
+        const int lane = ((int)t - g.vb_ptr[g.var_ptr[v] / g.sv]) & 31;
+        const int p0 = g.var_ptr[v];
+        for (int j = 0; j < deg; ++j) tslot[p0 + j] = (uint16_t)(base + 32 * j + lane);
     }
 }
 
@@ -188,31 +213,20 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     g.blocked_ok = 0; g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
     if (E == 0) return PDP_OK;
     g.ctas = 1;
-    if (!(PDP_PIPELINE || PDP_TMA)) {
-        const char* forced = getenv("PDP_B200_CTAS");
-        if (forced) g.ctas = (atoi(forced) == 2) ? 2 : 1;
-        else if (g.B > 0 && E / g.B >= PDP_CTAS_EDGES_PER_PROBLEM) g.ctas = 2;
-    }
+    const char* forced = getenv("PDP_B200_CTAS");
+    if (forced) g.ctas = (atoi(forced) == 2) ? 2 : 1;
+    else if (g.B > 0 && E / g.B >= PDP_CTAS_EDGES_PER_PROBLEM) g.ctas = 2;
     const int blk_v = PDP_BLK_V / g.ctas, blk_c = PDP_BLK_C / g.ctas;
+    // (V <= E: the degree sort below borrows E-sized scratch; batches of mostly isolated variables take the generic passes)
     const bool ok = monotone_maps && g.max_var_degree <= blk_v / 2 && g.max_clause_degree <= blk_c / 2 &&
-                    g.V > 0 && g.F > 0 && getenv("PDP_B200_NO_BLOCKED") == nullptr;
+                    g.V > 0 && g.F > 0 && g.V <= E && getenv("PDP_B200_NO_BLOCKED") == nullptr;
     if (!ok) {
         k_identity_layout<<<G1(E)>>>(g);
         LLK();
         return PDP_OK;
     }
-    g.sv = pick_stride(E, blk_v, g.max_var_degree, nsm * g.ctas);
     g.sc = pick_stride(E, blk_c, g.max_clause_degree, nsm * g.ctas);
-    g.nvb = (int32_t)(E / g.sv + 1);
     g.ncb = (int32_t)(E / g.sc + 1);
-    if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 4) + 2 * PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 4) + 2 * PDP_MAX_SMS + 2) {
-        pdp_set_error("pdp_create: block tables too small (nvb=%d ncb=%d)", g.nvb, g.ncb);
-        return PDP_ERR_WORKSPACE;
-    }
-    k_block_ptr<<<G1(g.nvb + 1)>>>(g.var_ptr, g.V, g.sv, g.nvb, g.vb_ptr);
-    LLK();
-    k_block_ptr<<<G1(g.ncb + 1)>>>(g.cl_ptr, g.F, g.sc, g.ncb, g.cb_ptr);
-    LLK();
 
     // scratch: the message arrays
     int32_t* S0 = reinterpret_cast<int32_t*>(c->s.eta[0]);
@@ -221,6 +235,7 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     int32_t* S3 = reinterpret_cast<int32_t*>(c->s.qs);
     int32_t* LV = reinterpret_cast<int32_t*>(c->s.qd);    // V-layout position -> clause-major slot
     int32_t* LQ = reinterpret_cast<int32_t*>(c->s.ext);   // C-layout position -> variable-major slot
+    uint16_t* TSLOT = reinterpret_cast<uint16_t*>(g.v_wadj);   // free until the variable side's write-out is coded (last step)
 
     // stable sort of (key, value) pairs held in S0 / S2; returns the buffers holding the result
     auto sort_pairs = [&](int64_t count, int64_t nkeys, int32_t** keys_out, int32_t** vals_out, int32_t** keys_free, int32_t** vals_free) -> int {
@@ -236,50 +251,91 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         *keys_out = dk.Current(); *vals_out = dv.Current(); *keys_free = dk.Alternate(); *vals_free = dv.Alternate();
         return PDP_OK;
     };
+    auto exclusive_scan = [&](int32_t* data, int64_t count) -> int {   // in place
+        size_t q = 0;
+        if (cub::DeviceScan::ExclusiveSum(nullptr, q, data, data, (int)count, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        if (q > c->cub_tmp_bytes) { pdp_set_error("pdp_create: scan scratch %zu > reserve %zu", q, c->cub_tmp_bytes); return PDP_ERR_WORKSPACE; }
+        if (cub::DeviceScan::ExclusiveSum(c->cub_tmp, q, data, data, (int)count, stream) != cudaSuccess) return PDP_ERR_CUDA;
+        c->launches++;
+        return PDP_OK;
+    };
     int32_t *K, *L, *KF, *LF;
     int rc;
+
+    // ---- variable blocks.  Per block: variables by descending degree, cut into groups of 32 (one warp each, nearly equal
+    //      trip counts); a group's edges are stored transposed and padded to its largest degree (pdp_sweep.cuh), so the
+    //      shared-memory plane must hold the block's PADDED slots: the edge budget of a block starts 4.5 % below the plane
+    //      and shrinks until the largest padded block fits (2-5 % padding on random k-SAT).
+    int32_t* d_max_slots = g.wo_tmp;
+    int budget = blk_v - blk_v / 22;
+    bool fits = false;
+    for (int attempt = 0; attempt < 8 && !fits; ++attempt) {
+        if (budget / 2 < g.max_var_degree) break;
+        g.sv = pick_stride(E, budget, g.max_var_degree, nsm * g.ctas);
+        g.nvb = (int32_t)(E / g.sv + 1);
+        if (nsm > PDP_MAX_SMS || g.nvb > E / (PDP_BLK_V / 4) + 2 * PDP_MAX_SMS + 2 || g.ncb > E / (PDP_BLK_C / 4) + 2 * PDP_MAX_SMS + 2 ||
+            g.nvb >= (1 << 17)) {
+            pdp_set_error("pdp_create: block tables too small (nvb=%d ncb=%d)", g.nvb, g.ncb);
+            return PDP_ERR_WORKSPACE;
+        }
+        k_block_ptr<<<G1(g.nvb + 1)>>>(g.var_ptr, g.V, g.sv, g.nvb, g.vb_ptr);
+        LLK();
+        k_key_vsort<<<G1(g.V)>>>(g, S0, S2);
+        LLK();
+        if ((rc = sort_pairs(g.V, (int64_t)g.nvb << 14, &K, &L, &KF, &LF)) != PDP_OK) return rc;
+        k_group_slots<<<G1(g.V)>>>(g, L, KF);
+        LLK();
+        if ((rc = exclusive_scan(KF, g.V)) != PDP_OK) return rc;
+        LCK(cudaMemsetAsync(d_max_slots, 0, sizeof(int32_t), stream));
+        k_fill_vsort<<<G1(g.V)>>>(g, L, KF, d_max_slots);
+        LLK();
+        int32_t max_slots = 0;
+        LCK(cudaMemcpyAsync(&max_slots, d_max_slots, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        LCK(cudaStreamSynchronize(stream));
+        fits = max_slots <= blk_v;
+        if (!fits) budget = (int)((int64_t)budget * blk_v / max_slots) - 64;   // scale by the overshoot, plus a margin
+    }
+    if (!fits) {   // degree distributions that do not pad well (a few huge variables among tiny ones): generic passes
+        g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
+        k_identity_layout<<<G1(E)>>>(g);
+        LLK();
+        return PDP_OK;
+    }
+    k_block_ptr<<<G1(g.ncb + 1)>>>(g.cl_ptr, g.F, g.sc, g.ncb, g.cb_ptr);
+    LLK();
+    k_fill_tslot<<<G1(g.V)>>>(g, TSLOT);
+    LLK();
 
     // ---- V-layout: edges sorted by (variable block, clause-major slot)
     k_key_vblock_of_c<<<G1(E)>>>(g, S0, S2);
     LLK();
     if ((rc = sort_pairs(E, g.nvb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
-    k_fill_vlayout<<<G1(E)>>>(g, K, L);
+    k_fill_vlayout<<<G1(E)>>>(g, L, TSLOT);
     LLK();
     LCK(cudaMemcpyAsync(LV, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
-    // ---- C-layout: edges sorted by (clause block, variable-major slot)
-    k_key_cblock_of_p<<<G1(E)>>>(g, S0, S2);
+    // ---- C-layout: the V-layout sequence sorted (stable) by clause block = (clause block, variable block, clause-major slot)
+    k_key_cblock_of_v<<<G1(E)>>>(g, LV, S0, S2);
     LLK();
     if ((rc = sort_pairs(E, g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
     k_fill_clayout<<<G1(E)>>>(g, K, L);
     LLK();
-    LCK(cudaMemcpyAsync(LQ, L, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToDevice, stream));
 
-    // ---- write-out orders: the edges of a block sorted by their destination position
+    // ---- destinations of the write-outs (write-out order = load order), run-length coded.  K / L still hold the clause
+    //      block and the clause-major slot of every C-layout position; KF / LF are free.
+    const int64_t nwords = E / 32 + 2;
+    uint32_t* wbits = reinterpret_cast<uint32_t*>(g.wo_tmp);
+    int32_t* wcnt = g.wo_tmp + nwords;
     for (int side = 0; side < 2; ++side) {
-        const bool var_side = (side == 0);
-        if (var_side) k_key_vblock_of_q<<<G1(E)>>>(g, LQ, S0, S2);
-        else k_key_cblock_of_v<<<G1(E)>>>(g, LV, S0, S2);
+        const bool var_side = (side == 1);     // clause side first: it reads K / L
+        if (var_side) k_wo_seq_var<<<G1(E)>>>(g, LV, KF, LF);
+        else k_wo_seq_clause<<<G1(E)>>>(g, L, K, KF, LF);
         LLK();
-        if ((rc = sort_pairs(E, var_side ? g.nvb : g.ncb, &K, &L, &KF, &LF)) != PDP_OK) return rc;
-        // K[w] = block, L[w] = destination position
-        k_fill_writeout<<<G1(E)>>>(E, K, L, var_side ? LQ : LV, var_side ? g.var_ptr : g.cl_ptr,
-                                    var_side ? g.vb_ptr : g.cb_ptr, var_side ? g.vsrc : g.csrc, var_side ? g.vdst : g.cdst);
+        k_wo_bits<<<G1(nwords)>>>(E, LF, KF, nwords, wbits, wcnt);
+        LLK();
+        if ((rc = exclusive_scan(wcnt, nwords)) != PDP_OK) return rc;
+        k_wo_pack<<<G1(nwords)>>>(E, KF, nwords, wbits, wcnt, var_side ? g.v_wrun : g.c_wrun, var_side ? g.v_wadj : g.c_wadj);
         LLK();
     }
-#if PDP_TMA
-    k_fill_staged_tables<<<G1(E)>>>(g);
-    LLK();
-#endif
-    // ---- per block: variables by descending degree (uniform trip counts inside a warp), clause degree
-    if (g.V <= E && g.max_var_degree < 16384 && g.nvb < (1 << 17)) {
-        k_key_vsort<<<G1(g.V)>>>(g, S0, S2);
-        LLK();
-        if ((rc = sort_pairs(g.V, (int64_t)g.nvb << 14, &K, &L, &KF, &LF)) != PDP_OK) return rc;
-        k_fill_vsort<<<G1(g.V)>>>(g, L);
-    } else {
-        k_fill_vsort<<<G1(g.V)>>>(g, nullptr);
-    }
-    LLK();
     k_clause_block_degree_init<<<G1(g.ncb)>>>(g);
     LLK();
     k_clause_block_degree_check<<<G1(g.F)>>>(g);
@@ -290,12 +346,16 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
 
 // ------------------------------------------------------------------------------------------------
 // self-check of the layout tables (tests): counts violated invariants into errs[0..7]
-//   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vinv wrong
+//   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vinv is not the transposed slot
 //   2 C-layout position outside its block / cinv wrong           3 variable write-out does not land on p_qpos
 //   4 clause write-out does not land on c_vpos                   5 vsort / cb_k wrong
 //   6 distinct write-out sources of the variable blocks (= E)    7 ... of the clause blocks (= E)
 // ------------------------------------------------------------------------------------------------
 namespace {
+__device__ __forceinline__ int wo_dest(const uint2* __restrict__ wrun, const int32_t* __restrict__ wadj, int w) {
+    const uint2 rb = wrun[w >> 5];
+    return wadj[(int)rb.y + __popc(rb.x & (0xffffffffu >> (31 - (w & 31))))] + w;
+}
 __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/32+1] x 2, zeroed */) {
     GS(c, g.E) {
         const int p = g.c_pos[c];
@@ -306,35 +366,38 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
     GS(blk, g.nvb) {
         const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
         const int e0 = g.var_ptr[v0], e1 = g.var_ptr[v1];
-        if (e1 - e0 > PDP_BLK_V / g.ctas) atomicAdd(&errs[1], 1);
-        for (int p = e0; p < e1; ++p) {
-            const int x = g.p_vpos[p];
-            if (x < e0 || x >= e1 || (int)(g.vinv[x] & 0x7fff) != p - e0 ||
-                ((g.vinv[x] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) atomicAdd(&errs[1], 1);
-        }
-        for (int w = e0; w < e1; ++w) {
-            const int p = e0 + (int)g.vsrc[w];
-            if (p < e0 || p >= e1 || g.p_qpos[p] != g.vdst[w]) { atomicAdd(&errs[3], 1); continue; }
-            if (w > e0 && g.vdst[w] <= g.vdst[w - 1]) atomicAdd(&errs[3], 1);
-            if (!(atomicOr(&seen[p >> 5], 1u << (p & 31)) & (1u << (p & 31)))) atomicAdd(&errs[6], 1);
-        }
-        for (int p = e0; p < e1 && PDP_TMA; ++p) {
-            const int x = (int)(g.vperm[p] & 0x7fff) + (e0 & ~3);
-            if (x != g.p_vpos[p] || ((g.vperm[p] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) atomicAdd(&errs[1], 1);
-        }
-        for (int w = e0; w < e1 && PDP_TMA; ++w) {
-            const int p = e0 + (int)g.vsrc[w];
-            if ((int)g.vsrc2[w] + (e0 & ~3) != g.p_vpos[p]) atomicAdd(&errs[3], 1);
-        }
+        const int cap = PDP_BLK_V / g.ctas;
+        if (e1 - e0 > cap) atomicAdd(&errs[1], 1);
+        // vsort: a permutation of the block's variables by descending degree; groups of 32 ranks, rows of 32 slots
         long long sum = 0;
-        for (int t = v0; t < v1; ++t) {
-            const int2 e = g.vsort[t];
-            const int v = e.x, lo = e.y & 0xffff, deg = e.y >> 16;
-            if (v < v0 || v >= v1 || lo != g.var_ptr[v] - e0 || deg != g.var_ptr[v + 1] - g.var_ptr[v]) atomicAdd(&errs[5], 1);
-            if (t > v0 && deg > (g.vsort[t - 1].y >> 16) && g.V <= g.E) atomicAdd(&errs[5], 1);
-            sum += v;
+        int run_base = 0;
+        for (int tg = v0; tg < v1; tg += 32) {
+            const int gn = min(32, v1 - tg);
+            const int base = g.vsort[tg].y & 0xffff;
+            const int maxdeg = (int)((unsigned)g.vsort[tg].y >> 16);
+            if (base != run_base || (base & 31) || base + 32 * maxdeg > cap) atomicAdd(&errs[5], 1);
+            for (int l = 0; l < gn; ++l) {
+                const int2 e = g.vsort[tg + l];
+                const int v = e.x, deg = (int)((unsigned)e.y >> 16);
+                if (v < v0 || v >= v1 || deg != g.var_ptr[v + 1] - g.var_ptr[v] || (e.y & 0xffff) != base) { atomicAdd(&errs[5], 1); continue; }
+                if (tg + l > v0 && deg > (int)((unsigned)g.vsort[tg + l - 1].y >> 16)) atomicAdd(&errs[5], 1);
+                sum += v;
+                for (int j = 0; j < deg; ++j) {
+                    const int p = g.var_ptr[v] + j;
+                    const int x = g.p_vpos[p];
+                    const int slot = base + 32 * j + l;
+                    if (x < e0 || x >= e1 || (int)(g.vinv[x] & 0x7fff) != slot ||
+                        ((g.vinv[x] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) { atomicAdd(&errs[1], 1); continue; }
+                    // write-out slot = load position: its destination must be this edge's C-layout position
+                    if (wo_dest(g.v_wrun, g.v_wadj, x) != g.p_qpos[p]) { atomicAdd(&errs[3], 1); continue; }
+                    if (!(atomicOr(&seen[x >> 5], 1u << (x & 31)) & (1u << (x & 31)))) atomicAdd(&errs[6], 1);
+                }
+            }
+            run_base += 32 * maxdeg;
         }
         if (sum != ((long long)v0 + v1 - 1) * (v1 - v0) / 2) atomicAdd(&errs[5], 1);
+        for (int w = e0 + 1; w < e1; ++w)
+            if (wo_dest(g.v_wrun, g.v_wadj, w) <= wo_dest(g.v_wrun, g.v_wadj, w - 1)) atomicAdd(&errs[3], 1);
     }
     GS(blk, g.ncb) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
@@ -345,13 +408,12 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
             if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
         }
         for (int w = e0; w < e1; ++w) {
-            const int c = e0 + (int)g.csrc[w];
-            if (c < e0 || c >= e1 || cvpos(g, c) != g.cdst[w]) { atomicAdd(&errs[4], 1); continue; }
-            if (w > e0 && g.cdst[w] <= g.cdst[w - 1]) atomicAdd(&errs[4], 1);
+            const int c = e0 + (int)g.cinv[w];
+            const int d = wo_dest(g.c_wrun, g.c_wadj, w);
+            if (c < e0 || c >= e1 || cvpos(g, c) != d) { atomicAdd(&errs[4], 1); continue; }
+            if (w > e0 && d <= wo_dest(g.c_wrun, g.c_wadj, w - 1)) atomicAdd(&errs[4], 1);
             if (!(atomicOr(&seen_c[c >> 5], 1u << (c & 31)) & (1u << (c & 31)))) atomicAdd(&errs[7], 1);
         }
-        for (int c = e0; c < e1 && PDP_TMA; ++c) if ((int)g.cperm[c] + (e0 & ~3) != cqpos(g, c)) atomicAdd(&errs[2], 1);
-        for (int w = e0; w < e1 && PDP_TMA; ++w) if ((int)g.csrc2[w] + (e0 & ~3) != cqpos(g, e0 + (int)g.csrc[w])) atomicAdd(&errs[4], 1);
         const int k = g.cb_k[blk];
         bool uni = (a1 > a0);
         for (int a = a0; a < a1; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != g.cl_ptr[a0 + 1] - g.cl_ptr[a0]) uni = false;
@@ -362,7 +424,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
 }  // namespace
 
 // d_errs: device int32[8], zeroed here.  host_info (nullable): {blocked_ok, nvb, ncb, sv, sc}.
-// Uses the eta[1] message buffer as scratch: call it before pdp_load_state.
+// Uses the eta message buffers as scratch: call it before pdp_load_state.
 extern "C" int pdp_debug_check_layout(pdp_ctx* c, int32_t* d_errs, int32_t* host_info, void* stream_) {
     if (!c || !d_errs) { pdp_set_error("pdp_debug_check_layout: null argument"); return PDP_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -139,16 +139,6 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     const bool frontier = s.ctrl[CTRL_CLOSED] != 0 && !(prm.flags & 4);   // flags bit 2: full-scan closure (A/B, tests)
     int executed = 0;
     if (gtid() == 0) { s.ctrl[CTRL_NEXT_CBLK] = 0; s.ctrl[CTRL_NEXT_VBLK] = 0; s.ctrl[CTRL_LOC_COUNT] = 0; s.ctrl[CTRL_LOC_NEXT] = 0; }
-#if PDP_TMA
-    __shared__ TmaSmem tma_sm;
-    TmaState tma_st;
-    tma_st.parity[0] = tma_st.parity[1] = 0u;
-    if (FAST) {
-        if (threadIdx.x == 0) { mbar_init(&tma_sm.bar[0], 1); mbar_init(&tma_sm.bar[1], 1); fence_mbar_init(); }
-        fence_proxy_async();
-        __syncthreads();
-    }
-#endif
 #ifdef PDP_PHASE_TIMING
 #define GRID_SYNC() do { const long long _g0 = clock64(); grid.sync(); if (threadIdx.x == 0 && A.trace) atomicAdd(&A.trace[7], (int)((clock64() - _g0) >> 10)); } while (0)
 #else
@@ -172,14 +162,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
         if (blocked) {
-#if PDP_TMA
-            tma_clause_pass(A, r, use_mask, smem_dyn, tma_sm, tma_st);
-#elif PDP_PIPELINE
-            pipe_clause_pass(A, r, use_mask, smem_dyn);
-#else
             blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn);
-#endif
-            if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) gen_clause_side<GEN_NAN>(A, r, use_mask);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
@@ -191,17 +174,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
-#if PDP_TMA
-            tma_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn, tma_sm, tma_st);
-#elif PDP_PIPELINE
-            pipe_var_pass(A, r, use_mask, has_prev, em_set, smem_dyn);
-#else
             blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn);
-#endif
-            if (!PDP_STICKY_INLINE && s.ctrl[CTRL_ANY_NAN]) {
-                gen_var_side<GEN_NAN, false>(A, r, use_mask, 0.f);
-                gen_stats<GEN_NAN>(A, w, has_prev, em_set);
-            }
         } else {
             gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
             gen_stats<GEN_ALL>(A, w, has_prev, em_set);
@@ -211,13 +184,13 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gtid() == 0) s.ctrl[CTRL_NEXT_CBLK] = 0;   // the variable pass is over; the next clause pass is a barrier away
         LOOP_T(19);
         // ---- decimate: decisions -> (score, argmax, fix, simplify)
-        decide_phase(A, iter, prm, has_prev, local_ok, blocked && PDP_STICKY_INLINE);   // the staged variants do not score
+        decide_phase(A, iter, prm, has_prev, local_ok, blocked);
         GRID_SYNC();
         LOOP_T(20);
         if (local_ok && s.ctrl[CTRL_CONV + (iter & 1)]) {
             // converged problems one CTA can walk: scoring, arg-max, fix, closure, CNF check, termination, CTA-local
             loc_decimate_all(A, iter, w, prm.pi, prm.check_termination != 0, FAST ? smem_dyn : nullptr,
-                             FAST ? ((PDP_PIPELINE || PDP_TMA) ? PDP_SWEEP_SMEM : SweepCfg<CTAS>::kSmem) : 0);
+                             FAST ? SweepCfg<CTAS>::kSmem : 0);
             LOOP_T(21);
             GRID_SYNC();
             LOOP_T(22);
@@ -305,20 +278,16 @@ int coop_blocks(pdp_ctx* ctx, K kernel) {
 
 }  // namespace
 
-static int32_t* g_trace = nullptr;   // per-process optional trace buffer (tests)
-static int32_t g_trace_cap = 0;
-
+// optional decimation trace of ONE context (tests): the buffer belongs to the caller, the context only keeps the pointer
 extern "C" int pdp_set_trace_buffer(pdp_ctx* ctx, int32_t* d_trace, int32_t capacity_events) {
-    (void)ctx;
-    g_trace = d_trace; g_trace_cap = d_trace ? capacity_events : 0;
+    if (!ctx) { pdp_set_error("pdp_set_trace_buffer: null context"); return PDP_ERR_ARG; }
+    ctx->trace = d_trace; ctx->trace_cap = d_trace ? capacity_events : 0;
     return PDP_OK;
 }
 
-int32_t* pdp_debug_trace_ptr() { return g_trace; }
-
 static KArgs make_args(pdp_ctx* ctx) {
     KArgs A;
-    A.g = ctx->g; A.s = ctx->s; A.trace = g_trace; A.trace_cap = g_trace_cap;
+    A.g = ctx->g; A.s = ctx->s; A.trace = ctx->trace; A.trace_cap = ctx->trace_cap;
     return A;
 }
 
@@ -339,7 +308,7 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
         static bool attr_set[64][2] = {{false}};
         const int two = (ctx->g.ctas == 2) ? 1 : 0;
         void* kern = two ? (void*)k_sp_run<true, false, 2> : (void*)k_sp_run<true, false, 1>;
-        const int smem = (PDP_PIPELINE || PDP_TMA) ? PDP_SWEEP_SMEM : (two ? SweepCfg<2>::kSmem : SweepCfg<1>::kSmem);
+        const int smem = two ? SweepCfg<2>::kSmem : SweepCfg<1>::kSmem;
         const int threads = two ? SweepCfg<2>::kThreads : SweepCfg<1>::kThreads;
         if (!attr_set[ctx->device & 63][two]) {
             PDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -386,65 +355,5 @@ extern "C" int pdp_trace_length(pdp_ctx* ctx, int32_t* host_out, void* stream_) 
     cudaStream_t stream = (cudaStream_t)stream_;
     PDP_CUDA_CHECK(cudaMemcpyAsync(host_out, ctx->s.ctrl + CTRL_TRACE_LEN, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     PDP_CUDA_CHECK(cudaStreamSynchronize(stream));
-    return PDP_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// profiling aid: one phase of the blocked passes in isolation over all blocks (read-only on the solver
-// state: outputs go to a caller-supplied scratch array).  phase 0 = variable load, 1 = variable
-// write-out, 2 = clause load, 3 = clause write-out; variant bit 0 = no shared-memory scatter / gather
-// (sequential shared-memory addresses), bit 1 = skip the 16-bit index tables
-// ------------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(PDP_SWEEP_THREADS, PDP_SWEEP_CTAS_PER_SM)
-k_phase_bench(const __grid_constant__ KArgs A, int phase, int variant, float* scratch) {
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
-    const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* PA = reinterpret_cast<float*>(smem_dyn);
-    float* PB = PA + PDP_BLK_V;
-    const int tid = threadIdx.x;
-    const bool seq = variant & 1, noidx = variant & 2;
-    const bool var_side = phase < 2;
-    const int nblk = var_side ? g.nvb : g.ncb;
-    float acc = 0.f;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int n0 = var_side ? g.vb_ptr[blk] : g.cb_ptr[blk], n1 = var_side ? g.vb_ptr[blk + 1] : g.cb_ptr[blk + 1];
-        if (n1 <= n0) continue;
-        const int e0 = var_side ? g.var_ptr[n0] : g.cl_ptr[n0];
-        const int ne = (var_side ? g.var_ptr[n1] : g.cl_ptr[n1]) - e0;
-        if (phase == 0) {
-            const float* sn = s.eta[0] + e0; const float* so = s.eta[1] + e0; const uint16_t* inv = g.vinv + e0;
-            for (int x = tid; x < ne; x += PDP_SWEEP_THREADS) {
-                const int l = noidx ? x : (seq ? ((inv[x] & 0) + x) : (inv[x] & 0x7fff));
-                PA[l] = sn[x]; PB[l] = so[x];
-            }
-        } else if (phase == 2) {
-            const float* q = s.qu + e0; const uint16_t* inv = g.cinv + e0;
-            for (int x = tid; x < ne; x += PDP_SWEEP_THREADS) {
-                const int l = noidx ? x : (seq ? ((inv[x] & 0) + x) : inv[x]);
-                PA[l] = q[x];
-            }
-        } else {
-            const uint16_t* src = (phase == 1 ? g.vsrc : g.csrc) + e0;
-            const int32_t* dst = (phase == 1 ? g.vdst : g.cdst) + e0;
-            for (int w = tid; w < ne; w += PDP_SWEEP_THREADS) {
-                const int l = noidx ? w : (seq ? ((src[w] & 0) + w) : src[w]);
-                scratch[dst[w]] = PA[l];
-            }
-        }
-        __syncthreads();
-        acc += PA[tid] + PB[tid];
-        __syncthreads();
-    }
-    if (acc == 123.456f) scratch[0] = acc;
-}
-}  // namespace
-
-extern "C" int pdp_debug_phase_bench(pdp_ctx* ctx, int phase, int variant, float* d_scratch, void* stream_) {
-    if (!ctx || !d_scratch || !ctx->g.blocked_ok) { pdp_set_error("pdp_debug_phase_bench: needs a blocked layout and a scratch array of E floats"); return PDP_ERR_ARG; }
-    KArgs A = make_args(ctx);
-    PDP_CUDA_CHECK(cudaFuncSetAttribute(k_phase_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, SweepCfg<1>::kSmem));
-    k_phase_bench<<<ctx->num_sms, PDP_SWEEP_THREADS, SweepCfg<1>::kSmem, (cudaStream_t)stream_>>>(A, phase, variant, d_scratch);
-    PDP_LAUNCH_CHECK(ctx);
     return PDP_OK;
 }

@@ -120,7 +120,7 @@ __global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const
         float P = 0.f, N = 0.f;
         for (int p = beg; p < end; ++p) {
             const int e = g.v_orig[p];
-            float y = L40(1.f - (eta_in ? eta_in[e] : dfs2[2 * (int64_t)e]));
+            float y = L40_1m(eta_in ? eta_in[e] : dfs2[2 * (int64_t)e]);
             if (em) y = y * em[e];
             const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
             P += (neg ? 0.f : 1.f) * y;
@@ -128,7 +128,7 @@ __global__ void k_sp_step_var(pdp_graph g, const float* __restrict__ dfs2, const
         }
         for (int p = beg; p < end; ++p) {
             const int64_t e = g.v_orig[p];
-            float y = L40(1.f - (eta_in ? eta_in[e] : dfs2[2 * e]));
+            float y = L40_1m(eta_in ? eta_in[e] : dfs2[2 * e]);
             if (em) y = y * em[e];
             float u, v, d;
             sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, ext_in ? ext_in[e] : dfs2[2 * e + 1], pi, u, v, d);
@@ -214,7 +214,7 @@ __global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* ou
         const float avi = (float)s.av[i];
         if (rebuild) {
             for (int p = beg; p < end; ++p) {
-                float y = L40(1.f - s.eta[buf ^ 1][g.p_vpos[p]]);
+                float y = L40_1m(s.eta[buf ^ 1][g.p_vpos[p]]);
                 if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
                 const bool neg = (g.v_cedge[p] & PDP_SIGN_BIT) != 0u;
                 P += (neg ? 0.f : 1.f) * y;
@@ -226,7 +226,7 @@ __global__ void k_store_state(pdp_graph g, pdp_state s, float* out_q3, float* ou
             const int qp = g.p_qpos[p], vp = g.p_vpos[p];
             float u = s.qu[qp], v = s.qs[qp], d = s.qd[qp];
             if (rebuild) {
-                float y = L40(1.f - s.eta[buf ^ 1][vp]);
+                float y = L40_1m(s.eta[buf ^ 1][vp]);
                 if (um) y = y * (avi * (float)s.af[g.v_cls[p]]);
                 float uu;
                 sp_var_update(P, N, y, (g.v_cedge[p] & PDP_SIGN_BIT) ? -1.f : 1.f, s.ext[p], pi, uu, v, d);

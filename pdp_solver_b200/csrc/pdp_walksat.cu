@@ -14,7 +14,6 @@
 
 #include "pdp_device.cuh"
 
-int32_t* pdp_debug_trace_ptr();   // pdp_loop.cu (profiling builds)
 
 namespace {
 
@@ -523,7 +522,7 @@ extern "C" int pdp_walksat(pdp_ctx* ctx, int32_t W, float epsilon, int32_t batch
     KArgs A;
     A.g = ctx->g; A.s = ctx->s; A.trace = nullptr; A.trace_cap = 0;
 #ifdef PDP_PHASE_TIMING
-    A.trace = pdp_debug_trace_ptr();
+    A.trace = ctx->trace;
 #endif
     WsArgs wa;
     wa.W = W; wa.epsilon = epsilon; wa.rep = rep; wa.rand_var = d_rand_var; wa.rand_coin = d_rand_coin; wa.seed = seed;

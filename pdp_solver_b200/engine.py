@@ -109,9 +109,6 @@ class Context(object):
         self._check(self._L.pdp_debug_check_layout(self._h, _ptr(errs), ctypes.byref(info), _stream()), "pdp_debug_check_layout")
         return errs.cpu().tolist(), dict(blocked=int(info[0]) & 15, ctas=int(info[0]) >> 4, nvb=int(info[1]), ncb=int(info[2]), sv=int(info[3]), sc=int(info[4]))
 
-    def phase_bench(self, phase, variant, scratch):
-        self._check(self._L.pdp_debug_phase_bench(self._h, int(phase), int(variant), _ptr(scratch), _stream()), "pdp_debug_phase_bench")
-
     def launch_count(self):
         return int(self._L.pdp_launch_count(self._h))
 

@@ -21,7 +21,6 @@ ap.add_argument("--alpha", type=float, default=4.2)
 ap.add_argument("--iterations", type=int, default=10)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--generic", action="store_true")
-ap.add_argument("--phases", action="store_true", help="time the memory phases of the blocked passes in isolation")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -59,22 +58,6 @@ for rep in range(a.repeat):
         ctx._trace.zero_()
     print("E=%d iterations=%d  %.3f ms  %.3f ms/iter  %.2f G edge-updates/s  %.1f GB/s algorithmic" % (
         E, done, ms, ms / max(done, 1), E * done / ms / 1e6, 20.0 * E * done / ms / 1e6))
-
-if a.phases:
-    scratch = torch.empty(E, device=dev)
-    bytes_per_edge = {0: 10.0, 1: 10.0, 2: 6.0, 3: 10.0}
-    names = {0: "var load", 1: "var write-out", 2: "clause load", 3: "clause write-out"}
-    for phase in range(4):
-        for variant in range(4):
-            for rep in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ctx.phase_bench(phase, variant, scratch)
-                e1.record()
-                torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            b = bytes_per_edge[phase] - (2.0 if variant & 2 else 0.0)
-            print("%-16s variant %d: %.3f ms  %.2f TB/s" % (names[phase], variant, ms, b * E / ms / 1e9))
 
 if os.environ.get("PDP_PROF_WALKSAT"):
     n_act = ctx.count_active_variables()
