@@ -27,6 +27,7 @@ struct KArgs {
     pdp_state s;
     int32_t* trace;      // optional decimation trace: triples (iteration, variable, sign)
     int32_t trace_cap;
+    int32_t stagger_c, stagger_v;   // cycles the second CTA of an SM waits at the start of a clause / variable pass
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -72,6 +72,8 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     // block count <= rounds * SMs + 1 with rounds * SMs <= E / (half a block) + SMs (pdp_layout.cu pick_stride;
     // nodes of degree above half a block disable the blocked path)
     const int64_t max_vb = E / (PDP_BLK_V / 4) + 2 * PDP_MAX_SMS + 2, max_cb = E / (PDP_BLK_C / 4) + 2 * PDP_MAX_SMS + 2;
+    g.vb_desc = k.take<pdp_blk>(max_vb + 1);
+    g.cb_desc = k.take<pdp_blk>(max_cb + 1);
     g.vb_ptr = k.take<int32_t>(max_vb + 1);
     g.cb_ptr = k.take<int32_t>(max_cb + 1);
     g.vinv = k.take<uint16_t>(E);
@@ -128,6 +130,7 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     s.stamp_c = k.take<int32_t>(F);
     s.stamp_v = k.take<int32_t>(V);
     s.ctrl = k.take<int32_t>(CTRL_SIZE);
+    s.sm_ctr = k.take<int32_t>(PDP_MAX_SMS);
     s.asg = k.take<int8_t>(V);
     s.ws_true = k.take<int32_t>(F);
     s.ws_deg = k.take<int32_t>(F);

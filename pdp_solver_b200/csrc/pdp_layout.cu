@@ -177,6 +177,31 @@ __global__ void k_clause_block_degree_check(pdp_graph g) {
     }
 }
 
+// block descriptors (after the run tables exist)
+__device__ __forceinline__ int run_of(const uint2* __restrict__ wrun, int w) {
+    const uint2 rb = wrun[w >> 5];
+    return (int)rb.y + __popc(rb.x & (0xffffffffu >> (31 - (w & 31))));
+}
+__global__ void k_fill_desc(pdp_graph g) {
+    GS(t, (int64_t)g.nvb + g.ncb) {
+        const bool var_side = t < g.nvb;
+        const int blk = var_side ? (int)t : (int)t - g.nvb;
+        const int32_t* bp = var_side ? g.vb_ptr : g.cb_ptr;
+        const int32_t* np = var_side ? g.var_ptr : g.cl_ptr;
+        const int32_t* bm = var_side ? g.bvm : g.bfm;
+        const uint2* wr = var_side ? g.v_wrun : g.c_wrun;
+        pdp_blk d;
+        d.n0 = bp[blk]; d.n1 = bp[blk + 1];
+        d.e0 = 0; d.ne = 0; d.b0 = 0; d.b1 = 0; d.run0 = 0; d.nruns = 0;
+        if (d.n1 > d.n0) {
+            d.e0 = np[d.n0]; d.ne = np[d.n1] - d.e0;
+            d.b0 = bm[d.n0]; d.b1 = bm[d.n1 - 1];
+            if (d.ne > 0) { d.run0 = run_of(wr, d.e0); d.nruns = run_of(wr, d.e0 + d.ne - 1) - d.run0 + 1; }
+        }
+        (var_side ? g.vb_desc : g.cb_desc)[blk] = d;
+    }
+}
+
 __global__ void k_identity_layout(pdp_graph g) {
     GS(c, g.E) {
         const int p = g.c_pos[c];
@@ -336,6 +361,8 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         k_wo_pack<<<G1(nwords)>>>(E, KF, nwords, wbits, wcnt, var_side ? g.v_wrun : g.c_wrun, var_side ? g.v_wadj : g.c_wadj);
         LLK();
     }
+    k_fill_desc<<<G1(g.nvb + g.ncb)>>>(g);
+    LLK();
     k_clause_block_degree_init<<<G1(g.ncb)>>>(g);
     LLK();
     k_clause_block_degree_check<<<G1(g.F)>>>(g);

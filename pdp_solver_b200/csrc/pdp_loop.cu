@@ -138,6 +138,17 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     const bool local_ok = A.g.contiguous_problems && rep == 1 && !(prm.flags & 2);
     const bool frontier = s.ctrl[CTRL_CLOSED] != 0 && !(prm.flags & 4);   // flags bit 2: full-scan closure (A/B, tests)
     int executed = 0;
+    int sm_rank = 0;
+    if (FAST && CTAS == 2) {   // rank of this CTA among the CTAs of its SM (the counters are zeroed before the launch)
+        __shared__ int sm_rank_s;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            sm_rank_s = atomicAdd(&s.sm_ctr[smid % PDP_MAX_SMS], 1) & 1;
+        }
+        __syncthreads();
+        sm_rank = sm_rank_s;
+    }
     if (gtid() == 0) { s.ctrl[CTRL_NEXT_CBLK] = 0; s.ctrl[CTRL_NEXT_VBLK] = 0; s.ctrl[CTRL_LOC_COUNT] = 0; s.ctrl[CTRL_LOC_NEXT] = 0; }
 #ifdef PDP_PHASE_TIMING
 #define GRID_SYNC() do { const long long _g0 = clock64(); grid.sync(); if (threadIdx.x == 0 && A.trace) atomicAdd(&A.trace[7], (int)((clock64() - _g0) >> 10)); } while (0)
@@ -162,7 +173,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
         if (blocked) {
-            blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn);
+            blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn, sm_rank);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
@@ -174,7 +185,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
-            blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn);
+            blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn, sm_rank);
         } else {
             gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
             gen_stats<GEN_ALL>(A, w, has_prev, em_set);
@@ -285,9 +296,20 @@ extern "C" int pdp_set_trace_buffer(pdp_ctx* ctx, int32_t* d_trace, int32_t capa
     return PDP_OK;
 }
 
+// default start offsets (cycles) of the second CTA of an SM, see blk_stagger (pdp_sweep.cuh); tunable through
+// PDP_B200_STAGGER_C / PDP_B200_STAGGER_V for experiments
+#ifndef PDP_STAGGER_C
+#define PDP_STAGGER_C 0
+#endif
+#ifndef PDP_STAGGER_V
+#define PDP_STAGGER_V 0
+#endif
 static KArgs make_args(pdp_ctx* ctx) {
     KArgs A;
     A.g = ctx->g; A.s = ctx->s; A.trace = ctx->trace; A.trace_cap = ctx->trace_cap;
+    A.stagger_c = PDP_STAGGER_C; A.stagger_v = PDP_STAGGER_V;
+    if (const char* e = getenv("PDP_B200_STAGGER_C")) A.stagger_c = atoi(e);
+    if (const char* e = getenv("PDP_B200_STAGGER_V")) A.stagger_v = atoi(e);
     return A;
 }
 
@@ -314,6 +336,7 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
             PDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set[ctx->device & 63][two] = true;
         }
+        if (two) PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.sm_ctr, 0, sizeof(int32_t) * PDP_MAX_SMS, stream));
         PDP_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(ctx->num_sms * (two ? 2 : 1)), dim3(threads), args, smem, stream));
     } else if (prm.full_state) {
         int blocks = coop_blocks(ctx, k_sp_run<false, true, 1>);

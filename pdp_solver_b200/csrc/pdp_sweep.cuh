@@ -47,7 +47,7 @@ __device__ __forceinline__ void row_mark(uint32_t* bits, int off, unsigned lanes
 #define PDP_UNROLL_CL4 4   // clause load: four-slot groups per thread in flight
 #endif
 #ifndef PDP_UNROLL_VL4
-#define PDP_UNROLL_VL4 2   // variable load (3 costs a spilled register under the 64-register cap, same speed)
+#define PDP_UNROLL_VL4 3   // variable load (measured: 2 -> 3 is +1 %)
 #endif
 #ifndef PDP_INPASS_SCORE
 #define PDP_INPASS_SCORE 1
@@ -71,13 +71,7 @@ __device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32
 }
 __device__ __forceinline__ uint32_t mnib(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 15u; }
 
-// run index of write-out slot w (global slot index): wrun[w / 32] = {run-start bits of the 32 slots, run starts before them - 1}
-__device__ __forceinline__ int wo_run_of(const uint2* __restrict__ wrun, int w) {
-    const uint2 rb = __ldg(&wrun[w >> 5]);
-    return (int)rb.y + __popc(rb.x & (0xffffffffu >> (31 - (w & 31))));
-}
-
-// geometry of one block of a pass
+// geometry of one block of a pass: one 32-byte descriptor (two 16-byte loads)
 struct BlkGeo {
     int n0, n1;      // node range
     int e0, ne;      // first slot / slots
@@ -85,26 +79,15 @@ struct BlkGeo {
     int run0, nruns; // write-out runs of the block: [run0, run0 + nruns)
     __device__ __forceinline__ bool multi() const { return b0 != b1; }
 };
-__device__ __forceinline__ BlkGeo clause_block(const pdp_graph& g, int blk) {
+__device__ __forceinline__ BlkGeo load_block(const pdp_blk* __restrict__ desc, int blk) {
+    const int4* p = reinterpret_cast<const int4*>(desc + blk);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
     BlkGeo B;
-    B.n0 = g.cb_ptr[blk]; B.n1 = g.cb_ptr[blk + 1];
-    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; B.run0 = 0; B.nruns = 0; return B; }
-    B.e0 = g.cl_ptr[B.n0]; B.ne = g.cl_ptr[B.n1] - B.e0;
-    B.b0 = g.bfm[B.n0]; B.b1 = g.bfm[B.n1 - 1];
-    B.run0 = 0; B.nruns = 0;
-    if (B.ne > 0) { B.run0 = wo_run_of(g.c_wrun, B.e0); B.nruns = wo_run_of(g.c_wrun, B.e0 + B.ne - 1) - B.run0 + 1; }
+    B.n0 = a.x; B.n1 = a.y; B.e0 = a.z; B.ne = a.w; B.b0 = b.x; B.b1 = b.y; B.run0 = b.z; B.nruns = b.w;
     return B;
 }
-__device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) {
-    BlkGeo B;
-    B.n0 = g.vb_ptr[blk]; B.n1 = g.vb_ptr[blk + 1];
-    if (B.n1 <= B.n0) { B.e0 = 0; B.ne = 0; B.b0 = B.b1 = 0; B.run0 = 0; B.nruns = 0; return B; }
-    B.e0 = g.var_ptr[B.n0]; B.ne = g.var_ptr[B.n1] - B.e0;
-    B.b0 = g.bvm[B.n0]; B.b1 = g.bvm[B.n1 - 1];
-    B.run0 = 0; B.nruns = 0;
-    if (B.ne > 0) { B.run0 = wo_run_of(g.v_wrun, B.e0); B.nruns = wo_run_of(g.v_wrun, B.e0 + B.ne - 1) - B.run0 + 1; }
-    return B;
-}
+__device__ __forceinline__ BlkGeo clause_block(const pdp_graph& g, int blk) { return load_block(g.cb_desc, blk); }
+__device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) { return load_block(g.vb_desc, blk); }
 
 // the block's run offsets -> shared memory (when they fit; the write-out reads them from global memory otherwise)
 template <int G, int CAP>
@@ -124,27 +107,34 @@ __device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict
                                                const int32_t* __restrict__ adj, const BlkGeo& B, const float* plane,
                                                const uint32_t* skip, const uint32_t* sticky,
                                                const float* old, float* out) {   // old may alias out (q is updated in place)
-    const int e0 = B.e0, ne = B.ne;
-    const int radj = ADJ_S ? B.run0 : 0;
-    auto one = [&](int l, uint2 rb, int w) {
+    // A warp takes 32 slots that share one word of the run table: slot w = w0 + 32 k + lane with w0 a multiple of 32, so
+    // the lane's bit mask is fixed and the table word is one broadcast load.  Slots before e0 / from e0 + ne on are idle.
+    const int lane = t & 31;
+    const int w0 = (B.e0 & ~31) + 32 * (t >> 5);
+    const int wend = B.e0 + B.ne;
+    const uint32_t lmask = 0xffffffffu >> (31 - lane);
+    adj -= ADJ_S ? B.run0 : 0;
+    auto one = [&](int w, int l, uint2 rb) {
         if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) return;
-        const int run = (int)rb.y + __popc(rb.x & (0xffffffffu >> (31 - (w & 31))));
-        const int d = adj[run - radj] + w;
+        const int d = adj[(int)rb.y + __popc(rb.x & lmask)] + w;
         float v = plane[l];
         if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
         out[d] = v;
     };
-    src += e0;
-    int x = t;
     constexpr int U = PDP_UNROLL_WO;
-    for (; x + (U - 1) * G < ne; x += U * G) {
+    constexpr int STEP = G;      // slots between two iterations of a warp (G / 32 warps x 32 slots)
+    int w = w0 + lane;
+    if (w < B.e0 && w < wend) w += STEP;      // (only the first 32 slots can lie before the region)
+    else if (w < B.e0) return;
+    // the head iteration above is folded in: a lane whose first slot precedes e0 starts one step later
+    for (; w + (U - 1) * STEP < wend; w += U * STEP) {
         int l[U]; uint2 rb[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = src[x + u * G] & SMASK; rb[u] = __ldg(&wrun[(e0 + x + u * G) >> 5]); }
+        for (int u = 0; u < U; ++u) { l[u] = src[w + u * STEP] & SMASK; rb[u] = __ldg(&wrun[(w + u * STEP) >> 5]); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) one(l[u], rb[u], e0 + x + u * G);
+        for (int u = 0; u < U; ++u) one(w + u * STEP, l[u], rb[u]);
     }
-    for (; x < ne; x += G) one(src[x] & SMASK, __ldg(&wrun[(e0 + x) >> 5]), e0 + x);
+    for (; w < wend; w += STEP) one(w, src[w] & SMASK, __ldg(&wrun[w >> 5]));
 }
 // flags: bit 0 = some slots are skipped, bit 1 = some slots are sticky, bit 2 = every slot is sticky
 template <int G, int CAP, unsigned SMASK>
@@ -485,9 +475,19 @@ __device__ __forceinline__ int feed_advance(const int* slot, int& par) {
     return nx;
 }
 
+// Two CTAs share an SM so that one's memory phases (load, write-out: DRAM latency, idle issue slots) overlap the other's
+// node phase (issue bound, no DRAM traffic).  Both leave a grid barrier at the same time, and with equal blocks they
+// would then run the same phase at the same time for the whole pass: the second CTA of an SM starts a pass about half a
+// block period late.
+__device__ __forceinline__ void blk_stagger(int sm_rank, int cycles) {
+    if (sm_rank == 0 || cycles <= 0) return;
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(256);
+}
+
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
 template <int CTAS>
-__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem) {
+__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, int sm_rank) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, BLK_C = Cfg::kBlkC, CAP = Cfg::kAdjCap;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
@@ -502,6 +502,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     __shared__ int sm_feed[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
+    if (CTAS == 2) blk_stagger(sm_rank, A.stagger_c);
     for (int blk = blockIdx.x; blk < g.ncb; blk = feed_advance(sm_feed, par)) {
         if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_CBLK], sm_feed, par, blk);
         const BlkGeo B = clause_block(g, blk);
@@ -526,7 +527,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
 // [buffer r], and q(t) [C-layout, in place] from eta(t-1)
 template <int CTAS>
-__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem) {
+__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem, int sm_rank) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, BLK_V = Cfg::kBlkV, BLK_C = Cfg::kBlkC, CAP = Cfg::kAdjCap;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
@@ -541,15 +542,20 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     const float* __restrict__ eo = s.eta[r];
     const int tid = threadIdx.x;
     KeyedReducer<StatAcc> red;
+    int acc_key = -1;
     __shared__ int sm_feed[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
+    if (CTAS == 2) blk_stagger(sm_rank, A.stagger_v);
     for (int blk = blockIdx.x; blk < g.nvb; blk = feed_advance(sm_feed, par)) {
         if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_VBLK], sm_feed, par, blk);
         const BlkGeo B = var_block(g, blk);
         if (B.n1 <= B.n0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
         const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
+        // statistics of single-problem blocks: the per-thread accumulators run across the blocks of one problem and are
+        // merged block-wide when the CTA moves on to another problem (and at the end of the pass)
+        if (!B.multi() && acc_key != B.b0) { if (acc_key >= 0) red.finish(s); acc_key = B.b0; }
         for (int i = tid; i < BLK_V / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }   // (padded slots: the whole plane)
         if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
@@ -574,7 +580,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
         ph_write_out<NT, CAP, 0x7fffu>(tid, g.vinv, g.v_wrun, g.v_wadj, adj_s, B, PA, skip, sm_any_skip, s.qu, sticky, s.qu);
-        red.finish(s);   // block-level merge of the statistics; its barriers also fence the planes
         PHASE_ADD(5);
     }
+    red.finish(s);
 }
