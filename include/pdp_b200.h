@@ -69,6 +69,14 @@ int pdp_reset(pdp_ctx* ctx, void* stream);
 /* SatCNFEvaluator.forward, reference pdp/nn/util.py:210-236.  d_pred [V] -> d_solved [B], d_n_unsat [B] */
 int pdp_cnf_eval(pdp_ctx* ctx, const float* d_pred, float* d_solved, float* d_n_unsat, void* stream);
 
+/* the same without a context, straight on the caller's edge list (any edge order): the form `SatCNFEvaluator` is called in
+ * by `_post_process_predictions` (reference pdp/trainer.py:125-148) on batches no solver context exists for.
+ * d_graph_map int32 [2,E], d_edge_feature [E], d_bfm [F]; d_scratch: pdp_cnf_eval_edges_scratch_bytes(F, B) bytes. */
+size_t pdp_cnf_eval_edges_scratch_bytes(int64_t F, int64_t B);
+int pdp_cnf_eval_edges(const int32_t* d_graph_map, const float* d_edge_feature, const int32_t* d_batch_function_map,
+                       int64_t E, int64_t V, int64_t F, int64_t B, const float* d_pred,
+                       float* d_solved, float* d_n_unsat, void* d_scratch, void* stream);
+
 /* _compute_energy, reference pdp/nn/solver.py:486-496.  d_assignment [V] in {-1,0,1}, d_av [V],
  * d_af [F] float 0/1 -> d_energy [B], d_unsat_fn [F] */
 int pdp_energy(pdp_ctx* ctx, const float* d_assignment, const float* d_av, const float* d_af,
@@ -114,7 +122,8 @@ int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float* d_prop_fs2
 int pdp_load_state_const(pdp_ctx* ctx, float qu, float qs, float qd, float eta, float ext, void* stream);
 /* writes the current message state in the caller's edge order: out_q3 [E,3], out_fs2 [E,2] */
 int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* stream);
-/* overwrite / read the SATProblem masks (float 0/1 like the reference's tensors); NULL = skip */
+/* overwrite / read the SATProblem masks (float 0/1 like the reference's tensors); NULL = skip.  Node masks installed this
+ * way count as the decimator's edge mask from the next sweep on (reference pdp/nn/solver.py:370-374). */
 int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af, const float* d_solution, void* stream);
 int pdp_get_masks(pdp_ctx* ctx, float* d_av, float* d_af, float* d_solution, float* d_is_sat,
                   uint8_t* d_active, float* d_edge_mask, void* stream);

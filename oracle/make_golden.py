@@ -585,6 +585,10 @@ def main():
         gen_replicated("rep_b3_a", cnfgen.random_batch(5, 30, 3, 3.7, 61), 120, 25, 0.5, 9, 3, t_max=30)
         gen_replicated("rep_b2_b", cnfgen.mixed_batch([(30, 3, 3.9), (20, 5, 14.0), (25, 3, 3.0)], 62), 100, 30, 0.4, 10, 2, t_max=25)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "replicated8":   # BASELINE.json configs[4] in miniature: -b 8 on mixed 3-/5-SAT
+        gen_replicated("rep_b8_mixed", cnfgen.mixed_batch([(40, 3, 4.2), (24, 5, 18.0), (60, 3, 4.0), (16, 5, 16.0), (30, 3, 4.2)], 63),
+                       120, 40, 0.5, 11, 8, t_max=30)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "neural":
         gen_neural("neural_pndnp_a", "p-nd-np", cnfgen.random_batch(4, 20, 3, 3.8, 51), 12, 5, (24, 16, 16, 8, 8))
         gen_neural("neural_pndnp_b", "p-nd-np", ragged_batch(52), 8, 6, (20, 12, 12, 6, 6))

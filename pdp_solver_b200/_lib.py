@@ -34,6 +34,8 @@ SIGNATURES = {
     "pdp_destroy": (ctypes.c_int, [P]),
     "pdp_reset": (ctypes.c_int, [P, P]),
     "pdp_cnf_eval": (ctypes.c_int, [P, P, P, P, P]),
+    "pdp_cnf_eval_edges_scratch_bytes": (ctypes.c_size_t, [I64, I64]),
+    "pdp_cnf_eval_edges": (ctypes.c_int, [P, P, P, I64, I64, I64, I64, P, P, P, P, P]),
     "pdp_energy": (ctypes.c_int, [P, P, P, P, P, P, P]),
     "pdp_energy_diff": (ctypes.c_int, [P, P, P, P, P, P]),
     "pdp_sp_step": (ctypes.c_int, [P, P, P, P, P, P, P, F32, P, P, P]),

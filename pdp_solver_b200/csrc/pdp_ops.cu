@@ -243,7 +243,12 @@ __global__ void k_set_masks(pdp_graph g, pdp_state s, const float* av, const flo
         if (i < g.V) { if (av) s.av[i] = (av[i] != 0.f) ? 1 : 0; if (sol) s.sol[i] = sol[i]; }
         if (i < g.F && af) s.af[i] = (af[i] != 0.f) ? 1 : 0;
         if (i < g.B) { s.masked[i] = 1; s.dirty[i] = 1; }
-        if (i == 0) { s.ctrl[CTRL_ANY_DIRTY] = 1; s.ctrl[CTRL_CLOSED] = 0; s.ctrl[CTRL_NATIVE] = 0; }   // masks from outside: closure unknown
+        if (i == 0) {
+            s.ctrl[CTRL_ANY_DIRTY] = 1; s.ctrl[CTRL_CLOSED] = 0; s.ctrl[CTRL_NATIVE] = 0;   // masks from outside: closure unknown
+            // node masks installed by the caller are part of the decimator state: the next sweep multiplies by the edge
+            // mask they imply, as the reference does from the iteration after a mask changed (solver.py:370-374)
+            if (av || af) { s.ctrl[CTRL_USE_MASK] = 1; s.ctrl[CTRL_EM_SET] = 1; }
+        }
     }
 }
 
@@ -335,6 +340,53 @@ extern "C" int pdp_cnf_eval(pdp_ctx* ctx, const float* d_pred, float* d_solved, 
     if (ctx->g.F > 0) { k_cnf_eval_count<<<GRID(ctx->g.F)>>>(ctx->g, ctx->s, d_pred); PDP_LAUNCH_CHECK(ctx); }
     k_cnf_eval_finish<<<GRID(ctx->g.B)>>>(ctx->g, ctx->s, d_solved, d_n_unsat);
     PDP_LAUNCH_CHECK(ctx);
+    return PDP_OK;
+}
+
+// ---- context-free CNF check on the caller's edge list (SatCNFEvaluator called on a batch nobody built a context for)
+namespace {
+__global__ void k_edges_mark_sat(const int32_t* __restrict__ evar, const int32_t* __restrict__ ecls, const float* __restrict__ sign,
+                                 const float* __restrict__ pred, int64_t E, int64_t V, int64_t F, uint8_t* clause_sat, int32_t* bad) {
+    for (int64_t e = gtid(); e < E; e += gthreads()) {
+        const int32_t v = evar[e], a = ecls[e];
+        if (v < 0 || v >= V || a < 0 || a >= F) { *bad = 1; continue; }
+        if (literal_true(sign[e], pred[v])) clause_sat[a] = 1;      // util.py:221-228 (benign race: every writer stores 1)
+    }
+}
+__global__ void k_edges_count_unsat(const uint8_t* __restrict__ clause_sat, const int32_t* __restrict__ bfm, int64_t F, int64_t B,
+                                    int32_t* n_unsat, int32_t* bad) {
+    for (int64_t a = gtid(); a < F; a += gthreads()) {
+        const int32_t b = bfm[a];
+        if (b < 0 || b >= B) { *bad = 1; continue; }
+        if (!clause_sat[a]) atomicAdd(&n_unsat[b], 1);
+    }
+}
+__global__ void k_edges_finish(const int32_t* __restrict__ n_unsat, int64_t B, float* solved, float* nun) {
+    for (int64_t b = gtid(); b < B; b += gthreads()) { nun[b] = (float)n_unsat[b]; solved[b] = n_unsat[b] == 0 ? 1.f : 0.f; }
+}
+}  // namespace
+
+extern "C" size_t pdp_cnf_eval_edges_scratch_bytes(int64_t F, int64_t B) {
+    return (size_t)((F + 3) / 4 * 4) + sizeof(int32_t) * (size_t)(B + 1);
+}
+
+extern "C" int pdp_cnf_eval_edges(const int32_t* d_graph_map, const float* d_edge_feature, const int32_t* d_bfm,
+                                  int64_t E, int64_t V, int64_t F, int64_t B, const float* d_pred,
+                                  float* d_solved, float* d_n_unsat, void* d_scratch, void* stream_) {
+    if (E < 0 || V < 0 || F < 0 || B < 0 || (B > 0 && (!d_solved || !d_n_unsat)) || !d_scratch || (E > 0 && (!d_graph_map || !d_edge_feature || !d_pred)) ||
+        (F > 0 && !d_bfm)) { pdp_set_error("pdp_cnf_eval_edges: bad argument"); return PDP_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, nsm = 148;
+    PDP_CUDA_CHECK(cudaGetDevice(&dev));
+    PDP_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    uint8_t* clause_sat = reinterpret_cast<uint8_t*>(d_scratch);
+    int32_t* n_unsat = reinterpret_cast<int32_t*>(clause_sat + (F + 3) / 4 * 4);
+    int32_t* bad = n_unsat + B;
+    PDP_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, pdp_cnf_eval_edges_scratch_bytes(F, B), stream));
+    if (E > 0) k_edges_mark_sat<<<pdp_grid(E, 256, nsm), 256, 0, stream>>>(d_graph_map, d_graph_map + E, d_edge_feature, d_pred, E, V, F, clause_sat, bad);
+    if (F > 0) k_edges_count_unsat<<<pdp_grid(F, 256, nsm), 256, 0, stream>>>(clause_sat, d_bfm, F, B, n_unsat, bad);
+    if (B > 0) k_edges_finish<<<pdp_grid(B, 256, nsm), 256, 0, stream>>>(n_unsat, B, d_solved, d_n_unsat);
+    PDP_CUDA_CHECK(cudaGetLastError());
     return PDP_OK;
 }
 

@@ -76,17 +76,38 @@ class PerceptronTanh(nn.Module):
 
 class SatCNFEvaluator(nn.Module):
     """Verdict and number of unsatisfied clauses per problem for a variable prediction
-    (reference util.py:203-236).  Integer-exact: a literal is true iff s*p + (1-s)/2 > 0.5 in fp32."""
+    (reference util.py:203-236).  Integer-exact: a literal is true iff s*p + (1-s)/2 > 0.5 in fp32.
+    Stateless: one pass over the caller's edge list (`pdp_cnf_eval_edges`), no solver context, nothing cached."""
 
     def __init__(self, device):
         super(SatCNFEvaluator, self).__init__()
         self._device = device
-        self._cache = None
 
     def forward(self, variable_prediction, graph_map, batch_variable_map, batch_function_map, edge_feature, meta_data):
-        key = (graph_map.data_ptr(), batch_variable_map.data_ptr(), batch_function_map.data_ptr(),
-               edge_feature.data_ptr(), tuple(graph_map.shape))
-        if self._cache is None or self._cache[0] != key:
-            self._cache = (key, Context(graph_map, batch_variable_map, batch_function_map, edge_feature))
-        solved, n_unsat = self._cache[1].cnf_eval(variable_prediction)
-        return solved.unsqueeze(1), n_unsat.unsqueeze(1)
+        return cnf_eval_edges(variable_prediction, graph_map, batch_variable_map, batch_function_map, edge_feature)
+
+
+def cnf_eval_edges(variable_prediction, graph_map, batch_variable_map, batch_function_map, edge_feature, batch_size=None):
+    import ctypes
+    from .. import _lib
+    dev = graph_map.device
+    if dev.type != "cuda":
+        raise _lib.PdpError("SatCNFEvaluator expects CUDA tensors (got %s); there is no CPU fallback" % dev)
+    L = _lib.load()
+    gm = graph_map.to(torch.int32).contiguous()
+    bfm = batch_function_map.to(torch.int32).contiguous()
+    ef = edge_feature.to(torch.float32).reshape(-1).contiguous()
+    pred = variable_prediction.to(torch.float32).reshape(-1).contiguous()
+    E, V, F = int(gm.shape[1]), int(batch_variable_map.shape[0]), int(bfm.shape[0])
+    if batch_size is None:
+        batch_size = int(batch_variable_map.max().item()) + 1 if V > 0 else 0
+    B = int(batch_size)
+    with torch.cuda.device(dev):
+        solved = torch.empty(B, dtype=torch.float32, device=dev)
+        n_unsat = torch.empty(B, dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(int(L.pdp_cnf_eval_edges_scratch_bytes(F, B)), 4), dtype=torch.uint8, device=dev)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else ctypes.c_void_p(0)
+        _lib.check(L.pdp_cnf_eval_edges(ptr(gm), ptr(ef), ptr(bfm), E, V, F, B, ptr(pred), ptr(solved), ptr(n_unsat),
+                                        ctypes.c_void_p(scratch.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "pdp_cnf_eval_edges", L)
+    return solved.unsqueeze(1), n_unsat.unsqueeze(1)
