@@ -21,6 +21,27 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_own_device(cls):
+    """Every public method of Context runs with the context's device current (the library launches on the current
+    device, on torch's current stream of that device): a context may be used while another GPU is current, e.g. by the
+    per-device worker threads of the multi-GPU predict path."""
+    import functools
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(self, *a, **k):
+            if torch.cuda.current_device() == self.device.index:
+                return fn(self, *a, **k)
+            with torch.cuda.device(self.device):
+                return fn(self, *a, **k)
+        return inner
+
+    for name, fn in list(vars(cls).items()):
+        if callable(fn) and not name.startswith("_"):
+            setattr(cls, name, wrap(fn))
+    return cls
+
+
 def _f32(t, device):
     if t is None:
         return None
@@ -31,6 +52,7 @@ def check(rc, what=""):
     _lib.check(rc, what)
 
 
+@_on_own_device
 class Context(object):
     """Factor graph of a batch + the mutable solver state (SATProblem and SequentialDecimator state of the
     reference, pdp/nn/solver.py:19-54 and pdp/nn/pdp_decimate.py:109-120)."""

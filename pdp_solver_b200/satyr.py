@@ -41,6 +41,8 @@ def build_parser():
     parser.add_argument("-d", "--dimacs", help="The input folder contains DIMACS files", action="store_true")
     parser.add_argument("-s", "--random_seed", help="Random seed", type=int, default=int(datetime.now().microsecond))
     parser.add_argument("-o", "--output", help="The JSON output file", default="")
+    parser.add_argument("-g", "--gpus", help="Number of GPUs the input segments are sharded over (default: all visible; "
+                        "not a reference option)", type=int, default=0)
     return parser
 
 

@@ -103,3 +103,35 @@ def test_cli_dimacs_input(tmp_path):
 def test_cli_refuses_cpu_mode(tmp_path):
     with pytest.raises(RuntimeError):
         _run_cli(tmp_path, ["-c"])
+
+
+def _many_rows_file(tmp_path, count, seed):
+    "a compact-JSON file of `count` small random 3-SAT problems (ids p0..), written like the reference reads them"
+    from pdp_solver_b200 import cnfgen
+    rng = np.random.Generator(np.random.PCG64(seed))
+    path = str(tmp_path / "many.json")
+    with open(path, "w") as f:
+        for j in range(count):
+            n = int(rng.integers(30, 90))
+            var, sgn = cnfgen.random_ksat(n, 3, 3.9, rng)          # [m, 3] each, clause-major
+            m = var.shape[0]
+            lits = [int((v + 1) * s) for v, s in zip(var.reshape(-1).tolist(), sgn.reshape(-1).tolist())]
+            cls = [c + 1 for c in range(m) for _ in range(3)]
+            f.write(json.dumps([[n, m], lits, cls, 0, ["p%d" % j]]) + "\n")
+    return path
+
+
+def test_cli_segments_are_device_independent(tmp_path):
+    """The output does not depend on how the DynamicBatchDivider segments are spread over GPUs: with a small memory limit
+    the input falls into many segments; `-g 1` and (when the box has them) `-g 2` give the same bytes, WalkSAT's random
+    draws included, and so does a second run with `-g 1`."""
+    import torch
+    path = _many_rows_file(tmp_path, 60, 5)
+    args = ["-l", "6000", "-w", "50", "-e", "0.5", "-s", "11"]
+    one = _run_cli(tmp_path, args + ["-g", "1"], test_path=path, iters="200")
+    again = _run_cli(tmp_path, args + ["-g", "1"], test_path=path, iters="200")
+    assert len(one) == 60 and one == again
+    assert sorted(json.loads(l)["ID"] for l in one) == sorted("p%d" % j for j in range(60))   # (the divider sorts by size)
+    if torch.cuda.device_count() >= 2:
+        two = _run_cli(tmp_path, args + ["-g", "2"], test_path=path, iters="200")
+        assert two == one
