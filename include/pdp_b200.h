@@ -127,6 +127,9 @@ int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* strea
 int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af, const float* d_solution, void* stream);
 int pdp_get_masks(pdp_ctx* ctx, float* d_av, float* d_af, float* d_solution, float* d_is_sat,
                   uint8_t* d_active, float* d_edge_mask, void* stream);
+/* installs the per-problem active mask (uint8 [B]) a caller's own termination callback produced between two
+ * one-iteration pdp_sp_run calls (reference pdp/nn/solver.py:376-384) */
+int pdp_set_active(pdp_ctx* ctx, const uint8_t* d_active, void* stream);
 int pdp_get_problem_flags(pdp_ctx* ctx, uint32_t* d_flags, int32_t* d_counters, int32_t* d_freeze_iter, void* stream);
 
 /* SATProblem.simplify / set_variables, reference pdp/nn/solver.py:180-285 (unit propagation and
@@ -144,7 +147,9 @@ typedef struct {
     int32_t full_state;         /* 1 = also keep q_s and q_* (the [E,3] state) exact    */
     int32_t flags;              /* bit 0: use the generic (thread per node) passes, not the blocked ones;
                                    bit 1: grid-wide decimation phases only (no CTA-local decimation);
-                                   bit 2: full-scan UP / peel closure in those phases (not the frontier lists) */
+                                   bit 2: full-scan UP / peel closure in those phases (not the frontier lists);
+                                   bit 3: check_termination = 1 keeps the active mask (trivial-survey test, early exit)
+                                          but leaves the solved-problem check to the caller (pdp_set_active) */
 } pdp_sp_params;
 
 /* PropagatorDecimatorSolverBase._forward_core for the p-d-p model, reference

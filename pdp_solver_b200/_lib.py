@@ -47,6 +47,7 @@ SIGNATURES = {
     "pdp_store_state": (ctypes.c_int, [P, P, P, P]),
     "pdp_set_masks": (ctypes.c_int, [P, P, P, P, P]),
     "pdp_get_masks": (ctypes.c_int, [P, P, P, P, P, P, P, P]),
+    "pdp_set_active": (ctypes.c_int, [P, P, P]),
     "pdp_get_problem_flags": (ctypes.c_int, [P, P, P, P, P]),
     "pdp_simplify": (ctypes.c_int, [P, P]),
     "pdp_set_variables": (ctypes.c_int, [P, P, P]),

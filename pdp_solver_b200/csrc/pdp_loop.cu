@@ -228,7 +228,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         ++executed;
         // ---- predict + termination: IdentityPredictor/_update_solution leave _solution as is
         if (prm.check_termination) {
-            if (s.ctrl[CTRL_ANY_DIRTY]) {
+            if (s.ctrl[CTRL_ANY_DIRTY] && !(prm.flags & 8)) {   // flags bit 3: the caller runs its own termination check
                 LOOP_T(23);
                 cnf_count_dirty(A);
                 GRID_SYNC();

@@ -498,6 +498,27 @@ extern "C" int pdp_set_masks(pdp_ctx* ctx, const float* d_av, const float* d_af,
     return PDP_OK;
 }
 
+// active_mask of _forward_core as a caller's termination callback left it (reference solver.py:376-384)
+namespace {
+__global__ void k_set_active(pdp_graph g, pdp_state s, const uint8_t* __restrict__ active) {
+    int n = 0;
+    for (int64_t b = gtid(); b < g.B; b += gthreads()) {
+        const uint8_t a = active[b] ? 1 : 0;
+        if (s.active[b] && !a) s.freeze_iter[b] = s.ctrl[CTRL_ITER];
+        if (!s.active[b] && a) s.freeze_iter[b] = -1;
+        n += (int)a - (int)s.active[b];
+        s.active[b] = a;
+    }
+    if (n) atomicAdd(&s.ctrl[CTRL_NUM_ACTIVE], n);
+}
+}  // namespace
+extern "C" int pdp_set_active(pdp_ctx* ctx, const uint8_t* d_active, void* stream_) {
+    NEED(ctx, d_active || ctx->g.B == 0, "pdp_set_active: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (ctx->g.B > 0) { k_set_active<<<GRID(ctx->g.B)>>>(ctx->g, ctx->s, d_active); PDP_LAUNCH_CHECK(ctx); }
+    return PDP_OK;
+}
+
 extern "C" int pdp_get_masks(pdp_ctx* ctx, float* d_av, float* d_af, float* d_sol, float* d_is_sat, uint8_t* d_active,
                              float* d_em, void* stream_) {
     NEED(ctx, true, "");

@@ -210,6 +210,10 @@ class Context(object):
         s = None if solution is None else _f32(solution, self.device).reshape(-1)
         self._check(self._L.pdp_set_masks(self._h, _ptr(a), _ptr(f), _ptr(s), _stream()), "pdp_set_masks")
 
+    def set_active(self, active):
+        a = active.to(device=self.device, dtype=torch.uint8).reshape(-1).contiguous()
+        self._check(self._L.pdp_set_active(self._h, _ptr(a), _stream()), "pdp_set_active")
+
     def get_masks(self, edge_mask=False):
         av, af, sol = self._new(self.V), self._new(self.F), self._new(self.V)
         is_sat = self._new(self.B)
@@ -253,13 +257,14 @@ class Context(object):
         return self._trace[: n.value].cpu()
 
     def sp_run(self, iterations, tolerance, t_max, check_termination=True, batch_replication=1, pi=0.0,
-               full_state=False, sync=False, generic=False, grid_decimation=False, full_closure=False):
+               full_state=False, sync=False, generic=False, grid_decimation=False, full_closure=False,
+               caller_terminates=False):
         """T iterations of propagate/decimate/predict in one persistent kernel.  Returns the device
         int32 tensor holding the number of executed iterations (or the int when sync=True).
         generic=True forces the thread-per-node passes (A/B against the blocked shared-memory passes);
         grid_decimation=True the grid-wide decimation phases; full_closure=True their full-scan UP / peel closure."""
         prm = SpParams(int(iterations), float(tolerance), int(t_max), float(pi), 1 if check_termination else 0,
-                       int(batch_replication), 1 if full_state else 0, (1 if generic else 0) | (2 if grid_decimation else 0) | (4 if full_closure else 0) | int(os.environ.get("PDP_B200_SP_FLAGS", "0"), 0))
+                       int(batch_replication), 1 if full_state else 0, (1 if generic else 0) | (2 if grid_decimation else 0) | (4 if full_closure else 0) | (8 if caller_terminates else 0) | int(os.environ.get("PDP_B200_SP_FLAGS", "0"), 0))
         self._timed("sp_run", lambda: self._check(
             self._L.pdp_sp_run(self._h, ctypes.byref(prm), _ptr(self._iters), _stream()), "pdp_sp_run"))
         if sync:

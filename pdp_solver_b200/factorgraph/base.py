@@ -72,8 +72,12 @@ class FactorGraphTrainerBase(object):
     def _segment_seed(self, k):
         return (int(self._config.get("random_seed", 0)) + 1000003 * k) % (2 ** 63)
 
-    def _predict_epoch(self, batches, post_processor, batch_replication, file):
+    def _predict_epoch(self, batches, post_processor, batch_replication, file, segment_stream=None):
         def segments():
+            if segment_stream is not None:        # lazily collated segments (FactorGraphDataset.segments)
+                for k, seg in enumerate(segment_stream):
+                    yield k, tuple(seg)
+                return
             k = 0
             for data in batches:
                 for i in range(len(data[0])):
@@ -194,8 +198,8 @@ class FactorGraphTrainerBase(object):
             max_cache_size=self._config.get("max_cache_size", 100000), batch_replication=batch_replication, rows=rows)
         if import_path_base is not None:
             self._load(import_path_base)
-        self._predict_epoch(dataset.batches(self._config["batch_size"], pin=True), post_processor, batch_replication,
-                            out_file)
+        self._predict_epoch(None, post_processor, batch_replication, out_file,
+                            segment_stream=dataset.segments(self._config["batch_size"], pin=True))
         for dev in self._devices:
             torch.cuda.synchronize(dev)
         duration = time.time() - start_time

@@ -193,6 +193,26 @@ class FactorGraphDataset(object):
         cols = [collate_segment([input_data[j] for j in ind], pin) for ind in segs]
         return tuple([c[k] for c in cols] for k in range(7))
 
+    def segments(self, batch_size, pin=False):
+        """The same segments as `batches`, one at a time and collated only when asked for: the multi-GPU predict path
+        hands them to the devices while later ones are still being built."""
+        n = len(self)
+        fh = None if self._rows is not None else open(self._input_file, "rb")
+        try:
+            for lo in range(0, n, batch_size):
+                if self._rows is not None:
+                    rows = self._rows[lo:lo + batch_size]
+                else:
+                    rows = []
+                    for pos, size in self._offsets[lo:lo + batch_size]:
+                        fh.seek(pos)
+                        rows.append(parse_row(fh.read(size)))
+                for ind in self.batch_divider.divide_indices([r[2].shape[1] for r in rows]):
+                    yield collate_segment([rows[j] for j in ind], pin)
+        finally:
+            if fh is not None:
+                fh.close()
+
     def batches(self, batch_size, pin=False):
         "what the reference's DataLoader(batch_size, shuffle=False, collate_fn=dag_collate_fn) yields"
         n = len(self)

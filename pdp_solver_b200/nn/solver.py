@@ -158,15 +158,11 @@ class _DeferredState(object):
 
 
 def _is_standard_termination(cb):
-    """The reference's trainer callback (trainer.py:150-162) -- or anything tagged as equivalent -- is
-    evaluated inside the persistent kernel; any other callable is honoured by stepping."""
-    if cb is None:
-        return False
-    if getattr(cb, "_pdp_standard_termination", False):
-        return True
-    fn = getattr(cb, "__func__", cb)
-    return getattr(fn, "__name__", "") == "_check_recurrence_termination" and \
-        hasattr(getattr(cb, "__self__", None), "_cnf_evaluator")
+    """Only a callable explicitly tagged `_pdp_standard_termination` -- the trainer's own
+    `_check_recurrence_termination` (reference trainer.py:150-162) carries the tag on its function object, so an
+    override in a subclass does not -- is evaluated inside the persistent kernel; any other callable is called after
+    every iteration, as the reference does."""
+    return cb is not None and bool(getattr(cb, "_pdp_standard_termination", False))
 
 
 class PropagatorDecimatorSolverBase(nn.Module):
@@ -271,9 +267,21 @@ class PropagatorDecimatorSolverBase(nn.Module):
             self.last_iterations = ctx.sp_run(iteration_num, dec._tolerance, dec._t_max,
                                               check_termination is not None, b, self._propagator.pi_value())
         else:
-            raise NotImplementedError(
-                "custom check_termination callbacks are not supported by the fused loop; tag the callable with "
-                "`_pdp_standard_termination = True` if it implements trainer._check_recurrence_termination semantics")
+            # an arbitrary callback (reference solver.py:376-384): one iteration per launch, the callback sees the
+            # active mask and the current solution and its verdict goes back into the context
+            done = 0
+            for _ in range(int(iteration_num)):
+                if int(ctx.sp_run(1, dec._tolerance, dec._t_max, True, b, self._propagator.pi_value(), sync=True,
+                                  caller_terminates=True)) == 0:
+                    break
+                done += 1
+                m = ctx.get_masks()
+                active_mask = m["active"].unsqueeze(1)
+                check_termination(active_mask, (m["sol"].unsqueeze(1), None), sat_problem)
+                ctx.set_active(active_mask[:, 0])
+                if int(active_mask.sum().item()) <= 0:
+                    break
+            self.last_iterations = torch.tensor([done], dtype=torch.int32, device=ctx.device)
         sat_problem._edge_mask_set = iteration_num > 0
         # the final message states are exported on first use (the predict path never looks at them)
         state = _DeferredState(ctx)

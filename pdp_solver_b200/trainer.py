@@ -121,3 +121,8 @@ class SatFactorGraphTrainer(FactorGraphTrainerBase):
         if rep > 1:
             ok = ok.reshape(rep, -1).any(0).repeat(rep)
         active[(active[:, 0] != 0) & ok, 0] = 0
+
+
+# the solvers evaluate exactly this method inside the persistent kernel (nn/solver.py _is_standard_termination); an
+# override in a subclass is a different function object without the tag and is called iteration by iteration
+SatFactorGraphTrainer._check_recurrence_termination._pdp_standard_termination = True

@@ -921,3 +921,55 @@ def test_stateless_cnf_evaluator():
         s2, u2 = ctx.cnf_eval(T(pred))
         assert maxdiff(C(s1[:, 0]), s_ref) == 0 and maxdiff(C(u1[:, 0]), u_ref) == 0
         assert maxdiff(C(s2), s_ref) == 0 and maxdiff(C(u2), u_ref) == 0
+
+
+def test_custom_termination_callback_is_honoured():
+    """A check_termination callable that is not the trainer's own method is called after every iteration (reference
+    solver.py:376-384) instead of being replaced by the in-kernel check: a re-implementation of the trainer's rule gives
+    the fused path's result bit for bit, a no-op callback (the base class's, reference base.py:303-305) keeps every
+    problem running for all T iterations, and a subclass override of the trainer's method is not mistaken for it."""
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.nn import solver as pdp_solver
+    from pdp_solver_b200.nn.util import SatCNFEvaluator
+    from pdp_solver_b200.trainer import SatFactorGraphTrainer
+    batch = cnfgen.random_batch(24, 60, 3, 3.7, 19)
+    gm, bvm, bfm, ef = T(batch[0]), T(batch[1]), T(batch[2]), T(batch[3]).unsqueeze(1)
+    model = pdp_solver.SurveyPropagatorSolver(dev(), "p-d-p", tolerance=0.02, t_max=30, local_search_iterations=0, epsilon=0.5)
+    ev = SatCNFEvaluator(dev())
+    calls = {"n": 0}
+
+    def own_rule(active, prediction, sat_problem):       # trainer.py:150-162 restated by a caller
+        calls["n"] += 1
+        out, _ = ev(prediction[0], sat_problem._graph_map, sat_problem._batch_variable_map, sat_problem._batch_function_map,
+                    sat_problem._edge_feature, None)
+        active[(active[:, 0] != 0) & (out[:, 0] > 0.5), 0] = 0
+
+    def noop(active, prediction, sat_problem):
+        calls["n"] += 1
+
+    def tagged(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    tagged._pdp_standard_termination = True
+
+    def run(cb, T_iters=120):
+        torch.manual_seed(3)
+        init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=1)
+        (pred, _), _ = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                             meta_data=None, is_training=False, iteration_num=T_iters, check_termination=cb, batch_replication=1)
+        m = model.last_problem._ctx.get_masks()
+        return C(pred), C(m["av"]), C(m["active"]), int(model.last_iterations.item())
+
+    fused = run(tagged)
+    stepped = run(own_rule)
+    assert calls["n"] == stepped[3] and stepped[3] == fused[3]
+    for a, b in zip(fused[:3], stepped[:3]):
+        assert np.array_equal(a, b)
+    calls["n"] = 0
+    free = run(noop, 40)
+    assert calls["n"] == 40 and free[3] == 40
+
+    class Sub(SatFactorGraphTrainer):
+        def _check_recurrence_termination(self, active, prediction, sat_problem):
+            pass
+    assert pdp_solver._is_standard_termination(SatFactorGraphTrainer._check_recurrence_termination)
+    assert not pdp_solver._is_standard_termination(Sub._check_recurrence_termination)
