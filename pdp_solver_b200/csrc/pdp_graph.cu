@@ -76,8 +76,10 @@ void carve(pdp_ctx* c, Carver& k, int64_t E, int64_t V, int64_t F, int64_t B) {
     g.cb_desc = k.take<pdp_blk>(max_cb + 1);
     g.vb_ptr = k.take<int32_t>(max_vb + 1);
     g.cb_ptr = k.take<int32_t>(max_cb + 1);
-    g.vinv = k.take<uint16_t>(E);
-    g.cinv = k.take<uint16_t>(E);
+    g.vfwd_cap = 2 * E + 64 * (max_vb + 1);   // (a block's last, partial group pads up to 31 lanes)
+    g.vfwd = k.take<uint16_t>(g.vfwd_cap + 8);
+    g.cfwd = k.take<uint16_t>(E + 8);
+    g.vb_t0 = k.take<int32_t>(max_vb + 2);
     g.v_wrun = k.take<uint2>(E / 32 + 2);
     g.c_wrun = k.take<uint2>(E / 32 + 2);
     g.v_wadj = k.take<int32_t>(E);

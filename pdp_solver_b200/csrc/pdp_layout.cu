@@ -1,7 +1,7 @@
 // pdp_layout.cu -- builds the blocked message layout of the SP sweep (pdp_common.cuh):
 // block partitions of both edge orders, the V-layout / C-layout positions of every edge, the 16-bit
-// local scatter / gather tables of the two passes (variable blocks: transposed by warp groups, pdp_sweep.cuh) and the
-// run-length coded destinations of their write-outs.  Runs once per batch inside pdp_create, entirely on the
+// node-order -> region-position tables of the two passes (variable blocks: transposed by warp groups, pdp_sweep.cuh) and
+// the run-length coded destinations of their write-outs.  Runs once per batch inside pdp_create, entirely on the
 // device (five stable radix sorts, three scans); the message arrays are not live yet and serve as scratch.
 #include <cub/cub.cuh>
 #include <stdlib.h>
@@ -50,7 +50,10 @@ __global__ void k_fill_vlayout(pdp_graph g, const int32_t* __restrict__ lv, cons
         const int c = lv[x];
         const int p = g.c_pos[c];
         g.p_vpos[p] = (int32_t)x;
-        g.vinv[x] = (uint16_t)(tslot[p] | ((g.v_cedge[p] & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
+        const uint32_t cv = g.c_var[c];
+        const int blk = g.var_ptr[cv & PDP_IDX_MASK] / g.sv;
+        const int e0 = g.var_ptr[g.vb_ptr[blk]];          // the block's region starts at its first variable-major slot
+        g.vfwd[(int64_t)g.vb_t0[blk] + tslot[p]] = (uint16_t)(((int)x - e0) | ((cv & PDP_SIGN_BIT) ? PDP_VINV_NEG : 0u));
     }
 }
 // keys of the C-layout sort, taken in V-layout order (variable block, clause-major slot): the clause block of the
@@ -67,7 +70,7 @@ __global__ void k_fill_clayout(pdp_graph g, const int32_t* __restrict__ kj, cons
     GS(x, g.E) {
         const int c = lq[x];
         g.p_qpos[g.c_pos[c]] = (int32_t)x;
-        g.cinv[x] = (uint16_t)(c - g.cl_ptr[g.cb_ptr[kj[x]]]);
+        g.cfwd[c] = (uint16_t)((int)x - g.cl_ptr[g.cb_ptr[kj[x]]]);
     }
 }
 // Write-out order = load order: a pass writes the result of the edge it loaded from position x of its own layout to
@@ -128,7 +131,8 @@ __global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
 // pad[t] = slots of the group that starts at rank t (32 x the degree of its first, largest member), 0 for other ranks.
 // Ranks are cut into groups of 32 from the first rank of every block.
 __global__ void k_group_slots(pdp_graph g, const int32_t* __restrict__ order, int32_t* pad) {
-    GS(t, g.V) {
+    GS(t, g.V + 1) {
+        if (t == g.V) { pad[t] = 0; continue; }      // (the scan then leaves the padded total in psum[V])
         const int v = order[t];
         const int t0 = g.vb_ptr[g.var_ptr[v] / g.sv];
         pad[t] = ((((int)t - t0) & 31) == 0) ? 32 * (g.var_ptr[v + 1] - g.var_ptr[v]) : 0;
@@ -148,6 +152,10 @@ __global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order, con
         if (tg == (int)t) worst = max(worst, base + 32 * deg);     // end of this group's slots = padded size so far
     }
     if (worst) atomicMax(max_slots, worst);
+}
+// t0 of a variable block in g.vfwd = padded slots of all earlier blocks
+__global__ void k_block_t0(pdp_graph g, const int32_t* __restrict__ psum) {
+    GS(blk, (int64_t)g.nvb + 1) g.vb_t0[blk] = psum[blk == g.nvb ? g.V : g.vb_ptr[blk]];
 }
 // padded transposed slots: lane l = rank within the group, row j = the j-th edge (pdp_sweep.cuh var_group)
 __global__ void k_fill_tslot(pdp_graph g, uint16_t* tslot) {
@@ -192,9 +200,11 @@ __global__ void k_fill_desc(pdp_graph g) {
         const uint2* wr = var_side ? g.v_wrun : g.c_wrun;
         pdp_blk d;
         d.n0 = bp[blk]; d.n1 = bp[blk + 1];
-        d.e0 = 0; d.ne = 0; d.b0 = 0; d.b1 = 0; d.run0 = 0; d.nruns = 0;
+        d.e0 = 0; d.ne = 0; d.b0 = 0; d.b1 = 0; d.run0 = 0; d.nruns = 0; d.t0 = 0; d.tn = 0; d.pad_[0] = d.pad_[1] = 0;
         if (d.n1 > d.n0) {
             d.e0 = np[d.n0]; d.ne = np[d.n1] - d.e0;
+            d.t0 = var_side ? g.vb_t0[blk] : d.e0;
+            d.tn = var_side ? g.vb_t0[blk + 1] - g.vb_t0[blk] : d.ne;
             d.b0 = bm[d.n0]; d.b1 = bm[d.n1 - 1];
             if (d.ne > 0) { d.run0 = run_of(wr, d.e0); d.nruns = run_of(wr, d.e0 + d.ne - 1) - d.run0 + 1; }
         }
@@ -244,13 +254,13 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     const int blk_v = PDP_BLK_V / g.ctas, blk_c = PDP_BLK_C / g.ctas;
     // (V <= E: the degree sort below borrows E-sized scratch; batches of mostly isolated variables take the generic passes)
     const bool ok = monotone_maps && g.max_var_degree <= blk_v / 2 && g.max_clause_degree <= blk_c / 2 &&
-                    g.V > 0 && g.F > 0 && g.V <= E && getenv("PDP_B200_NO_BLOCKED") == nullptr;
+                    g.V > 0 && g.F > 0 && g.V < E && getenv("PDP_B200_NO_BLOCKED") == nullptr;
     if (!ok) {
         k_identity_layout<<<G1(E)>>>(g);
         LLK();
         return PDP_OK;
     }
-    g.sc = pick_stride(E, blk_c, g.max_clause_degree, nsm * g.ctas);
+    g.sc = pick_stride(E, blk_c - 8, g.max_clause_degree, nsm * g.ctas);   // (8 words of alignment slack in the plane)
     g.ncb = (int32_t)(E / g.sc + 1);
 
     // scratch: the message arrays
@@ -288,11 +298,12 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
     int rc;
 
     // ---- variable blocks.  Per block: variables by descending degree, cut into groups of 32 (one warp each, nearly equal
-    //      trip counts); a group's edges are stored transposed and padded to its largest degree (pdp_sweep.cuh), so the
-    //      shared-memory plane must hold the block's PADDED slots: the edge budget of a block starts 4.5 % below the plane
-    //      and shrinks until the largest padded block fits (2-5 % padding on random k-SAT).
+    //      trip counts); a group's entries of the position table g.vfwd are stored transposed and padded to its largest
+    //      degree (pdp_sweep.cuh; 2-5 % padding on random k-SAT).  The padded slots of a block are addressed with 16 bits
+    //      (vsort.y): the edge budget of a block shrinks until the largest padded block stays below that.
     int32_t* d_max_slots = g.wo_tmp;
-    int budget = blk_v - blk_v / 22;
+    int budget = blk_v;
+    const int slot_limit = 65535 - 32;
     bool fits = false;
     for (int attempt = 0; attempt < 8 && !fits; ++attempt) {
         if (budget / 2 < g.max_var_degree) break;
@@ -308,17 +319,21 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         k_key_vsort<<<G1(g.V)>>>(g, S0, S2);
         LLK();
         if ((rc = sort_pairs(g.V, (int64_t)g.nvb << 14, &K, &L, &KF, &LF)) != PDP_OK) return rc;
-        k_group_slots<<<G1(g.V)>>>(g, L, KF);
+        k_group_slots<<<G1(g.V + 1)>>>(g, L, KF);
         LLK();
-        if ((rc = exclusive_scan(KF, g.V)) != PDP_OK) return rc;
+        if ((rc = exclusive_scan(KF, g.V + 1)) != PDP_OK) return rc;
         LCK(cudaMemsetAsync(d_max_slots, 0, sizeof(int32_t), stream));
         k_fill_vsort<<<G1(g.V)>>>(g, L, KF, d_max_slots);
         LLK();
-        int32_t max_slots = 0;
+        k_block_t0<<<G1(g.nvb + 1)>>>(g, KF);
+        LLK();
+        int32_t max_slots = 0, total_slots = 0;
         LCK(cudaMemcpyAsync(&max_slots, d_max_slots, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        LCK(cudaMemcpyAsync(&total_slots, KF + g.V, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
         LCK(cudaStreamSynchronize(stream));
-        fits = max_slots <= blk_v;
-        if (!fits) budget = (int)((int64_t)budget * blk_v / max_slots) - 64;   // scale by the overshoot, plus a margin
+        if (total_slots > g.vfwd_cap) break;    // pads too badly for the position table: generic passes
+        fits = max_slots <= slot_limit;
+        if (!fits) budget = (int)((int64_t)budget * slot_limit / max_slots) - 64;   // scale by the overshoot, plus a margin
     }
     if (!fits) {   // degree distributions that do not pad well (a few huge variables among tiny ones): generic passes
         g.nvb = 0; g.ncb = 0; g.sv = 1; g.sc = 1;
@@ -373,8 +388,8 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
 
 // ------------------------------------------------------------------------------------------------
 // self-check of the layout tables (tests): counts violated invariants into errs[0..7]
-//   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vinv is not the transposed slot
-//   2 C-layout position outside its block / cinv wrong           3 variable write-out does not land on p_qpos
+//   0 position maps inconsistent between the two edge orders     1 V-layout position outside its block / vfwd is not its position
+//   2 C-layout position outside its block / cfwd wrong           3 variable write-out does not land on p_qpos
 //   4 clause write-out does not land on c_vpos                   5 vsort / cb_k wrong
 //   6 distinct write-out sources of the variable blocks (= E)    7 ... of the clause blocks (= E)
 // ------------------------------------------------------------------------------------------------
@@ -393,8 +408,9 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
     GS(blk, g.nvb) {
         const int v0 = g.vb_ptr[blk], v1 = g.vb_ptr[blk + 1];
         const int e0 = g.var_ptr[v0], e1 = g.var_ptr[v1];
-        const int cap = PDP_BLK_V / g.ctas;
-        if (e1 - e0 > cap) atomicAdd(&errs[1], 1);
+        const int cap = 65535;
+        if (e1 - e0 > PDP_BLK_V / g.ctas || g.vb_desc[blk].t0 != g.vb_t0[blk] || g.vb_desc[blk].e0 != e0 || g.vb_desc[blk].ne != e1 - e0) atomicAdd(&errs[1], 1);
+        const uint16_t* fw = g.vfwd + g.vb_t0[blk];
         // vsort: a permutation of the block's variables by descending degree; groups of 32 ranks, rows of 32 slots
         long long sum = 0;
         int run_base = 0;
@@ -413,8 +429,8 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
                     const int p = g.var_ptr[v] + j;
                     const int x = g.p_vpos[p];
                     const int slot = base + 32 * j + l;
-                    if (x < e0 || x >= e1 || (int)(g.vinv[x] & 0x7fff) != slot ||
-                        ((g.vinv[x] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) { atomicAdd(&errs[1], 1); continue; }
+                    if (x < e0 || x >= e1 || (int)(fw[slot] & 0x7fff) != x - e0 ||
+                        ((fw[slot] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) { atomicAdd(&errs[1], 1); continue; }
                     // write-out slot = load position: its destination must be this edge's C-layout position
                     if (wo_dest(g.v_wrun, g.v_wadj, x) != g.p_qpos[p]) { atomicAdd(&errs[3], 1); continue; }
                     if (!(atomicOr(&seen[x >> 5], 1u << (x & 31)) & (1u << (x & 31)))) atomicAdd(&errs[6], 1);
@@ -429,18 +445,16 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
     GS(blk, g.ncb) {
         const int a0 = g.cb_ptr[blk], a1 = g.cb_ptr[blk + 1];
         const int e0 = g.cl_ptr[a0], e1 = g.cl_ptr[a1];
-        if (e1 - e0 > PDP_BLK_C / g.ctas) atomicAdd(&errs[2], 1);
+        if (e1 - e0 > PDP_BLK_C / g.ctas - 8 || g.cb_desc[blk].t0 != e0 || g.cb_desc[blk].e0 != e0 || g.cb_desc[blk].ne != e1 - e0) atomicAdd(&errs[2], 1);
         for (int c = e0; c < e1; ++c) {
             const int x = cqpos(g, c);
-            if (x < e0 || x >= e1 || (int)g.cinv[x] != c - e0) atomicAdd(&errs[2], 1);
+            if (x < e0 || x >= e1 || (int)g.cfwd[c] != x - e0) { atomicAdd(&errs[2], 1); continue; }
+            // write-out slot = region position: its destination must be this edge's V-layout position
+            if (cvpos(g, c) != wo_dest(g.c_wrun, g.c_wadj, x)) { atomicAdd(&errs[4], 1); continue; }
+            if (!(atomicOr(&seen_c[x >> 5], 1u << (x & 31)) & (1u << (x & 31)))) atomicAdd(&errs[7], 1);
         }
-        for (int w = e0; w < e1; ++w) {
-            const int c = e0 + (int)g.cinv[w];
-            const int d = wo_dest(g.c_wrun, g.c_wadj, w);
-            if (c < e0 || c >= e1 || cvpos(g, c) != d) { atomicAdd(&errs[4], 1); continue; }
-            if (w > e0 && d <= wo_dest(g.c_wrun, g.c_wadj, w - 1)) atomicAdd(&errs[4], 1);
-            if (!(atomicOr(&seen_c[c >> 5], 1u << (c & 31)) & (1u << (c & 31)))) atomicAdd(&errs[7], 1);
-        }
+        for (int w = e0 + 1; w < e1; ++w)
+            if (wo_dest(g.c_wrun, g.c_wadj, w) <= wo_dest(g.c_wrun, g.c_wadj, w - 1)) atomicAdd(&errs[4], 1);
         const int k = g.cb_k[blk];
         bool uni = (a1 > a0);
         for (int a = a0; a < a1; ++a) if (g.cl_ptr[a + 1] - g.cl_ptr[a] != g.cl_ptr[a0 + 1] - g.cl_ptr[a0]) uni = false;

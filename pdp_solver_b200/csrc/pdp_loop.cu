@@ -126,7 +126,7 @@ __device__ __forceinline__ void termination_phase(const KArgs& A, int iter, int 
 template <bool FAST, bool FULL, int CTAS>
 __global__ void __launch_bounds__(FAST ? SweepCfg<CTAS>::kThreads : 256, FAST ? CTAS : 1)
 k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params prm, int32_t* d_iters_done) {
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
     cg::grid_group grid = cg::this_grid();
     const pdp_state& s = A.s;
     int iter = s.ctrl[CTRL_ITER];
@@ -139,6 +139,14 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
     const bool frontier = s.ctrl[CTRL_CLOSED] != 0 && !(prm.flags & 4);   // flags bit 2: full-scan closure (A/B, tests)
     int executed = 0;
     int sm_rank = 0;
+    // completion barrier of the blocked passes' bulk copies: one mbarrier for the kernel's lifetime (static shared memory:
+    // the CTA-local decimation borrows the dynamic part)
+    __shared__ __align__(8) uint64_t sm_bulk_bar;
+    BulkBar bb{&sm_bulk_bar, 0u};
+    if (FAST) {
+        if (threadIdx.x == 0) mbar_init(&sm_bulk_bar, 1);
+        __syncthreads();
+    }
     if (FAST && CTAS == 2) {   // rank of this CTA among the CTAs of its SM (the counters are zeroed before the launch)
         __shared__ int sm_rank_s;
         if (threadIdx.x == 0) {
@@ -173,7 +181,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         if (gen_left > 0) --gen_left;
         // ---- propagate, clause side: eta(t) from q(t-1)   (pdp_propagate.py:161-175)
         if (blocked) {
-            blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn, sm_rank);
+            blk_clause_pass<CTAS>(A, r, use_mask, smem_dyn, sm_rank, bb);
         } else {
             gen_clause_side<GEN_ALL>(A, r, use_mask);
         }
@@ -185,7 +193,7 @@ k_sp_run(const __grid_constant__ KArgs A, const __grid_constant__ pdp_sp_params 
         // ---- propagate, variable side: q(t) from eta(t-1) (pdp_propagate.py:184-218), fused with the
         //      decimator statistics of eta(t) against eta(t-1) (pdp_decimate.py:127-143)
         if (blocked) {
-            blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn, sm_rank);
+            blk_var_pass<CTAS>(A, r, use_mask, has_prev, em_set, smem_dyn, sm_rank, bb);
         } else {
             gen_var_side<GEN_ALL, FULL>(A, r, use_mask, prm.pi);
             gen_stats<GEN_ALL>(A, w, has_prev, em_set);

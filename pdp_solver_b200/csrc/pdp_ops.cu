@@ -184,9 +184,11 @@ __global__ void k_load_state(pdp_graph g, pdp_state s, const float* __restrict__
         s.qu[qp] = dq3[3 * e]; s.qs[qp] = dq3[3 * e + 1]; s.qd[qp] = dq3[3 * e + 2];
         const float eta = dfs2[2 * e];
         s.eta[buf][g.p_vpos[p]] = eta; s.ext[p] = dfs2[2 * e + 1];
-        // the blocked variable pass borrows the sign bit of the old surveys: surveys that arrive with one
-        // (not a probability) go through the generic passes for the one iteration that reads them
-        if (__float_as_uint(eta) >> 31) s.ctrl[CTRL_GEN_ITERS] = 1;
+        // the blocked passes borrow the sign bits of the messages they read and write: messages that arrive with one (not
+        // a probability) go through the generic passes until no message can carry a sign any more -- the first iteration
+        // reads them, the second reads the q the first derived from them (a survey below 0 makes exp(opp) > 1 and q < 0);
+        // a clause-side survey is an exponential and a q derived from surveys >= 0 is >= +0
+        if ((__float_as_uint(eta) | __float_as_uint(dq3[3 * e])) >> 31) s.ctrl[CTRL_GEN_ITERS] = 2;
     }
 }
 
@@ -195,7 +197,7 @@ __global__ void k_load_state_const(pdp_graph g, pdp_state s, float qu, float qs,
     for (int64_t p = gtid(); p < g.E; p += gthreads()) {
         s.qu[p] = qu; s.qs[p] = qs; s.qd[p] = qd; s.eta[buf][p] = eta; s.ext[p] = ext;
     }
-    if (gtid() == 0 && (__float_as_uint(eta) >> 31)) s.ctrl[CTRL_GEN_ITERS] = 1;
+    if (gtid() == 0 && ((__float_as_uint(eta) | __float_as_uint(qu)) >> 31)) s.ctrl[CTRL_GEN_ITERS] = 2;
 }
 
 // thread per variable; when the [E,3] state was not tracked every iteration, q_s and q_* are

@@ -1,23 +1,32 @@
 // pdp_sweep.cuh -- the blocked shared-memory passes of the SP sweep (product path of pdp_sp_run, included by
 // pdp_device.cuh).  Layout: pdp_common.cuh / DESIGN.md.  One CTA walks blocks of whole nodes; per block
-//     load      contiguous 128-bit reads of the block's message region, scattered into NODE order in shared memory
-//               through a 16-bit local index (g.vinv / g.cinv);
-//     node      the per-node arithmetic, in place, without shared-memory bank conflicts:
-//                 clauses of a uniform-degree block: thread a reads X[k * a + j] (k odd: conflict-free);
-//                 variables: a WARP owns 32 variables of (nearly) equal degree and the block stores their edges
-//                 transposed -- row j of the group holds the j-th edge of every member that has one, so lane l reads
-//                 word `row start + l`: consecutive banks, and the ascending-edge accumulation order of the reference
-//                 (torch.mm(sparse, dense) on CPU) is the row order;
-//     write-out the results in ascending destination order.  Consecutive slots hit consecutive destinations (a RUN:
-//               the edges between this block and one block of the other side), so destinations are not stored per edge:
-//               one bit per slot marks the start of a run, one 32-bit count per 32 slots gives the run index, one
-//               32-bit offset per run gives `destination - slot`.  The run offsets of a block are staged in shared memory.
+//     load      the block's message region comes into shared memory AS IT LIES in global memory, by bulk-asynchronous
+//               copies (cp.async.bulk.shared.global + mbarrier complete_tx: issued by one thread, no registers, no issue
+//               slots; the other CTA of the SM computes meanwhile).  The run table of the write-out and the run offsets
+//               ride along;
+//     node      the per-node arithmetic IN PLACE: a 16-bit table (g.cfwd / g.vfwd), read once per pass and coalesced in node
+//               order, gives the region position x of every node-order slot; the node reads plane[x] and puts its result
+//               back into plane[x].
+//                 clauses: a thread owns a clause, its K table entries are consecutive;
+//                 variables: a WARP owns 32 variables of (nearly) equal degree and the table stores their entries
+//                 transposed -- row j of the group holds the j-th edge of every member that has one, lane l reads entry
+//                 `row start + l`; the ascending-edge accumulation order of the reference (torch.mm(sparse, dense) on
+//                 CPU) is the row order;
+//     write-out the plane streams out in region order = ascending destination order.  Consecutive slots hit consecutive
+//               destinations (a RUN: the edges between this block and one block of the other side), so destinations are
+//               not stored per edge: one bit per slot marks the start of a run, one 32-bit count per 32 slots gives the
+//               run index, one 32-bit offset per run gives `destination - slot`.  No global load in this phase.
+// A slot's value in the plane carries two markers for the write-out (results are >= +0 or NaN):
+//     PDP_SLOT_SKIP (-inf)   the node left the slot alone (frozen problem inside a block that still has work);
+//     sign bit               the problem is on the sticky-NaN path: keep a NaN that is already stored at the destination
+//                            (the reference blends mask*new + (1-mask)*old arithmetically: 0*NaN = NaN, pdp_propagate.py:175,218).
 // Dynamic shared memory of a CTA (SweepCfg<CTAS>::kSmem bytes):
-//   [0, 4 * kBlkC)      clause pass: plane X;  variable pass: planes PA | PB (kBlkV words each)
-//   then 4 * kBitWords  skip bits: slots of nodes the pass leaves alone (frozen problems inside a block that has work)
-//   then 4 * kBitWords  sticky bits: slots of problems on the sticky-NaN path
-//   then 4 * kAdjCap B  run offsets of the block being written out
+//   [0, kPlaneBytes)       clause pass: plane X;  variable pass: planes PA | PB (kPlaneV words each)
+//   then 8 * kRunWords     run table words of the block
+//   then 4 * kAdjCap       run offsets of the block
 #pragma once
+
+#define PDP_SLOT_SKIP 0xff800000u
 
 __device__ __forceinline__ bool blk_problem_runs(const pdp_state& s, int b) { return s.active[b] != 0; }
 
@@ -29,25 +38,13 @@ __device__ __forceinline__ bool blk_idle(const pdp_state& s, int b0, int b1) {
     return __syncthreads_or(any) == 0;
 }
 
-__device__ __forceinline__ void blk_mark_skip(uint32_t* bits, int lo, int hi) {
-    for (int l = lo; l < hi; ++l) atomicOr(&bits[l >> 5], 1u << (l & 31));
-}
-// the same for one row of a transposed variable group: the slots `off + lane` of the lanes in `lanes`
-__device__ __forceinline__ void row_mark(uint32_t* bits, int off, unsigned lanes) {
-    if (!lanes) return;   // warp-uniform
-    const int w = off >> 5, sh = off & 31;
-    if (lane_id() == 0) atomicOr(&bits[w], lanes << sh);
-    if (lane_id() == 1 && sh) { const unsigned hi = lanes >> (32 - sh); if (hi) atomicOr(&bits[w + 1], hi); }
-}
-
 #ifndef PDP_UNROLL_WO
-#define PDP_UNROLL_WO 6    // write-out: slots per thread in flight (two loads each)
+#define PDP_UNROLL_WO 4    // write-out: slots per thread in flight
 #endif
-#ifndef PDP_UNROLL_CL4
-#define PDP_UNROLL_CL4 4   // clause load: four-slot groups per thread in flight
-#endif
-#ifndef PDP_UNROLL_VL4
-#define PDP_UNROLL_VL4 3   // variable load (measured: 2 -> 3 is +1 %)
+#ifndef PDP_L2_PREFETCH
+#define PDP_L2_PREFETCH 2    // what of the next block is pulled into L2 while the current block is worked on: 0 nothing,
+                             // 1 tables and messages, 2 tables only (measured on 8 x n = 1M: 1 loses 3 % to 0 -- the messages of 296 CTAs
+                             // crowd each other out of L2 before they are used)
 #endif
 #ifndef PDP_INPASS_SCORE
 #define PDP_INPASS_SCORE 1
@@ -56,189 +53,250 @@ __device__ __forceinline__ void row_mark(uint32_t* bits, int off, unsigned lanes
 #define PDP_COLD __forceinline__
 #endif
 
-// The memory phases read their contiguous streams four slots per thread and instruction (128-bit loads of the fp32
-// streams, 64-bit loads of the 16-bit tables).  A block's region starts at an arbitrary element of 256-byte aligned
-// arrays, so up to three head and three tail slots go through the scalar path.
-struct Vec4Range { int head, nvec, tail0; };
-template <typename T>
-__device__ __forceinline__ Vec4Range vec4_range(const T* p32, int ne) {   // p32: the region's start in a 4-byte array
-    Vec4Range R;
-    R.head = (int)((16u - ((unsigned)(uintptr_t)p32 & 15u)) & 15u) >> 2;
-    if (R.head > ne) R.head = ne;
-    R.nvec = (ne - R.head) >> 2;
-    R.tail0 = R.head + 4 * R.nvec;
-    return R;
+// ------------------------------------------------------------------------------------------------
+// bulk-asynchronous copies global -> shared (the 1-D form of TMA) completing on an mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t mnib(const uint32_t* words, int pos) { return (__ldcg(words + (pos >> 5)) >> (pos & 31)) & 15u; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses of this thread (and, after a barrier, of the CTA) ordered before later async-proxy accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// one thread: [p, p + bytes) -> L2, rounded outwards to 16-byte units (a hint: no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, int bytes) {
+    if (bytes <= 0) return;
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)((((uintptr_t)p + bytes + 15) & ~(uintptr_t)15) - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
+// all threads: wait for the phase with this parity.  A copy that never completes (a bug) traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && spin > 64) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > (1ll << 32)) __trap();
+        }
+    }
+}
 
-// geometry of one block of a pass: one 32-byte descriptor (two 16-byte loads)
+// geometry of one block of a pass: one 48-byte descriptor (three 16-byte loads)
 struct BlkGeo {
     int n0, n1;      // node range
     int e0, ne;      // first slot / slots
     int b0, b1;      // problem range
     int run0, nruns; // write-out runs of the block: [run0, run0 + nruns)
+    int t0, tn;      // first entry / entries of the block in the position table
     __device__ __forceinline__ bool multi() const { return b0 != b1; }
 };
 __device__ __forceinline__ BlkGeo load_block(const pdp_blk* __restrict__ desc, int blk) {
     const int4* p = reinterpret_cast<const int4*>(desc + blk);
-    const int4 a = __ldg(p), b = __ldg(p + 1);
+    const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     BlkGeo B;
-    B.n0 = a.x; B.n1 = a.y; B.e0 = a.z; B.ne = a.w; B.b0 = b.x; B.b1 = b.y; B.run0 = b.z; B.nruns = b.w;
+    B.n0 = a.x; B.n1 = a.y; B.e0 = a.z; B.ne = a.w; B.b0 = b.x; B.b1 = b.y; B.run0 = b.z; B.nruns = b.w; B.t0 = c.x; B.tn = c.y;
     return B;
 }
 __device__ __forceinline__ BlkGeo clause_block(const pdp_graph& g, int blk) { return load_block(g.cb_desc, blk); }
 __device__ __forceinline__ BlkGeo var_block(const pdp_graph& g, int blk) { return load_block(g.vb_desc, blk); }
 
-// the block's run offsets -> shared memory (when they fit; the write-out reads them from global memory otherwise)
-template <int G, int CAP>
-__device__ __forceinline__ void ph_stage_runs(int t, const int32_t* __restrict__ wadj, const BlkGeo& B, int32_t* adj_s) {
-    if (B.nruns > CAP) return;
-    for (int i = t; i < B.nruns; i += G) adj_s[i] = __ldg(&wadj[B.run0 + i]);
+// Where the pieces of a block land in shared memory.  Bulk copies move whole 16-byte units: every source range is widened
+// to 16-byte boundaries and the consumer indexes with the offset of its first element.
+struct BlkStage {
+    int a0, nbytes;      // message region: first element copied (a multiple of 4 <= e0), bytes
+    int shift;           // e0 - a0: region position x sits at plane[shift + x]
+    int w0, wbytes;      // run table: first word copied (even, <= e0 >> 5), bytes
+    int r0, rbytes;      // run offsets: first offset copied (a multiple of 4 <= run0), bytes (0: not staged, the write-out reads g.*_wadj)
+};
+template <int CAP>
+__device__ __forceinline__ BlkStage blk_stage(const BlkGeo& B) {
+    BlkStage S;
+    S.a0 = B.e0 & ~3;
+    S.shift = B.e0 - S.a0;
+    S.nbytes = 4 * (((B.e0 + B.ne + 3) & ~3) - S.a0);
+    S.w0 = (B.e0 >> 5) & ~1;
+    S.wbytes = 8 * (((((B.e0 + B.ne - 1) >> 5) + 2) & ~1) - S.w0);
+    S.r0 = B.run0 & ~3;
+    const int nr = ((B.run0 + B.nruns + 3) & ~3) - S.r0;
+    S.rbytes = nr <= CAP ? 4 * nr : 0;
+    return S;
 }
 
-// write-out: slots [0, ne) of the block = the positions of its own region, in load order (`src` is the load table:
-// position -> local node slot, SMASK strips its flag bit); destinations ascend.
-// STICKY: 0 = off, 1 = slots flagged in `sticky` bits, 2 = every slot.  A sticky slot keeps a NaN that is already
-// stored at its destination in `old` (the reference blends mask*new + (1-mask)*old arithmetically: 0*NaN = NaN,
-// pdp_propagate.py:175,218).  One slot per thread and instruction: with four consecutive slots per thread a warp's
-// stores would be strided by four elements and every destination sector written four times.
-template <int G, bool SKIP, int STICKY, bool ADJ_S, unsigned SMASK>
-__device__ __forceinline__ void ph_write_out_t(int t, const uint16_t* __restrict__ src, const uint2* __restrict__ wrun,
-                                               const int32_t* __restrict__ adj, const BlkGeo& B, const float* plane,
-                                               const uint32_t* skip, const uint32_t* sticky,
-                                               const float* old, float* out) {   // old may alias out (q is updated in place)
-    // A warp takes 32 slots that share one word of the run table: slot w = w0 + 32 k + lane with w0 a multiple of 32, so
+// write-out: slots [e0, e0 + ne) of the block = the positions of its own region; destinations ascend.  One slot per thread
+// and instruction (with several consecutive slots per thread a warp's stores would be strided and every destination sector
+// written several times).  Everything but the store (and the rare sticky re-read) is shared memory.
+// plane: the shifted plane (slot w at plane[w - e0]);  wrun_s: the staged run table (word i of the table at wrun_s[i - w0]);
+// adj: run offsets, biased so that adj[run] is the offset of global run `run` (shared memory or g.*_wadj).
+template <int G>
+__device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, const float* plane, const uint2* wrun_s, int w0,
+                                             const int32_t* adj, const float* old, float* out) {   // old may alias out (q is updated in place)
+    // A warp takes 32 slots that share one word of the run table: slot w = wb + 32 k + lane with wb a multiple of 32, so
     // the lane's bit mask is fixed and the table word is one broadcast load.  Slots before e0 / from e0 + ne on are idle.
     const int lane = t & 31;
-    const int w0 = (B.e0 & ~31) + 32 * (t >> 5);
     const int wend = B.e0 + B.ne;
     const uint32_t lmask = 0xffffffffu >> (31 - lane);
-    adj -= ADJ_S ? B.run0 : 0;
-    auto one = [&](int w, int l, uint2 rb) {
-        if (SKIP && ((skip[l >> 5] >> (l & 31)) & 1u)) return;
+    const uint32_t* pl = reinterpret_cast<const uint32_t*>(plane) - B.e0;
+    const uint2* wr = wrun_s - w0;
+    auto one = [&](int w, uint32_t raw, uint2 rb) {
+        if (raw == PDP_SLOT_SKIP) return;
         const int d = adj[(int)rb.y + __popc(rb.x & lmask)] + w;
-        float v = plane[l];
-        if (STICKY == 2 || (STICKY == 1 && ((sticky[l >> 5] >> (l & 31)) & 1u))) { const float ov = old[d]; if (ov != ov) v = ov; }
-        out[d] = v;
+        if ((int32_t)raw < 0) {                           // sticky (or a NaN that happens to carry a sign: harmless)
+            raw &= 0x7fffffffu;
+            const float ov = old[d];
+            if (ov != ov) raw = __float_as_uint(ov);
+        }
+        out[d] = __uint_as_float(raw);
     };
     constexpr int U = PDP_UNROLL_WO;
-    constexpr int STEP = G;      // slots between two iterations of a warp (G / 32 warps x 32 slots)
-    int w = w0 + lane;
-    if (w < B.e0 && w < wend) w += STEP;      // (only the first 32 slots can lie before the region)
-    else if (w < B.e0) return;
-    // the head iteration above is folded in: a lane whose first slot precedes e0 starts one step later
-    for (; w + (U - 1) * STEP < wend; w += U * STEP) {
-        int l[U]; uint2 rb[U];
+    int w = (B.e0 & ~31) + 32 * (t >> 5) + lane;
+    if (w < B.e0) w += G;                                 // (only the first 32 slots can lie before the region)
+    for (; w + (U - 1) * G < wend; w += U * G) {
+        uint32_t raw[U]; uint2 rb[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { l[u] = src[w + u * STEP] & SMASK; rb[u] = __ldg(&wrun[(w + u * STEP) >> 5]); }
+        for (int u = 0; u < U; ++u) { raw[u] = pl[w + u * G]; rb[u] = wr[(w + u * G) >> 5]; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) one(w + u * STEP, l[u], rb[u]);
+        for (int u = 0; u < U; ++u) one(w + u * G, raw[u], rb[u]);
     }
-    for (; w < wend; w += STEP) one(w, src[w] & SMASK, __ldg(&wrun[w >> 5]));
-}
-// flags: bit 0 = some slots are skipped, bit 1 = some slots are sticky, bit 2 = every slot is sticky
-template <int G, int CAP, unsigned SMASK>
-__device__ __forceinline__ void ph_write_out(int t, const uint16_t* __restrict__ src, const uint2* __restrict__ wrun,
-                                             const int32_t* __restrict__ wadj, const int32_t* adj_s, const BlkGeo& B,
-                                             const float* plane, const uint32_t* skip, int flags, float* out,
-                                             const uint32_t* sticky, const float* old) {
-    if (B.nruns <= CAP) {
-        if (flags == 0) ph_write_out_t<G, false, 0, true, SMASK>(t, src, wrun, adj_s, B, plane, skip, sticky, old, out);
-        else if (flags & 4) ph_write_out_t<G, true, 2, true, SMASK>(t, src, wrun, adj_s, B, plane, skip, sticky, old, out);
-        else ph_write_out_t<G, true, 1, true, SMASK>(t, src, wrun, adj_s, B, plane, skip, sticky, old, out);
-    } else {
-        if (flags & 4) ph_write_out_t<G, true, 2, false, SMASK>(t, src, wrun, wadj, B, plane, skip, sticky, old, out);
-        else ph_write_out_t<G, true, 1, false, SMASK>(t, src, wrun, wadj, B, plane, skip, sticky, old, out);
-    }
+    for (; w < wend; w += G) one(w, pl[w], wr[w >> 5]);
 }
 
-// clause pass, load phase: x = log(max(q_u, 1e-40)) * em, scattered into clause-major order.
-// e0 = first C-layout position of the block (the mask bits are indexed by position).
-template <int G, bool MASKED>
-__device__ __forceinline__ void ph_clause_load(int t, const float* __restrict__ qsrc, const uint16_t* __restrict__ inv,
-                                               const uint32_t* __restrict__ qmask, int e0, int ne, float* X) {
-    auto put = [&](float q, int l, bool m) {
-        float v = L40(q);
-        if (MASKED && m) v = v * 0.f;
-        X[l] = v;
-    };
-    const Vec4Range R = vec4_range(qsrc, ne);
-    if (t < R.head) put(qsrc[t], inv[t], MASKED ? mbit(qmask, e0 + t) : false);
-    if (t < ne - R.tail0) put(qsrc[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(qmask, e0 + R.tail0 + t) : false);
-    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(qsrc + R.head);
-    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
-    const int pos0 = e0 + R.head;     // a multiple of 4: the four mask bits of a group sit in one word
-    constexpr int U = PDP_UNROLL_CL4;
-    int x = t;
-    for (; x + (U - 1) * G < R.nvec; x += U * G) {
-        float4 q[U]; uint2 l[U]; uint32_t m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { q[u] = q4[x + u * G]; l[u] = i4[x + u * G]; m[u] = MASKED ? mnib(qmask, pos0 + 4 * (x + u * G)) : 0u; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            put(q[u].x, (int)(l[u].x & 0xffffu), m[u] & 1u); put(q[u].y, (int)(l[u].x >> 16), m[u] & 2u);
-            put(q[u].z, (int)(l[u].y & 0xffffu), m[u] & 4u); put(q[u].w, (int)(l[u].y >> 16), m[u] & 8u);
+// the edge-mask bits of the block's region (indexed by layout position) -> sign bits of the plane (its values are >= +0 or
+// NaN).  Only the words that have a bit set cost anything.
+template <int G>
+__device__ __forceinline__ void ph_apply_mask(int t, const uint32_t* __restrict__ mask, const BlkGeo& B, float* plane) {
+    uint32_t* pl = reinterpret_cast<uint32_t*>(plane) - B.e0;
+    const int W0 = B.e0 >> 5, W1 = (B.e0 + B.ne - 1) >> 5, wend = B.e0 + B.ne;
+    for (int i = W0 + t; i <= W1; i += G) {
+        uint32_t m = __ldcg(mask + i);
+        while (m) {
+            const int pos = 32 * i + __ffs(m) - 1;
+            m &= m - 1;
+            if (pos >= B.e0 && pos < wend) pl[pos] |= 0x80000000u;
         }
     }
-    for (; x < R.nvec; x += G) {
-        const float4 q = q4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(qmask, pos0 + 4 * x) : 0u;
-        put(q.x, (int)(l.x & 0xffffu), m & 1u); put(q.y, (int)(l.x >> 16), m & 2u);
-        put(q.z, (int)(l.y & 0xffffu), m & 4u); put(q.w, (int)(l.y >> 16), m & 8u);
-    }
 }
 
-// one clause of K literals held in X[lo .. lo+K): surveys in place.  Returns whether a NaN was produced.
-template <int K>
-__device__ __forceinline__ bool blk_clause_body(float* X, int lo) {
+// one clause of K literals: surveys in place.  X: shifted plane; fw: the clause's K table entries.  MASKED: the sign bit of a
+// loaded q marks a masked edge (x = log(q) * 0).  stk: sign bit to put on the results.  Returns whether a NaN was produced.
+template <int K, bool MASKED>
+__device__ __forceinline__ bool blk_clause_body(float* X, const int (&pos)[K], uint32_t stk) {
     float x[K];
     float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < K; ++j) { x[j] = X[lo + j]; tot += x[j]; }
+    for (int j = 0; j < K; ++j) {
+        const uint32_t raw = __float_as_uint(X[pos[j]]);
+        float v = L40(__uint_as_float(MASKED ? (raw & 0x7fffffffu) : raw));
+        if (MASKED && (int32_t)raw < 0) v = v * 0.f;
+        x[j] = v;
+        tot += v;
+    }
     bool made_nan = false;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const float nv = X30(tot - x[j]);
         made_nan |= (nv != nv);
-        X[lo + j] = nv;
+        X[pos[j]] = __uint_as_float(__float_as_uint(nv) | stk);
     }
     return made_nan;
 }
-__device__ __forceinline__ bool blk_clause_body_any(float* X, int lo, int k) {
+template <bool MASKED>
+__device__ __forceinline__ bool blk_clause_body_any(float* X, const uint16_t* __restrict__ fw, int k, uint32_t stk) {
     float tot = 0.f;
-    for (int j = 0; j < k; ++j) tot += X[lo + j];
-    bool made_nan = false;
     for (int j = 0; j < k; ++j) {
-        const float nv = X30(tot - X[lo + j]);
+        const uint32_t raw = __float_as_uint(X[fw[j]]);
+        float v = L40(__uint_as_float(MASKED ? (raw & 0x7fffffffu) : raw));
+        if (MASKED && (int32_t)raw < 0) v = v * 0.f;
+        tot += v;
+    }
+    bool made_nan = false;
+    // (a second pass over the inputs: a slot is overwritten right after its own value has been used, the slots differ)
+    for (int j = 0; j < k; ++j) {
+        const int p = fw[j];
+        const uint32_t raw = __float_as_uint(X[p]);
+        float v = L40(__uint_as_float(MASKED ? (raw & 0x7fffffffu) : raw));
+        if (MASKED && (int32_t)raw < 0) v = v * 0.f;
+        const float nv = X30(tot - v);
         made_nan |= (nv != nv);
-        X[lo + j] = nv;
+        X[p] = __uint_as_float(__float_as_uint(nv) | stk);
     }
     return made_nan;
 }
 
-// clause pass, node phase: thread per clause
-template <int G>
-__device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, int ku,
-                                               float* X, uint32_t* skip, int* any_skip, uint32_t* sticky) {
+// clause pass, node phase: thread per clause.  Blocks whose clauses all have K literals: the table entries of a thread's
+// next clause are fetched while the current one is worked on.
+template <int G, int K, bool MASKED>
+__device__ __forceinline__ void ph_clause_node_k(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, float* X, uint32_t stk_blk) {
     const bool multi = B.multi();
-    for (int a = B.n0 + t; a < B.n1; a += G) {
-        int lo, k;
-        if (ku) { k = ku; lo = (a - B.n0) * ku; }
-        else { lo = g.cl_ptr[a] - B.e0; k = g.cl_ptr[a + 1] - B.e0 - lo; }
+    const uint16_t* __restrict__ fw = g.cfwd + B.t0 + K * t;      // entries of clause n0 + t; the thread's next clause is G further
+    int a = B.n0 + t;
+    int nxt[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) nxt[j] = (a < B.n1) ? (int)fw[j] : 0;
+    for (; a < B.n1; a += G) {
+        int pos[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) pos[j] = nxt[j];
+        fw += K * G;
+        if (a + G < B.n1) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) nxt[j] = fw[j];
+        }
         int b = B.b0;
+        uint32_t stk = stk_blk;
         if (multi) {
             b = g.bfm[a];
-            if (!blk_problem_runs(s, b)) { blk_mark_skip(skip, lo, lo + k); atomicOr(any_skip, 1); continue; }
-            if (s.nanflag[b]) { blk_mark_skip(sticky, lo, lo + k); atomicOr(any_skip, 2); }
+            if (!blk_problem_runs(s, b)) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) X[pos[j]] = __uint_as_float(PDP_SLOT_SKIP);
+                continue;
+            }
+            stk = s.nanflag[b] ? 0x80000000u : 0u;
         }
-        bool made_nan;
-        switch (k) {
-            case 3: made_nan = blk_clause_body<3>(X, lo); break;
-            case 4: made_nan = blk_clause_body<4>(X, lo); break;
-            case 5: made_nan = blk_clause_body<5>(X, lo); break;
-            case 2: made_nan = blk_clause_body<2>(X, lo); break;
-            default: made_nan = blk_clause_body_any(X, lo, k); break;
+        if (blk_clause_body<K, MASKED>(X, pos, stk)) s.nanpend[b] = 1;
+    }
+}
+// ... and blocks of mixed clause degrees
+template <int G, bool MASKED>
+__device__ __forceinline__ void ph_clause_node_any(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, float* X, uint32_t stk_blk) {
+    const bool multi = B.multi();
+    const uint16_t* __restrict__ fwb = g.cfwd + B.t0;     // entry of clause-major slot c: fwb[c - e0]
+    for (int a = B.n0 + t; a < B.n1; a += G) {
+        const int lo = g.cl_ptr[a] - B.e0, k = g.cl_ptr[a + 1] - B.e0 - lo;
+        const uint16_t* __restrict__ fw = fwb + lo;
+        int b = B.b0;
+        uint32_t stk = stk_blk;
+        if (multi) {
+            b = g.bfm[a];
+            if (!blk_problem_runs(s, b)) {
+                for (int j = 0; j < k; ++j) X[fw[j]] = __uint_as_float(PDP_SLOT_SKIP);
+                continue;
+            }
+            stk = s.nanflag[b] ? 0x80000000u : 0u;
         }
-        if (made_nan) s.nanpend[b] = 1;
+        if (blk_clause_body_any<MASKED>(X, fw, k, stk)) s.nanpend[b] = 1;
+    }
+}
+// ku = common degree of the block's clauses (0: mixed)
+template <int G, bool MASKED>
+__device__ __forceinline__ void ph_clause_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, int ku, float* X, uint32_t stk_blk) {
+    switch (ku) {
+        case 3: ph_clause_node_k<G, 3, MASKED>(t, g, s, B, X, stk_blk); break;
+        case 4: ph_clause_node_k<G, 4, MASKED>(t, g, s, B, X, stk_blk); break;
+        case 5: ph_clause_node_k<G, 5, MASKED>(t, g, s, B, X, stk_blk); break;
+        case 2: ph_clause_node_k<G, 2, MASKED>(t, g, s, B, X, stk_blk); break;
+        default: ph_clause_node_any<G, MASKED>(t, g, s, B, X, stk_blk); break;
     }
 }
 
@@ -254,49 +312,10 @@ __device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
 }
 __device__ __forceinline__ float fand(uint32_t mask, float a) { return __uint_as_float(__float_as_uint(a) & mask); }
 
-// variable pass, load phase.  The surveys are non-negative, so their sign bits carry the two per-edge
-// flags the variable loops need: PA (new survey) sign = edge masked, PB (old survey) sign = negative literal.
-template <int G, bool MASKED>
-__device__ __forceinline__ void ph_var_load(int t, const float* __restrict__ sn, const float* __restrict__ so, const uint16_t* __restrict__ inv,
-                                            const uint32_t* __restrict__ vmask, int e0, int ne, float* PA, float* PB) {
-    auto put = [&](float n, float o, uint32_t iv, bool m) {
-        const int l = iv & 0x7fff;
-        PA[l] = __uint_as_float(__float_as_uint(n) | ((MASKED && m) ? 0x80000000u : 0u));
-        PB[l] = __uint_as_float(__float_as_uint(o) ^ ((iv & PDP_VINV_NEG) << 16));
-    };
-    const Vec4Range R = vec4_range(sn, ne);
-    if (t < R.head) put(sn[t], so[t], inv[t], MASKED ? mbit(vmask, e0 + t) : false);
-    if (t < ne - R.tail0) put(sn[R.tail0 + t], so[R.tail0 + t], inv[R.tail0 + t], MASKED ? mbit(vmask, e0 + R.tail0 + t) : false);
-    const float4* __restrict__ n4 = reinterpret_cast<const float4*>(sn + R.head);
-    const float4* __restrict__ o4 = reinterpret_cast<const float4*>(so + R.head);
-    const uint2* __restrict__ i4 = reinterpret_cast<const uint2*>(inv + R.head);
-    const int pos0 = e0 + R.head;
-    constexpr int U = PDP_UNROLL_VL4;
-    int x = t;
-    for (; x + (U - 1) * G < R.nvec; x += U * G) {
-        float4 n[U], o[U]; uint2 l[U]; uint32_t m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            n[u] = n4[x + u * G]; o[u] = o4[x + u * G]; l[u] = i4[x + u * G];
-            m[u] = MASKED ? mnib(vmask, pos0 + 4 * (x + u * G)) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            put(n[u].x, o[u].x, l[u].x & 0xffffu, m[u] & 1u); put(n[u].y, o[u].y, l[u].x >> 16, m[u] & 2u);
-            put(n[u].z, o[u].z, l[u].y & 0xffffu, m[u] & 4u); put(n[u].w, o[u].w, l[u].y >> 16, m[u] & 8u);
-        }
-    }
-    for (; x < R.nvec; x += G) {
-        const float4 n = n4[x], o = o4[x]; const uint2 l = i4[x]; const uint32_t m = MASKED ? mnib(vmask, pos0 + 4 * x) : 0u;
-        put(n.x, o.x, l.x & 0xffffu, m & 1u); put(n.y, o.y, l.x >> 16, m & 2u);
-        put(n.z, o.z, l.y & 0xffffu, m & 4u); put(n.w, o.w, l.y >> 16, m & 8u);
-    }
-}
-
 // One warp-group of a variable block: 32 variables of consecutive rank in the block's descending-degree order
-// (g.vsort), lane l <-> rank 32 * group + l.  The group owns 32 * (degree of its first member) slots from its base
-// (a multiple of 32): row j = slots [base + 32 j, base + 32 j + 32), lane l's j-th edge sits at base + 32 j + l.
-// Slots of members with fewer edges than the first one are padding (never written, never read): 2-5 % of a block.
+// (g.vsort), lane l <-> rank 32 * group + l.  The group owns 32 * (degree of its first member) entries of the position table
+// from its base (a multiple of 32): row j = entries [base + 32 j, base + 32 j + 32), lane l's j-th edge is entry base + 32 j + l.
+// Entries of members with fewer edges than the first one are padding (never written, never read): 2-5 % of a block.
 struct VarGroup {
     int i, deg, base, maxdeg;
     bool have;
@@ -319,21 +338,20 @@ __device__ __forceinline__ VarGroup var_group(const pdp_graph& g, const BlkGeo& 
 // variable pass, SurveyScorer (pdp_predict.py:155-192) of the variables whose problem asked for it (want_score): same
 // operations and order as score_variable() on the new surveys held in PA (sign bit = edge masked; for an active variable
 // the edge mask is the clause mask the scorer multiplies with, an inactive variable's score is never looked at) and the
-// literal signs held in PB.  pi == 0 on the blocked path: the external force does not enter.
+// literal signs of the table.  pi == 0 on the blocked path: the external force does not enter.
 // (The reference's pos / neg incidence products hold explicit zeros, 0 * f: they only matter when f is NaN, and then
 // the sum over all edges is NaN as well and with it bias and the score: the per-sign sums skip them.)
 template <int G>
-__device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B,
-                                             const float* __restrict__ PA, const float* __restrict__ PB) {
+__device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, const float* __restrict__ PA) {
     VAR_GROUP_LOOP(grp, B, G, t) {
         const VarGroup V = var_group(g, B, grp);
         if (!(V.have && s.want_score[B.multi() ? g.bvm[V.i] : B.b0])) continue;
         float ps = 0.f, ns = 0.f, as = 0.f;
-        const float* __restrict__ pa = PA + V.base + lane_id();
-        const float* __restrict__ pb = PB + V.base + lane_id();
+        const uint16_t* __restrict__ fw = g.vfwd + B.t0 + V.base + lane_id();
         for (int j = 0; j < V.deg; ++j) {
-            const uint32_t nb = __float_as_uint(pa[32 * j]), ob = __float_as_uint(pb[32 * j]);
-            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);
+            const uint32_t en = fw[32 * j];
+            const uint32_t nb = __float_as_uint(PA[en & 0x7fffu]);
+            const uint32_t negm = 0u - (en >> 15);
             const float f = L10(1.f - __uint_as_float(nb & 0x7fffffffu)) * ((nb >> 31) ? 0.f : 1.f);
             ps += fand(~negm, f);
             ns += fand(negm, f);
@@ -343,56 +361,60 @@ __device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pd
     }
 }
 
-// variable pass, node phase: ordered sums, decimator statistics, update.
-// Requires eta(t-1) >= +0 or NaN without sign (the sign bits are borrowed, see ph_var_load).
+// variable pass, node phase: ordered sums, decimator statistics, update.  PA: eta(t) (sign bit = edge masked), then q(t);
+// PB: eta(t-1), then y.  Both shifted planes, indexed by region position.
 // (As in the scorer, the explicit zeros 0 * y of the reference's per-sign sums are skipped: a NaN y makes the sum of its
 // own sign NaN, and every message of the variable reads both sums -- `same` the one of its sign, `opp` the other.)
-// MULTI: the block holds several problems: frozen ones are left alone (skip bits), those on the sticky-NaN path are
-// flagged (sticky bits); a row is one 32-bit word of the bit arrays, written whole by the warp that owns the group.
+// MULTI: the block holds several problems: frozen ones are left alone (PDP_SLOT_SKIP), those on the sticky-NaN path get
+// the sticky sign.
 template <int G, bool MULTI, bool MASKED, bool PREV>
 __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask,
-                                            bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t* skip, int* any_skip,
-                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats, uint32_t* sticky) {
+                                            bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t stk_blk,
+                                            KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
     const int lane = t & 31;
     VAR_GROUP_LOOP(grp, B, G, t) {
         const VarGroup V = var_group(g, B, grp);
+        const uint16_t* __restrict__ fw = g.vfwd + B.t0 + V.base + lane;
         int b = B.b0;
         bool runs = V.have;
+        uint32_t stk = stk_blk;
         if (MULTI) {
-            bool stk = false;
-            if (V.have) { b = g.bvm[V.i]; runs = blk_problem_runs(s, b); stk = runs && s.nanflag[b]; }
-            const unsigned skip_l = __ballot_sync(0xffffffffu, V.have && !runs);
-            const unsigned stk_l = __ballot_sync(0xffffffffu, stk);
-            if (lane == 0 && (skip_l | stk_l)) atomicOr(any_skip, (skip_l ? 1 : 0) | (stk_l ? 2 : 0));
-            for (int j = 0; j < V.maxdeg; ++j) {
-                const unsigned on = __ballot_sync(0xffffffffu, j < V.deg);
-                if (lane == 0) { skip[(V.base >> 5) + j] = on & skip_l; sticky[(V.base >> 5) + j] = on & stk_l; }
+            if (V.have) {
+                b = g.bvm[V.i]; runs = blk_problem_runs(s, b); stk = (runs && s.nanflag[b]) ? 0x80000000u : 0u;
+                if (!runs) for (int j = 0; j < V.deg; ++j) PA[fw[32 * j] & 0x7fffu] = __uint_as_float(PDP_SLOT_SKIP);
             }
-            if (!__any_sync(0xffffffffu, runs)) continue;
         }
         if (!runs) continue;
         const uint32_t act = (uint32_t)s.av[V.i];
-        float* __restrict__ pa = PA + V.base + lane;
-        float* __restrict__ pb = PB + V.base + lane;
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < V.deg; ++j) {
-            const uint32_t nb = __float_as_uint(pa[32 * j]), ob = __float_as_uint(pb[32 * j]);
-            const uint32_t negm = (uint32_t)((int32_t)ob >> 31);    // all ones: negative literal
-            const float xn = __uint_as_float(nb & 0x7fffffffu), xo = __uint_as_float(ob & 0x7fffffffu);
-            float y = L40_1m(xo);
-            if (MASKED && use_mask && (int32_t)nb < 0) y = y * 0.f;      // edge masked
-            // y <= +0 (or NaN): stored as |y| under the literal's sign bit
-            pb[32 * j] = __uint_as_float((__float_as_uint(y) & 0x7fffffffu) | (ob & 0x80000000u));
-            P += fand(~negm, y);
-            N += fand(negm, y);
-            const float c = X30S(xn);
-            n0 += xn * c; d0 += c;
-            if (PREV) {
-                float d = fabsf(xo - xn);
-                if (MASKED && em_set && (int32_t)nb < 0) d = d * 0.f;
-                const float cd = X30S(d);
-                n1 += d * cd; d1 += cd;
+        // the table entries of a row are fetched four rows ahead (global memory: the CTAs leave no L1 to speak of)
+        uint32_t eq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        for (int j0 = 0; j0 < V.deg; j0 += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (j0 + k >= V.deg) break;
+                const uint32_t en = eq[k];
+                if (j0 + k + 4 < V.deg) eq[k] = fw[32 * (j0 + k + 4)];
+                const int x = en & 0x7fffu;
+                const uint32_t negm = 0u - (en >> 15);                  // all ones: negative literal
+                const uint32_t nb = __float_as_uint(PA[x]);
+                const float xo = PB[x];
+                const float xn = __uint_as_float(nb & 0x7fffffffu);
+                float y = L40_1m(xo);
+                if (MASKED && use_mask && (int32_t)nb < 0) y = y * 0.f;      // edge masked
+                PB[x] = y;
+                P += fand(~negm, y);
+                N += fand(negm, y);
+                const float c = X30S(xn);
+                n0 += xn * c; d0 += c;
+                if (PREV) {
+                    float d = fabsf(xo - xn);
+                    if (MASKED && em_set && (int32_t)nb < 0) d = d * 0.f;
+                    const float cd = X30S(d);
+                    n1 += d * cd; d1 += cd;
+                }
             }
         }
         {
@@ -420,14 +442,21 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         sp_var_prepare(P, N, 1.f, sb_pos, opp_pos, O_pos);
         sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
         bool made_nan = false;
-#pragma unroll 4
-        for (int j = 0; j < V.deg; ++j) {
-            const uint32_t yb = __float_as_uint(pb[32 * j]);
-            const uint32_t negm = (uint32_t)((int32_t)yb >> 31);
-            const float y = __uint_as_float(yb | 0x80000000u);   // -|y|
-            const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
-            made_nan |= (u != u);
-            pa[32 * j] = u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        for (int j0 = 0; j0 < V.deg; j0 += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (j0 + k >= V.deg) break;
+                const uint32_t en = eq[k];
+                if (j0 + k + 4 < V.deg) eq[k] = fw[32 * (j0 + k + 4)];
+                const int x = en & 0x7fffu;
+                const uint32_t negm = 0u - (en >> 15);
+                const float y = PB[x];
+                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
+                made_nan |= (u != u);
+                PA[x] = __uint_as_float(__float_as_uint(u) | stk);
+            }
         }
         if (made_nan) s.nanpend[b] = 1;
     }
@@ -485,17 +514,21 @@ __device__ __forceinline__ void blk_stagger(int sm_rank, int cycles) {
     while (clock64() - t0 < cycles) __nanosleep(256);
 }
 
+// state of the CTA's bulk-copy barrier: one mbarrier for the kernel's lifetime, its phase parity carried in a register
+struct BulkBar {
+    uint64_t* bar;
+    uint32_t parity;
+};
+
 // clause pass of iteration t: eta(t) [buffer r^1, V-layout] from q(t-1) [C-layout]
 template <int CTAS>
-__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, int sm_rank) {
+__device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
-    constexpr int NT = Cfg::kThreads, BLK_C = Cfg::kBlkC, CAP = Cfg::kAdjCap;
+    constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* X = reinterpret_cast<float*>(smem);
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
-    uint32_t* sticky = skip + Cfg::kBitWords;
-    int32_t* adj_s = reinterpret_cast<int32_t*>(sticky + Cfg::kBitWords);
-    __shared__ int sm_any_skip;
+    float* X0 = reinterpret_cast<float*>(smem);
+    uint2* wrun_s = reinterpret_cast<uint2*>(smem + Cfg::kPlaneBytes);
+    int32_t* adj_s = reinterpret_cast<int32_t*>(smem + Cfg::kPlaneBytes + 8 * Cfg::kRunWords);
     const float* __restrict__ qin = s.qu;
     float* __restrict__ eout = s.eta[r ^ 1];
     const int tid = threadIdx.x;
@@ -506,37 +539,57 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     for (int blk = blockIdx.x; blk < g.ncb; blk = feed_advance(sm_feed, par)) {
         if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_CBLK], sm_feed, par, blk);
         const BlkGeo B = clause_block(g, blk);
-        if (B.n1 <= B.n0) continue;
+        if (B.n1 <= B.n0 || B.ne <= 0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
-        for (int i = tid; i < (B.ne + 31) / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }
-        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         PHASE_T0();
-        ph_stage_runs<NT, CAP>(tid, g.c_wadj, B, adj_s);
-        if (use_mask && (B.multi() || s.masked[B.b0])) ph_clause_load<NT, true>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-        else ph_clause_load<NT, false>(tid, qin + B.e0, g.cinv + B.e0, g.qmask, B.e0, B.ne, X);
-        __syncthreads();
+        const BlkStage S = blk_stage<CAP>(B);
+        if (tid == 0) {
+            fence_proxy_async();      // the previous block's generic-proxy accesses of the planes precede these copies
+            mbar_expect_tx(bb.bar, (uint32_t)(S.nbytes + S.wbytes + S.rbytes));
+            bulk_g2s(X0, qin + S.a0, S.nbytes, bb.bar);
+            bulk_g2s(wrun_s, g.c_wrun + S.w0, S.wbytes, bb.bar);
+            if (S.rbytes) bulk_g2s(adj_s, g.c_wadj + S.r0, S.rbytes, bb.bar);
+            // the next block's streams -> L2 while this one is worked on (its index was fetched above)
+            const int nx = sm_feed[par];
+            if (PDP_L2_PREFETCH && nx < g.ncb) {
+                const BlkGeo N = clause_block(g, nx);
+                if (N.ne > 0) {
+                    if (PDP_L2_PREFETCH == 1) bulk_prefetch_l2(qin + N.e0, 4 * N.ne);
+                    bulk_prefetch_l2(g.cfwd + N.t0, 2 * N.tn);
+                    bulk_prefetch_l2(g.c_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                    bulk_prefetch_l2(g.c_wadj + N.run0, 4 * N.nruns);
+                }
+            }
+        }
+        float* X = X0 + S.shift;
+        const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
+        const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
+        const int ku = g.cb_k[blk];
+        mbar_wait(bb.bar, bb.parity);
+        bb.parity ^= 1u;
+        if (masked) { ph_apply_mask<NT>(tid, g.qmask, B, X); __syncthreads(); }
         PHASE_ADD(0);
-        ph_clause_node<NT>(tid, g, s, B, g.cb_k[blk], X, skip, &sm_any_skip, sticky);
+        if (masked) ph_clause_node<NT, true>(tid, g, s, B, ku, X, stk_blk);
+        else ph_clause_node<NT, false>(tid, g, s, B, ku, X, stk_blk);
         __syncthreads();
         PHASE_ADD(1);
-        ph_write_out<NT, CAP, 0xffffu>(tid, g.cinv, g.c_wrun, g.c_wadj, adj_s, B, X, skip, sm_any_skip, eout, sticky, s.eta[r]);
+        ph_write_out<NT>(tid, B, X, wrun_s, S.w0, S.rbytes ? adj_s - S.r0 : g.c_wadj, s.eta[r], eout);
         PHASE_ADD(2);
     }
+    fence_proxy_async();   // this pass's stores precede the bulk copies of the next pass (other CTAs, after the grid barrier)
 }
 
 // variable pass of iteration t: the decimator statistics of eta(t) [buffer r^1] against eta(t-1)
 // [buffer r], and q(t) [C-layout, in place] from eta(t-1)
 template <int CTAS>
-__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem, int sm_rank) {
+__device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
-    constexpr int NT = Cfg::kThreads, BLK_V = Cfg::kBlkV, BLK_C = Cfg::kBlkC, CAP = Cfg::kAdjCap;
+    constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
-    float* PA = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
-    float* PB = PA + BLK_V;                       // eta(t-1), then y
-    uint32_t* skip = reinterpret_cast<uint32_t*>(smem + 4 * BLK_C);
-    uint32_t* sticky = skip + Cfg::kBitWords;
-    int32_t* adj_s = reinterpret_cast<int32_t*>(sticky + Cfg::kBitWords);
-    __shared__ int sm_any_skip;
+    float* PA0 = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
+    float* PB0 = PA0 + Cfg::kPlaneV;               // eta(t-1), then y
+    uint2* wrun_s = reinterpret_cast<uint2*>(smem + Cfg::kPlaneBytes);
+    int32_t* adj_s = reinterpret_cast<int32_t*>(smem + Cfg::kPlaneBytes + 8 * Cfg::kRunWords);
     __shared__ BlkStats sm_st;
     const float* __restrict__ en = s.eta[r ^ 1];
     const float* __restrict__ eo = s.eta[r];
@@ -550,27 +603,49 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     for (int blk = blockIdx.x; blk < g.nvb; blk = feed_advance(sm_feed, par)) {
         if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_VBLK], sm_feed, par, blk);
         const BlkGeo B = var_block(g, blk);
-        if (B.n1 <= B.n0) continue;
+        if (B.n1 <= B.n0 || B.ne <= 0) continue;
         if (blk_idle(s, B.b0, B.b1)) continue;
+        PHASE_T0();
+        const BlkStage S = blk_stage<CAP>(B);
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bb.bar, (uint32_t)(2 * S.nbytes + S.wbytes + S.rbytes));
+            bulk_g2s(PA0, en + S.a0, S.nbytes, bb.bar);
+            bulk_g2s(PB0, eo + S.a0, S.nbytes, bb.bar);
+            bulk_g2s(wrun_s, g.v_wrun + S.w0, S.wbytes, bb.bar);
+            if (S.rbytes) bulk_g2s(adj_s, g.v_wadj + S.r0, S.rbytes, bb.bar);
+            const int nx = sm_feed[par];
+            if (PDP_L2_PREFETCH && nx < g.nvb) {
+                const BlkGeo N = var_block(g, nx);
+                if (N.ne > 0) {
+                    if (PDP_L2_PREFETCH == 1) { bulk_prefetch_l2(en + N.e0, 4 * N.ne); bulk_prefetch_l2(eo + N.e0, 4 * N.ne); }
+                    bulk_prefetch_l2(g.vfwd + N.t0, 2 * N.tn);
+                    bulk_prefetch_l2(g.vsort + N.n0, 8 * (N.n1 - N.n0));
+                    bulk_prefetch_l2(g.v_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                    bulk_prefetch_l2(g.v_wadj + N.run0, 4 * N.nruns);
+                }
+            }
+        }
+        float* PA = PA0 + S.shift;
+        float* PB = PB0 + S.shift;
         const bool local_stats = B.multi() && (B.b1 - B.b0 < PDP_STAT_SLOTS);   // else: registers (one problem) or global atomics
         // statistics of single-problem blocks: the per-thread accumulators run across the blocks of one problem and are
         // merged block-wide when the CTA moves on to another problem (and at the end of the pass)
         if (!B.multi() && acc_key != B.b0) { if (acc_key >= 0) red.finish(s); acc_key = B.b0; }
-        for (int i = tid; i < BLK_V / 32; i += NT) { skip[i] = 0u; sticky[i] = 0u; }   // (padded slots: the whole plane)
-        if (tid == 0) sm_any_skip = (!B.multi() && s.nanflag[B.b0]) ? 4 : 0;
         if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
-        PHASE_T0();
-        ph_stage_runs<NT, CAP>(tid, g.v_wadj, B, adj_s);
-        if ((use_mask || em_set) && (B.multi() || s.masked[B.b0])) ph_var_load<NT, true>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-        else ph_var_load<NT, false>(tid, en + B.e0, eo + B.e0, g.vinv + B.e0, g.vmask, B.e0, B.ne, PA, PB);
-        __syncthreads();
+        const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
+        const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
+        const bool scoring = PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1]);
+        mbar_wait(bb.bar, bb.parity);
+        bb.parity ^= 1u;
+        if (masked) ph_apply_mask<NT>(tid, g.vmask, B, PA);
+        if (masked || local_stats) __syncthreads();
         PHASE_ADD(3);
-        // SurveyScorer of problems about to converge, while the new surveys are still in the planes (the node phase
+        // SurveyScorer of problems about to converge, while the new surveys are still in the plane (the node phase
         // overwrites them); its own loop, so that the node phase's code is the same with and without it
-        if (PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1])) ph_var_score<NT>(tid, g, s, B, PA, PB);
+        if (scoring) { ph_var_score<NT>(tid, g, s, B, PA); __syncthreads(); }
         {
-            const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
-#define VN_CALL(MU, MA, PR) ph_var_node<NT, MU, MA, PR>(tid, g, s, B, use_mask, em_set, PA, PB, skip, &sm_any_skip, red, sm_st, local_stats, sticky)
+#define VN_CALL(MU, MA, PR) ph_var_node<NT, MU, MA, PR>(tid, g, s, B, use_mask, em_set, PA, PB, stk_blk, red, sm_st, local_stats)
             if (B.multi()) { if (has_prev) VN_CALL(true, true, true); else VN_CALL(true, true, false); }
             else if (masked) { if (has_prev) VN_CALL(false, true, true); else VN_CALL(false, true, false); }
             else { if (has_prev) VN_CALL(false, false, true); else VN_CALL(false, false, false); }
@@ -579,8 +654,9 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         __syncthreads();
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-        ph_write_out<NT, CAP, 0x7fffu>(tid, g.vinv, g.v_wrun, g.v_wadj, adj_s, B, PA, skip, sm_any_skip, s.qu, sticky, s.qu);
+        ph_write_out<NT>(tid, B, PA, wrun_s, S.w0, S.rbytes ? adj_s - S.r0 : g.v_wadj, s.qu, s.qu);
         PHASE_ADD(5);
     }
     red.finish(s);
+    fence_proxy_async();
 }

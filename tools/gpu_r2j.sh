@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; rm -f gpurun_out/r2j_*
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2j_tests.log
+timeout 300 python tools/prof_sweep.py --problems 8 --iterations 20 --repeat 3 2>&1 | grep "^E=" >> gpurun_out/r2j_sweep.log
+PDP_B200_LIB=$PWD/pdp_solver_b200/csrc/libpdp_b200_alt_pt.so PDP_PHASE_TIMING=2 timeout 300 python tools/prof_sweep.py --problems 8 --iterations 20 --repeat 1 2>&1 | grep -v "^layout" >> gpurun_out/r2j_sweep.log
+ncu --set full --clock-control none --import-source on -k regex:k_sp_run -c 1 -f -o gpurun_out/r2j_sp_run \
+    python tools/prof_sweep.py --problems 8 --iterations 12 > gpurun_out/r2j_sp_run.log 2>&1
+cat gpurun_out/r2j_tests.log gpurun_out/r2j_sweep.log

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out; rm -f gpurun_out/r2l_*
+timeout 300 python tools/prof_sweep.py --problems 2 --iterations 5 --repeat 1 > gpurun_out/r2l_first.log 2>&1
+tail -3 gpurun_out/r2l_first.log
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r2l_tests.log
+timeout 300 python tools/prof_sweep.py --problems 8 --iterations 20 --repeat 3 2>&1 | grep "^E=" >> gpurun_out/r2l_sweep.log
+PDP_B200_LIB=$PWD/pdp_solver_b200/csrc/libpdp_b200_alt_pt.so PDP_PHASE_TIMING=2 timeout 300 python tools/prof_sweep.py --problems 8 --iterations 20 --repeat 1 2>&1 | grep -v "^layout" >> gpurun_out/r2l_sweep.log
+timeout 300 python tools/prof_sweep.py --problems 5000 --n 100 --iterations 50 --repeat 3 2>&1 | grep "^E=" >> gpurun_out/r2l_sweep.log
+cat gpurun_out/r2l_tests.log gpurun_out/r2l_sweep.log
