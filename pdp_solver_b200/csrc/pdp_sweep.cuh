@@ -93,6 +93,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// explicit shared-window accesses (32-bit addresses).  The node phases index the planes through the position table; as
+// volatile statements these keep the order they are written in, which is how two rows are interleaved by hand below.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+
 // geometry of one block of a pass: one 48-byte descriptor (three 16-byte loads)
 struct BlkGeo {
     int n0, n1;      // node range
@@ -387,34 +394,45 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         if (!runs) continue;
         const uint32_t act = (uint32_t)s.av[V.i];
         float P = 0.f, N = 0.f, n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
-        // the table entries of a row are fetched four rows ahead (global memory: the CTAs leave no L1 to speak of)
+        // Rows go two at a time: both rows' shared-memory reads, then their arithmetic (two independent chains), then their
+        // writes.  (Row by row the compiler cannot move the reads of one row above the write of the row before -- the planes
+        // are indexed through the table -- and the logarithm chains of a warp run back to back.)  The table entries are
+        // fetched four rows ahead: global memory, the CTAs leave no L1 to speak of.
+        const uint32_t pa_s = smem_u32(PA), pb_off = (uint32_t)((const char*)PB - (const char*)PA);
         uint32_t eq[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        auto stat_row = [&](uint32_t en, uint32_t nb, float xo, float y) {
+            const float xn = __uint_as_float(nb & 0x7fffffffu);
+            if (en >> 15) N += y; else P += y;          // (the reference adds 0 * y to the other sum: x + 0 = x, see above for NaN)
+            const float c = X30S(xn);
+            n0 += xn * c; d0 += c;
+            if (PREV) {
+                float d = fabsf(xo - xn);
+                if (MASKED && em_set && (int32_t)nb < 0) d = d * 0.f;
+                const float cd = X30S(d);
+                n1 += d * cd; d1 += cd;
+            }
+        };
         for (int j0 = 0; j0 < V.deg; j0 += 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (j0 + k >= V.deg) break;
-                const uint32_t en = eq[k];
-                if (j0 + k + 4 < V.deg) eq[k] = fw[32 * (j0 + k + 4)];
-                const int x = en & 0x7fffu;
-                const uint32_t negm = 0u - (en >> 15);                  // all ones: negative literal
-                const uint32_t nb = __float_as_uint(PA[x]);
-                const float xo = PB[x];
-                const float xn = __uint_as_float(nb & 0x7fffffffu);
-                float y = L40_1m(xo);
-                if (MASKED && use_mask && (int32_t)nb < 0) y = y * 0.f;      // edge masked
-                PB[x] = y;
-                P += fand(~negm, y);
-                N += fand(negm, y);
-                const float c = X30S(xn);
-                n0 += xn * c; d0 += c;
-                if (PREV) {
-                    float d = fabsf(xo - xn);
-                    if (MASKED && em_set && (int32_t)nb < 0) d = d * 0.f;
-                    const float cd = X30S(d);
-                    n1 += d * cd; d1 += cd;
-                }
+            for (int h = 0; h < 4; h += 2) {
+                const int j = j0 + h;
+                if (j >= V.deg) break;
+                const bool vb = j + 1 < V.deg;
+                const uint32_t ea = eq[h], eb = vb ? eq[h + 1] : eq[h];
+                if (j + 4 < V.deg) eq[h] = fw[32 * (j + 4)];
+                if (j + 5 < V.deg) eq[h + 1] = fw[32 * (j + 5)];
+                const uint32_t aa = pa_s + ((ea & 0x7fffu) << 2), ab = pa_s + ((eb & 0x7fffu) << 2);
+                const uint32_t nba = lds_u32(aa); const float xoa = lds_f32(aa + pb_off);
+                const uint32_t nbb = lds_u32(ab); const float xob = lds_f32(ab + pb_off);
+                float ya = L40_1m(xoa), yb = L40_1m(xob);
+                if (MASKED && use_mask && (int32_t)nba < 0) ya = ya * 0.f;      // edge masked
+                if (MASKED && use_mask && (int32_t)nbb < 0) yb = yb * 0.f;
+                sts_f32(aa + pb_off, ya);
+                if (vb) sts_f32(ab + pb_off, yb);
+                stat_row(ea, nba, xoa, ya);
+                if (vb) stat_row(eb, nbb, xob, yb);
             }
         }
         {
@@ -444,20 +462,31 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         bool made_nan = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        // q <= 1 (total >= u) or NaN: bit 30 of the results' OR tells whether a NaN was produced.  (A q >= 2 out of surveys
+        // that are no probabilities sets it as well: the problem then takes the sticky path for nothing, same results.)
+        uint32_t nan_or = 0u;
+        auto fin_row = [&](uint32_t en, float y) {
+            const bool neg = (en >> 15) != 0u;
+            return sp_var_finish(neg ? sb_neg : sb_pos, neg ? opp_neg : opp_pos, neg ? O_neg : O_pos, y);
+        };
         for (int j0 = 0; j0 < V.deg; j0 += 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (j0 + k >= V.deg) break;
-                const uint32_t en = eq[k];
-                if (j0 + k + 4 < V.deg) eq[k] = fw[32 * (j0 + k + 4)];
-                const int x = en & 0x7fffu;
-                const uint32_t negm = 0u - (en >> 15);
-                const float y = PB[x];
-                const float u = sp_var_finish(fsel(negm, sb_neg, sb_pos), fsel(negm, opp_neg, opp_pos), fsel(negm, O_neg, O_pos), y);
-                made_nan |= (u != u);
-                PA[x] = __uint_as_float(__float_as_uint(u) | stk);
+            for (int h = 0; h < 4; h += 2) {
+                const int j = j0 + h;
+                if (j >= V.deg) break;
+                const bool vb = j + 1 < V.deg;
+                const uint32_t ea = eq[h], eb = vb ? eq[h + 1] : eq[h];
+                if (j + 4 < V.deg) eq[h] = fw[32 * (j + 4)];
+                if (j + 5 < V.deg) eq[h + 1] = fw[32 * (j + 5)];
+                const uint32_t aa = pa_s + ((ea & 0x7fffu) << 2), ab = pa_s + ((eb & 0x7fffu) << 2);
+                const float ya = lds_f32(aa + pb_off), yb = lds_f32(ab + pb_off);
+                const uint32_t ua = __float_as_uint(fin_row(ea, ya)), ub = __float_as_uint(fin_row(eb, yb));
+                nan_or |= ua | ub;     // (row b of an odd tail repeats row a)
+                sts_u32(aa, ua | stk);
+                if (vb) sts_u32(ab, ub | stk);
             }
         }
+        made_nan = (nan_or & 0x40000000u) != 0u;
         if (made_nan) s.nanpend[b] = 1;
     }
 }
