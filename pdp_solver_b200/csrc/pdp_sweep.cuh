@@ -71,6 +71,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 // generic-proxy accesses of this thread (and, after a barrier, of the CTA) ordered before later async-proxy accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ... the same for shared memory only (before a bulk copy overwrites a plane the CTA has just read): does not wait for the
+// thread's outstanding global stores, which the full fence does (3 000 cycles per block right after a write-out, measured)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // one thread: [p, p + bytes) -> L2, rounded outwards to 16-byte units (a hint: no completion to wait for)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, int bytes) {
     if (bytes <= 0) return;
@@ -141,24 +144,30 @@ __device__ __forceinline__ BlkStage blk_stage(const BlkGeo& B) {
     return S;
 }
 
-// write-out: slots [e0, e0 + ne) of the block = the positions of its own region; destinations ascend.  One slot per thread
-// and instruction (with several consecutive slots per thread a warp's stores would be strided and every destination sector
-// written several times).  Everything but the store (and the rare sticky re-read) is shared memory.
-// plane: the shifted plane (slot w at plane[w - e0]);  wrun_s: the staged run table (word i of the table at wrun_s[i - w0]);
-// adj: run offsets, biased so that adj[run] is the offset of global run `run` (shared memory or g.*_wadj).
-template <int G>
-__device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, const float* plane, const uint2* wrun_s, int w0,
-                                             const int32_t* adj, const float* old, float* out) {   // old may alias out (q is updated in place)
-    // A warp takes 32 slots that share one word of the run table: slot w = wb + 32 k + lane with wb a multiple of 32, so
-    // the lane's bit mask is fixed and the table word is one broadcast load.  Slots before e0 / from e0 + ne on are idle.
+// write-out: slots [wlo, wend) of the block's region (a segment of it); destinations ascend.  One slot per thread and
+// instruction (with several consecutive slots per thread a warp's stores would be strided and every destination sector
+// written several times).  Everything but the store (and the rare sticky re-read) is shared memory, addressed in the shared
+// window: plane_sa = address of slot 0's word (slot w at plane_sa + 4 w), wrun_sa = address of run table word 0 (word i at
+// wrun_sa + 8 i), adj_sa = address of run 0's offset (ADJ_S) or adj_g = g.*_wadj (a block with too many runs to stage).
+template <int G, bool ADJ_S>
+__device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_t plane_sa, uint32_t wrun_sa, uint32_t adj_sa,
+                                               const int32_t* __restrict__ adj_g, const float* old, float* out) {   // old may alias out (q is updated in place)
+    // A warp takes 32 slots that share one word of the run table: slot w = row + lane with row a multiple of 32, so the
+    // lane's bit mask is fixed and the table word is one broadcast load.  The rows are warp-uniform; a lane whose slot lies
+    // outside [wlo, wend) idles.
     const int lane = t & 31;
-    const int wend = B.e0 + B.ne;
-    const uint32_t lmask = 0xffffffffu >> (31 - lane);
-    const uint32_t* pl = reinterpret_cast<const uint32_t*>(plane) - B.e0;
-    const uint2* wr = wrun_s - w0;
-    auto one = [&](int w, uint32_t raw, uint2 rb) {
-        if (raw == PDP_SLOT_SKIP) return;
-        const int d = adj[(int)rb.y + __popc(rb.x & lmask)] + w;
+    uint32_t lmask;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(lmask));
+    auto one = [&](int w, uint32_t raw, uint32_t rbx, uint32_t rby) {
+        const bool valid = w >= wlo && w < wend;
+        const int run = (int)rby + __popc(rbx & lmask);
+        int d = w;
+        if (valid) d += ADJ_S ? (int)lds_u32(adj_sa + 4u * (uint32_t)run) : __ldg(adj_g + run);
+        if (!__any_sync(0xffffffffu, valid && (int32_t)raw < 0)) {      // nothing skipped, nothing sticky in this row: the rule
+            if (valid) out[d] = __uint_as_float(raw);
+            return;
+        }
+        if (!valid || raw == PDP_SLOT_SKIP) return;
         if ((int32_t)raw < 0) {                           // sticky (or a NaN that happens to carry a sign: harmless)
             raw &= 0x7fffffffu;
             const float ov = old[d];
@@ -167,16 +176,33 @@ __device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, const float
         out[d] = __uint_as_float(raw);
     };
     constexpr int U = PDP_UNROLL_WO;
-    int w = (B.e0 & ~31) + 32 * (t >> 5) + lane;
-    if (w < B.e0) w += G;                                 // (only the first 32 slots can lie before the region)
-    for (; w + (U - 1) * G < wend; w += U * G) {
-        uint32_t raw[U]; uint2 rb[U];
+    int row = (wlo & ~31) + 32 * (t >> 5);                // warp-uniform
+    for (; row + (U - 1) * G < wend; row += U * G) {
+        uint32_t raw[U], rbx[U], rby[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { raw[u] = pl[w + u * G]; rb[u] = wr[(w + u * G) >> 5]; }
+        for (int u = 0; u < U; ++u) {
+            const int w = row + u * G + lane;
+            raw[u] = (w >= wlo && w < wend) ? lds_u32(plane_sa + 4u * (uint32_t)w) : 0u;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx[u]), "=r"(rby[u]) : "r"(wrun_sa + 8u * (uint32_t)((row + u * G) >> 5)));
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) one(w + u * G, raw[u], rb[u]);
+        for (int u = 0; u < U; ++u) one(row + u * G + lane, raw[u], rbx[u], rby[u]);
     }
-    for (; w < wend; w += G) one(w, pl[w], wr[w >> 5]);
+    for (; row < wend; row += G) {
+        const int w = row + lane;
+        uint32_t rbx, rby;
+        const uint32_t raw = (w >= wlo && w < wend) ? lds_u32(plane_sa + 4u * (uint32_t)w) : 0u;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wrun_sa + 8u * (uint32_t)(row >> 5)));
+        one(w, raw, rbx, rby);
+    }
+}
+template <int G>
+__device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, int wlo, int wend, const float* plane, const uint2* wrun_s, int w0,
+                                             const int32_t* adj_s, int r0, const int32_t* adj_g, const float* old, float* out) {
+    const uint32_t plane_sa = smem_u32(plane) - 4u * (uint32_t)B.e0;
+    const uint32_t wrun_sa = smem_u32(wrun_s) - 8u * (uint32_t)w0;
+    if (adj_s) ph_write_out_t<G, true>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
+    else ph_write_out_t<G, false>(t, wlo, wend, plane_sa, wrun_sa, 0u, adj_g, old, out);
 }
 
 // the edge-mask bits of the block's region (indexed by layout position) -> sign bits of the plane (its values are >= +0 or
@@ -519,11 +545,16 @@ __device__ __forceinline__ void stats_slots_commit(const pdp_state& s, BlkStats&
 // Block hand-out of one pass.  Static (block b to CTA b mod grid) when one CTA owns the SM: the CTAs then finish within
 // 1-2 % of each other.  With two CTAs per SM the pair drifts apart, the early one waits at the grid barrier and its
 // partner finishes alone at half the SM's warps (10 % of the iteration, measured), so the blocks after a CTA's first one
-// come from a counter; the next index is fetched while the current block is processed.
-// thread 0, at the top of a block: the index of the block after `blk`, left in slot[par] for feed_advance
+// come from a counter.  Nothing on the way to a block's bulk copies may wait for global memory: the counter is read TWO
+// blocks ahead (thread 0 picks up, at the top of a block, the ticket it drew at the top of the block before and draws the
+// next one), and the descriptor of the next block is fetched during the current block's write-out and handed over in
+// shared memory (NextBlk).
+struct Feeder {
+    int pending;    // (thread 0) ticket drawn at the top of the previous block: index of the block after the next one
+};
 template <bool DYN>
-__device__ __forceinline__ void feed_fetch(int* ctr, int* slot, int par, int blk) {
-    slot[par] = DYN ? (int)gridDim.x + atomicAdd(ctr, 1) : blk + (int)gridDim.x;
+__device__ __forceinline__ int feed_draw(int* ctr, int blk_static) {
+    return DYN ? (int)gridDim.x + atomicAdd(ctr, 1) : blk_static;
 }
 // all threads, after the block's last use of shared memory
 __device__ __forceinline__ int feed_advance(const int* slot, int& par) {
@@ -543,6 +574,33 @@ __device__ __forceinline__ void blk_stagger(int sm_rank, int cycles) {
     while (clock64() - t0 < cycles) __nanosleep(256);
 }
 
+// The planes of the NEXT block are filled while the current block is written out: the write-out goes through the plane in
+// PDP_WO_SEGS segments, a block barrier after each; what lies behind the barrier is dead and thread 0 issues the bulk copy
+// of the next block's words there (same mbarrier phase as the rest of that block's copies, opened with the byte count of
+// the whole block).  Only blocks that are certain to be processed are preloaded (their problems' activity does not change
+// inside a pass); the state below lives in thread 0.
+#ifndef PDP_WO_SEGS
+#define PDP_WO_SEGS 1
+#endif
+struct Preload {
+    int blk;        // block whose copies were opened ahead (-1: none)
+    int words;      // words of its (first) plane issued so far
+};
+// thread 0: will the blocked pass process block N?  1 yes, 2 no, 0 not looked at (a block of very many problems)
+__device__ __forceinline__ int blk_will_run(const pdp_state& s, const BlkGeo& N) {
+    if (N.n1 <= N.n0 || N.ne <= 0) return 2;
+    if (N.b1 - N.b0 >= 128) return 0;
+    for (int b = N.b0; b <= N.b1; ++b) if (blk_problem_runs(s, b)) return 1;
+    return 2;
+}
+// The descriptor of the block a CTA takes next is fetched (by thread 0, while the CTA waits for the current block's copies)
+// and handed over in shared memory: at the top of the next block nothing stands between the barrier and the bulk copies.
+struct NextBlk {
+    BlkGeo B;
+    int blk;        // the block B describes (-1: nothing)
+    int state;      // blk_will_run
+};
+
 // state of the CTA's bulk-copy barrier: one mbarrier for the kernel's lifetime, its phase parity carried in a register
 struct BulkBar {
     uint64_t* bar;
@@ -554,6 +612,7 @@ template <int CTAS>
 __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
+    constexpr int SEGW = (((Cfg::kBlkC + 8 + PDP_WO_SEGS - 1) / PDP_WO_SEGS) + 3) & ~3;   // plane words of a write-out segment
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* X0 = reinterpret_cast<float*>(smem);
     uint2* wrun_s = reinterpret_cast<uint2*>(smem + Cfg::kPlaneBytes);
@@ -562,33 +621,40 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     float* __restrict__ eout = s.eta[r ^ 1];
     const int tid = threadIdx.x;
     __shared__ int sm_feed[2];
+    __shared__ NextBlk sm_next[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
+    Preload pre{-1, 0};
+    Feeder fd;
+    fd.pending = (tid == 0) ? feed_draw<DYN>(&s.ctrl[CTRL_NEXT_CBLK], (int)blockIdx.x + (int)gridDim.x) : 0;
+    if (tid < 2) sm_next[tid].blk = -1;
+    __syncthreads();
     if (CTAS == 2) blk_stagger(sm_rank, A.stagger_c);
     for (int blk = blockIdx.x; blk < g.ncb; blk = feed_advance(sm_feed, par)) {
-        if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_CBLK], sm_feed, par, blk);
-        const BlkGeo B = clause_block(g, blk);
-        if (B.n1 <= B.n0 || B.ne <= 0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
+        int nx = 0;      // (thread 0) the block after this one
+        if (tid == 0) {
+            nx = fd.pending;
+            fd.pending = feed_draw<DYN>(&s.ctrl[CTRL_NEXT_CBLK], nx + (int)gridDim.x);
+            sm_feed[par] = nx;
+        }
+        BlkGeo B;
+        int known = 0;
+        if (sm_next[par ^ 1].blk == blk) { B = sm_next[par ^ 1].B; known = sm_next[par ^ 1].state; }
+        else B = clause_block(g, blk);
+        if (known == 2) continue;
+        if (known == 0) {
+            if (B.n1 <= B.n0 || B.ne <= 0) continue;
+            if (blk_idle(s, B.b0, B.b1)) continue;
+        }
         PHASE_T0();
         const BlkStage S = blk_stage<CAP>(B);
         if (tid == 0) {
-            fence_proxy_async();      // the previous block's generic-proxy accesses of the planes precede these copies
-            mbar_expect_tx(bb.bar, (uint32_t)(S.nbytes + S.wbytes + S.rbytes));
-            bulk_g2s(X0, qin + S.a0, S.nbytes, bb.bar);
+            fence_proxy_async_smem();      // the previous block's generic-proxy accesses of the planes precede these copies
+            if (pre.blk != blk) { mbar_expect_tx(bb.bar, (uint32_t)(S.nbytes + S.wbytes + S.rbytes)); pre.words = 0; }
+            if (4 * pre.words < S.nbytes) bulk_g2s(X0 + pre.words, qin + S.a0 + pre.words, S.nbytes - 4 * pre.words, bb.bar);
             bulk_g2s(wrun_s, g.c_wrun + S.w0, S.wbytes, bb.bar);
             if (S.rbytes) bulk_g2s(adj_s, g.c_wadj + S.r0, S.rbytes, bb.bar);
-            // the next block's streams -> L2 while this one is worked on (its index was fetched above)
-            const int nx = sm_feed[par];
-            if (PDP_L2_PREFETCH && nx < g.ncb) {
-                const BlkGeo N = clause_block(g, nx);
-                if (N.ne > 0) {
-                    if (PDP_L2_PREFETCH == 1) bulk_prefetch_l2(qin + N.e0, 4 * N.ne);
-                    bulk_prefetch_l2(g.cfwd + N.t0, 2 * N.tn);
-                    bulk_prefetch_l2(g.c_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
-                    bulk_prefetch_l2(g.c_wadj + N.run0, 4 * N.nruns);
-                }
-            }
+            pre.blk = -1;
         }
         float* X = X0 + S.shift;
         const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
@@ -602,7 +668,44 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         else ph_clause_node<NT, false>(tid, g, s, B, ku, X, stk_blk);
         __syncthreads();
         PHASE_ADD(1);
-        ph_write_out<NT>(tid, B, X, wrun_s, S.w0, S.rbytes ? adj_s - S.r0 : g.c_wadj, s.eta[r], eout);
+        {
+            // write-out in segments of the plane.  After the first one thread 0 looks at the next block (descriptor for the
+            // hand-over, tables -> L2, its copies opened); behind every later one the next block's words move in.
+            BlkStage NS; NS.a0 = 0; NS.nbytes = 0; NS.wbytes = 0; NS.rbytes = 0;
+            const int wbeg = B.e0 - S.shift;      // slot of plane word 0
+#pragma unroll 1
+            for (int k = 0; k < PDP_WO_SEGS; ++k) {
+                const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
+                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, X, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.c_wadj, s.eta[r], eout);
+                if (k == 0 && tid == 0 && nx < g.ncb) {
+                    const BlkGeo N = clause_block(g, nx);
+                    const int st = blk_will_run(s, N);
+                    sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = st;
+                    if (PDP_L2_PREFETCH && N.ne > 0) {
+                        if (PDP_L2_PREFETCH == 1) bulk_prefetch_l2(qin + N.e0, 4 * N.ne);
+                        bulk_prefetch_l2(g.cfwd + N.t0, 2 * N.tn);
+                        bulk_prefetch_l2(g.c_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                        bulk_prefetch_l2(g.c_wadj + N.run0, 4 * N.nruns);
+                    }
+                    if (PDP_WO_SEGS > 1 && st == 1) {
+                        NS = blk_stage<CAP>(N);
+                        mbar_expect_tx(bb.bar, (uint32_t)(NS.nbytes + NS.wbytes + NS.rbytes));
+                        pre.blk = nx; pre.words = 0;
+                    }
+                }
+                if (k + 1 < PDP_WO_SEGS) {
+                    __syncthreads();
+                    if (tid == 0 && pre.blk >= 0) {
+                        const int upto = min((k + 1) * SEGW, NS.nbytes >> 2);
+                        if (upto > pre.words) {
+                            fence_proxy_async_smem();
+                            bulk_g2s(X0 + pre.words, qin + NS.a0 + pre.words, 4 * (upto - pre.words), bb.bar);
+                            pre.words = upto;
+                        }
+                    }
+                }
+            }
+        }
         PHASE_ADD(2);
     }
     fence_proxy_async();   // this pass's stores precede the bulk copies of the next pass (other CTAs, after the grid barrier)
@@ -614,6 +717,7 @@ template <int CTAS>
 __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
+    constexpr int SEGW = (((Cfg::kPlaneV + PDP_WO_SEGS - 1) / PDP_WO_SEGS) + 3) & ~3;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* PA0 = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
     float* PB0 = PA0 + Cfg::kPlaneV;               // eta(t-1), then y
@@ -626,34 +730,44 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     KeyedReducer<StatAcc> red;
     int acc_key = -1;
     __shared__ int sm_feed[2];
+    __shared__ NextBlk sm_next[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
+    Preload pre{-1, 0};
+    Feeder fd;
+    fd.pending = (tid == 0) ? feed_draw<DYN>(&s.ctrl[CTRL_NEXT_VBLK], (int)blockIdx.x + (int)gridDim.x) : 0;
+    if (tid < 2) sm_next[tid].blk = -1;
+    __syncthreads();
     if (CTAS == 2) blk_stagger(sm_rank, A.stagger_v);
     for (int blk = blockIdx.x; blk < g.nvb; blk = feed_advance(sm_feed, par)) {
-        if (tid == 0) feed_fetch<DYN>(&s.ctrl[CTRL_NEXT_VBLK], sm_feed, par, blk);
-        const BlkGeo B = var_block(g, blk);
-        if (B.n1 <= B.n0 || B.ne <= 0) continue;
-        if (blk_idle(s, B.b0, B.b1)) continue;
+        int nx = 0;
+        if (tid == 0) {
+            nx = fd.pending;
+            fd.pending = feed_draw<DYN>(&s.ctrl[CTRL_NEXT_VBLK], nx + (int)gridDim.x);
+            sm_feed[par] = nx;
+        }
+        BlkGeo B;
+        int known = 0;
+        if (sm_next[par ^ 1].blk == blk) { B = sm_next[par ^ 1].B; known = sm_next[par ^ 1].state; }
+        else B = var_block(g, blk);
+        if (known == 2) continue;
+        if (known == 0) {
+            if (B.n1 <= B.n0 || B.ne <= 0) continue;
+            if (blk_idle(s, B.b0, B.b1)) continue;
+        }
         PHASE_T0();
         const BlkStage S = blk_stage<CAP>(B);
         if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bb.bar, (uint32_t)(2 * S.nbytes + S.wbytes + S.rbytes));
-            bulk_g2s(PA0, en + S.a0, S.nbytes, bb.bar);
-            bulk_g2s(PB0, eo + S.a0, S.nbytes, bb.bar);
+            fence_proxy_async_smem();
+            if (pre.blk != blk) {
+                mbar_expect_tx(bb.bar, (uint32_t)(2 * S.nbytes + S.wbytes + S.rbytes));
+                bulk_g2s(PB0, eo + S.a0, S.nbytes, bb.bar);
+                pre.words = 0;
+            }
+            if (4 * pre.words < S.nbytes) bulk_g2s(PA0 + pre.words, en + S.a0 + pre.words, S.nbytes - 4 * pre.words, bb.bar);
             bulk_g2s(wrun_s, g.v_wrun + S.w0, S.wbytes, bb.bar);
             if (S.rbytes) bulk_g2s(adj_s, g.v_wadj + S.r0, S.rbytes, bb.bar);
-            const int nx = sm_feed[par];
-            if (PDP_L2_PREFETCH && nx < g.nvb) {
-                const BlkGeo N = var_block(g, nx);
-                if (N.ne > 0) {
-                    if (PDP_L2_PREFETCH == 1) { bulk_prefetch_l2(en + N.e0, 4 * N.ne); bulk_prefetch_l2(eo + N.e0, 4 * N.ne); }
-                    bulk_prefetch_l2(g.vfwd + N.t0, 2 * N.tn);
-                    bulk_prefetch_l2(g.vsort + N.n0, 8 * (N.n1 - N.n0));
-                    bulk_prefetch_l2(g.v_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
-                    bulk_prefetch_l2(g.v_wadj + N.run0, 4 * N.nruns);
-                }
-            }
+            pre.blk = -1;
         }
         float* PA = PA0 + S.shift;
         float* PB = PB0 + S.shift;
@@ -683,7 +797,47 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         __syncthreads();
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-        ph_write_out<NT>(tid, B, PA, wrun_s, S.w0, S.rbytes ? adj_s - S.r0 : g.v_wadj, s.qu, s.qu);
+        {
+            // write-out in segments of plane PA (see the clause pass); the next block's old surveys move into PB (dead
+            // since the node phase) as soon as its copies are opened, its new surveys into PA behind the write-out
+            BlkStage NS; NS.a0 = 0; NS.nbytes = 0; NS.wbytes = 0; NS.rbytes = 0;
+            const int wbeg = B.e0 - S.shift;
+#pragma unroll 1
+            for (int k = 0; k < PDP_WO_SEGS; ++k) {
+                const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
+                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, PA, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.v_wadj, s.qu, s.qu);
+                if (k == 0 && tid == 0 && nx < g.nvb) {
+                    const BlkGeo N = var_block(g, nx);
+                    const int st = blk_will_run(s, N);
+                    sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = st;
+                    if (PDP_L2_PREFETCH && N.ne > 0) {
+                        if (PDP_L2_PREFETCH == 1) { bulk_prefetch_l2(en + N.e0, 4 * N.ne); bulk_prefetch_l2(eo + N.e0, 4 * N.ne); }
+                        bulk_prefetch_l2(g.vfwd + N.t0, 2 * N.tn);
+                        bulk_prefetch_l2(g.vsort + N.n0, 8 * (N.n1 - N.n0));
+                        bulk_prefetch_l2(g.v_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                        bulk_prefetch_l2(g.v_wadj + N.run0, 4 * N.nruns);
+                    }
+                    if (PDP_WO_SEGS > 1 && st == 1) {
+                        NS = blk_stage<CAP>(N);
+                        fence_proxy_async_smem();
+                        mbar_expect_tx(bb.bar, (uint32_t)(2 * NS.nbytes + NS.wbytes + NS.rbytes));
+                        bulk_g2s(PB0, eo + NS.a0, NS.nbytes, bb.bar);
+                        pre.blk = nx; pre.words = 0;
+                    }
+                }
+                if (k + 1 < PDP_WO_SEGS) {
+                    __syncthreads();
+                    if (tid == 0 && pre.blk >= 0) {
+                        const int upto = min((k + 1) * SEGW, NS.nbytes >> 2);
+                        if (upto > pre.words) {
+                            fence_proxy_async_smem();
+                            bulk_g2s(PA0 + pre.words, en + NS.a0 + pre.words, 4 * (upto - pre.words), bb.bar);
+                            pre.words = upto;
+                        }
+                    }
+                }
+            }
+        }
         PHASE_ADD(5);
     }
     red.finish(s);
