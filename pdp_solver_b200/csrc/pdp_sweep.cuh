@@ -153,47 +153,62 @@ template <int G, bool ADJ_S>
 __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_t plane_sa, uint32_t wrun_sa, uint32_t adj_sa,
                                                const int32_t* __restrict__ adj_g, const float* old, float* out) {   // old may alias out (q is updated in place)
     // A warp takes 32 slots that share one word of the run table: slot w = row + lane with row a multiple of 32, so the
-    // lane's bit mask is fixed and the table word is one broadcast load.  The rows are warp-uniform; a lane whose slot lies
-    // outside [wlo, wend) idles.
-    const int lane = t & 31;
+    // lane's bit mask is fixed and the table word is one broadcast load.  Rows that lie entirely inside [wlo, wend) go
+    // through the main loop without a bounds check; the (at most two) partial rows at the ends are left to two warps.
+    const int lane = t & 31, warp = t >> 5;
     uint32_t lmask;
     asm("mov.u32 %0, %%lanemask_le;" : "=r"(lmask));
-    auto one = [&](int w, uint32_t raw, uint32_t rbx, uint32_t rby) {
-        const bool valid = w >= wlo && w < wend;
+    auto dest = [&](int w, uint32_t rbx, uint32_t rby) {
         const int run = (int)rby + __popc(rbx & lmask);
-        int d = w;
-        if (valid) d += ADJ_S ? (int)lds_u32(adj_sa + 4u * (uint32_t)run) : __ldg(adj_g + run);
-        if (!__any_sync(0xffffffffu, valid && (int32_t)raw < 0)) {      // nothing skipped, nothing sticky in this row: the rule
-            if (valid) out[d] = __uint_as_float(raw);
-            return;
-        }
-        if (!valid || raw == PDP_SLOT_SKIP) return;
-        if ((int32_t)raw < 0) {                           // sticky (or a NaN that happens to carry a sign: harmless)
-            raw &= 0x7fffffffu;
-            const float ov = old[d];
-            if (ov != ov) raw = __float_as_uint(ov);
-        }
+        return w + (ADJ_S ? (int)lds_u32(adj_sa + 4u * (uint32_t)run) : __ldg(adj_g + run));
+    };
+    auto special = [&](int d, uint32_t raw) {       // a slot with a marker (sign bit): skipped, or sticky
+        if (raw == PDP_SLOT_SKIP) return;
+        raw &= 0x7fffffffu;                         // sticky (or a NaN that happens to carry a sign: harmless)
+        const float ov = old[d];
+        if (ov != ov) raw = __float_as_uint(ov);
         out[d] = __uint_as_float(raw);
     };
+    const int rf0 = (wlo + 31) & ~31, rf1 = wend & ~31;      // full rows: [rf0, rf1)
     constexpr int U = PDP_UNROLL_WO;
-    int row = (wlo & ~31) + 32 * (t >> 5);                // warp-uniform
-    for (; row + (U - 1) * G < wend; row += U * G) {
+    int row = rf0 + 32 * warp;
+    uint32_t pa = plane_sa + 4u * (uint32_t)(row + lane), wa = wrun_sa + 8u * (uint32_t)(row >> 5);
+    for (; row + (U - 1) * G < rf1; row += U * G, pa += 4u * U * G, wa += 8u * U * (G / 32)) {
         uint32_t raw[U], rbx[U], rby[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int w = row + u * G + lane;
-            raw[u] = (w >= wlo && w < wend) ? lds_u32(plane_sa + 4u * (uint32_t)w) : 0u;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx[u]), "=r"(rby[u]) : "r"(wrun_sa + 8u * (uint32_t)((row + u * G) >> 5)));
+            raw[u] = lds_u32(pa + 4u * u * G);
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx[u]), "=r"(rby[u]) : "r"(wa + 8u * u * (G / 32)));
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) one(row + u * G + lane, raw[u], rbx[u], rby[u]);
+        for (int u = 0; u < U; ++u) {
+            const int d = dest(row + u * G + lane, rbx[u], rby[u]);
+            if (!__any_sync(0xffffffffu, (int32_t)raw[u] < 0)) out[d] = __uint_as_float(raw[u]);      // the rule: no marker in the row
+            else if ((int32_t)raw[u] < 0) special(d, raw[u]);
+            else out[d] = __uint_as_float(raw[u]);
+        }
     }
-    for (; row < wend; row += G) {
-        const int w = row + lane;
+    for (; row < rf1; row += G, pa += 4u * G, wa += 8u * (G / 32)) {
         uint32_t rbx, rby;
-        const uint32_t raw = (w >= wlo && w < wend) ? lds_u32(plane_sa + 4u * (uint32_t)w) : 0u;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wrun_sa + 8u * (uint32_t)(row >> 5)));
-        one(w, raw, rbx, rby);
+        const uint32_t raw = lds_u32(pa);
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wa));
+        const int d = dest(row + lane, rbx, rby);
+        if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
+    }
+    // partial rows: the one holding wlo (when wlo is not a multiple of 32) and the one holding wend - 1
+    const int r_head = wlo & ~31, r_tail = (wend - 1) & ~31;
+    int er = -1;
+    if (warp == 0 && r_head < rf0) er = r_head;
+    else if (warp == 1 && r_tail >= rf1 && !(r_tail == r_head && r_head < rf0)) er = r_tail;
+    if (er >= 0) {
+        const int w = er + lane;
+        if (w >= wlo && w < wend) {
+            uint32_t rbx, rby;
+            const uint32_t raw = lds_u32(plane_sa + 4u * (uint32_t)w);
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wrun_sa + 8u * (uint32_t)(er >> 5)));
+            const int d = dest(w, rbx, rby);
+            if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
+        }
     }
 }
 template <int G>
