@@ -420,6 +420,10 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
                                             bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t stk_blk,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
     const int lane = t & 31;
+    // shared-window address of plane PA / distance to PB, pinned in registers (left to itself the compiler re-derives the
+    // window base from %cgaid at every use)
+    uint32_t pa_s = smem_u32(PA), pb_off = (uint32_t)((const char*)PB - (const char*)PA);
+    asm volatile("" : "+r"(pa_s), "+r"(pb_off));
     VAR_GROUP_LOOP(grp, B, G, t) {
         const VarGroup V = var_group(g, B, grp);
         const uint16_t* __restrict__ fw = g.vfwd + B.t0 + V.base + lane;
@@ -439,7 +443,6 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         // writes.  (Row by row the compiler cannot move the reads of one row above the write of the row before -- the planes
         // are indexed through the table -- and the logarithm chains of a warp run back to back.)  The table entries are
         // fetched four rows ahead: global memory, the CTAs leave no L1 to speak of.
-        const uint32_t pa_s = smem_u32(PA), pb_off = (uint32_t)((const char*)PB - (const char*)PA);
         uint32_t eq[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
