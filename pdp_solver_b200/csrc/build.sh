@@ -8,7 +8,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="$ARCH -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -Wno-deprecated-declarations --expt-relaxed-constexpr"
-SRCS="pdp_graph pdp_layout pdp_ops pdp_loop pdp_walksat pdp_host"
+SRCS="pdp_graph pdp_layout pdp_ops pdp_loop pdp_walksat pdp_host pdp_edge_nn"
 stale() {  # $1 = object, $2 = source
   [ ! -f "$1" ] || [ "$2" -nt "$1" ] || [ pdp_common.cuh -nt "$1" ] || [ pdp_device.cuh -nt "$1" ] || [ pdp_sweep.cuh -nt "$1" ] || [ ../../include/pdp_b200.h -nt "$1" ] || [ build.sh -nt "$1" ]
 }

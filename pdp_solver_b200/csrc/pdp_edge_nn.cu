@@ -1,0 +1,439 @@
+// pdp_edge_nn.cu -- the dense per-edge layers of the neural model types (p-nd-np, np-nd-np) on the 5th-generation tensor
+// cores: tcgen05.mma (kind::tf32) issued by one thread per CTA, accumulators in tensor memory, operands in shared memory.
+//
+//   pdp_edge_mlp_forward   out[e, :] = act(A[e, :] W^T + b) * mask[e]          one dense layer over edge (or node) rows
+//   pdp_edge_gru_forward   h'[e, :]  = GRUCell([x | feature], h)[e, :]         torch.nn.GRUCell, gates fused in the epilogue
+//
+// replace the nn.Linear / nn.GRUCell calls of MessageAggregator.forward (reference pdp/nn/util.py:51-77),
+// NeuralDecimator.forward (pdp_decimate.py:51-87), NeuralMessagePasser.forward (pdp_propagate.py:47-95) and
+// NeuralPredictor.forward (pdp_predict.py:49-91).  A row's input is the concatenation of up to three row-major sources
+// (message state | edge feature | hidden state): no torch.cat copy is ever made.
+//
+// Precision.  The reference is fp32; one tf32 product has 11 significant bits.  Every product is therefore taken three
+// times (A_hi B_hi + A_lo B_hi + A_hi B_lo with x_hi = x truncated to tf32, x_lo = x - x_hi truncated to tf32): the
+// dropped terms are below 2^-21 of the product, the accumulation is fp32 in tensor memory.
+//
+// One CTA per SM, persistent over tiles of 128 rows.  Per tile and N-pass (<= 256 accumulator columns; the accumulator is
+// double-buffered in the 512 columns of tensor memory, so the epilogue of one pass runs under the MMAs of the next), K
+// goes by in chunks of 16 through a ring of shared-memory stages:
+//   warps 0-7  stage the A chunk: two threads per row, each reads 8 floats of it (64-bit loads where the sources allow,
+//              the next chunk's loads in flight while the current one is converted), splits them, writes the hi and lo
+//              operand tiles in the canonical K-major layout of the tensor core (8-row x 16-byte core matrices; 16-byte
+//              column group g of a tile of R rows at g * 16 R, row r of it at + 16 r: core matrices contiguous, SBO = 128 B,
+//              LBO = 16 R);
+//   warp 17    one thread brings the chunk's weights with ONE bulk-asynchronous copy: the host side stores W pre-split and
+//              pre-tiled, chunk after chunk, exactly as the shared-memory image (pdp_solver_b200/nn/tensor_ops.py);
+//   warp 16    one thread issues the chunk's tcgen05.mma (2 k-steps x 3 terms x N-blocks) and commits them to the stage's
+//              `empty` barrier; after the pass's last chunk it commits to the accumulator buffer's barrier;
+//   warps 8-15 epilogue: tcgen05.ld of the accumulator rows (thread = row, two warps per lane quadrant), bias / activation /
+//              GRU gate arithmetic, 64-bit stores; then hand the accumulator buffer back.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pdp_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;        // rows per tile = accumulator lanes
+constexpr int kChunkK = 16;        // K elements per stage: 4 column groups of 16 bytes, 2 MMA k-steps
+constexpr int kThreads = 576;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 MMA issuer, 17 B producer
+constexpr int kPrefetch = 6;       // chunks of A loads in flight per producer thread
+constexpr int kMaxNTot = 256;      // accumulator columns per pass (GRU: 4 gate blocks of 64 hidden units); two buffers
+
+enum { EPI_LINEAR = 0, EPI_GRU = 1 };
+enum { ACT_NONE = 0, ACT_LOGSIGMOID = 1 };
+
+struct EdgeNNArgs {
+    const float* src[3];       // row-major sources of the A rows, concatenated along K
+    int32_t ks[3];             // their column counts (0: unused)
+    int32_t k_total;           // sum of ks
+    int32_t k_chunks;          // ceil(k_total / 16)
+    int64_t rows;              // E
+    const float* w_img;        // weights, split and tiled: [pass][chunk]{hi [4][n_tot][4], lo [4][n_tot][4]}
+    const float* bias;         // LINEAR: [passes * n_tot]; GRU: [passes][4][n_blk] = r, z, i_n, h_n
+    int32_t n_blk;             // columns per tcgen05.mma (multiple of 16, <= 256)
+    int32_t n_mma;             // N-blocks per pass
+    int32_t n_tot;             // n_blk * n_mma
+    int32_t passes;
+    int32_t n_out;             // LINEAR: output columns (<= passes * n_tot); GRU: hidden size H
+    int32_t act;               // LINEAR
+    const float* row_mask;     // [rows] or null: LINEAR multiplies the output; GRU blends mask * h' + (1 - mask) * h
+    const float* h_old;        // GRU: [rows, H] (also source 0 of A)
+    float* out;                // [rows, n_out]
+    int32_t stages;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory"); }
+__device__ __forceinline__ void mb_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t a = s_u32(b);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && spin > 256) {       // a barrier that never completes is a bug: trap instead of hanging the device
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > (1ll << 31)) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* b) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(b)) : "memory"); }
+// D[tmem] (+)= A[smem] B[smem]^T, tf32 inputs, fp32 accumulation
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: start address, LBO (next 16-byte column group), SBO (next 8 rows)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
+           ((uint64_t)1 << 46);     // descriptor version of sm_100
+}
+// instruction descriptor of kind::tf32: D fp32, A and B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t instr_desc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// 16 consecutive accumulator columns of this thread's lane
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float logsigmoidf(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }   // F.logsigmoid
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// element k of the concatenated row
+__device__ __forceinline__ float a_elem(const EdgeNNArgs& P, int64_t row, int k) {
+    if (k < P.ks[0]) return __ldg(P.src[0] + row * P.ks[0] + k);
+    k -= P.ks[0];
+    if (k < P.ks[1]) return __ldg(P.src[1] + row * P.ks[1] + k);
+    k -= P.ks[1];
+    if (k < P.ks[2]) return __ldg(P.src[2] + row * P.ks[2] + k);
+    return 0.f;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__ EdgeNNArgs P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_full_a[4], bar_full_b[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[3 * kMaxNTot];          // the layer's (padded) bias: passes * n_tot values
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = P.stages;
+    const uint32_t a_bytes = 2u * kTileM * kChunkK * 4u;                 // hi + lo
+    const uint32_t b_bytes = 2u * (uint32_t)P.n_tot * kChunkK * 4u;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    for (int i = tid; i < P.passes * P.n_tot; i += kThreads) s_bias[i] = __ldg(P.bias + i);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mb_init(&bar_full_a[s], 256); mb_init(&bar_full_b[s], 1); mb_init(&bar_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {    // the accumulators: all 512 columns of tensor memory (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int64_t n_tiles = (P.rows + kTileM - 1) / kTileM;
+    const int units = P.passes * P.k_chunks;       // chunk iterations per tile
+    // every role walks the same sequence of (tile, pass, chunk) and keeps its own ring position
+    if (warp < 8) {
+        // ---------------- A producers: threads r and r + 128 <-> row r of the tile, column groups {0,1} / {2,3} of the chunk
+        const int r = tid & 127, half = tid >> 7;
+        int s = 0; uint32_t ph = 0;
+        // where the 8 columns [k0, k0 + 8) of a row come from: one source at an even offset with 8-byte aligned rows ->
+        // four 64-bit loads; anything else (a span across two sources, an odd offset, rows of odd length) element by element
+        auto load8 = [&](int64_t row, int k0, float (&v)[8]) {
+            int k = k0, si = 0;
+            while (si < 2 && k >= P.ks[si]) { k -= P.ks[si]; ++si; }
+            if (k + 8 <= P.ks[si] && !((k | P.ks[si]) & 1)) {
+                const float2* p2 = reinterpret_cast<const float2*>(P.src[si] + row * P.ks[si] + k);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 t2 = __ldg(p2 + j); v[2 * j] = t2.x; v[2 * j + 1] = t2.y; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = a_elem(P, row, k0 + j);
+            }
+        };
+        // kPrefetch chunks of loads are in flight per thread (a ring of register buffers, refilled as it is consumed): the
+        // rows come from HBM, and with one chunk in flight a thread would move 32 bytes per memory latency
+        constexpr int D = kPrefetch;
+        float buf[D][8];
+        const int64_t tile_step = (int64_t)gridDim.x * kTileM;
+        const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int64_t total = my_tiles * units;
+        int64_t pf_row = (int64_t)blockIdx.x * kTileM + r;      // prefetch cursor: row of this thread in the tile, chunk unit
+        int pf_u = 0;
+        int64_t c_row = pf_row;                                  // consumer cursor
+        int c_u = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (d < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + 8 * half, buf[d]);
+            if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
+        }
+        for (int64_t g0 = 0; g0 < total; g0 += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (g0 + d >= total) break;
+                const bool live = c_row < P.rows;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = live ? buf[d][j] : 0.f;
+                if (g0 + d + D < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + 8 * half, buf[d]);
+                if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
+                mb_wait(&bar_empty[s], ph ^ 1u);
+                unsigned char* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                    const int g = 2 * half + gg;
+                    uint4 hi, lo;
+                    uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+                    uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x = v[4 * gg + j];
+                        const uint32_t hb = __float_as_uint(x) & 0xffffe000u;
+                        hp[j] = hb;
+                        lp[j] = __float_as_uint(x - __uint_as_float(hb)) & 0xffffe000u;
+                    }
+                    *reinterpret_cast<uint4*>(st + (size_t)g * (kTileM * 16) + (size_t)r * 16) = hi;
+                    *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + (size_t)g * (kTileM * 16) + (size_t)r * 16) = lo;
+                }
+                fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
+                mb_arrive(&bar_full_a[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++c_u == units) { c_u = 0; c_row += tile_step; }
+            }
+        }
+    } else if (warp == 17 && lane == 0) {
+        // ---------------- B producer: one bulk copy per chunk
+        int s = 0; uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = 0; u < units; ++u) {
+                mb_wait(&bar_empty[s], ph ^ 1u);
+                mb_expect_tx(&bar_full_b[s], b_bytes);
+                bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full_b[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 16 && lane == 0) {
+        // ---------------- MMA issuer
+        const uint32_t idesc = instr_desc(kTileM, P.n_blk);
+        const uint32_t lbo_a = kTileM * 16, lbo_b = (uint32_t)P.n_tot * 16;
+        const uint64_t desc_hi_a = smem_desc(0, lbo_a, 128), desc_hi_b = smem_desc(0, lbo_b, 128);
+        const uint32_t smem_a4 = s_u32(smem) >> 4, stage4 = stage_bytes >> 4;
+        const uint32_t a_lo4 = (kTileM * kChunkK * 4) >> 4, b_off4 = a_bytes >> 4, b_lo4 = ((uint32_t)P.n_tot * kChunkK * 4) >> 4;
+        int s = 0; uint32_t ph = 0, acc_ph[2] = {0u, 0u};
+        int ab = 0;                                     // accumulator buffer of this pass
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int p = 0; p < P.passes; ++p) {
+                mb_wait(&bar_acc_empty[ab], acc_ph[ab] ^ 1u);       // the epilogue has read this buffer's previous contents
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * kMaxNTot);
+                for (int c = 0; c < P.k_chunks; ++c) {
+                    mb_wait(&bar_full_a[s], ph);
+                    mb_wait(&bar_full_b[s], ph);
+                    tc_fence_after();
+                    // descriptors = constant upper parts | (address >> 4): everything below is 32-bit adds on the low word
+                    const uint32_t sa4 = (smem_a4 + (uint32_t)s * stage4);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {      // hi hi, lo hi, hi lo
+                            const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
+                            const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
+                            const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
+                            for (int nb = 0; nb < P.n_mma; ++nb)
+                                tc_mma_tf32(tacc + (uint32_t)(nb * P.n_blk), desc_hi_a | a4, desc_hi_b | (b4 + (uint32_t)(nb * P.n_blk)), idesc, acc);
+                        }
+                    }
+                    tc_commit(&bar_empty[s]);        // the stage is free once these MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(&bar_acc_full[ab]);
+                acc_ph[ab] ^= 1u;
+                ab ^= 1;
+            }
+        }
+    }
+    if (warp >= 8 && warp < 16) {
+        // ---------------- epilogue: thread <-> accumulator lane = row of the tile; two warps per lane quadrant, each takes
+        //                  every other group of 16 columns.  A thread's 16 results are contiguous in its output row: 64-bit
+        //                  accesses (rows are 8-byte aligned when their length is even), two full sectors per thread
+        const int q = warp & 3;                      // lane quadrant this warp may read (warp index mod 4)
+        const int hh = (warp - 8) >> 2;              // which half of the column groups
+        const int r = q * 32 + lane;
+        const uint32_t tlane0 = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec2 = !(P.n_out & 1);
+        uint32_t acc_ph[2] = {0u, 0u};
+        int ab = 0;
+        auto store16 = [&](float* dst, const float (&y)[16], int nvalid) {      // nvalid of the 16 values exist
+            if (vec2 && nvalid == 16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) reinterpret_cast<float2*>(dst)[j] = make_float2(y[2 * j], y[2 * j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j < nvalid) dst[j] = y[j];
+            }
+        };
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * kTileM + r;
+            const bool live = row < P.rows;
+            const float mk = (live && P.row_mask) ? __ldg(P.row_mask + row) : 1.f;
+            for (int p = 0; p < P.passes; ++p) {
+                mb_wait(&bar_acc_full[ab], acc_ph[ab]);
+                acc_ph[ab] ^= 1u;
+                tc_fence_after();
+                const uint32_t tlane = tlane0 + (uint32_t)(ab * kMaxNTot);
+                if (EPI == EPI_LINEAR) {
+                    for (int c0 = 16 * hh; c0 < P.n_tot; c0 += 32) {
+                        float v[16];
+                        tc_ld16(tlane + (uint32_t)c0, v);
+                        const int n0 = p * P.n_tot + c0;
+                        if (!live || n0 >= P.n_out) continue;
+                        float y[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float t = v[j] + s_bias[n0 + j];
+                            if (P.act == ACT_LOGSIGMOID) t = logsigmoidf(t);
+                            if (P.row_mask) t *= mk;
+                            y[j] = t;
+                        }
+                        store16(P.out + row * P.n_out + n0, y, min(16, P.n_out - n0));
+                    }
+                } else {
+                    // the pass holds hidden units [p * nh, (p + 1) * nh): columns [0,nh) r, [nh,2nh) z, [2nh,3nh) W_in x, [3nh,4nh) W_hn h
+                    const int nh = P.n_tot / 4;
+                    const float* bs = s_bias + (size_t)p * P.n_tot;
+                    for (int c0 = 16 * hh; c0 < nh; c0 += 32) {
+                        float vr[16], vz[16], vi[16], vh[16];
+                        tc_ld16(tlane + (uint32_t)c0, vr);
+                        tc_ld16(tlane + (uint32_t)(nh + c0), vz);
+                        tc_ld16(tlane + (uint32_t)(2 * nh + c0), vi);
+                        tc_ld16(tlane + (uint32_t)(3 * nh + c0), vh);
+                        const int u0 = p * nh + c0;
+                        if (!live || u0 >= P.n_out) continue;
+                        const int nvalid = min(16, P.n_out - u0);
+                        float ho[16], y[16];
+                        const float* hp = P.h_old + row * P.n_out + u0;
+                        if (vec2 && nvalid == 16) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(hp) + j); ho[2 * j] = t2.x; ho[2 * j + 1] = t2.y; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) ho[j] = j < nvalid ? __ldg(hp + j) : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float rg = sigmoidf_(vr[j] + bs[c0 + j]);
+                            const float zg = sigmoidf_(vz[j] + bs[nh + c0 + j]);
+                            const float ng = tanhf(vi[j] + bs[2 * nh + c0 + j] + rg * (vh[j] + bs[3 * nh + c0 + j]));
+                            float hn = (1.f - zg) * ng + zg * ho[j];
+                            if (P.row_mask) hn = mk * hn + (1.f - mk) * ho[j];
+                            y[j] = hn;
+                        }
+                        store16(P.out + row * P.n_out + u0, y, nvalid);
+                    }
+                }
+                tc_fence_before();
+                mb_arrive(&bar_acc_empty[ab]);
+                ab ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+int launch(const EdgeNNArgs& P, int epi, cudaStream_t stream) {
+    int dev = 0, sms = 0, cc = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { pdp_set_error("pdp_edge_nn: no CUDA device"); return PDP_ERR_CUDA; }
+    if (cc < 10) { pdp_set_error("pdp_edge_nn: tcgen05 needs sm_100a"); return PDP_ERR_UNSUPPORTED; }
+    const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
+    const size_t smem = stage * P.stages;
+    void* kern = epi == EPI_GRU ? (void*)k_edge_nn<EPI_GRU> : (void*)k_edge_nn<EPI_LINEAR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: shared memory %zu: %s", smem, cudaGetErrorString(e)); return PDP_ERR_CUDA; }
+    const int64_t n_tiles = (P.rows + kTileM - 1) / kTileM;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    if (epi == EPI_GRU) k_edge_nn<EPI_GRU><<<grid, kThreads, smem, stream>>>(P);
+    else k_edge_nn<EPI_LINEAR><<<grid, kThreads, smem, stream>>>(P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: launch -> %s", cudaGetErrorString(e)); return PDP_ERR_CUDA; }
+    return PDP_OK;
+}
+
+bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2, const float* x3, int k3, int64_t rows, const float* w_img,
+                 const float* bias, int n_blk, int n_mma, int passes, const char* who) {
+    P.src[0] = x1; P.src[1] = x2; P.src[2] = x3;
+    P.ks[0] = k1 > 0 ? k1 : 0; P.ks[1] = k2 > 0 ? k2 : 0; P.ks[2] = k3 > 0 ? k3 : 0;
+    P.k_total = P.ks[0] + P.ks[1] + P.ks[2];
+    P.k_chunks = (P.k_total + kChunkK - 1) / kChunkK;
+    P.rows = rows; P.w_img = w_img; P.bias = bias;
+    P.n_blk = n_blk; P.n_mma = n_mma; P.n_tot = n_blk * n_mma; P.passes = passes;
+    if (P.k_total <= 0 || !w_img || !bias || n_blk < 16 || n_blk > 256 || (n_blk & 15) || n_mma < 1 || P.n_tot > kMaxNTot || passes < 1 ||
+        (k1 > 0 && !x1) || (k2 > 0 && !x2) || (k3 > 0 && !x3) || ((uintptr_t)w_img & 15) || passes * n_blk * n_mma > 3 * kMaxNTot) {
+        pdp_set_error("%s: bad argument (k=%d n_blk=%d n_mma=%d passes=%d)", who, P.k_total, n_blk, n_mma, passes);
+        return false;
+    }
+    const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
+    int st = (int)((200 * 1024) / stage);
+    P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
+    return true;
+}
+
+}  // namespace
+
+// One dense layer over rows: out[rows, n_out] = act([x1 | x2 | x3] W^T + bias) (* row_mask).  w_img / bias: the tiled
+// weight image and padded bias built by pdp_solver_b200/nn/tensor_ops.py (n_blk columns per MMA, n_mma blocks per pass).
+extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* x3, int32_t k3, int64_t rows,
+                                    const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,
+                                    int32_t act, const float* row_mask, float* out, void* stream) {
+    if (rows <= 0) return PDP_OK;
+    EdgeNNArgs P;
+    memset(&P, 0, sizeof(P));
+    if (!fill_common(P, x1, k1, x2, k2, x3, k3, rows, w_img, bias, n_blk, n_mma, passes, "pdp_edge_mlp_forward")) return PDP_ERR_ARG;
+    if (!out || n_out < 1 || n_out > passes * P.n_tot) { pdp_set_error("pdp_edge_mlp_forward: bad output shape"); return PDP_ERR_ARG; }
+    P.n_out = n_out; P.act = act; P.row_mask = row_mask; P.out = out;
+    return launch(P, EPI_LINEAR, (cudaStream_t)stream);
+}
+
+// torch.nn.GRUCell over rows: h'[rows, H] from input [x1 | x2] and hidden state h (row-major [rows, H]); every pass holds
+// the four gate blocks (r, z, W_in x, W_hn h) of n_blk * n_mma / 4 hidden units.  row_mask blends h' with h (frozen rows).
+extern "C" int pdp_edge_gru_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* h, int32_t hidden, int64_t rows,
+                                    const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes,
+                                    const float* row_mask, float* out, void* stream) {
+    if (rows <= 0) return PDP_OK;
+    EdgeNNArgs P;
+    memset(&P, 0, sizeof(P));
+    if (!fill_common(P, h, hidden, x1, k1, x2, k2, rows, w_img, bias, n_blk, n_mma, passes, "pdp_edge_gru_forward")) return PDP_ERR_ARG;   // rows = [h | x1 | x2]
+    if (!out || !h || hidden < 1 || (P.n_tot & 63) || hidden > passes * (P.n_tot / 4) || out == h) {
+        pdp_set_error("pdp_edge_gru_forward: bad shape (hidden=%d n_tot=%d passes=%d) or out aliases h", hidden, P.n_tot, passes);
+        return PDP_ERR_ARG;
+    }
+    P.n_out = hidden; P.row_mask = row_mask; P.h_old = h; P.out = out;
+    return launch(P, EPI_GRU, (cudaStream_t)stream);
+}
