@@ -2,6 +2,7 @@
 import torch
 import torch.nn as nn
 
+from . import tensor_ops
 from .pdp_propagate import edge_problem_mask
 
 
@@ -37,8 +38,9 @@ def problem_argmax(x, bvm, B):
 
 class NeuralDecimator(nn.Module):
     """The neural (non-greedy) decimator of `p-nd-np` / `np-nd-np` (reference pdp_decimate.py:21-100): one GRU
-    cell per message direction over the edges; same sub-module names (state-dict compatible).  The GRU cells are
-    library GEMMs + pointwise kernels (torch), fp32 like the reference.
+    cell per message direction over the edges; same sub-module names (state-dict compatible).  The GRU cells run on the
+    tensor cores (pdp_edge_gru_forward: tcgen05 tf32 three-term split = fp32 accuracy, gates fused); PDP_B200_NN=torch
+    keeps them on the library GEMMs for A/B comparisons.
 
     message_dimension == (3, 1) is widened to (3, 2) as the reference needs to run at all: its SurveyPropagator
     returns a 2-column function state (pdp_propagate.py:221) while solver.py:555 sizes the cell for 1 (SURVEY.md
@@ -71,6 +73,14 @@ class NeuralDecimator(nn.Module):
         mask = edge_problem_mask(sat_problem, active_mask)
         variable_state, function_state = message_state[0], message_state[1]
         ef = sat_problem._edge_feature
+        if tensor_ops.use_tensor_cores():
+            # both GRU cells on the tensor cores, gates and the frozen-problem blend fused in the epilogue (csrc/pdp_edge_nn.cu)
+            tc = self.__dict__.setdefault("_tc_cells", {})
+            if not tc:
+                tc["v"] = tensor_ops.TensorGRU(self._variable_rnn_cell)
+                tc["f"] = tensor_ops.TensorGRU(self._function_rnn_cell)
+            return (tc["v"]([variable_state, ef], init_state[0], row_mask=mask),
+                    tc["f"]([function_state, ef], init_state[1], row_mask=mask))
         new_v = self._variable_rnn_cell(torch.cat((variable_state, ef), 1), init_state[0])
         new_f = self._function_rnn_cell(torch.cat((function_state, ef), 1), init_state[1])
         if mask is not None:   # frozen problems keep their state (reference :75,83)

@@ -42,10 +42,10 @@ class NeuralPredictor(nn.Module):
         ef = sat_problem._edge_feature
         variable_prediction = function_prediction = None
         if self._variable_classifier is not None:
-            agg = self._variable_aggregator(torch.cat((dvs, ef), 1), None, ctx, True, edge_mask)
+            agg = self._variable_aggregator((dvs, ef), None, ctx, True, edge_mask)
             variable_prediction = self._variable_classifier(agg)
         if self._function_classifier is not None:
-            agg = self._function_aggregator(torch.cat((dfs, ef), 1), None, ctx, False, edge_mask)
+            agg = self._function_aggregator((dfs, ef), None, ctx, False, edge_mask)
             function_prediction = self._function_classifier(agg)
         return variable_prediction, function_prediction
 

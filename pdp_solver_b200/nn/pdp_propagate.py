@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import util
+from . import tensor_ops, util
 
 
 def edge_problem_mask(sat_problem, active_mask):
@@ -50,10 +50,10 @@ class NeuralMessagePasser(nn.Module):
         variable_state, function_state = init_state
         ef = sat_problem._edge_feature
         # variables --> functions (reference :69-78)
-        new_f = self._variable_aggregator(torch.cat((dvs, ef), 1), ef, ctx, True, edge_mask)
+        new_f = self._variable_aggregator((dvs, ef), ef, ctx, True, edge_mask)
         function_state = new_f if mask is None else mask * new_f + (1 - mask) * function_state
         # functions --> variables (reference :80-89)
-        new_v = self._function_aggregator(torch.cat((dfs, ef), 1), ef, ctx, False, edge_mask)
+        new_v = self._function_aggregator((dfs, ef), ef, ctx, False, edge_mask)
         variable_state = new_v if mask is None else mask * new_v + (1 - mask) * variable_state
         return variable_state, function_state
 
@@ -103,8 +103,16 @@ class SurveyPropagator(nn.Module):
         ctx = sat_problem._ctx
         if not self._include_adaptors:
             return ctx.sp_step(dq, df, edge_mask, init_state[0], init_state[1], active_mask, self._pi_value)
-        x_log = F.logsigmoid(self._function_input_projector(dq))            # reference :163-164
-        proj = self._variable_input_projector(df)                           # reference :179-182
+        if tensor_ops.use_tensor_cores():
+            tc = self.__dict__.setdefault("_tc_layers", {})
+            if not tc:
+                tc["f"] = tensor_ops.TensorLinear(self._function_input_projector)
+                tc["v"] = tensor_ops.TensorLinear(self._variable_input_projector)
+            x_log = tc["f"]([dq], act=tensor_ops.ACT_LOGSIGMOID)           # reference :163-164
+            proj = tc["v"]([df])                                            # reference :179-182
+        else:
+            x_log = F.logsigmoid(self._function_input_projector(dq))
+            proj = self._variable_input_projector(df)
         eta_in = torch.sigmoid(proj[:, 0])
         ext = torch.sign(proj[:, 1])
         return ctx.sp_step_adapted(x_log, eta_in, ext, edge_mask, init_state[0], init_state[1], active_mask, self._pi_value)

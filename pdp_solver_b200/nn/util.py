@@ -4,6 +4,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..engine import Context
+from . import tensor_ops
 
 
 class MessageAggregator(nn.Module):
@@ -36,18 +37,40 @@ class MessageAggregator(nn.Module):
 
     def forward(self, state, feature, ctx, by_variable, edge_mask=None):
         """`ctx`, `by_variable` replace the reference's (mask, mask_transpose) sparse matrices: the node side
-        the edges are summed on (reference util.py:51-77)."""
-        if self._mem_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0:
-            state = F.logsigmoid(self._W2_m(F.logsigmoid(self._W1_m(state))))
-        if edge_mask is not None:
-            state = state * edge_mask
+        the edges are summed on (reference util.py:51-77).  `state` is the layer input or the list of row-major pieces
+        whose concatenation it is (the tensor-core layers read the pieces in place: no torch.cat)."""
+        pieces = list(state) if isinstance(state, (list, tuple)) else [state]
+        tc = tensor_ops.use_tensor_cores()
+        pre = self._mem_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0
+        if pre and tc:
+            # W1 -> logsigmoid -> W2 -> logsigmoid (-> * edge_mask) on the tensor cores (csrc/pdp_edge_nn.cu)
+            hidden = self._tc("_W1_m")(pieces, act=tensor_ops.ACT_LOGSIGMOID)
+            state = self._tc("_W2_m")([hidden], act=tensor_ops.ACT_LOGSIGMOID, row_mask=edge_mask)
+        else:
+            state = pieces[0] if len(pieces) == 1 else torch.cat(pieces, 1)
+            if pre:
+                state = F.logsigmoid(self._W2_m(F.logsigmoid(self._W1_m(state))))
+            if edge_mask is not None:
+                state = state * edge_mask
         node_sum, loo = ctx.edge_aggregate(state, by_variable, leave_one_out=not self._include_self_message)
         aggregated_state = node_sum if self._include_self_message else loo
+        post = self._agg_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0
+        if post and tc:
+            srcs = [aggregated_state] + ([feature] if feature is not None else [])
+            hidden = self._tc("_W1_a")(srcs, act=tensor_ops.ACT_LOGSIGMOID)
+            return self._tc("_W2_a")([hidden], act=tensor_ops.ACT_LOGSIGMOID)
         if feature is not None:
             aggregated_state = torch.cat((aggregated_state, feature), 1)
-        if self._agg_hidden_dimension > 0 and self._mem_agg_hidden_dimension > 0:
+        if post:
             aggregated_state = F.logsigmoid(self._W2_a(F.logsigmoid(self._W1_a(aggregated_state))))
         return aggregated_state
+
+    def _tc(self, name):
+        "the tensor-core image of one of the module's nn.Linear layers (rebuilt when its parameters change)"
+        cache = self.__dict__.setdefault("_tc_layers", {})
+        if name not in cache:
+            cache[name] = tensor_ops.TensorLinear(getattr(self, name))
+        return cache[name]
 
 
 class Perceptron(nn.Module):

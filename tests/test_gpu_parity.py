@@ -973,3 +973,79 @@ def test_custom_termination_callback_is_honoured():
             pass
     assert pdp_solver._is_standard_termination(SatFactorGraphTrainer._check_recurrence_termination)
     assert not pdp_solver._is_standard_termination(Sub._check_recurrence_termination)
+
+
+TC_LINEAR_SPECS = [(1000, 150, 1, 100, 1), (128, 100, 0, 50, 1), (333, 50, 1, 100, 1), (20000, 100, 0, 150, 1), (513, 150, 0, 2, 0), (77, 150, 0, 1, 1)]
+
+
+@pytest.mark.parametrize("spec", TC_LINEAR_SPECS, ids=lambda s: "E%d_%d+%d_to_%d" % s[:4])
+def test_tensor_core_linear_vs_fp64(spec):
+    """pdp_edge_mlp_forward (tcgen05 kind::tf32, three-term split) against the same layer in fp64: the dense layers of
+    MessageAggregator.forward (reference util.py:51-77) with the edge feature read as a second source, logsigmoid and the
+    edge mask fused.  fp32-grade accuracy: 2e-5 absolute on O(1)-O(10) pre-activations (torch's own fp32 layer: ~1e-6)."""
+    from pdp_solver_b200.nn import tensor_ops as TO
+    E, k1, k2, n, act = spec
+    torch.manual_seed(E + n)
+    lin = torch.nn.Linear(k1 + k2, n, bias=(n != 50)).to(dev())
+    x1 = torch.randn(E, k1, device=dev())
+    src = [x1] + ([torch.sign(torch.randn(E, k2, device=dev()))] if k2 else [])
+    mask = (torch.rand(E, 1, device=dev()) > 0.2).float()
+    out = TO.TensorLinear(lin)(src, act=act, row_mask=mask)
+    ref = torch.cat(src, 1).double() @ lin.weight.double().t()
+    if lin.bias is not None:
+        ref = ref + lin.bias.double()
+    if act:
+        ref = torch.nn.functional.logsigmoid(ref)
+    ref = ref * mask.double()
+    assert out.shape == (E, n)
+    assert (out.double() - ref).abs().max().item() < 2e-5
+    # a changed parameter rebuilds the weight image
+    with torch.no_grad():
+        lin.weight.mul_(0.5)
+    out2 = TO.TensorLinear(lin)(src, act=0)
+    ref2 = torch.cat(src, 1).double() @ lin.weight.double().t() + (lin.bias.double() if lin.bias is not None else 0.0)
+    assert (out2.double() - ref2).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("spec", [(1000, 150, 1, 150), (257, 3, 1, 150), (129, 2, 1, 150), (20000, 150, 1, 150)], ids=lambda s: "E%d_%d+%d_h%d" % s)
+def test_tensor_core_gru_vs_fp64(spec):
+    """pdp_edge_gru_forward against torch.nn.GRUCell in fp64 (the two cells of NeuralDecimator.forward, reference
+    pdp_decimate.py:51-87), with the frozen-problem blend of rows whose mask is 0"""
+    from pdp_solver_b200.nn import tensor_ops as TO
+    E, kx1, kx2, H = spec
+    torch.manual_seed(E)
+    cell = torch.nn.GRUCell(kx1 + kx2, H).to(dev())
+    x1, x2 = torch.randn(E, kx1, device=dev()), torch.sign(torch.randn(E, kx2, device=dev()))
+    h = torch.rand(E, H, device=dev()) * 2 - 1
+    mask = (torch.rand(E, 1, device=dev()) > 0.2).float()
+    out = TO.TensorGRU(cell)([x1, x2], h, row_mask=mask)
+    c64 = torch.nn.GRUCell(kx1 + kx2, H).to(dev()).double()
+    c64.load_state_dict({k: v.double() for k, v in cell.state_dict().items()})
+    ref = c64(torch.cat((x1, x2), 1).double(), h.double())
+    ref = mask.double() * ref + (1 - mask.double()) * h.double()
+    assert (out.double() - ref).abs().max().item() < 2e-5
+    assert torch.equal(out[mask[:, 0] == 0], h[mask[:, 0] == 0])      # frozen rows keep their state bit for bit
+
+
+@pytest.mark.parametrize("path", golden("neural_*.npz"), ids=name)
+def test_neural_tensor_core_path_equals_library_gemm_path(path, monkeypatch):
+    """the same forward() with the dense layers on tcgen05 (the product path) and on the library GEMMs (PDP_B200_NN=torch):
+    predictions and final states agree to 5e-5 -- the tensor-core path is an fp32-grade drop-in, not a different model"""
+    z = load(path)
+    gm, bvm, bfm, ef = T(z["graph_map"]), T(z["bvm"]), T(z["bfm"]), T(z["ef"])
+    init = ((T(z["init_p0"]), T(z["init_p1"])), (T(z["init_d0"]), T(z["init_d1"])))
+
+    def termination(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+    outs = []
+    for mode in ("tcgen05", "torch"):
+        monkeypatch.setenv("PDP_B200_NN", mode)
+        model = _neural_model(z)
+        with torch.no_grad():
+            (vp, _), (ps, ds) = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                                      meta_data=None, is_training=False, iteration_num=int(z["T"]), check_termination=termination,
+                                      simplify=True, batch_replication=1)
+        outs.append([C(vp), C(ps[0]), C(ps[1]), C(ds[0]), C(ds[1])])
+    for a, b in zip(*outs):
+        assert maxdiff(a, b) < 5e-5
