@@ -37,7 +37,7 @@ namespace {
 constexpr int kTileM = 128;        // rows per tile = accumulator lanes
 constexpr int kChunkK = 16;        // K elements per stage: 4 column groups of 16 bytes, 2 MMA k-steps
 constexpr int kThreads = 576;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 MMA issuer, 17 B producer
-constexpr int kPrefetch = 6;       // chunks of A loads in flight per producer thread
+constexpr int kPrefetch = 4;       // chunks of A loads in flight per producer thread
 constexpr int kMaxNTot = 256;      // accumulator columns per pass (GRU: 4 gate blocks of 64 hidden units); two buffers
 
 enum { EPI_LINEAR = 0, EPI_GRU = 1 };
@@ -113,8 +113,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float logsigmoidf(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }   // F.logsigmoid
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Epilogue activations on the special-function unit (ex2 / lg2 / rcp: relative error ~1e-6 on O(1) arguments, an order
+// below the three-term product's own error); the IEEE forms cost the epilogue warps four times the issue slots, and the
+// epilogue shares the SM's schedulers with the operand staging.
+__device__ __forceinline__ float logsigmoidf(float x) { return fminf(x, 0.f) - __logf(1.f + __expf(-fabsf(x))); }   // F.logsigmoid
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 2.f * sigmoidf_(2.f * x) - 1.f; }
 
 // element k of the concatenated row
 __device__ __forceinline__ float a_elem(const EdgeNNArgs& P, int64_t row, int k) {
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     const uint32_t stage_bytes = a_bytes + b_bytes;
     for (int i = tid; i < P.passes * P.n_tot; i += kThreads) s_bias[i] = __ldg(P.bias + i);
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mb_init(&bar_full_a[s], 256); mb_init(&bar_full_b[s], 1); mb_init(&bar_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 256); }
+        for (int s = 0; s < S; ++s) { mb_init(&bar_full_a[s], 8); mb_init(&bar_full_b[s], 1); mb_init(&bar_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) {    // the accumulators: all 512 columns of tensor memory (one CTA per SM)
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                     *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + (size_t)g * (kTileM * 16) + (size_t)r * 16) = lo;
                 }
                 fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
-                mb_arrive(&bar_full_a[s]);
+                __syncwarp();
+                if (lane == 0) mb_arrive(&bar_full_a[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
                 if (++s == S) { s = 0; ph ^= 1u; }
                 if (++c_u == units) { c_u = 0; c_row += tile_step; }
             }
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                         for (int j = 0; j < 16; ++j) {
                             const float rg = sigmoidf_(vr[j] + bs[c0 + j]);
                             const float zg = sigmoidf_(vz[j] + bs[nh + c0 + j]);
-                            const float ng = tanhf(vi[j] + bs[2 * nh + c0 + j] + rg * (vh[j] + bs[3 * nh + c0 + j]));
+                            const float ng = tanhf_(vi[j] + bs[2 * nh + c0 + j] + rg * (vh[j] + bs[3 * nh + c0 + j]));
                             float hn = (1.f - zg) * ng + zg * ho[j];
                             if (P.row_mask) hn = mk * hn + (1.f - mk) * ho[j];
                             y[j] = hn;
@@ -354,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                     }
                 }
                 tc_fence_before();
-                mb_arrive(&bar_acc_empty[ab]);
+                __syncwarp();
+                if (lane == 0) mb_arrive(&bar_acc_empty[ab]);
                 ab ^= 1;
             }
         }

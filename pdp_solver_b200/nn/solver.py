@@ -294,22 +294,38 @@ class PropagatorDecimatorSolverBase(nn.Module):
         ctx = sat_problem._ctx
         propagator_state, decimator_state = init_propagator_state, init_decimator_state
         active_mask = None if check_termination is None else torch.ones(ctx.B, 1, dtype=torch.uint8, device=ctx.device)
-        edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
-        masked = bool((edge_mask.sum() < ctx.E).item())
         standard = check_termination is not None and _is_standard_termination(check_termination)
         rep = sat_problem._batch_replication
         fixes = isinstance(self._decimator, pdp_decimate.SequentialDecimator)
-        done = 0
-        for _ in range(int(iteration_num)):
+        # No host round trip inside the loop (the reference takes several per iteration, solver.py:365-384):
+        #  * the edge mask always rides in the decimator state -- multiplying by an all-ones mask is exact, so whether
+        #    anything is masked yet need not be known on the host;
+        #  * the executed-iteration count lives on the device: an iteration counts iff some problem was active when it began;
+        #  * "every problem has retired" reaches the host through a pinned flag copied asynchronously and looked at exactly
+        #    two iterations later (deterministic: the same number of iterations -- and of random draws -- runs every time).
+        #    The two iterations that run past that point change nothing: every message and hidden state of a retired
+        #    problem is blended back (mask * new + (1 - mask) * old with mask 0), and the prediction is a function of
+        #    those states.
+        edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
+        done_dev = torch.zeros((), dtype=torch.int32, device=ctx.device)
+        flags = torch.empty(2, dtype=torch.int32).pin_memory() if check_termination is not None else None
+        events = [None, None]
+        for it in range(int(iteration_num)):
+            if flags is not None:
+                ev = events[it & 1]
+                if ev is not None:
+                    ev.synchronize()       # (iteration it - 2: long finished unless the device is two iterations behind)
+                    if int(flags[it & 1]) <= 0:
+                        break
+                done_dev += (active_mask.sum() > 0).to(torch.int32)
+            else:
+                done_dev += 1
             propagator_state = self._propagator(propagator_state, decimator_state, sat_problem, False, active_mask)
             decimator_state = self._decimator(decimator_state, propagator_state, sat_problem, False, active_mask)
             sat_problem._edge_mask_set = True
             if fixes:
                 edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
-                masked = bool((edge_mask.sum() < ctx.E).item())
-            if masked:
-                decimator_state = tuple(decimator_state[:2]) + (edge_mask,)     # solver.py:373-374
-            done += 1
+            decimator_state = tuple(decimator_state[:2]) + (edge_mask,)     # solver.py:373-374
             if check_termination is not None:
                 prediction = self._predictor(decimator_state, sat_problem)
                 solution = sat_problem.update_solution(prediction[0])
@@ -321,9 +337,11 @@ class PropagatorDecimatorSolverBase(nn.Module):
                     active_mask[(active_mask[:, 0] == 1) & ok, 0] = 0
                 else:
                     check_termination(active_mask, (solution, prediction[1]), sat_problem)
-                if int(active_mask.sum().item()) <= 0:
-                    break
-        self.last_iterations = torch.tensor([done], dtype=torch.int32, device=ctx.device)
+                flags[it & 1:(it & 1) + 1].copy_(active_mask.sum().to(torch.int32).reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events[it & 1] = ev
+        self.last_iterations = done_dev.reshape(1)
         return propagator_state, decimator_state
 
     def _local_search(self, sat_problem, batch_replication):
