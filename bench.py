@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config0", "config1", "config2", "config3", "config4"],
+                    help="BASELINE.json configs[i]; config3 (default) is the configuration the metric is quoted on")
     ap.add_argument("--problems", type=int, default=8, help="problems per GPU")
     ap.add_argument("--n", type=int, default=1000000)
     ap.add_argument("--k", type=int, default=3)
@@ -275,7 +277,7 @@ def run_b200_arm(a, rank, world, local_rank):
 
     def one_step(tensors, from_host, timed):
         torch.manual_seed(1 + rank)
-        if from_host:
+        if from_host and tensors[0].device.type == "cpu":     # (warm-up of the end-to-end leg)
             gm, bvm, bfm, ef = [t.to(dev, non_blocking=True) for t in tensors]
         else:
             gm, bvm, bfm, ef = tensors
@@ -305,6 +307,32 @@ def run_b200_arm(a, rank, world, local_rank):
                 stats["loop_updates"] += upd
         return pred
 
+    copy_stream = torch.cuda.Stream(dev)
+
+    class Staged(object):
+        """end-to-end leg: every step's batch is copied from pinned host memory inside the timed region, on a copy stream,
+        into one of two device buffers -- the copy of step i+1 runs under the kernels of step i (the same double buffering as
+        FactorGraphTrainerBase._predict_epoch); the copy of step i+2 waits until step i has released its buffer"""
+
+        def __init__(self, tensors):
+            self.host, self.bufs, self.ready, self.freed = tensors, [None, None], [None, None], [None, None]
+
+        def stage(self, k):
+            with torch.cuda.stream(copy_stream):
+                if self.freed[k & 1] is not None:
+                    copy_stream.wait_event(self.freed[k & 1])
+                self.bufs[k & 1] = [t.to(dev, non_blocking=True) for t in self.host]
+                self.ready[k & 1] = torch.cuda.Event()
+                self.ready[k & 1].record(copy_stream)
+
+        def take(self, k):
+            torch.cuda.current_stream(dev).wait_event(self.ready[k & 1])
+            return self.bufs[k & 1]
+
+        def release(self, k):
+            self.freed[k & 1] = torch.cuda.Event()
+            self.freed[k & 1].record(torch.cuda.current_stream(dev))
+
     def timed_region(tensors, from_host):
         for k in stats:
             stats[k] = 0 if isinstance(stats[k], int) else 0.0
@@ -316,8 +344,17 @@ def run_b200_arm(a, rank, world, local_rank):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(a.steps):
-            one_step(tensors, from_host, True)
+        if from_host:
+            st = Staged(tensors)
+            st.stage(0)
+            for i in range(a.steps):
+                if i + 1 < a.steps:
+                    st.stage(i + 1)
+                one_step(st.take(i), True, True)
+                st.release(i)
+        else:
+            for _ in range(a.steps):
+                one_step(tensors, False, True)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -426,11 +463,188 @@ def config0_solved(dev):
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# the other configurations of BASELINE.json as driver-parsable lines: `--workload config0|config1|config2|config4`
+# --------------------------------------------------------------------------------------------------
+def other_workload(a):
+    """(name, model type, per-rank batch builder, T, W, replication list, metric, unit)"""
+    from pdp_solver_b200 import cnfgen
+    w = a.workload
+    if w == "config0":
+        return dict(name="p-d-p SP + 100-iteration WalkSAT, random 3-SAT n=100 m/n=4.20, batch 5000 per GPU, T=1000 (BASELINE.json configs[0])",
+                    model="p-d-p", batch=lambda seed: cnfgen.random_batch(5000, 100, 3, 4.2, seed), T=1000, W=100, reps=[1],
+                    metric="cnfs_solved_per_s", unit="CNFs/s", cpu=dict(B=20, n=100, k=3, alpha=4.2, T=1000, W=100))
+    if w == "config1":
+        return dict(name="p-nd-np (SP with neural decimator and predictor, random-init weights) random 3-SAT n=10000 m/n=4.20, 8 problems per GPU, T=20 (BASELINE.json configs[1])",
+                    model="p-nd-np", batch=lambda seed: cnfgen.random_batch(8, 10000, 3, 4.2, seed), T=20, W=100, reps=[1],
+                    metric="edge_updates_per_s", unit="edge-updates/s", cpu=dict(B=1, n=2000, k=3, alpha=4.2, T=3, W=2))
+    if w == "config2":
+        return dict(name="np-nd-np (fully neural PDP, random-init weights) random 4-SAT n=1000 m/n=9.00, 32 problems per GPU, T=20 (BASELINE.json configs[2])",
+                    model="np-nd-np", batch=lambda seed: cnfgen.random_batch(32, 1000, 4, 9.0, seed), T=20, W=100, reps=[1],
+                    metric="edge_updates_per_s", unit="edge-updates/s", cpu=dict(B=2, n=1000, k=4, alpha=9.0, T=3, W=2))
+
+    def mixed(seed):      # mixed random 3-/5-SAT, n = 500 ... 50 000
+        specs = [(500, 3, 4.0), (500, 5, 18.0), (5000, 3, 4.0), (5000, 5, 18.0), (50000, 3, 4.0), (50000, 5, 18.0)]
+        return cnfgen.mixed_batch([sp for sp in specs for _ in range(2)], seed)
+    return dict(name="p-d-p SP + 100-iteration WalkSAT with batch replication -b 1..64, mixed random 3-SAT (m/n=4.0) / 5-SAT (m/n=18) n=500..50000, 12 problems per GPU, T=600 (BASELINE.json configs[4])",
+                model="p-d-p", batch=mixed, T=600, W=100, reps=[1, 8, 64], metric="cnfs_solved_per_s", unit="CNFs/s",
+                cpu=dict(B=2, n=500, k=3, alpha=4.2, T=50, W=10))
+
+
+def build_b200_model(model_type, dev, W, a):
+    import torch
+    from pdp_solver_b200.nn import solver as S, util as U
+    if model_type == "p-d-p":
+        return S.SurveyPropagatorSolver(dev, "p-d-p", tolerance=a.tolerance, t_max=a.t_max, local_search_iterations=W, epsilon=a.epsilon)
+    H, MH, AH, MAH, CH = 150, 100, 100, 50, 50
+    torch.manual_seed(1)
+    clf = U.Perceptron(H, CH, 1)
+    if model_type == "p-nd-np":
+        m = S.NeuralSurveyPropagatorSolver(dev, "m", 1, 0, H, MH, AH, MAH, 1, variable_classifier=clf, local_search_iterations=W, epsilon=a.epsilon)
+    else:
+        m = S.NeuralPropagatorDecimatorSolver(dev, "m", 1, 0, H, H, MH, AH, MAH, 1, variable_classifier=clf, local_search_iterations=W, epsilon=a.epsilon)
+    return m.to(dev).eval()
+
+
+def run_other_workload(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    spec = other_workload(a)
+    if a.impl == "reference":
+        if rank == 0:
+            print(json.dumps(other_reference_line(a, spec)))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = spec["batch"](a.seed + 17 * rank)
+    host = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in batch]
+    E, V, B = batch[0].shape[1], batch[1].shape[0], int(batch[1].max()) + 1
+    resident = [t.to(dev) for t in host]
+    model = build_b200_model(spec["model"], dev, spec["W"], a)
+
+    def termination(active, prediction, sat_problem):
+        raise RuntimeError("unreachable")
+    termination._pdp_standard_termination = True
+
+    def forward(tensors, rep):
+        gm, bvm, bfm, ef = tensors
+        with torch.no_grad():
+            init = model.get_init_state(gm, bvm, bfm, ef, None, randomized=False, batch_replication=rep)
+            (pred, _), _ = model(init_state=init, graph_map=gm, batch_variable_map=bvm, batch_function_map=bfm, edge_feature=ef,
+                                 meta_data=None, is_training=False, iteration_num=spec["T"], check_termination=termination,
+                                 batch_replication=rep)
+        from pdp_solver_b200.nn.util import cnf_eval_edges
+        solved, _ = cnf_eval_edges(pred, gm, bvm, bfm, ef, batch_size=B)
+        return pred, solved
+
+    def measure(rep, from_host):
+        tot = {"solved": 0.0, "updates": 0.0}
+
+        def step(timed):
+            torch.manual_seed(1 + rank)
+            tens = [t.to(dev, non_blocking=True) for t in host] if from_host else resident
+            pred, solved = forward(tens, rep)
+            if from_host:
+                pred.cpu(); solved.cpu()
+            if timed:
+                tot["solved"] += float((solved > 0.5).sum().item())
+                tot["updates"] += float(E) * rep * float(model.last_iterations.reshape(-1)[0].item())
+        for _ in range(a.warmup):
+            step(False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step(True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            g = torch.tensor([tot["solved"], tot["updates"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            tot["solved"], tot["updates"] = [float(x) for x in g.tolist()]
+        units = tot["solved"] if spec["metric"] == "cnfs_solved_per_s" else tot["updates"]
+        return ms, units, tot
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sweep = []
+    for rep in spec["reps"]:
+        ms, units, tot = measure(rep, False)
+        ms_e, units_e, _ = measure(rep, True)
+        sweep.append({"batch_replication": rep, "value": units / (ms / 1e3), "ms_per_step": ms / a.steps, "e2e_value": units_e / (ms_e / 1e3),
+                      "e2e_ms_per_step": ms_e / a.steps, "cnfs_solved_per_step": tot["solved"] / a.steps,
+                      "cnfs_per_s": world * B * a.steps / (ms / 1e3), "edge_updates_per_s": tot["updates"] / (ms / 1e3)})
+    sampler.stop_flag = True
+    if rank == 0:
+        head = sweep[0]
+        h2d = sum(int(t.numel() * t.element_size()) for t in host)
+        line = {"metric": spec["metric"], "value": head["value"], "unit": spec["unit"], "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if spec["model"] == "p-d-p" else "f32 (dense layers: tf32 x 3 split on tcgen05)", "data": "synthetic",
+                "config": {"workload": spec["name"], "model_type": spec["model"], "edges_per_gpu": E, "variables_per_gpu": V, "problems_per_gpu": B,
+                           "T": spec["T"], "walksat_iterations": spec["W"], "init": "deterministic (predict path)",
+                           "l2": "flushed by the step itself: every step re-ingests its batch and rewrites its message arrays" if E * 48 < 126e6
+                           else "inputs larger than L2", "sharding": "problems sharded across ranks, no per-iteration collective"},
+                "e2e": {"value": head["e2e_value"], "unit": spec["unit"], "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": (V * 4 + B * 4) * world,
+                        "ms_per_step": head["e2e_ms_per_step"]},
+                "gpu_launches": int(model.last_problem._ctx.launch_count()) * a.steps, "replication_sweep": sweep if len(sweep) > 1 else None,
+                "edge_updates_per_s": head["edge_updates_per_s"], "cnfs_per_s": head["cnfs_per_s"], "roofline": None, "clocks": sampler.summary()}
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = other_reference_line(a, spec)["cpu_baseline"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_reference_line(a, spec):
+    """the reference's CPU path on a bounded sample of the workload (same model type, fewer / smaller problems, fewer iterations)"""
+    import torch
+    from oracle import ref_timing
+    from pdp_solver_b200 import cnfgen
+    c = spec["cpu"]
+    if not ref_timing.available():
+        cb = {"unavailable": "reference tree absent (baseline/_ref)"}
+        return {"impl": "reference", "metric": spec["metric"], "unit": spec["unit"], "cpu_baseline": cb}
+    cores = ref_timing.pin_threads()
+    model = ref_timing.build_model(spec["model"], torch.device("cpu"), c["W"], a.epsilon, a.tolerance, a.t_max)
+    batch = cnfgen.random_batch(c["B"], c["n"], c["k"], c["alpha"], a.seed + 999)
+    r = ref_timing.timed_forward(model, batch, c["T"], torch.device("cpu"), seed=a.seed)
+    if spec["metric"] == "cnfs_solved_per_s":
+        value = r["solved"] / r["total_s"]
+    else:
+        value = r["edges"] * max(r["iterations"], 1) / r["total_s"]
+    cb = {"value": value, "unit": spec["unit"], "cores": cores, "kind": "reference",
+          "sample": "%d problems of random %d-SAT n=%d m/n=%.2f, T=%d, %d WalkSAT iterations: one forward of the unmodified reference with use_cuda=False, %.2f s (%d iterations executed, %d solved)"
+                    % (c["B"], c["k"], c["n"], c["alpha"], c["T"], c["W"], r["total_s"], r["iterations"], r["solved"]),
+          "s_per_iteration": r["loop_s"] / max(r["iterations"], 1), "setup_s": r["setup_s"],
+          "cnfs_per_s": c["B"] / r["total_s"], "edge_updates_per_s": r["edges"] * max(r["iterations"], 1) / r["total_s"]}
+    return {"impl": "reference", "metric": spec["metric"], "value": value, "unit": spec["unit"], "n_gpus": a.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": 1e3 * r["total_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["name"], "model_type": spec["model"]}, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": spec["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.workload != "config3":
+        if world == 1 and a.gpus > 1 and a.impl != "reference":
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29531"] + sys.argv
+            sys.exit(subprocess.call(cmd))
+        run_other_workload(a, rank, world, local_rank)
+        return
     if a.impl == "reference":
         run_reference_arm(a, rank, world)
         return

@@ -37,6 +37,18 @@ def build_model(model_type, device, W, epsilon, tol=0.02, t_max=100):
         return solver.SurveyPropagatorSolver(device, "sp", tolerance=tol, t_max=t_max, local_search_iterations=W, epsilon=epsilon)
     if model_type == "walk-sat":
         return solver.WalkSATSolver(device, "ws", iteration_num=W, epsilon=epsilon)
+    if model_type in ("p-nd-np", "np-nd-np"):     # dims of config/Predict/PDP-np-nd-np-*.yaml, random-init weights
+        trainer = compat.load_reference()[5]
+        H, MH, AH, MAH, CH = 150, 100, 100, 50, 50
+        torch.manual_seed(1)
+        clf = trainer.Perceptron(H, CH, 1)          # reference trainer.py:20-29
+        if model_type == "p-nd-np":
+            m = solver.NeuralSurveyPropagatorSolver(device, "m", 1, 0, H, MH, AH, MAH, 1, variable_classifier=clf,
+                                                    local_search_iterations=W, epsilon=epsilon)
+        else:
+            m = solver.NeuralPropagatorDecimatorSolver(device, "m", 1, 0, H, H, MH, AH, MAH, 1, variable_classifier=clf,
+                                                       local_search_iterations=W, epsilon=epsilon)
+        return m.to(device).eval()
     raise ValueError(model_type)
 
 

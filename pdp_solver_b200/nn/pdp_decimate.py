@@ -183,6 +183,8 @@ class ReinforceDecimator(nn.Module):
     every edge's external force becomes the sign of its variable's SP bias, which the propagator and scorer feed
     back through their pi terms.  Problems whose surveys moved by at most 0.01 are retired."""
 
+    _draws_per_iteration = True       # one coin per iteration: the solver loop must stop exactly where the reference stops
+
     def __init__(self, device, scorer, decimation_probability=0.5):
         super(ReinforceDecimator, self).__init__()
         self._device = device

@@ -306,6 +306,9 @@ class PropagatorDecimatorSolverBase(nn.Module):
         #    The two iterations that run past that point change nothing: every message and hidden state of a retired
         #    problem is blended back (mask * new + (1 - mask) * old with mask 0), and the prediction is a function of
         #    those states.
+        # (a decimator that draws random numbers every iteration -- reinforce -- and a caller's own termination callback
+        #  keep the reference's immediate stop: extra iterations would consume draws / call the callback again)
+        lag = 2 if (standard and not getattr(self._decimator, "_draws_per_iteration", False)) else 0
         edge_mask = ctx.get_masks(edge_mask=True)["em"].unsqueeze(1)
         done_dev = torch.zeros((), dtype=torch.int32, device=ctx.device)
         flags = torch.empty(2, dtype=torch.int32).pin_memory() if check_termination is not None else None
@@ -337,10 +340,14 @@ class PropagatorDecimatorSolverBase(nn.Module):
                     active_mask[(active_mask[:, 0] == 1) & ok, 0] = 0
                 else:
                     check_termination(active_mask, (solution, prediction[1]), sat_problem)
-                flags[it & 1:(it & 1) + 1].copy_(active_mask.sum().to(torch.int32).reshape(1), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-                events[it & 1] = ev
+                if lag == 0:
+                    if int(active_mask.sum().item()) <= 0:
+                        break
+                else:
+                    flags[it & 1:(it & 1) + 1].copy_(active_mask.sum().to(torch.int32).reshape(1), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events[it & 1] = ev
         self.last_iterations = done_dev.reshape(1)
         return propagator_state, decimator_state
 
