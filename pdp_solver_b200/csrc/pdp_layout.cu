@@ -90,18 +90,17 @@ __global__ void k_wo_seq_clause(pdp_graph g, const int32_t* __restrict__ lq, con
 }
 
 // run-length coding of the destinations: slot w starts a run unless it continues the previous slot's block and
-// destination.  One thread per 32 slots: bits[word], cnt[word] = popc(bits).
+// destination.  One warp per 32 slots (coalesced reads, the word is a ballot): bits[word], cnt[word] = popc(bits).
 __global__ void k_wo_bits(int64_t E, const int32_t* __restrict__ kb, const int32_t* __restrict__ dst, int64_t nwords,
                           uint32_t* bits, int32_t* cnt) {
-    GS(word, nwords) {
-        uint32_t b = 0u;
-        const int64_t w0 = word * 32;
-        for (int i = 0; i < 32 && w0 + i < E; ++i) {
-            const int64_t w = w0 + i;
-            if (w == 0 || kb[w] != kb[w - 1] || dst[w] != dst[w - 1] + 1) b |= 1u << i;
-        }
-        bits[word] = b;
-        cnt[word] = __popc(b);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t word = warp0; word < nwords; word += nwarps) {
+        const int64_t w = word * 32 + lane;
+        bool start = false;
+        if (w < E) start = (w == 0) || kb[w] != kb[w - 1] || dst[w] != dst[w - 1] + 1;
+        const uint32_t b = __ballot_sync(0xffffffffu, start);
+        if (lane == 0) { bits[word] = b; cnt[word] = __popc(b); }
     }
 }
 // rank[word] = run starts before the word (exclusive scan of cnt): wrun[word] = {bits, rank - 1}, wadj[run] = dst - slot
@@ -128,14 +127,14 @@ __global__ void k_key_vsort(pdp_graph g, int32_t* key, int32_t* val) {
         val[v] = (int32_t)v;
     }
 }
-// pad[t] = slots of the group that starts at rank t (32 x the degree of its first, largest member), 0 for other ranks.
+// pad[t] = slots of the group that starts at rank t (64 x the row PAIRS of its first, largest member), 0 for other ranks.
 // Ranks are cut into groups of 32 from the first rank of every block.
 __global__ void k_group_slots(pdp_graph g, const int32_t* __restrict__ order, int32_t* pad) {
     GS(t, g.V + 1) {
         if (t == g.V) { pad[t] = 0; continue; }      // (the scan then leaves the padded total in psum[V])
         const int v = order[t];
         const int t0 = g.vb_ptr[g.var_ptr[v] / g.sv];
-        pad[t] = ((((int)t - t0) & 31) == 0) ? 32 * (g.var_ptr[v + 1] - g.var_ptr[v]) : 0;
+        pad[t] = ((((int)t - t0) & 31) == 0) ? 64 * ((g.var_ptr[v + 1] - g.var_ptr[v] + 1) >> 1) : 0;   // rows go in pairs
     }
 }
 // psum = exclusive scan of pad: psum[first rank of a group] - psum[first rank of its block] is the group's base slot
@@ -149,7 +148,7 @@ __global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order, con
         const int deg = g.var_ptr[v + 1] - g.var_ptr[v];
         const int base = psum[tg] - psum[t0];
         g.vsort[t] = make_int2(v, (base & 0xffff) | (deg << 16));
-        if (tg == (int)t) worst = max(worst, base + 32 * deg);     // end of this group's slots = padded size so far
+        if (tg == (int)t) worst = max(worst, base + 64 * ((deg + 1) >> 1));     // end of this group's slots = padded size so far
     }
     if (worst) atomicMax(max_slots, worst);
 }
@@ -157,14 +156,15 @@ __global__ void k_fill_vsort(pdp_graph g, const int32_t* __restrict__ order, con
 __global__ void k_block_t0(pdp_graph g, const int32_t* __restrict__ psum) {
     GS(blk, (int64_t)g.nvb + 1) g.vb_t0[blk] = psum[blk == g.nvb ? g.V : g.vb_ptr[blk]];
 }
-// padded transposed slots: lane l = rank within the group, row j = the j-th edge (pdp_sweep.cuh var_group)
+// padded transposed slots: lane l = rank within the group, row j = the j-th edge; the entries of rows 2k and 2k+1 of a lane sit
+// side by side (one 32-bit load per row pair): slot = base + 64 k + 2 l + (j & 1)  (pdp_sweep.cuh var_group)
 __global__ void k_fill_tslot(pdp_graph g, uint16_t* tslot) {
     GS(t, g.V) {
         const int2 e = g.vsort[t];
         const int v = e.x, base = e.y & 0xffff, deg = (int)((unsigned)e.y >> 16);
         const int lane = ((int)t - g.vb_ptr[g.var_ptr[v] / g.sv]) & 31;
         const int p0 = g.var_ptr[v];
-        for (int j = 0; j < deg; ++j) tslot[p0 + j] = (uint16_t)(base + 32 * j + lane);
+        for (int j = 0; j < deg; ++j) tslot[p0 + j] = (uint16_t)(base + 64 * (j >> 1) + 2 * lane + (j & 1));
     }
 }
 
@@ -370,7 +370,7 @@ int pdp_build_layout(pdp_ctx* c, cudaStream_t stream, bool monotone_maps) {
         if (var_side) k_wo_seq_var<<<G1(E)>>>(g, LV, KF, LF);
         else k_wo_seq_clause<<<G1(E)>>>(g, L, K, KF, LF);
         LLK();
-        k_wo_bits<<<G1(nwords)>>>(E, LF, KF, nwords, wbits, wcnt);
+        k_wo_bits<<<G1(nwords * 32)>>>(E, LF, KF, nwords, wbits, wcnt);
         LLK();
         if ((rc = exclusive_scan(wcnt, nwords)) != PDP_OK) return rc;
         k_wo_pack<<<G1(nwords)>>>(E, KF, nwords, wbits, wcnt, var_side ? g.v_wrun : g.c_wrun, var_side ? g.v_wadj : g.c_wadj);
@@ -418,7 +418,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
             const int gn = min(32, v1 - tg);
             const int base = g.vsort[tg].y & 0xffff;
             const int maxdeg = (int)((unsigned)g.vsort[tg].y >> 16);
-            if (base != run_base || (base & 31) || base + 32 * maxdeg > cap) atomicAdd(&errs[5], 1);
+            if (base != run_base || (base & 63) || base + 64 * ((maxdeg + 1) >> 1) > cap) atomicAdd(&errs[5], 1);
             for (int l = 0; l < gn; ++l) {
                 const int2 e = g.vsort[tg + l];
                 const int v = e.x, deg = (int)((unsigned)e.y >> 16);
@@ -428,7 +428,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
                 for (int j = 0; j < deg; ++j) {
                     const int p = g.var_ptr[v] + j;
                     const int x = g.p_vpos[p];
-                    const int slot = base + 32 * j + l;
+                    const int slot = base + 64 * (j >> 1) + 2 * l + (j & 1);
                     if (x < e0 || x >= e1 || (int)(fw[slot] & 0x7fff) != x - e0 ||
                         ((fw[slot] & PDP_VINV_NEG) != 0) != ((g.v_cedge[p] & PDP_SIGN_BIT) != 0)) { atomicAdd(&errs[1], 1); continue; }
                     // write-out slot = load position: its destination must be this edge's C-layout position
@@ -436,7 +436,7 @@ __global__ void k_check_layout(pdp_graph g, int32_t* errs, uint32_t* seen /* [E/
                     if (!(atomicOr(&seen[x >> 5], 1u << (x & 31)) & (1u << (x & 31)))) atomicAdd(&errs[6], 1);
                 }
             }
-            run_base += 32 * maxdeg;
+            run_base += 64 * ((maxdeg + 1) >> 1);
         }
         if (sum != ((long long)v0 + v1 - 1) * (v1 - v0) / 2) atomicAdd(&errs[5], 1);
         for (int w = e0 + 1; w < e1; ++w)

@@ -361,9 +361,10 @@ __device__ __forceinline__ float fsel(uint32_t mask, float a, float b) {
 __device__ __forceinline__ float fand(uint32_t mask, float a) { return __uint_as_float(__float_as_uint(a) & mask); }
 
 // One warp-group of a variable block: 32 variables of consecutive rank in the block's descending-degree order
-// (g.vsort), lane l <-> rank 32 * group + l.  The group owns 32 * (degree of its first member) entries of the position table
-// from its base (a multiple of 32): row j = entries [base + 32 j, base + 32 j + 32), lane l's j-th edge is entry base + 32 j + l.
-// Entries of members with fewer edges than the first one are padding (never written, never read): 2-5 % of a block.
+// (g.vsort), lane l <-> rank 32 * group + l.  The group owns 64 * ceil(degree of its first member / 2) entries of the
+// position table from its base (a multiple of 64): rows go in pairs, the 16-bit entries of rows 2k and 2k+1 of lane l sit side
+// by side at base + 64 k + 2 l (one 32-bit load per row pair).  Entries of members with fewer edges than the first one are
+// padding (never written; read only as the unused half of a pair): 2-7 % of a block.
 struct VarGroup {
     int i, deg, base, maxdeg;
     bool have;
@@ -395,9 +396,9 @@ __device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pd
         const VarGroup V = var_group(g, B, grp);
         if (!(V.have && s.want_score[B.multi() ? g.bvm[V.i] : B.b0])) continue;
         float ps = 0.f, ns = 0.f, as = 0.f;
-        const uint16_t* __restrict__ fw = g.vfwd + B.t0 + V.base + lane_id();
+        const uint32_t* __restrict__ fw = reinterpret_cast<const uint32_t*>(g.vfwd + B.t0 + V.base) + lane_id();
         for (int j = 0; j < V.deg; ++j) {
-            const uint32_t en = fw[32 * j];
+            const uint32_t en = (fw[32 * (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
             const uint32_t nb = __float_as_uint(PA[en & 0x7fffu]);
             const uint32_t negm = 0u - (en >> 15);
             const float f = L10(1.f - __uint_as_float(nb & 0x7fffffffu)) * ((nb >> 31) ? 0.f : 1.f);
@@ -426,14 +427,14 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
     asm volatile("" : "+r"(pa_s), "+r"(pb_off));
     VAR_GROUP_LOOP(grp, B, G, t) {
         const VarGroup V = var_group(g, B, grp);
-        const uint16_t* __restrict__ fw = g.vfwd + B.t0 + V.base + lane;
+        const uint32_t* __restrict__ fw = reinterpret_cast<const uint32_t*>(g.vfwd + B.t0 + V.base) + lane;   // row pair k: fw[32 k]
         int b = B.b0;
         bool runs = V.have;
         uint32_t stk = stk_blk;
         if (MULTI) {
             if (V.have) {
                 b = g.bvm[V.i]; runs = blk_problem_runs(s, b); stk = (runs && s.nanflag[b]) ? 0x80000000u : 0u;
-                if (!runs) for (int j = 0; j < V.deg; ++j) PA[fw[32 * j] & 0x7fffu] = __uint_as_float(PDP_SLOT_SKIP);
+                if (!runs) for (int j = 0; j < V.deg; ++j) PA[(fw[32 * (j >> 1)] >> (16 * (j & 1))) & 0x7fffu] = __uint_as_float(PDP_SLOT_SKIP);
             }
         }
         if (!runs) continue;
@@ -443,9 +444,11 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         // writes.  (Row by row the compiler cannot move the reads of one row above the write of the row before -- the planes
         // are indexed through the table -- and the logarithm chains of a warp run back to back.)  The table entries are
         // fetched four rows ahead: global memory, the CTAs leave no L1 to speak of.
-        uint32_t eq[4];
+        // table entries: one 32-bit word per row pair, fetched two pairs (four rows) ahead
+        const int npair = (V.deg + 1) >> 1;
+        uint32_t eq[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        for (int k = 0; k < 2; ++k) eq[k] = (k < npair) ? fw[32 * k] : 0u;
         auto stat_row = [&](uint32_t en, uint32_t nb, float xo, float y) {
             const float xn = __uint_as_float(nb & 0x7fffffffu);
             if (en >> 15) N += y; else P += y;          // (the reference adds 0 * y to the other sum: x + 0 = x, see above for NaN)
@@ -458,15 +461,15 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
                 n1 += d * cd; d1 += cd;
             }
         };
-        for (int j0 = 0; j0 < V.deg; j0 += 4) {
+        for (int k0 = 0; k0 < npair; k0 += 2) {
 #pragma unroll
-            for (int h = 0; h < 4; h += 2) {
-                const int j = j0 + h;
-                if (j >= V.deg) break;
-                const bool vb = j + 1 < V.deg;
-                const uint32_t ea = eq[h], eb = vb ? eq[h + 1] : eq[h];
-                if (j + 4 < V.deg) eq[h] = fw[32 * (j + 4)];
-                if (j + 5 < V.deg) eq[h + 1] = fw[32 * (j + 5)];
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + h;
+                if (k >= npair) break;
+                const bool vb = 2 * k + 1 < V.deg;
+                const uint32_t ew = eq[h];
+                if (k + 2 < npair) eq[h] = fw[32 * (k + 2)];
+                const uint32_t ea = ew & 0xffffu, eb = vb ? (ew >> 16) : ea;
                 const uint32_t aa = pa_s + ((ea & 0x7fffu) << 2), ab = pa_s + ((eb & 0x7fffu) << 2);
                 const uint32_t nba = lds_u32(aa); const float xoa = lds_f32(aa + pb_off);
                 const uint32_t nbb = lds_u32(ab); const float xob = lds_f32(ab + pb_off);
@@ -505,7 +508,7 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
         sp_var_prepare(P, N, -1.f, sb_neg, opp_neg, O_neg);
         bool made_nan = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) eq[k] = (k < V.deg) ? (uint32_t)fw[32 * k] : 0u;
+        for (int k = 0; k < 2; ++k) eq[k] = (k < npair) ? fw[32 * k] : 0u;
         // q <= 1 (total >= u) or NaN: bit 30 of the results' OR tells whether a NaN was produced.  (A q >= 2 out of surveys
         // that are no probabilities sets it as well: the problem then takes the sticky path for nothing, same results.)
         uint32_t nan_or = 0u;
@@ -513,15 +516,15 @@ __device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp
             const bool neg = (en >> 15) != 0u;
             return sp_var_finish(neg ? sb_neg : sb_pos, neg ? opp_neg : opp_pos, neg ? O_neg : O_pos, y);
         };
-        for (int j0 = 0; j0 < V.deg; j0 += 4) {
+        for (int k0 = 0; k0 < npair; k0 += 2) {
 #pragma unroll
-            for (int h = 0; h < 4; h += 2) {
-                const int j = j0 + h;
-                if (j >= V.deg) break;
-                const bool vb = j + 1 < V.deg;
-                const uint32_t ea = eq[h], eb = vb ? eq[h + 1] : eq[h];
-                if (j + 4 < V.deg) eq[h] = fw[32 * (j + 4)];
-                if (j + 5 < V.deg) eq[h + 1] = fw[32 * (j + 5)];
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + h;
+                if (k >= npair) break;
+                const bool vb = 2 * k + 1 < V.deg;
+                const uint32_t ew = eq[h];
+                if (k + 2 < npair) eq[h] = fw[32 * (k + 2)];
+                const uint32_t ea = ew & 0xffffu, eb = vb ? (ew >> 16) : ea;
                 const uint32_t aa = pa_s + ((ea & 0x7fffu) << 2), ab = pa_s + ((eb & 0x7fffu) << 2);
                 const float ya = lds_f32(aa + pb_off), yb = lds_f32(ab + pb_off);
                 const uint32_t ua = __float_as_uint(fin_row(ea, ya)), ub = __float_as_uint(fin_row(eb, yb));
