@@ -35,9 +35,13 @@
 namespace {
 
 constexpr int kTileM = 128;        // rows per tile = accumulator lanes
-constexpr int kChunkK = 16;        // K elements per stage: 4 column groups of 16 bytes, 2 MMA k-steps
+#ifndef PDP_NN_CHUNK_K
+#define PDP_NN_CHUNK_K 16     // (32 halves the per-chunk barrier traffic but leaves two stages: GRU 5.2 ms vs 4.25 ms at 1.2 M rows)
+#endif
+constexpr int kChunkK = PDP_NN_CHUNK_K;   // K elements per stage (16 or 32): kChunkK / 4 column groups of 16 bytes, kChunkK / 8 MMA k-steps
+constexpr int kHalfK = kChunkK / 2;       // elements of a row chunk per producer thread (two threads per row)
 constexpr int kThreads = 576;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 MMA issuer, 17 B producer
-constexpr int kPrefetch = 4;       // chunks of A loads in flight per producer thread
+constexpr int kPrefetch = kChunkK == 16 ? 4 : 2;       // chunks of A loads in flight per producer thread
 constexpr int kMaxNTot = 256;      // accumulator columns per pass (GRU: 4 gate blocks of 64 hidden units); two buffers
 
 enum { EPI_LINEAR = 0, EPI_GRU = 1 };
@@ -68,18 +72,33 @@ __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cv
 __device__ __forceinline__ void mb_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory"); }
 __device__ __forceinline__ void mb_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory"); }
+// SLEEP: the waiting warp backs off between polls.  The one thread that issues the MMAs shares its scheduler with four
+// other warps; warps that spin on a barrier would take most of that scheduler's issue slots away from it.
+template <bool SLEEP = true>
 __device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
     const uint32_t a = s_u32(b);
     uint32_t done = 0;
     long long t0 = 0;
     for (int spin = 0; !done; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (!done && spin > 256) {       // a barrier that never completes is a bug: trap instead of hanging the device
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > (1ll << 31)) __trap();
+        if (!done) {
+            if (SLEEP) __nanosleep(spin < 4 ? 40 : 200);
+            if (spin > 256) {       // a barrier that never completes is a bug: trap instead of hanging the device
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > (1ll << 31)) __trap();
+            }
         }
     }
 }
+#ifndef PDP_NN_TERMS
+#define PDP_NN_TERMS 3      // (profiling experiments only: fewer terms = wrong results)
+#endif
+#ifdef PDP_NN_TIMING
+__device__ unsigned long long g_nn_wait[8];     // cycles waited: 0 A-prod on empty, 1 B-prod on empty, 2 issuer on full_a, 3 on full_b, 4 on acc_empty, 5 epilogue on acc_full, 6 issuer total, 7 epilogue busy
+#define MB_WAIT_T(bar, par, slot) do { const long long _t0 = clock64(); mb_wait<((slot) < 2 || (slot) > 4)>(bar, par); if ((threadIdx.x & 31) == 0) atomicAdd(&g_nn_wait[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define MB_WAIT_T(bar, par, slot) mb_wait<((slot) < 2 || (slot) > 4)>(bar, par)     // slots 2-4: the MMA issuer polls without backing off
+#endif
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
 }
@@ -133,7 +152,7 @@ __device__ __forceinline__ float a_elem(const EdgeNNArgs& P, int64_t row, int k)
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__ EdgeNNArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_full_a[4], bar_full_b[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_bias[3 * kMaxNTot];          // the layer's (padded) bias: passes * n_tot values
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     const uint32_t stage_bytes = a_bytes + b_bytes;
     for (int i = tid; i < P.passes * P.n_tot; i += kThreads) s_bias[i] = __ldg(P.bias + i);
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mb_init(&bar_full_a[s], 8); mb_init(&bar_full_b[s], 1); mb_init(&bar_empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mb_init(&bar_full[s], 9); mb_init(&bar_empty[s], 1); }     // full: 8 A-producer warps + the weight copy (arrive + bytes)
         for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -165,22 +184,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         int s = 0; uint32_t ph = 0;
         // where the 8 columns [k0, k0 + 8) of a row come from: one source at an even offset with 8-byte aligned rows ->
         // four 64-bit loads; anything else (a span across two sources, an odd offset, rows of odd length) element by element
-        auto load8 = [&](int64_t row, int k0, float (&v)[8]) {
+        auto load8 = [&](int64_t row, int k0, float (&v)[kHalfK]) {
             int k = k0, si = 0;
             while (si < 2 && k >= P.ks[si]) { k -= P.ks[si]; ++si; }
-            if (k + 8 <= P.ks[si] && !((k | P.ks[si]) & 1)) {
+            if (k + kHalfK <= P.ks[si] && !((k | P.ks[si]) & 1)) {
                 const float2* p2 = reinterpret_cast<const float2*>(P.src[si] + row * P.ks[si] + k);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 t2 = __ldg(p2 + j); v[2 * j] = t2.x; v[2 * j + 1] = t2.y; }
+                for (int j = 0; j < kHalfK / 2; ++j) { const float2 t2 = __ldg(p2 + j); v[2 * j] = t2.x; v[2 * j + 1] = t2.y; }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = a_elem(P, row, k0 + j);
+                for (int j = 0; j < kHalfK; ++j) v[j] = a_elem(P, row, k0 + j);
             }
         };
         // kPrefetch chunks of loads are in flight per thread (a ring of register buffers, refilled as it is consumed): the
         // rows come from HBM, and with one chunk in flight a thread would move 32 bytes per memory latency
         constexpr int D = kPrefetch;
-        float buf[D][8];
+        float buf[D][kHalfK];
         const int64_t tile_step = (int64_t)gridDim.x * kTileM;
         const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
         const int64_t total = my_tiles * units;
@@ -190,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         int c_u = 0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            if (d < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + 8 * half, buf[d]);
+            if (d < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + kHalfK * half, buf[d]);
             if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
         }
         for (int64_t g0 = 0; g0 < total; g0 += D) {
@@ -198,16 +217,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             for (int d = 0; d < D; ++d) {
                 if (g0 + d >= total) break;
                 const bool live = c_row < P.rows;
-                float v[8];
+                float v[kHalfK];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = live ? buf[d][j] : 0.f;
-                if (g0 + d + D < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + 8 * half, buf[d]);
+                for (int j = 0; j < kHalfK; ++j) v[j] = live ? buf[d][j] : 0.f;
+                if (g0 + d + D < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + kHalfK * half, buf[d]);
                 if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
-                mb_wait(&bar_empty[s], ph ^ 1u);
+                MB_WAIT_T(&bar_empty[s], ph ^ 1u, 0);
                 unsigned char* st = smem + (size_t)s * stage_bytes;
 #pragma unroll
-                for (int gg = 0; gg < 2; ++gg) {
-                    const int g = 2 * half + gg;
+                for (int gg = 0; gg < kHalfK / 4; ++gg) {
+                    const int g = (kHalfK / 4) * half + gg;
                     uint4 hi, lo;
                     uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
                     uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
@@ -223,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                 }
                 fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mb_arrive(&bar_full_a[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
+                if (lane == 0) mb_arrive(&bar_full[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
                 if (++s == S) { s = 0; ph ^= 1u; }
                 if (++c_u == units) { c_u = 0; c_row += tile_step; }
             }
@@ -233,9 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         int s = 0; uint32_t ph = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int u = 0; u < units; ++u) {
-                mb_wait(&bar_empty[s], ph ^ 1u);
-                mb_expect_tx(&bar_full_b[s], b_bytes);
-                bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full_b[s]);
+                MB_WAIT_T(&bar_empty[s], ph ^ 1u, 1);
+                mb_expect_tx(&bar_full[s], b_bytes);
+                bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full[s]);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -250,19 +269,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         int ab = 0;                                     // accumulator buffer of this pass
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int p = 0; p < P.passes; ++p) {
-                mb_wait(&bar_acc_empty[ab], acc_ph[ab] ^ 1u);       // the epilogue has read this buffer's previous contents
+                MB_WAIT_T(&bar_acc_empty[ab], acc_ph[ab] ^ 1u, 4);       // the epilogue has read this buffer's previous contents
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(ab * kMaxNTot);
                 for (int c = 0; c < P.k_chunks; ++c) {
-                    mb_wait(&bar_full_a[s], ph);
-                    mb_wait(&bar_full_b[s], ph);
+                    MB_WAIT_T(&bar_full[s], ph, 2);
                     tc_fence_after();
+#ifdef PDP_NN_TIMING
+                    const long long _m0 = clock64();
+#endif
                     // descriptors = constant upper parts | (address >> 4): everything below is 32-bit adds on the low word
                     const uint32_t sa4 = (smem_a4 + (uint32_t)s * stage4);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
+                    for (int ks = 0; ks < kChunkK / 8; ++ks) {
 #pragma unroll
-                        for (int term = 0; term < 3; ++term) {      // hi hi, lo hi, hi lo
+                        for (int term = 0; term < PDP_NN_TERMS; ++term) {      // hi hi, lo hi, hi lo
                             const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
                             const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
                             const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
@@ -270,7 +291,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                                 tc_mma_tf32(tacc + (uint32_t)(nb * P.n_blk), desc_hi_a | a4, desc_hi_b | (b4 + (uint32_t)(nb * P.n_blk)), idesc, acc);
                         }
                     }
+#ifdef PDP_NN_TIMING
+                    const long long _m1 = clock64();
+#endif
                     tc_commit(&bar_empty[s]);        // the stage is free once these MMAs have read it
+#ifdef PDP_NN_TIMING
+                    atomicAdd(&g_nn_wait[6], (unsigned long long)(_m1 - _m0));
+                    atomicAdd(&g_nn_wait[7], (unsigned long long)(clock64() - _m1));
+#endif
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(&bar_acc_full[ab]);
@@ -304,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             const bool live = row < P.rows;
             const float mk = (live && P.row_mask) ? __ldg(P.row_mask + row) : 1.f;
             for (int p = 0; p < P.passes; ++p) {
-                mb_wait(&bar_acc_full[ab], acc_ph[ab]);
+                MB_WAIT_T(&bar_acc_full[ab], acc_ph[ab], 5);
                 acc_ph[ab] ^= 1u;
                 tc_fence_after();
                 const uint32_t tlane = tlane0 + (uint32_t)(ab * kMaxNTot);
@@ -415,6 +443,17 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
 
 // One dense layer over rows: out[rows, n_out] = act([x1 | x2 | x3] W^T + bias) (* row_mask).  w_img / bias: the tiled
 // weight image and padded bias built by pdp_solver_b200/nn/tensor_ops.py (n_blk columns per MMA, n_mma blocks per pass).
+#ifdef PDP_NN_TIMING
+extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
+    if (host8 && cudaMemcpyFromSymbol(host8, g_nn_wait, sizeof(unsigned long long) * 8) != cudaSuccess) return PDP_ERR_CUDA;
+    if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(g_nn_wait, z, sizeof(z)) != cudaSuccess) return PDP_ERR_CUDA; }
+    return PDP_OK;
+}
+#endif
+
+// K elements per chunk of the weight image (the host side builds the images accordingly)
+extern "C" int pdp_edge_nn_chunk_k(void) { return kChunkK; }
+
 extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* x3, int32_t k3, int64_t rows,
                                     const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,
                                     int32_t act, const float* row_mask, float* out, void* stream) {

@@ -12,7 +12,6 @@ import torch
 
 from .. import _lib
 
-CHUNK_K = 16
 ACT_NONE, ACT_LOGSIGMOID = 0, 1
 
 
@@ -23,13 +22,19 @@ def _tf32_split(w):
     return hi, lo
 
 
+def chunk_k():
+    "K elements per chunk of the weight image: the kernel's compile-time constant"
+    return int(_lib.load().pdp_edge_nn_chunk_k())
+
+
 def _image(wp, passes, n_tot):
-    "wp: [passes * n_tot, k_pad] -> [passes, chunks, 2, 4, n_tot, 4] contiguous"
+    "wp: [passes * n_tot, k_pad] -> [passes, chunks, 2, groups, n_tot, 4] contiguous (groups = chunk_k / 4 columns of 16 bytes)"
     k_pad = wp.shape[1]
-    chunks = k_pad // CHUNK_K
+    ck = chunk_k()
+    chunks = k_pad // ck
     hi, lo = _tf32_split(wp)
     both = torch.stack((hi, lo), 0)                                 # [2, P * n_tot, k_pad]
-    both = both.view(2, passes, n_tot, chunks, 4, 4)                # [term, pass, row, chunk, group, j]
+    both = both.view(2, passes, n_tot, chunks, ck // 4, 4)          # [term, pass, row, chunk, group, j]
     return both.permute(1, 3, 0, 4, 2, 5).contiguous()             # [pass, chunk, term, group, row, j]
 
 
@@ -69,7 +74,7 @@ class TensorLinear(object):
         self.n_out, self.k = n, k
         self.n_blk, self.n_mma, self.passes = _round_up(n, 16), 1, 1
         n_tot = self.n_blk
-        wp = torch.zeros(n_tot, _round_up(k, CHUNK_K), dtype=torch.float32, device=w.device)
+        wp = torch.zeros(n_tot, _round_up(k, chunk_k()), dtype=torch.float32, device=w.device)
         wp[:n, :k] = w
         self.image = _image(wp, 1, n_tot)
         self.bias = torch.zeros(n_tot, dtype=torch.float32, device=w.device)
@@ -123,7 +128,7 @@ class TensorGRU(object):
         passes = (H + nh - 1) // nh
         n_tot = 4 * nh
         k = kx + H
-        wp = torch.zeros(passes, 4, nh, _round_up(k, CHUNK_K), dtype=torch.float32, device=dev)
+        wp = torch.zeros(passes, 4, nh, _round_up(k, chunk_k()), dtype=torch.float32, device=dev)
         bp = torch.zeros(passes, 4, nh, dtype=torch.float32, device=dev)
         for p in range(passes):
             u0, u1 = p * nh, min(H, (p + 1) * nh)

@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Where the roles of k_edge_nn wait (profiling build -DPDP_NN_TIMING, PDP_B200_LIB=...alt_nnt.so)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pdp_solver_b200 import _lib
+from pdp_solver_b200.nn import tensor_ops as T
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 300000
+dev = torch.device("cuda:0")
+cell = torch.nn.GRUCell(151, 150).to(dev)
+x1, x2, h = torch.randn(E, 150, device=dev), torch.sign(torch.randn(E, 1, device=dev)), torch.rand(E, 150, device=dev)
+tg = T.TensorGRU(cell)
+tg([x1, x2], h); torch.cuda.synchronize()
+L = _lib.load()
+buf = (ctypes.c_ulonglong * 8)()
+L.pdp_edge_nn_wait_counters(buf, 1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); tg([x1, x2], h); e1.record(); torch.cuda.synchronize()
+L.pdp_edge_nn_wait_counters(buf, 0)
+ms = e0.elapsed_time(e1)
+cyc = ms * 1e-3 * 1.965e9
+names = ["A producers on empty (8 warps)", "B producer on empty", "issuer on full_a", "issuer on full_b", "issuer on acc_empty", "epilogue on acc_full (8 warps)", "issuer: MMA issue", "issuer: commit"]
+print("GRU E=%d: %.3f ms = %.0f cycles per CTA" % (E, ms, cyc))
+for i, n in enumerate(names):
+    per = buf[i] / 148.0 / (8 if "8 warps" in n else 1)
+    print("  %-34s %10.0f cycles per CTA (%.0f %% of the kernel)" % (n, per, 100 * per / cyc))
