@@ -137,7 +137,11 @@ int pdp_load_state(pdp_ctx* ctx, const float* d_prop_q3, const float* d_prop_fs2
 /* the same for a state whose every edge carries the same values, as get_init_state(randomized=False)
  * returns (reference pdp/nn/pdp_predict.py:203-206: variable_state = 1/3, function_state = [0.5, 0]) */
 int pdp_load_state_const(pdp_ctx* ctx, float qu, float qs, float qd, float eta, float ext, void* stream);
-/* writes the current message state in the caller's edge order: out_q3 [E,3], out_fs2 [E,2] */
+/* writes the current message state in the caller's edge order: out_q3 [E,3], out_fs2 [E,2] 
+ * Columns 1:3 of the [E,3] state (q_s, q_*) are tracked exactly only by a pdp_sp_run with full_state = 1; otherwise they are
+ * re-derived on export from the previous surveys with the CURRENT masks: for a problem whose last iteration fixed a variable they
+ * can differ from the reference's on the edges next to the fix (column 0, q_u, and the surveys are always exact; the predict path
+ * reads neither). */
 int pdp_store_state(pdp_ctx* ctx, float* d_out_q3, float* d_out_fs2, void* stream);
 /* overwrite / read the SATProblem masks (float 0/1 like the reference's tensors); NULL = skip.  Node masks installed this
  * way count as the decimator's edge mask from the next sweep on (reference pdp/nn/solver.py:370-374). */

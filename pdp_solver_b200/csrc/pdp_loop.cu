@@ -335,15 +335,13 @@ extern "C" int pdp_sp_run(pdp_ctx* ctx, const pdp_sp_params* params, int32_t* d_
     const bool fast = ctx->g.blocked_ok && !prm.full_state && prm.pi == 0.f && !(prm.flags & 1);
     if (fast) {
         // one or two CTAs per SM holding the whole shared memory: co-residency of the cooperative grid is guaranteed
-        static bool attr_set[64][2] = {{false}};
         const int two = (ctx->g.ctas == 2) ? 1 : 0;
         void* kern = two ? (void*)k_sp_run<true, false, 2> : (void*)k_sp_run<true, false, 1>;
         const int smem = two ? SweepCfg<2>::kSmem : SweepCfg<1>::kSmem;
         const int threads = two ? SweepCfg<2>::kThreads : SweepCfg<1>::kThreads;
-        if (!attr_set[ctx->device & 63][two]) {
-            PDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set[ctx->device & 63][two] = true;
-        }
+        // (set on every launch: a per-device "already set" table would be shared, unsynchronised, by the worker threads of the
+        //  multi-GPU predict path; the call costs a microsecond)
+        PDP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (two) PDP_CUDA_CHECK(cudaMemsetAsync(ctx->s.sm_ctr, 0, sizeof(int32_t) * PDP_MAX_SMS, stream));
         PDP_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(ctx->num_sms * (two ? 2 : 1)), dim3(threads), args, smem, stream));
     } else if (prm.full_state) {
