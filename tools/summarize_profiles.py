@@ -90,7 +90,58 @@ if os.path.exists(src):
         f.write("| kernel | launches | ms | share |\n|---|---|---|---|\n")
         for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
             f.write("| `%s` | %d | %.3f | %.1f %% |\n" % (n, a[0], a[1], 100 * a[1] / tot))
-for name in (tag + "_bench.json", tag + "_bench_reference.json"):
-    if os.path.exists(os.path.join(G, name)):
+for name in [tag + "_bench.json", tag + "_bench_reference.json", tag + "_edge_nn_timing.log"] + [tag + "_bench_config%d.json" % i for i in (0, 1, 2, 4)]:
+    if os.path.exists(os.path.join(G, name)) and os.path.getsize(os.path.join(G, name)) > 0:
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
+
+# ---- the tensor-core GRU kernel
+rep2 = os.path.join(G, tag + "_edge_gru.ncu-rep")
+if os.path.exists(rep2):
+    raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r2 = list(csv.reader(raw2.split("\n")))
+    m2 = {n: (r2[2][i], r2[1][i]) for i, n in enumerate(r2[0])}
+    want2 = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+             "launch__shared_mem_per_block_dynamic", "sm__inst_issued.avg.per_cycle_active",
+             "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+             "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+             "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+             "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+             "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+             "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+    rows_gru = 300000
+    lines2 = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep2,
+                             os.path.join(ROOT, "pdp_solver_b200", "csrc", "pdp_edge_nn.o"), "k_edge_nnILi1", "24"],
+                            capture_output=True, text=True).stdout
+    with open(os.path.join(P, tag + "_edge_gru_ncu.md"), "w") as f:
+        f.write("# ncu --set full: k_edge_nn<GRU> (pdp_edge_gru_forward: tcgen05 kind::tf32, three-term split, TMEM accumulators)\n\n")
+        f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:k_edge_nn -c 1 python tools/prof_edge_nn.py %d` "
+                "(GRU cell 151 | 150 -> 150 over %d rows: 3 passes x 19 K-chunks x 3 tf32 terms of M128 x N256 x K8 MMAs per tile of 128 rows = "
+                "%.3g tensor flop in the launch).  Numbers under the profiler are not bench values; `%s_edge_nn_timing.log` has the CUDA-event times.\n\n"
+                % (rows_gru, rows_gru, 2.0 * rows_gru * 304 * 768 * 3, tag))
+        f.write("| metric | value | unit |\n|---|---|---|\n")
+        for n in want2:
+            if n in m2:
+                f.write("| %s | %s | %s |\n" % (n, m2[n][0], m2[n][1]))
+        f.write("\n## hot spots by source line\n\n```\n" + lines2 + "```\n")
+
+# ---- SASS evidence: the Blackwell-specific instructions of the two hot kernels
+def mnemonics(obj, pats):
+    out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    cnt = {}
+    import re
+    for ln in out.split("\n"):
+        mm = re.search(r"\s(" + "|".join(pats) + r")[A-Z0-9_.]*", ln)
+        if mm:
+            k = mm.group(0).strip()
+            cnt[k] = cnt.get(k, 0) + 1
+    return cnt
+with open(os.path.join(P, tag + "_blackwell_sass.txt"), "w") as f:
+    f.write("cuobjdump -sass, instruction mnemonics that only exist on sm_100 (counts over the object file)\n\n")
+    for obj, what in (("pdp_edge_nn.o", "tcgen05 edge layers (k_edge_nn): UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTCATOMSWS = tcgen05.alloc/dealloc, UBLKCP = cp.async.bulk"),
+                      ("pdp_loop.o", "persistent SP loop (k_sp_run): UBLKCP = cp.async.bulk, SYNCS = mbarrier")):
+        c = mnemonics(os.path.join(ROOT, "pdp_solver_b200", "csrc", obj), ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UBLKCP", "UBLKPF", "SYNCS", "UTMALDG"])
+        f.write("%s -- %s\n" % (obj, what))
+        for k in sorted(c):
+            f.write("    %-40s %d\n" % (k, c[k]))
+        f.write("\n")
 print("profiles written; DRAM bytes per edge-update %.2f" % per)
