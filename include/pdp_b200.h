@@ -116,6 +116,7 @@ int pdp_edge_aggregate(pdp_ctx* ctx, int32_t by_variable, const float* d_state, 
  *   of MessageAggregator.forward, reference pdp/nn/util.py:51-77, and of the classifiers (act = 0).
  * pdp_edge_gru_forward: out[rows, hidden] = torch.nn.GRUCell([x1|x2], h), blended with h where row_mask is 0 -- the two cells of
  *   NeuralDecimator.forward, reference pdp/nn/pdp_decimate.py:51-87.  out must not alias h. */
+int pdp_edge_nn_swizzle(void);   /* 1: the weight images use the 64-byte swizzled operand layout (nn/tensor_ops.py follows) */
 int pdp_edge_nn_chunk_k(void);   /* K elements per chunk of the weight images (16 or 32): the host side tiles W accordingly */
 int pdp_edge_mlp_forward(const float* d_x1, int32_t k1, const float* d_x2, int32_t k2, const float* d_x3, int32_t k3, int64_t rows,
                          const float* d_w_img, const float* d_bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,

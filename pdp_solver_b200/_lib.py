@@ -43,6 +43,7 @@ SIGNATURES = {
     "pdp_edge_aggregate": (ctypes.c_int, [P, I32, P, I32, P, P, P]),
     "pdp_edge_mlp_forward": (ctypes.c_int, [P, I32, P, I32, P, I32, I64, P, P, I32, I32, I32, I32, I32, P, P, P]),
     "pdp_edge_nn_chunk_k": (ctypes.c_int, []),
+    "pdp_edge_nn_swizzle": (ctypes.c_int, []),
     "pdp_edge_gru_forward": (ctypes.c_int, [P, I32, P, I32, P, I32, I64, P, P, I32, I32, I32, P, P, P]),
     "pdp_score": (ctypes.c_int, [P, P, P, F32, P, P]),
     "pdp_load_state": (ctypes.c_int, [P, P, P, P, P, P]),

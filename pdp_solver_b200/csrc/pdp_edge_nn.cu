@@ -17,16 +17,17 @@
 // double-buffered in the 512 columns of tensor memory, so the epilogue of one pass runs under the MMAs of the next), K
 // goes by in chunks of 16 through a ring of shared-memory stages:
 //   warps 0-7  stage the A chunk: two threads per row, each reads 8 floats of it (64-bit loads where the sources allow,
-//              the next chunk's loads in flight while the current one is converted), splits them, writes the hi and lo
+//              the next chunks' loads in flight while the current one is converted), splits them, writes the hi and lo
 //              operand tiles in the canonical K-major layout of the tensor core (8-row x 16-byte core matrices; 16-byte
 //              column group g of a tile of R rows at g * 16 R, row r of it at + 16 r: core matrices contiguous, SBO = 128 B,
 //              LBO = 16 R);
 //   warp 17    one thread brings the chunk's weights with ONE bulk-asynchronous copy: the host side stores W pre-split and
 //              pre-tiled, chunk after chunk, exactly as the shared-memory image (pdp_solver_b200/nn/tensor_ops.py);
-//   warp 16    one thread issues the chunk's tcgen05.mma (2 k-steps x 3 terms x N-blocks) and commits them to the stage's
+//   warps 16, 18  one thread each, in turn, issues a chunk's tcgen05.mma (2 k-steps x 3 terms x N-blocks) and commits them to the stage's
 //              `empty` barrier; after the pass's last chunk it commits to the accumulator buffer's barrier;
 //   warps 8-15 epilogue: tcgen05.ld of the accumulator rows (thread = row, two warps per lane quadrant), bias / activation /
 //              GRU gate arithmetic, 64-bit stores; then hand the accumulator buffer back.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -40,7 +41,7 @@ constexpr int kTileM = 128;        // rows per tile = accumulator lanes
 #endif
 constexpr int kChunkK = PDP_NN_CHUNK_K;   // K elements per stage (16 or 32): kChunkK / 4 column groups of 16 bytes, kChunkK / 8 MMA k-steps
 constexpr int kHalfK = kChunkK / 2;       // elements of a row chunk per producer thread (two threads per row)
-constexpr int kThreads = 576;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 MMA issuer, 17 B producer
+constexpr int kThreads = 608;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 and 18 MMA issuers, 17 B producer
 constexpr int kPrefetch = kChunkK == 16 ? 4 : 2;       // chunks of A loads in flight per producer thread
 constexpr int kMaxNTot = 256;      // accumulator columns per pass (GRU: 4 gate blocks of 64 hidden units); two buffers
 
@@ -48,6 +49,7 @@ enum { EPI_LINEAR = 0, EPI_GRU = 1 };
 enum { ACT_NONE = 0, ACT_LOGSIGMOID = 1 };
 
 struct EdgeNNArgs {
+    alignas(64) CUtensorMap tmap_w;   // the weight image as a 2-D tensor [rows of 64 floats]: one chunk = one box (PDP_NN_TMAP)
     const float* src[3];       // row-major sources of the A rows, concatenated along K
     int32_t ks[3];             // their column counts (0: unused)
     int32_t k_total;           // sum of ks
@@ -90,17 +92,38 @@ __device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
         }
     }
 }
+#ifndef PDP_NN_SWIZZLE
+#define PDP_NN_SWIZZLE 1      // operand tiles in the 64-byte swizzled K-major layout (0: no swizzle, K chunks of 16 only with 1)
+#endif
+#ifndef PDP_NN_TMAP
+#define PDP_NN_TMAP 0         // 1: weights by tiled TMA (tensor map, UTMALDG) instead of the linear bulk copy (measured: 4.45 vs 4.11 ms
+                             // for the GRU cell over 1.2 M rows -- the copy is not what limits the pipeline)
+#endif
 #ifndef PDP_NN_TERMS
 #define PDP_NN_TERMS 3      // (profiling experiments only: fewer terms = wrong results)
 #endif
 #ifdef PDP_NN_TIMING
+__device__ long long g_nn_log[96][8];       // CTA 0, first 96 chunks: 0 producer sees empty, 1 producer arrives, 2 B copy issued, 3 issuer sees full, 4 MMAs issued, 5 commit done
+#define NN_LOG(chunk_, ev_) do { if (blockIdx.x == 0 && (chunk_) < 96) g_nn_log[chunk_][ev_] = clock64(); } while (0)
 __device__ unsigned long long g_nn_wait[8];     // cycles waited: 0 A-prod on empty, 1 B-prod on empty, 2 issuer on full_a, 3 on full_b, 4 on acc_empty, 5 epilogue on acc_full, 6 issuer total, 7 epilogue busy
 #define MB_WAIT_T(bar, par, slot) do { const long long _t0 = clock64(); mb_wait<((slot) < 2 || (slot) > 4)>(bar, par); if ((threadIdx.x & 31) == 0) atomicAdd(&g_nn_wait[slot], (unsigned long long)(clock64() - _t0)); } while (0)
 #else
 #define MB_WAIT_T(bar, par, slot) mb_wait<((slot) < 2 || (slot) > 4)>(bar, par)     // slots 2-4: the MMA issuer polls without backing off
+#define NN_LOG(chunk_, ev_) do {} while (0)
 #endif
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+// tiled TMA: the box at (0, row) of a 2-D tensor map -> shared memory (rows of 256 bytes: the box is a contiguous range)
+__device__ __forceinline__ void tmap_load_2d(void* dst, const CUtensorMap* tm, int row, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(s_u32(bar)) : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,9 +135,10 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
                  ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // shared-memory matrix descriptor, K-major, no swizzle: start address, LBO (next 16-byte column group), SBO (next 8 rows)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
-           ((uint64_t)1 << 46);     // descriptor version of sm_100
+           ((uint64_t)1 << 46) |    // descriptor version of sm_100
+           ((uint64_t)(layout_type & 7u) << 61);   // 0 no swizzle, 2 128-byte, 4 64-byte, 6 32-byte swizzle
 }
 // instruction descriptor of kind::tf32: D fp32, A and B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ uint32_t instr_desc(int m, int n) {
@@ -154,14 +178,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t issue_turn;                  // number of the chunk whose MMAs may be issued next
     __shared__ float s_bias[3 * kMaxNTot];          // the layer's (padded) bias: passes * n_tot values
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a broadcast: the compiler treats the role dispatch as warp-uniform)
     const int S = P.stages;
     const uint32_t a_bytes = 2u * kTileM * kChunkK * 4u;                 // hi + lo
     const uint32_t b_bytes = 2u * (uint32_t)P.n_tot * kChunkK * 4u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     for (int i = tid; i < P.passes * P.n_tot; i += kThreads) s_bias[i] = __ldg(P.bias + i);
     if (tid == 0) {
+        issue_turn = 0u;
         for (int s = 0; s < S; ++s) { mb_init(&bar_full[s], 9); mb_init(&bar_empty[s], 1); }     // full: 8 A-producer warps + the weight copy (arrive + bytes)
         for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                 if (g0 + d + D < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + kHalfK * half, buf[d]);
                 if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
                 MB_WAIT_T(&bar_empty[s], ph ^ 1u, 0);
+                if (tid == 0) NN_LOG((int)(g0 + d), 0);
                 unsigned char* st = smem + (size_t)s * stage_bytes;
 #pragma unroll
                 for (int gg = 0; gg < kHalfK / 4; ++gg) {
@@ -237,12 +265,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                         hp[j] = hb;
                         lp[j] = __float_as_uint(x - __uint_as_float(hb)) & 0xffffe000u;
                     }
-                    *reinterpret_cast<uint4*>(st + (size_t)g * (kTileM * 16) + (size_t)r * 16) = hi;
-                    *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + (size_t)g * (kTileM * 16) + (size_t)r * 16) = lo;
+#if PDP_NN_SWIZZLE
+                    // rows of 64 bytes, the 16-byte unit g of row r at unit g ^ ((r >> 1) & 3): Swizzle<2,4,3>
+                    const size_t off = (size_t)r * 64 + (size_t)((g ^ ((r >> 1) & 3)) << 4);
+#else
+                    const size_t off = (size_t)g * (kTileM * 16) + (size_t)r * 16;
+#endif
+                    *reinterpret_cast<uint4*>(st + off) = hi;
+                    *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + off) = lo;
                 }
                 fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mb_arrive(&bar_full[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
+                if (tid == 0) NN_LOG((int)(g0 + d), 1);
                 if (++s == S) { s = 0; ph ^= 1u; }
                 if (++c_u == units) { c_u = 0; c_row += tile_step; }
             }
@@ -250,59 +285,92 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     } else if (warp == 17 && lane == 0) {
         // ---------------- B producer: one bulk copy per chunk
         int s = 0; uint32_t ph = 0;
+        int gb = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int u = 0; u < units; ++u) {
+            for (int u = 0; u < units; ++u, ++gb) {
                 MB_WAIT_T(&bar_empty[s], ph ^ 1u, 1);
+                NN_LOG(gb, 2);
                 mb_expect_tx(&bar_full[s], b_bytes);
+#if PDP_NN_TMAP
+                tmap_load_2d(smem + (size_t)s * stage_bytes + a_bytes, &P.tmap_w, u * (int)(b_bytes >> 8), &bar_full[s]);
+#else
                 bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full[s]);
+#endif
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 16 && lane == 0) {
-        // ---------------- MMA issuer
+    } else if (warp == 16 || warp == 18) {
+        // ---------------- MMA issuers: two warps take the chunks in turn.  The whole warp walks the loop so that descriptors
+        //                  and addresses are warp-uniform values (uniform registers: a lone thread's per-thread values cost
+        //                  five R2UR moves per MMA, 150-180 cycles of issue time each); one elected lane issues.  Around a
+        //                  chunk's MMAs a warp waits for the stage, fences and commits: with two warps one's bookkeeping runs
+        //                  under the other's MMAs.  The MMAs of a pass accumulate into one buffer and must be issued in chunk
+        //                  order: a turn counter in shared memory hands the pipe from one warp to the other (commit tracks the
+        //                  issuing thread's own MMAs; the pipe runs in issue order, so the last chunk's completion implies
+        //                  the whole pass).
+        const int me = (warp == 16) ? 0 : 1;
         const uint32_t idesc = instr_desc(kTileM, P.n_blk);
         const uint32_t lbo_a = kTileM * 16, lbo_b = (uint32_t)P.n_tot * 16;
+#if PDP_NN_SWIZZLE
+        // K-major, 64-byte swizzle: rows of 64 bytes, 8-row atoms of 512 bytes one after the other (SBO = 512); a k-step of 8
+        // elements = 32 bytes further along the row (the hardware applies the XOR to the address it computes)
+        const uint64_t desc_hi_a = smem_desc(0, 16, 512, 4), desc_hi_b = smem_desc(0, 16, 512, 4);
+        const uint32_t kstep4 = 32u >> 4, nrow4 = 64u >> 4;
+#else
         const uint64_t desc_hi_a = smem_desc(0, lbo_a, 128), desc_hi_b = smem_desc(0, lbo_b, 128);
+#endif
         const uint32_t smem_a4 = s_u32(smem) >> 4, stage4 = stage_bytes >> 4;
         const uint32_t a_lo4 = (kTileM * kChunkK * 4) >> 4, b_off4 = a_bytes >> 4, b_lo4 = ((uint32_t)P.n_tot * kChunkK * 4) >> 4;
-        int s = 0; uint32_t ph = 0, acc_ph[2] = {0u, 0u};
+        int s = 0; uint32_t ph = 0, acc_ph0 = 0u, acc_ph1 = 0u;
         int ab = 0;                                     // accumulator buffer of this pass
+        uint32_t g = 0;                                 // running chunk number
+        volatile uint32_t* turn = &issue_turn;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int p = 0; p < P.passes; ++p) {
-                MB_WAIT_T(&bar_acc_empty[ab], acc_ph[ab] ^ 1u, 4);       // the epilogue has read this buffer's previous contents
-                tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(ab * kMaxNTot);
-                for (int c = 0; c < P.k_chunks; ++c) {
-                    MB_WAIT_T(&bar_full[s], ph, 2);
-                    tc_fence_after();
-#ifdef PDP_NN_TIMING
-                    const long long _m0 = clock64();
+                for (int c = 0; c < P.k_chunks; ++c, ++g) {
+                    if ((int)(g & 1u) == me) {
+                        if (c == 0) MB_WAIT_T(&bar_acc_empty[ab], (ab ? acc_ph1 : acc_ph0) ^ 1u, 4);   // the epilogue has read this buffer's previous contents
+#if !defined(PDP_NN_EXP_NOFULL)
+                        MB_WAIT_T(&bar_full[s], ph, 2);
 #endif
-                    // descriptors = constant upper parts | (address >> 4): everything below is 32-bit adds on the low word
-                    const uint32_t sa4 = (smem_a4 + (uint32_t)s * stage4);
+                        NN_LOG((int)g, 3);
+                        while (*turn != g) { }              // the other warp has issued chunk g - 1
+                        tc_fence_after();
+                        // descriptors = constant upper parts | (address >> 4): everything below is 32-bit adds on the low word
+                        const uint32_t sa4 = (smem_a4 + (uint32_t)s * stage4);
+                        const bool leader = elect_one();
 #pragma unroll
-                    for (int ks = 0; ks < kChunkK / 8; ++ks) {
+                        for (int ks = 0; ks < kChunkK / 8; ++ks) {
 #pragma unroll
-                        for (int term = 0; term < PDP_NN_TERMS; ++term) {      // hi hi, lo hi, hi lo
-                            const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
-                            const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
-                            const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
-                            for (int nb = 0; nb < P.n_mma; ++nb)
-                                tc_mma_tf32(tacc + (uint32_t)(nb * P.n_blk), desc_hi_a | a4, desc_hi_b | (b4 + (uint32_t)(nb * P.n_blk)), idesc, acc);
+                            for (int term = 0; term < PDP_NN_TERMS; ++term) {      // hi hi, lo hi, hi lo
+#if PDP_NN_SWIZZLE
+                                const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * kstep4;
+                                const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * kstep4;
+                                const uint32_t nb4 = (uint32_t)P.n_blk * nrow4;
+#else
+                                const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
+                                const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
+                                const uint32_t nb4 = (uint32_t)P.n_blk;
+#endif
+                                const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
+                                for (int nb = 0; nb < P.n_mma; ++nb)
+                                    if (leader) tc_mma_tf32(tacc + (uint32_t)(nb * P.n_blk), desc_hi_a | a4, desc_hi_b | (b4 + (uint32_t)nb * nb4), idesc, acc);
+                            }
                         }
+                        NN_LOG((int)g, 4);
+                        if (leader) {
+                            __threadfence_block();
+                            *turn = g + 1;                       // hand the pipe over
+                            tc_commit(&bar_empty[s]);            // the stage is free once these MMAs have read it
+                            if (c == P.k_chunks - 1) tc_commit(&bar_acc_full[ab]);
+                        }
+                        __syncwarp();
+                        NN_LOG((int)g, 5);
                     }
-#ifdef PDP_NN_TIMING
-                    const long long _m1 = clock64();
-#endif
-                    tc_commit(&bar_empty[s]);        // the stage is free once these MMAs have read it
-#ifdef PDP_NN_TIMING
-                    atomicAdd(&g_nn_wait[6], (unsigned long long)(_m1 - _m0));
-                    atomicAdd(&g_nn_wait[7], (unsigned long long)(clock64() - _m1));
-#endif
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(&bar_acc_full[ab]);
-                acc_ph[ab] ^= 1u;
+                if (ab) acc_ph1 ^= 1u; else acc_ph0 ^= 1u;
                 ab ^= 1;
             }
         }
@@ -401,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     }
 }
 
-int launch(const EdgeNNArgs& P, int epi, cudaStream_t stream) {
+int launch(EdgeNNArgs& P, int epi, cudaStream_t stream) {
     int dev = 0, sms = 0, cc = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { pdp_set_error("pdp_edge_nn: no CUDA device"); return PDP_ERR_CUDA; }
@@ -411,6 +479,30 @@ int launch(const EdgeNNArgs& P, int epi, cudaStream_t stream) {
     void* kern = epi == EPI_GRU ? (void*)k_edge_nn<EPI_GRU> : (void*)k_edge_nn<EPI_LINEAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: shared memory %zu: %s", smem, cudaGetErrorString(e)); return PDP_ERR_CUDA; }
+#if PDP_NN_TMAP
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+                pdp_set_error("pdp_edge_nn: cuTensorMapEncodeTiled not available"); return PDP_ERR_CUDA;
+            }
+            encode = (EncodeFn)fn;
+        }
+        const size_t b_bytes = 2u * (size_t)P.n_tot * kChunkK * 4u;
+        const cuuint64_t rows_total = (cuuint64_t)P.passes * P.k_chunks * (b_bytes >> 8);
+        const cuuint64_t gdim[2] = {64, rows_total};
+        const cuuint64_t gstr[1] = {256};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(b_bytes >> 8)};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult cr = encode(const_cast<CUtensorMap*>(&P.tmap_w), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P.w_img), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { pdp_set_error("pdp_edge_nn: cuTensorMapEncodeTiled -> %d (box rows %u)", (int)cr, box[1]); return PDP_ERR_CUDA; }
+    }
+#endif
     const int64_t n_tiles = (P.rows + kTileM - 1) / kTileM;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     if (epi == EPI_GRU) k_edge_nn<EPI_GRU><<<grid, kThreads, smem, stream>>>(P);
@@ -444,8 +536,12 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
 // One dense layer over rows: out[rows, n_out] = act([x1 | x2 | x3] W^T + bias) (* row_mask).  w_img / bias: the tiled
 // weight image and padded bias built by pdp_solver_b200/nn/tensor_ops.py (n_blk columns per MMA, n_mma blocks per pass).
 #ifdef PDP_NN_TIMING
+extern "C" int pdp_edge_nn_event_log(long long* host_96x8) {
+    return cudaMemcpyFromSymbol(host_96x8, g_nn_log, sizeof(long long) * 96 * 8) == cudaSuccess ? PDP_OK : PDP_ERR_CUDA;
+}
 extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
     if (host8 && cudaMemcpyFromSymbol(host8, g_nn_wait, sizeof(unsigned long long) * 8) != cudaSuccess) return PDP_ERR_CUDA;
+    (void)0;
     if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(g_nn_wait, z, sizeof(z)) != cudaSuccess) return PDP_ERR_CUDA; }
     return PDP_OK;
 }
@@ -453,6 +549,9 @@ extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
 
 // K elements per chunk of the weight image (the host side builds the images accordingly)
 extern "C" int pdp_edge_nn_chunk_k(void) { return kChunkK; }
+// 1: the weight images are rows of 64 bytes with the 16-byte units of row n at unit ^ ((n >> 1) & 3); 0: column groups of [n_tot][16 bytes]
+extern "C" int pdp_edge_nn_swizzle(void) { return PDP_NN_SWIZZLE; }
+static_assert(!PDP_NN_SWIZZLE || kChunkK == 16, "the 64-byte swizzle is the layout of 16-element K chunks");
 
 extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* x3, int32_t k3, int64_t rows,
                                     const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,

@@ -416,8 +416,11 @@ __device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pd
 // own sign NaN, and every message of the variable reads both sums -- `same` the one of its sign, `opp` the other.)
 // MULTI: the block holds several problems: frozen ones are left alone (PDP_SLOT_SKIP), those on the sticky-NaN path get
 // the sticky sign.
+#ifndef PDP_VNODE_INLINE
+#define PDP_VNODE_INLINE __forceinline__
+#endif
 template <int G, bool MULTI, bool MASKED, bool PREV>
-__device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask,
+__device__ PDP_VNODE_INLINE void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask,
                                             bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t stk_blk,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
     const int lane = t & 31;

@@ -28,13 +28,23 @@ def chunk_k():
 
 
 def _image(wp, passes, n_tot):
-    "wp: [passes * n_tot, k_pad] -> [passes, chunks, 2, groups, n_tot, 4] contiguous (groups = chunk_k / 4 columns of 16 bytes)"
+    """wp: [passes * n_tot, k_pad] -> the shared-memory image of every (pass, K chunk): {hi, lo} x one operand tile.
+    No swizzle: [groups = chunk_k / 4][n_tot][4 floats] (column groups of 16 bytes).  64-byte swizzle (chunk_k = 16):
+    [n_tot][4 units][4 floats] with the 16-byte unit g of row n stored at unit g ^ ((n >> 1) & 3)."""
     k_pad = wp.shape[1]
     ck = chunk_k()
     chunks = k_pad // ck
     hi, lo = _tf32_split(wp)
     both = torch.stack((hi, lo), 0)                                 # [2, P * n_tot, k_pad]
     both = both.view(2, passes, n_tot, chunks, ck // 4, 4)          # [term, pass, row, chunk, group, j]
+    if int(_lib.load().pdp_edge_nn_swizzle()):
+        rows = torch.arange(n_tot, device=wp.device)
+        slot = torch.arange(ck // 4, device=wp.device).view(1, -1) ^ ((rows >> 1) & 3).view(-1, 1)      # [row, group] -> unit
+        src = torch.empty_like(slot)
+        src.scatter_(1, slot, torch.arange(ck // 4, device=wp.device).view(1, -1).expand(n_tot, -1))    # unit -> group stored there
+        idx = src.view(1, 1, n_tot, 1, ck // 4, 1).expand(2, passes, n_tot, chunks, ck // 4, 4)
+        both = torch.gather(both, 4, idx)                           # [term, pass, row, chunk, unit, j]
+        return both.permute(1, 3, 0, 2, 4, 5).contiguous()         # [pass, chunk, term, row, unit, j]
     return both.permute(1, 3, 0, 4, 2, 5).contiguous()             # [pass, chunk, term, group, row, j]
 
 

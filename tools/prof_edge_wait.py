@@ -24,3 +24,13 @@ print("GRU E=%d: %.3f ms = %.0f cycles per CTA" % (E, ms, cyc))
 for i, n in enumerate(names):
     per = buf[i] / 148.0 / (8 if "8 warps" in n else 1)
     print("  %-34s %10.0f cycles per CTA (%.0f %% of the kernel)" % (n, per, 100 * per / cyc))
+
+log = (ctypes.c_longlong * (96 * 8))()
+L.pdp_edge_nn_event_log(log)
+import numpy as np
+ev = np.array(list(log), dtype=np.int64).reshape(96, 8)
+t0 = ev[0, 0]
+print("CTA 0, chunks 40..71 (cycles since the first event): producer sees empty | producer arrives | B copy issued | issuer sees full | MMAs issued | committed")
+for c in range(40, 72):
+    print("  chunk %2d: " % c + "  ".join("%8d" % (ev[c, k] - t0) for k in range(6)) + "   full-empty %6d  mma-full %6d   empty(c+4) - issued(c) %6d" % (ev[c, 3] - ev[c, 0], ev[c, 4] - ev[c, 3], ev[c + 4, 0] - ev[c, 4]))
+print("chunk period (MMAs issued, chunks 40..71): %.0f cycles" % ((ev[71, 4] - ev[40, 4]) / 31.0))
