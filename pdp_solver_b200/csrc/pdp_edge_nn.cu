@@ -17,7 +17,9 @@
 // double-buffered in the 512 columns of tensor memory, so the epilogue of one pass runs under the MMAs of the next), K
 // goes by in chunks of 16 through a ring of shared-memory stages:
 //   warps 0-7  stage the A chunk: two threads per row, each reads 8 floats of it (64-bit loads where the sources allow,
-//              the next chunks' loads in flight while the current one is converted), splits them, writes the hi and lo
+//              the next chunks' loads in flight while the current one is converted; row-strided, so they live on L1 hits --
+//              a coalesced variant with eight lanes per row chunk measured the same for the GRU cell and 10 % slower for the
+//              small layers), splits them, writes the hi and lo
 //              operand tiles in the canonical K-major layout of the tensor core (8-row x 16-byte core matrices; 16-byte
 //              column group g of a tile of R rows at g * 16 R, row r of it at + 16 r: core matrices contiguous, SBO = 128 B,
 //              LBO = 16 R);
@@ -30,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pdp_common.cuh"
 
@@ -290,10 +293,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             for (int u = 0; u < units; ++u, ++gb) {
                 MB_WAIT_T(&bar_empty[s], ph ^ 1u, 1);
                 NN_LOG(gb, 2);
-                mb_expect_tx(&bar_full[s], b_bytes);
 #if PDP_NN_TMAP
+                mb_expect_tx(&bar_full[s], b_bytes);
                 tmap_load_2d(smem + (size_t)s * stage_bytes + a_bytes, &P.tmap_w, u * (int)(b_bytes >> 8), &bar_full[s]);
 #else
+                mb_expect_tx(&bar_full[s], b_bytes);
                 bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full[s]);
 #endif
                 if (++s == S) { s = 0; ph ^= 1u; }
@@ -331,9 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                 for (int c = 0; c < P.k_chunks; ++c, ++g) {
                     if ((int)(g & 1u) == me) {
                         if (c == 0) MB_WAIT_T(&bar_acc_empty[ab], (ab ? acc_ph1 : acc_ph0) ^ 1u, 4);   // the epilogue has read this buffer's previous contents
-#if !defined(PDP_NN_EXP_NOFULL)
                         MB_WAIT_T(&bar_full[s], ph, 2);
-#endif
                         NN_LOG((int)g, 3);
                         while (*turn != g) { }              // the other warp has issued chunk g - 1
                         tc_fence_after();
@@ -526,8 +528,11 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
         return false;
     }
     const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
-    int st = (int)((200 * 1024) / stage);
+    // Few stages on purpose: what the ring does not take stays L1, and the row-strided reads of the operand staging and of the
+    // epilogue live on L1 hits (GRU cell over 1.2 M rows: 4 stages 4.14 ms, 3 stages 3.61 ms, 2 stages 3.50 ms)
+    int st = (int)((100 * 1024) / stage);
     P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
+    if (const char* e = getenv("PDP_B200_NN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= P.stages) P.stages = v; }   // (profiling)
     return true;
 }
 
