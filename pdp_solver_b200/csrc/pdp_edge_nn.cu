@@ -532,7 +532,7 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
     // epilogue live on L1 hits (GRU cell over 1.2 M rows: 4 stages 4.14 ms, 3 stages 3.61 ms, 2 stages 3.50 ms)
     int st = (int)((100 * 1024) / stage);
     P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
-    if (const char* e = getenv("PDP_B200_NN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= P.stages) P.stages = v; }   // (profiling)
+    if (const char* e = getenv("PDP_B200_NN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4 && (size_t)v * stage <= 200 * 1024) P.stages = v; }   // (profiling)
     return true;
 }
 
