@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--cpu-iterations", type=int, default=3)
     ap.add_argument("--cpu-walksat", type=int, default=2)
     ap.add_argument("--cpu-port", action="store_true", help="time the C oracle port even when the reference is present")
+    ap.add_argument("--strong-problems", type=int, default=64, help="problems of the fixed batch of the strong-scaling line (0: skip it)")
+    ap.add_argument("--strong-n", type=int, default=0, help="variables per problem of that batch (0: --n)")
     return ap.parse_args()
 
 
@@ -377,6 +379,24 @@ def run_b200_arm(a, rank, world, local_rank):
     ms_e, upd_e, solved_e, _, _ = timed_region(host, True)
     sampler.stop_flag = True
 
+    strong = None
+    if a.strong_problems > 0:
+        # rank 0 drives ALL the box's GPUs through the product's multi-GPU predict path; the other ranks free their
+        # devices' SMs (no kernel, no NCCL call) and wait for a key in the rendezvous store
+        store = dist.distributed_c10d._get_default_store() if world > 1 else None
+        if rank == 0:
+            try:
+                del resident
+                torch.cuda.empty_cache()
+                strong = strong_scaling_line(a, world)
+            except Exception as e:
+                strong = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if store is not None:
+                store.set("pdp_strong_done", "1")
+        else:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            store.wait(["pdp_strong_done"])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -420,6 +440,8 @@ def run_b200_arm(a, rank, world, local_rank):
                      "edge_updates_per_launch": st["loop_updates"] / a.steps, "launch_ms": st["loop_ms"] / a.steps},
         "clocks": sampler.summary(),
     }
+    if strong is not None:
+        line["strong_scaling_fixed_batch"] = strong
     if not a.no_config0 and world == 1:
         line["config0_cnfs_solved"] = config0_solved(dev)
     if not a.no_cpu_baseline:
@@ -428,6 +450,47 @@ def run_b200_arm(a, rank, world, local_rank):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling_line(a, world):
+    """A FIXED batch through the product's own multi-GPU predict path (FactorGraphTrainerBase._predict_epoch: one host
+    process, one worker thread + copy/compute streams per device, DynamicBatchDivider-style segments handed out to the
+    devices; replaces the reference's nn.DataParallel wrapper, src/pdp/factorgraph/base.py:96-97): `--strong-problems`
+    problems of the workload's size, one per segment, pinned host tensors, H2D / D2H and the per-problem output text
+    inside the timed region.  Runs in rank 0 on all `world` GPUs while the other ranks wait on the host."""
+    import io
+    import logging
+    import torch
+    from pdp_solver_b200 import cnfgen
+    from pdp_solver_b200.trainer import SatFactorGraphTrainer
+    n = a.strong_n or a.n
+    cfg = {"model_type": "p-d-p", "model_name": "bench", "tolerance": a.tolerance, "t_max": a.t_max, "local_search_iteration": a.walksat,
+           "epsilon": a.epsilon, "test_recurrence_num": a.iterations, "random_seed": a.seed, "gpus": world, "hidden_dim": 1,
+           "test_batch_limit": 1 << 40, "batch_size": 1, "verbose": False}
+    trainer = SatFactorGraphTrainer(cfg, True, logging.getLogger("bench"))
+    distinct = []        # (eight distinct instances, cycled: generating 64 on the host would take a minute)
+    for j in range(min(8, a.strong_problems)):
+        gm, bvm, bfm, ef = cnfgen.random_batch(1, n, a.k, a.alpha, a.seed + 5000 + j)
+        distinct.append([torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (gm, bvm, bfm, ef)])
+    segs = []
+    for j in range(a.strong_problems):
+        t = distinct[j % len(distinct)]
+        segs.append((t[0], t[1], t[2], t[3], None, torch.zeros(1, 1), [["s%d" % j]]))
+    E = sum(int(sg[0].shape[1]) for sg in segs)
+
+    def run():
+        out = io.StringIO()
+        t0 = time.perf_counter()
+        trainer._predict_epoch(None, trainer._post_process_predictions, 1, out, segment_stream=iter(segs))
+        for dev in trainer._devices:
+            torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, out.getvalue().count("\n")
+    run()                      # warm-up: module loading, allocator, workspace sizes
+    secs, lines = run()
+    return {"workload": "%d problems of random %d-SAT n=%d m/n=%.2f (one per segment), p-d-p T=%d + %d WalkSAT iterations, through "
+                        "FactorGraphTrainerBase._predict_epoch on %d GPU(s) of one process" % (a.strong_problems, a.k, n, a.alpha, a.iterations, a.walksat, world),
+            "n_gpus": world, "seconds": secs, "cnfs_per_s": a.strong_problems / secs, "edge_updates_per_s": float(E) * a.iterations / secs,
+            "output_lines": lines, "scaling": "strong", "timing": "host wall clock around the call, all devices synchronised"}
 
 
 def config0_solved(dev):
