@@ -276,6 +276,7 @@ def run_b200_arm(a, rank, world, local_rank):
     termination._pdp_standard_termination = True
 
     stats = {"updates": 0.0, "solved": 0, "launches": 0, "loop_ms": 0.0, "loop_updates": 0.0, "ws_ms": 0.0}
+    out_h = {"pred": torch.empty(V, dtype=torch.float32).pin_memory(), "solved": torch.empty(B, dtype=torch.float32).pin_memory()}
 
     def one_step(tensors, from_host, timed):
         torch.manual_seed(1 + rank)
@@ -289,11 +290,10 @@ def run_b200_arm(a, rank, world, local_rank):
                              check_termination=termination, batch_replication=1)
         ctx = model.last_problem._ctx
         solved, _ = ctx.cnf_eval(pred)
-        if from_host:
-            pred_h = pred.to("cpu", non_blocking=False)
-            solved_h = solved.cpu()
-        else:
-            solved_h = None
+        if from_host:      # the step's result back to (pinned) host memory, then wait for it
+            out_h["pred"].copy_(pred.reshape(-1), non_blocking=True)
+            out_h["solved"].copy_(solved.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         if timed:
             _, _, freeze = ctx.problem_flags()
             iters = int(model.last_iterations.item())
