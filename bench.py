@@ -550,7 +550,7 @@ def other_workload(a):
         specs = [(500, 3, 4.0), (500, 5, 18.0), (5000, 3, 4.0), (5000, 5, 18.0), (50000, 3, 4.0), (50000, 5, 18.0)]
         return cnfgen.mixed_batch([sp for sp in specs for _ in range(2)], seed)
     return dict(name="p-d-p SP + 100-iteration WalkSAT with batch replication -b 1..64, mixed random 3-SAT (m/n=4.0) / 5-SAT (m/n=18) n=500..50000, 12 problems per GPU, T=600 (BASELINE.json configs[4])",
-                model="p-d-p", batch=mixed, T=600, W=100, reps=[1, 8, 64], metric="cnfs_solved_per_s", unit="CNFs/s",
+                model="p-d-p", batch=mixed, T=600, W=100, reps=[1, 8, 64], metric="edge_updates_per_s", unit="edge-updates/s",
                 cpu=dict(B=2, n=500, k=3, alpha=4.2, T=50, W=10))
 
 

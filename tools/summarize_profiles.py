@@ -55,7 +55,7 @@ with open(os.path.join(P, tag + "_sp_run_ncu.md"), "w") as f:
         if n in m:
             f.write("| %s | %s | %s |\n" % (n, m[n][0], m[n][1]))
     f.write("\nDRAM bytes per edge-update: **%.2f B** (algorithmic 20 B; messages 24 B incl. the second survey buffer of the "
-            "convergence statistic + 12 B of 16/32-bit layout tables + bit masks / node pointers).\n" % per)
+            "convergence statistic + 2 x 2 B of node-order position tables + run tables, block descriptors, degree-sorted variable list).\n" % per)
     f.write("Warp instructions per edge-update: %.2f (thread instructions: see the first line of the table below); issue slots busy %s %%.\n\n" % (
         float(m["smsp__inst_executed.sum"][0].replace(",", "")) / edge_updates,
         m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]))
