@@ -318,14 +318,22 @@ def run_b200_arm(a, rank, world, local_rank):
 
         def __init__(self, tensors):
             self.host, self.bufs, self.ready, self.freed = tensors, [None, None], [None, None], [None, None]
+            self.spans = []
+
+        def copy_ms(self):
+            "mean duration of one step's host-to-device copy on the copy stream (call after a synchronize)"
+            return sum(b.elapsed_time(e) for b, e in self.spans) / max(len(self.spans), 1)
 
         def stage(self, k):
             with torch.cuda.stream(copy_stream):
                 if self.freed[k & 1] is not None:
                     copy_stream.wait_event(self.freed[k & 1])
+                begin = torch.cuda.Event(enable_timing=True)
+                begin.record(copy_stream)
                 self.bufs[k & 1] = [t.to(dev, non_blocking=True) for t in self.host]
-                self.ready[k & 1] = torch.cuda.Event()
+                self.ready[k & 1] = torch.cuda.Event(enable_timing=True)
                 self.ready[k & 1].record(copy_stream)
+                self.spans.append((begin, self.ready[k & 1]))
 
         def take(self, k):
             torch.cuda.current_stream(dev).wait_event(self.ready[k & 1])
@@ -360,15 +368,17 @@ def run_b200_arm(a, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        copy_ms = st.copy_ms() if from_host else 0.0
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms, copy_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, copy_ms = [float(x) for x in t.tolist()]
             agg = torch.tensor([stats["updates"], stats["solved"], stats["launches"]], device=dev, dtype=torch.float64)
             dist.all_reduce(agg, op=dist.ReduceOp.SUM)
             tot_upd, tot_solved, tot_launch = [float(x) for x in agg.tolist()]
         else:
             tot_upd, tot_solved, tot_launch = stats["updates"], stats["solved"], stats["launches"]
+        stats["h2d_ms"] = copy_ms
         return ms, tot_upd, tot_solved, tot_launch, dict(stats)
 
     os.environ["PDP_B200_TIMING"] = "1"
@@ -376,7 +386,7 @@ def run_b200_arm(a, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms, upd, solved, launches, st = timed_region(resident, False)
-    ms_e, upd_e, solved_e, _, _ = timed_region(host, True)
+    ms_e, upd_e, solved_e, _, st_e = timed_region(host, True)
     sampler.stop_flag = True
 
     strong = None
@@ -431,7 +441,12 @@ def run_b200_arm(a, rank, world, local_rank):
                                     "other(ingest,simplify,fill,io)": (ms - st["loop_ms"] - st["ws_ms"]) / a.steps},
         "e2e": {"value": upd_e / (ms_e / 1e3), "unit": "edge-updates/s", "h2d_bytes_per_step": h2d_bytes * world,
                 "d2h_bytes_per_step": (V * 4 + B * 4) * world, "ms_per_step": ms_e / a.steps,
-                "cnfs_solved_per_s": solved_e / (ms_e / 1e3)},
+                "cnfs_solved_per_s": solved_e / (ms_e / 1e3),
+                # the copy of step i+1 runs on its own stream under the kernels of step i: its duration (max over ranks) and
+                # rank 0's phases in this leg say whether the copy, or the kernels beside it, bend the end-to-end curve
+                "h2d_ms_per_step_max_rank": st_e["h2d_ms"],
+                "phase_ms_per_step_rank0": {"sp_loop": st_e["loop_ms"] / a.steps, "walksat": st_e["ws_ms"] / a.steps,
+                                            "other(ingest,simplify,fill,io)": (ms_e - st_e["loop_ms"] - st_e["ws_ms"]) / a.steps}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_sp_run (persistent SP propagate/decimate loop)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
