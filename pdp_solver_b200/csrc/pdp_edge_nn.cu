@@ -46,7 +46,10 @@ constexpr int kChunkK = PDP_NN_CHUNK_K;   // K elements per stage (16 or 32): kC
 constexpr int kHalfK = kChunkK / 2;       // elements of a row chunk per producer thread (two threads per row)
 constexpr int kThreads = 608;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 and 18 MMA issuers, 17 B producer
 constexpr int kPrefetch = kChunkK == 16 ? 4 : 2;       // chunks of A loads in flight per producer thread
-constexpr int kMaxNTot = 256;      // accumulator columns per pass (GRU: 4 gate blocks of 64 hidden units); two buffers
+constexpr int kMaxNTot = 320;      // accumulator columns per pass.  Two buffers in the 512 columns of tensor memory: at 0 and 256
+                                   // when a pass has <= 256 columns; wider passes (the GRU cell: 4 gates x 76 units = 304) put the
+                                   // second buffer at 512 - n_tot, and the columns the two share are drained first (see the epilogue)
+constexpr int kMmaN = 256;         // widest tcgen05.mma: a wider pass takes two per k-step and term
 
 enum { EPI_LINEAR = 0, EPI_GRU = 1 };
 enum { ACT_NONE = 0, ACT_LOGSIGMOID = 1 };
@@ -59,10 +62,10 @@ struct EdgeNNArgs {
     int32_t k_chunks;          // ceil(k_total / 16)
     int64_t rows;              // E
     const float* w_img;        // weights, split and tiled: [pass][chunk]{hi [4][n_tot][4], lo [4][n_tot][4]}
-    const float* bias;         // LINEAR: [passes * n_tot]; GRU: [passes][4][n_blk] = r, z, i_n, h_n
-    int32_t n_blk;             // columns per tcgen05.mma (multiple of 16, <= 256)
-    int32_t n_mma;             // N-blocks per pass
-    int32_t n_tot;             // n_blk * n_mma
+    const float* bias;         // LINEAR: [passes * n_tot]; GRU: [passes][n_tot / 4 units][4] = r, z, i_n, h_n of every unit
+    int32_t n_blk;             // (as passed: n_tot = n_blk * n_mma)
+    int32_t n_mma;
+    int32_t n_tot;             // accumulator columns per pass (multiple of 16, <= kMaxNTot): MMAs of kMmaN columns + the rest
     int32_t passes;
     int32_t n_out;             // LINEAR: output columns (<= passes * n_tot); GRU: hidden size H
     int32_t act;               // LINEAR
@@ -179,10 +182,10 @@ __device__ __forceinline__ float a_elem(const EdgeNNArgs& P, int64_t row, int k)
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__ EdgeNNArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2], bar_ovl[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t issue_turn;                  // number of the chunk whose MMAs may be issued next
-    __shared__ float s_bias[3 * kMaxNTot];          // the layer's (padded) bias: passes * n_tot values
+    __shared__ float s_bias[768];                   // the layer's (padded) bias: passes * n_tot values
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a broadcast: the compiler treats the role dispatch as warp-uniform)
     const int S = P.stages;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     if (tid == 0) {
         issue_turn = 0u;
         for (int s = 0; s < S; ++s) { mb_init(&bar_full[s], 9); mb_init(&bar_empty[s], 1); }     // full: 8 A-producer warps + the weight copy (arrive + bytes)
-        for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mb_init(&bar_acc_full[b], 1); mb_init(&bar_acc_empty[b], 8); mb_init(&bar_ovl[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) {    // the accumulators: all 512 columns of tensor memory (one CTA per SM)
@@ -207,6 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
 
     const int64_t n_tiles = (P.rows + kTileM - 1) / kTileM;
     const int units = P.passes * P.k_chunks;       // chunk iterations per tile
+    // accumulator buffers: columns [0, n_tot) and [buf1, buf1 + n_tot); they share n_ovl columns when a pass is wider than 256
+    const uint32_t buf1 = P.n_tot > 256 ? (uint32_t)(512 - P.n_tot) : 256u;
+    const int n_ovl = P.n_tot > 256 ? 2 * P.n_tot - 512 : 0;
     // every role walks the same sequence of (tile, pass, chunk) and keeps its own ring position
     if (warp < 8) {
         // ---------------- A producers: threads r and r + 128 <-> row r of the tile, column groups {0,1} / {2,3} of the chunk
@@ -313,28 +319,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         //                  issuing thread's own MMAs; the pipe runs in issue order, so the last chunk's completion implies
         //                  the whole pass).
         const int me = (warp == 16) ? 0 : 1;
-        const uint32_t idesc = instr_desc(kTileM, P.n_blk);
-        const uint32_t lbo_a = kTileM * 16, lbo_b = (uint32_t)P.n_tot * 16;
+        const int w0 = P.n_tot < kMmaN ? P.n_tot : kMmaN, w1 = P.n_tot - w0;      // columns of the two MMAs of a k-step and term
+        const uint32_t idesc0 = instr_desc(kTileM, w0), idesc1 = instr_desc(kTileM, w1 > 0 ? w1 : 16);
+        const uint32_t lbo_a = kTileM * 16;
 #if PDP_NN_SWIZZLE
         // K-major, 64-byte swizzle: rows of 64 bytes, 8-row atoms of 512 bytes one after the other (SBO = 512); a k-step of 8
         // elements = 32 bytes further along the row (the hardware applies the XOR to the address it computes)
         const uint64_t desc_hi_a = smem_desc(0, 16, 512, 4), desc_hi_b = smem_desc(0, 16, 512, 4);
         const uint32_t kstep4 = 32u >> 4, nrow4 = 64u >> 4;
 #else
+        const uint32_t lbo_b = (uint32_t)P.n_tot * 16;
         const uint64_t desc_hi_a = smem_desc(0, lbo_a, 128), desc_hi_b = smem_desc(0, lbo_b, 128);
 #endif
         const uint32_t smem_a4 = s_u32(smem) >> 4, stage4 = stage_bytes >> 4;
         const uint32_t a_lo4 = (kTileM * kChunkK * 4) >> 4, b_off4 = a_bytes >> 4, b_lo4 = ((uint32_t)P.n_tot * kChunkK * 4) >> 4;
-        int s = 0; uint32_t ph = 0, acc_ph0 = 0u, acc_ph1 = 0u;
+        int s = 0; uint32_t ph = 0, acc_ph0 = 0u, acc_ph1 = 0u, ovl_ph0 = 0u, ovl_ph1 = 0u;
         int ab = 0;                                     // accumulator buffer of this pass
         uint32_t g = 0;                                 // running chunk number
+        bool first_pass = true;
         volatile uint32_t* turn = &issue_turn;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int p = 0; p < P.passes; ++p) {
-                const uint32_t tacc = tmem_base + (uint32_t)(ab * kMaxNTot);
+                const uint32_t tacc = tmem_base + (ab ? buf1 : 0u);
                 for (int c = 0; c < P.k_chunks; ++c, ++g) {
                     if ((int)(g & 1u) == me) {
-                        if (c == 0) MB_WAIT_T(&bar_acc_empty[ab], (ab ? acc_ph1 : acc_ph0) ^ 1u, 4);   // the epilogue has read this buffer's previous contents
+                        if (c == 0) {
+                            MB_WAIT_T(&bar_acc_empty[ab], (ab ? acc_ph1 : acc_ph0) ^ 1u, 4);   // the epilogue has read this buffer's previous contents
+                            // ... and, of the pass before this one (the other buffer), the columns the two buffers share
+                            if (n_ovl > 0 && !first_pass) MB_WAIT_T(&bar_ovl[ab ^ 1], ab ? ovl_ph0 : ovl_ph1, 4);
+                        }
                         MB_WAIT_T(&bar_full[s], ph, 2);
                         NN_LOG((int)g, 3);
                         while (*turn != g) { }              // the other warp has issued chunk g - 1
@@ -349,15 +362,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
 #if PDP_NN_SWIZZLE
                                 const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * kstep4;
                                 const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * kstep4;
-                                const uint32_t nb4 = (uint32_t)P.n_blk * nrow4;
+                                const uint32_t nb4 = (uint32_t)w0 * nrow4;
 #else
                                 const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
                                 const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
-                                const uint32_t nb4 = (uint32_t)P.n_blk;
+                                const uint32_t nb4 = (uint32_t)w0;
 #endif
                                 const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
-                                for (int nb = 0; nb < P.n_mma; ++nb)
-                                    if (leader) tc_mma_tf32(tacc + (uint32_t)(nb * P.n_blk), desc_hi_a | a4, desc_hi_b | (b4 + (uint32_t)nb * nb4), idesc, acc);
+                                if (leader) {
+                                    tc_mma_tf32(tacc, desc_hi_a | a4, desc_hi_b | b4, idesc0, acc);
+                                    if (w1 > 0) tc_mma_tf32(tacc + (uint32_t)w0, desc_hi_a | a4, desc_hi_b | (b4 + nb4), idesc1, acc);
+                                }
                             }
                         }
                         NN_LOG((int)g, 4);
@@ -373,6 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
                 if (ab) acc_ph1 ^= 1u; else acc_ph0 ^= 1u;
+                if (n_ovl > 0 && !first_pass) { if (ab) ovl_ph0 ^= 1u; else ovl_ph1 ^= 1u; }      // (the other buffer's barrier was waited for)
+                first_pass = false;
                 ab ^= 1;
             }
         }
@@ -405,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                 MB_WAIT_T(&bar_acc_full[ab], acc_ph[ab], 5);
                 acc_ph[ab] ^= 1u;
                 tc_fence_after();
-                const uint32_t tlane = tlane0 + (uint32_t)(ab * kMaxNTot);
+                const uint32_t tlane = tlane0 + (ab ? buf1 : 0u);
                 if (EPI == EPI_LINEAR) {
                     for (int c0 = 16 * hh; c0 < P.n_tot; c0 += 32) {
                         float v[16];
@@ -423,37 +440,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                         store16(P.out + row * P.n_out + n0, y, min(16, P.n_out - n0));
                     }
                 } else {
-                    // the pass holds hidden units [p * nh, (p + 1) * nh): columns [0,nh) r, [nh,2nh) z, [2nh,3nh) W_in x, [3nh,4nh) W_hn h
-                    const int nh = P.n_tot / 4;
+                    // the pass holds hidden units [p * nh, (p + 1) * nh), four columns each: r, z, W_in x, W_hn h of the unit.  A
+                    // group of 16 columns = four whole units.  The columns this buffer shares with the other one go first (of
+                    // buffer 0 its last n_ovl columns, of buffer 1 its first): once every warp has read its part of them, the
+                    // MMAs of the next pass -- into the other buffer -- may start, under the rest of this epilogue.
+                    const int nh = P.n_tot / 4, ngrp = P.n_tot / 16, novl = n_ovl / 16;
+                    const int g_first = ab ? 0 : ngrp - novl;
                     const float* bs = s_bias + (size_t)p * P.n_tot;
-                    for (int c0 = 16 * hh; c0 < nh; c0 += 32) {
-                        float vr[16], vz[16], vi[16], vh[16];
-                        tc_ld16(tlane + (uint32_t)c0, vr);
-                        tc_ld16(tlane + (uint32_t)(nh + c0), vz);
-                        tc_ld16(tlane + (uint32_t)(2 * nh + c0), vi);
-                        tc_ld16(tlane + (uint32_t)(3 * nh + c0), vh);
-                        const int u0 = p * nh + c0;
+                    bool handed = novl == 0;
+                    for (int i = hh; i < ngrp; i += 2) {
+                        if (!handed && i >= novl) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mb_arrive(&bar_ovl[ab]);
+                            handed = true;
+                        }
+                        int grp = i + g_first;
+                        if (grp >= ngrp) grp -= ngrp;
+                        float v[16];
+                        tc_ld16(tlane + (uint32_t)(16 * grp), v);
+                        const int u0 = p * nh + 4 * grp;
                         if (!live || u0 >= P.n_out) continue;
-                        const int nvalid = min(16, P.n_out - u0);
-                        float ho[16], y[16];
+                        const int nvalid = min(4, P.n_out - u0);
+                        float ho[4], y[4];
                         const float* hp = P.h_old + row * P.n_out + u0;
-                        if (vec2 && nvalid == 16) {
+                        if (vec2 && nvalid == 4) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(hp) + j); ho[2 * j] = t2.x; ho[2 * j + 1] = t2.y; }
+                            for (int j = 0; j < 2; ++j) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(hp) + j); ho[2 * j] = t2.x; ho[2 * j + 1] = t2.y; }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) ho[j] = j < nvalid ? __ldg(hp + j) : 0.f;
+                            for (int j = 0; j < 4; ++j) ho[j] = j < nvalid ? __ldg(hp + j) : 0.f;
                         }
+                        const float* bg = bs + 16 * grp;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float rg = sigmoidf_(vr[j] + bs[c0 + j]);
-                            const float zg = sigmoidf_(vz[j] + bs[nh + c0 + j]);
-                            const float ng = tanhf_(vi[j] + bs[2 * nh + c0 + j] + rg * (vh[j] + bs[3 * nh + c0 + j]));
+                        for (int j = 0; j < 4; ++j) {
+                            const float rg = sigmoidf_(v[4 * j] + bg[4 * j]);
+                            const float zg = sigmoidf_(v[4 * j + 1] + bg[4 * j + 1]);
+                            const float ng = tanhf_(v[4 * j + 2] + bg[4 * j + 2] + rg * (v[4 * j + 3] + bg[4 * j + 3]));
                             float hn = (1.f - zg) * ng + zg * ho[j];
                             if (P.row_mask) hn = mk * hn + (1.f - mk) * ho[j];
                             y[j] = hn;
                         }
-                        store16(P.out + row * P.n_out + u0, y, nvalid);
+                        float* dst = P.out + row * P.n_out + u0;
+                        if (vec2 && nvalid == 4) {
+                            reinterpret_cast<float2*>(dst)[0] = make_float2(y[0], y[1]);
+                            reinterpret_cast<float2*>(dst)[1] = make_float2(y[2], y[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (j < nvalid) dst[j] = y[j];
+                        }
+                    }
+                    if (!handed) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mb_arrive(&bar_ovl[ab]);
                     }
                 }
                 tc_fence_before();
@@ -522,8 +562,8 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
     P.k_chunks = (P.k_total + kChunkK - 1) / kChunkK;
     P.rows = rows; P.w_img = w_img; P.bias = bias;
     P.n_blk = n_blk; P.n_mma = n_mma; P.n_tot = n_blk * n_mma; P.passes = passes;
-    if (P.k_total <= 0 || !w_img || !bias || n_blk < 16 || n_blk > 256 || (n_blk & 15) || n_mma < 1 || P.n_tot > kMaxNTot || passes < 1 ||
-        (k1 > 0 && !x1) || (k2 > 0 && !x2) || (k3 > 0 && !x3) || ((uintptr_t)w_img & 15) || passes * n_blk * n_mma > 3 * kMaxNTot) {
+    if (P.k_total <= 0 || !w_img || !bias || n_blk < 16 || (n_blk & 15) || n_mma < 1 || P.n_tot > kMaxNTot || passes < 1 ||
+        (k1 > 0 && !x1) || (k2 > 0 && !x2) || (k3 > 0 && !x3) || ((uintptr_t)w_img & 15) || passes * n_blk * n_mma > 768) {
         pdp_set_error("%s: bad argument (k=%d n_blk=%d n_mma=%d passes=%d)", who, P.k_total, n_blk, n_mma, passes);
         return false;
     }
@@ -565,13 +605,13 @@ extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2
     EdgeNNArgs P;
     memset(&P, 0, sizeof(P));
     if (!fill_common(P, x1, k1, x2, k2, x3, k3, rows, w_img, bias, n_blk, n_mma, passes, "pdp_edge_mlp_forward")) return PDP_ERR_ARG;
-    if (!out || n_out < 1 || n_out > passes * P.n_tot) { pdp_set_error("pdp_edge_mlp_forward: bad output shape"); return PDP_ERR_ARG; }
+    if (!out || n_out < 1 || n_out > passes * P.n_tot || P.n_tot > 256) { pdp_set_error("pdp_edge_mlp_forward: bad output shape"); return PDP_ERR_ARG; }
     P.n_out = n_out; P.act = act; P.row_mask = row_mask; P.out = out;
     return launch(P, EPI_LINEAR, (cudaStream_t)stream);
 }
 
 // torch.nn.GRUCell over rows: h'[rows, H] from input [x1 | x2] and hidden state h (row-major [rows, H]); every pass holds
-// the four gate blocks (r, z, W_in x, W_hn h) of n_blk * n_mma / 4 hidden units.  row_mask blends h' with h (frozen rows).
+// n_blk * n_mma / 4 hidden units, four accumulator columns each (r, z, W_in x, W_hn h).  row_mask blends h' with h (frozen rows).
 extern "C" int pdp_edge_gru_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* h, int32_t hidden, int64_t rows,
                                     const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes,
                                     const float* row_mask, float* out, void* stream) {
@@ -579,7 +619,7 @@ extern "C" int pdp_edge_gru_forward(const float* x1, int32_t k1, const float* x2
     EdgeNNArgs P;
     memset(&P, 0, sizeof(P));
     if (!fill_common(P, h, hidden, x1, k1, x2, k2, rows, w_img, bias, n_blk, n_mma, passes, "pdp_edge_gru_forward")) return PDP_ERR_ARG;   // rows = [h | x1 | x2]
-    if (!out || !h || hidden < 1 || (P.n_tot & 63) || hidden > passes * (P.n_tot / 4) || out == h) {
+    if (!out || !h || hidden < 1 || (P.n_tot & 15) || hidden > passes * (P.n_tot / 4) || out == h) {
         pdp_set_error("pdp_edge_gru_forward: bad shape (hidden=%d n_tot=%d passes=%d) or out aliases h", hidden, P.n_tot, passes);
         return PDP_ERR_ARG;
     }

@@ -96,6 +96,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// the whole CTA waits for a phase: one warp polls the barrier word, the others sleep at the block barrier (a polling warp
+// takes issue slots from the SM's other CTA: 512 polling threads were 4.5 % of the kernel's instructions).  The polling
+// warp's acquire and the block barrier order the copied bytes before every thread's reads.
+#ifndef PDP_WAIT_WARP0
+#define PDP_WAIT_WARP0 1
+#endif
+__device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
+#if PDP_WAIT_WARP0
+    if (threadIdx.x < 32) mbar_wait(bar, parity);
+    __syncthreads();
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 // explicit shared-window accesses (32-bit addresses).  The node phases index the planes through the position table; as
 // volatile statements these keep the order they are written in, which is how two rows are interleaved by hand below.
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -149,7 +164,9 @@ __device__ __forceinline__ BlkStage blk_stage(const BlkGeo& B) {
 // written several times).  Everything but the store (and the rare sticky re-read) is shared memory, addressed in the shared
 // window: plane_sa = address of slot 0's word (slot w at plane_sa + 4 w), wrun_sa = address of run table word 0 (word i at
 // wrun_sa + 8 i), adj_sa = address of run 0's offset (ADJ_S) or adj_g = g.*_wadj (a block with too many runs to stage).
-template <int G, bool ADJ_S>
+// MARK: the block may hold markers (several problems, or a problem on the sticky-NaN path).  Without them a row costs no
+// vote and no branch; the sign bit is cleared on the way out (a NaN result may carry one).
+template <int G, bool ADJ_S, bool MARK>
 __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_t plane_sa, uint32_t wrun_sa, uint32_t adj_sa,
                                                const int32_t* __restrict__ adj_g, const float* old, float* out) {   // old may alias out (q is updated in place)
     // A warp takes 32 slots that share one word of the run table: slot w = row + lane with row a multiple of 32, so the
@@ -183,7 +200,8 @@ __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int d = dest(row + u * G + lane, rbx[u], rby[u]);
-            if (!__any_sync(0xffffffffu, (int32_t)raw[u] < 0)) out[d] = __uint_as_float(raw[u]);      // the rule: no marker in the row
+            if (!MARK) out[d] = __uint_as_float(raw[u] & 0x7fffffffu);
+            else if (!__any_sync(0xffffffffu, (int32_t)raw[u] < 0)) out[d] = __uint_as_float(raw[u]);      // the rule: no marker in the row
             else if ((int32_t)raw[u] < 0) special(d, raw[u]);
             else out[d] = __uint_as_float(raw[u]);
         }
@@ -193,7 +211,8 @@ __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_
         const uint32_t raw = lds_u32(pa);
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wa));
         const int d = dest(row + lane, rbx, rby);
-        if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
+        if (!MARK) out[d] = __uint_as_float(raw & 0x7fffffffu);
+        else if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
     }
     // partial rows: the one holding wlo (when wlo is not a multiple of 32) and the one holding wend - 1
     const int r_head = wlo & ~31, r_tail = (wend - 1) & ~31;
@@ -207,27 +226,44 @@ __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_
             const uint32_t raw = lds_u32(plane_sa + 4u * (uint32_t)w);
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rbx), "=r"(rby) : "r"(wrun_sa + 8u * (uint32_t)(er >> 5)));
             const int d = dest(w, rbx, rby);
-            if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
+            if (!MARK) out[d] = __uint_as_float(raw & 0x7fffffffu);
+            else if ((int32_t)raw < 0) special(d, raw); else out[d] = __uint_as_float(raw);
         }
     }
 }
+#ifndef PDP_WO_NOMARK
+#define PDP_WO_NOMARK 1
+#endif
 template <int G>
 __device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, int wlo, int wend, const float* plane, const uint2* wrun_s, int w0,
-                                             const int32_t* adj_s, int r0, const int32_t* adj_g, const float* old, float* out) {
+                                             const int32_t* adj_s, int r0, const int32_t* adj_g, const float* old, float* out, bool marks) {
     const uint32_t plane_sa = smem_u32(plane) - 4u * (uint32_t)B.e0;
     const uint32_t wrun_sa = smem_u32(wrun_s) - 8u * (uint32_t)w0;
-    if (adj_s) ph_write_out_t<G, true>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
-    else ph_write_out_t<G, false>(t, wlo, wend, plane_sa, wrun_sa, 0u, adj_g, old, out);
+    if (adj_s) {
+        if (PDP_WO_NOMARK && !marks) ph_write_out_t<G, true, false>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
+        else ph_write_out_t<G, true, true>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
+    } else ph_write_out_t<G, false, true>(t, wlo, wend, plane_sa, wrun_sa, 0u, adj_g, old, out);
 }
 
 // the edge-mask bits of the block's region (indexed by layout position) -> sign bits of the plane (its values are >= +0 or
-// NaN).  Only the words that have a bit set cost anything.
+// NaN).  Only the words that have a bit set cost anything.  The first two words of every thread (all of them at the block
+// sizes of the two-CTA configuration) are fetched BEFORE the CTA waits for the block's copies: their latency hides there.
+struct MaskWords { uint32_t m[2]; };
 template <int G>
-__device__ __forceinline__ void ph_apply_mask(int t, const uint32_t* __restrict__ mask, const BlkGeo& B, float* plane) {
+__device__ __forceinline__ MaskWords ph_mask_fetch(int t, const uint32_t* __restrict__ mask, const BlkGeo& B) {
+    MaskWords M;
+    const int W0 = B.e0 >> 5, W1 = (B.e0 + B.ne - 1) >> 5;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const int i = W0 + t + k * G; M.m[k] = (i <= W1) ? __ldcg(mask + i) : 0u; }
+    return M;
+}
+template <int G>
+__device__ __forceinline__ void ph_apply_mask(int t, const uint32_t* __restrict__ mask, const BlkGeo& B, float* plane, const MaskWords& M) {
     uint32_t* pl = reinterpret_cast<uint32_t*>(plane) - B.e0;
     const int W0 = B.e0 >> 5, W1 = (B.e0 + B.ne - 1) >> 5, wend = B.e0 + B.ne;
-    for (int i = W0 + t; i <= W1; i += G) {
-        uint32_t m = __ldcg(mask + i);
+    int k = 0;
+    for (int i = W0 + t; i <= W1; i += G, ++k) {
+        uint32_t m = (k < 2) ? M.m[k < 1 ? 0 : 1] : __ldcg(mask + i);
         while (m) {
             const int pos = 32 * i + __ffs(m) - 1;
             m &= m - 1;
@@ -684,9 +720,11 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
         const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
         const int ku = g.cb_k[blk];
-        mbar_wait(bb.bar, bb.parity);
+        MaskWords MW; MW.m[0] = 0u; MW.m[1] = 0u;
+        if (masked) MW = ph_mask_fetch<NT>(tid, g.qmask, B);
+        mbar_wait_cta(bb.bar, bb.parity);
         bb.parity ^= 1u;
-        if (masked) { ph_apply_mask<NT>(tid, g.qmask, B, X); __syncthreads(); }
+        if (masked) { ph_apply_mask<NT>(tid, g.qmask, B, X, MW); __syncthreads(); }
         PHASE_ADD(0);
         if (masked) ph_clause_node<NT, true>(tid, g, s, B, ku, X, stk_blk);
         else ph_clause_node<NT, false>(tid, g, s, B, ku, X, stk_blk);
@@ -700,7 +738,7 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
 #pragma unroll 1
             for (int k = 0; k < PDP_WO_SEGS; ++k) {
                 const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
-                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, X, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.c_wadj, s.eta[r], eout);
+                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, X, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.c_wadj, s.eta[r], eout, B.multi() || stk_blk != 0u);
                 if (k == 0 && tid == 0 && nx < g.ncb) {
                     const BlkGeo N = clause_block(g, nx);
                     const int st = blk_will_run(s, N);
@@ -803,10 +841,12 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
         const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
         const bool scoring = PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1]);
-        mbar_wait(bb.bar, bb.parity);
+        MaskWords MW; MW.m[0] = 0u; MW.m[1] = 0u;
+        if (masked) MW = ph_mask_fetch<NT>(tid, g.vmask, B);
+        mbar_wait_cta(bb.bar, bb.parity);
         bb.parity ^= 1u;
-        if (masked) ph_apply_mask<NT>(tid, g.vmask, B, PA);
-        if (masked || local_stats) __syncthreads();
+        if (masked) ph_apply_mask<NT>(tid, g.vmask, B, PA, MW);
+        if (masked || (local_stats && !PDP_WAIT_WARP0)) __syncthreads();
         PHASE_ADD(3);
         // SurveyScorer of problems about to converge, while the new surveys are still in the plane (the node phase
         // overwrites them); its own loop, so that the node phase's code is the same with and without it
@@ -829,7 +869,7 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
 #pragma unroll 1
             for (int k = 0; k < PDP_WO_SEGS; ++k) {
                 const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
-                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, PA, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.v_wadj, s.qu, s.qu);
+                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, PA, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.v_wadj, s.qu, s.qu, B.multi() || stk_blk != 0u);
                 if (k == 0 && tid == 0 && nx < g.nvb) {
                     const BlkGeo N = var_block(g, nx);
                     const int st = blk_will_run(s, N);

@@ -118,7 +118,9 @@ class TensorLinear(object):
 
 class TensorGRU(object):
     "h' = GRUCell([x1 | x2], h), optionally blended with h where row_mask == 0 (torch.nn.GRUCell semantics)"
-    NH = 64       # hidden units per pass: four gate blocks of 64 columns = one 256-column accumulator buffer
+    MAX_COLS = 304    # accumulator columns per pass: four per hidden unit (r, z, W_in x, W_hn h).  Two passes cover the 150 hidden
+                      # units of the reference's models (2 x 76): the operand rows are staged once per pass, and wider passes do
+                      # not fit twice into the 512 columns of tensor memory (304 + 304 share 96, which the epilogue drains first)
 
     def __init__(self, cell):
         self._cell = cell
@@ -134,24 +136,29 @@ class TensorGRU(object):
         dev = wih.device
         bih = c.bias_ih.detach().float() if c.bias_ih is not None else torch.zeros(3 * H, device=dev)
         bhh = c.bias_hh.detach().float() if c.bias_hh is not None else torch.zeros(3 * H, device=dev)
-        nh = self.NH
-        passes = (H + nh - 1) // nh
+        passes = (4 * H + self.MAX_COLS - 1) // self.MAX_COLS
+        nh = _round_up((H + passes - 1) // passes, 4)          # hidden units per pass: 16 accumulator columns = four whole units
         n_tot = 4 * nh
+        if passes * n_tot > 768:
+            raise _lib.PdpError("TensorGRU: %d hidden units do not fit three passes" % H)
         k = kx + H
-        wp = torch.zeros(passes, 4, nh, _round_up(k, chunk_k()), dtype=torch.float32, device=dev)
-        bp = torch.zeros(passes, 4, nh, dtype=torch.float32, device=dev)
+        # [pass, unit, gate, K]: the four accumulator columns of a unit sit side by side
+        wp = torch.zeros(passes, nh, 4, _round_up(k, chunk_k()), dtype=torch.float32, device=dev)
+        bp = torch.zeros(passes, nh, 4, dtype=torch.float32, device=dev)
         for p in range(passes):
             u0, u1 = p * nh, min(H, (p + 1) * nh)
             m = u1 - u0
+            if m <= 0:
+                continue
             # the kernel's rows are [h | x]: the hidden state first, so that both big sources start at even columns (64-bit loads)
-            for gate in range(2):        # r, z: input and hidden parts accumulate into the same columns
-                wp[p, gate, :m, :H] = whh[gate * H + u0: gate * H + u1]
-                wp[p, gate, :m, H:k] = wih[gate * H + u0: gate * H + u1]
-                bp[p, gate, :m] = bih[gate * H + u0: gate * H + u1] + bhh[gate * H + u0: gate * H + u1]
-            wp[p, 2, :m, H:k] = wih[2 * H + u0: 2 * H + u1]      # W_in x   (+ b_in)
-            wp[p, 3, :m, :H] = whh[2 * H + u0: 2 * H + u1]       # W_hn h   (+ b_hn), multiplied by r in the epilogue
-            bp[p, 2, :m] = bih[2 * H + u0: 2 * H + u1]
-            bp[p, 3, :m] = bhh[2 * H + u0: 2 * H + u1]
+            for gate in range(2):        # r, z: input and hidden parts accumulate into the same column
+                wp[p, :m, gate, :H] = whh[gate * H + u0: gate * H + u1]
+                wp[p, :m, gate, H:k] = wih[gate * H + u0: gate * H + u1]
+                bp[p, :m, gate] = bih[gate * H + u0: gate * H + u1] + bhh[gate * H + u0: gate * H + u1]
+            wp[p, :m, 2, H:k] = wih[2 * H + u0: 2 * H + u1]      # W_in x   (+ b_in)
+            wp[p, :m, 3, :H] = whh[2 * H + u0: 2 * H + u1]       # W_hn h   (+ b_hn), multiplied by r in the epilogue
+            bp[p, :m, 2] = bih[2 * H + u0: 2 * H + u1]
+            bp[p, :m, 3] = bhh[2 * H + u0: 2 * H + u1]
         self.hidden, self.kx = H, kx
         self.n_blk, self.n_mma, self.passes = n_tot, 1, passes
         self.image = _image(wp.view(passes * n_tot, -1), passes, n_tot)

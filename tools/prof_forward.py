@@ -18,6 +18,8 @@ ap.add_argument("--n", type=int, default=1000000)
 ap.add_argument("--k", type=int, default=3)
 ap.add_argument("--alpha", type=float, default=4.2)
 ap.add_argument("--iterations", type=int, default=100)
+ap.add_argument("--module-only", action="store_true", help="skip the raw Context stages (launch lists of the module path)")
+ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 gm, bvm, bfm, ef = [torch.from_numpy(x).to(dev) for x in cnfgen.random_batch(a.problems, a.n, a.k, a.alpha, 1)]
@@ -42,7 +44,7 @@ class Stages(object):
         print("  %-28s %8.3f ms (wall %.3f ms)" % ("total", self.ev[0].elapsed_time(self.ev[-1]), wall * 1e3))
 
 
-for rep in range(3):
+for rep in range(0 if a.module_only else a.reps):
     torch.cuda.synchronize()
     st = Stages()
     st.mark("start")
@@ -82,7 +84,7 @@ def termination(active, prediction, sat_problem):
 
 
 termination._pdp_standard_termination = True
-for rep in range(3):
+for rep in range(a.reps):
     torch.cuda.synchronize()
     st = Stages()
     st.mark("start")
