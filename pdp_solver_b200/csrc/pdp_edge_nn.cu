@@ -18,8 +18,8 @@
 // goes by in chunks of 16 through a ring of shared-memory stages:
 //   warps 0-7  stage the A chunk: two threads per row, each reads 8 floats of it (64-bit loads where the sources allow,
 //              the next chunks' loads in flight while the current one is converted; row-strided, so they live on L1 hits --
-//              a coalesced variant with eight lanes per row chunk measured the same for the GRU cell and 10 % slower for the
-//              small layers), splits them, writes the hi and lo
+//              a coalesced variant with eight lanes per row chunk -- 64-bit loads of four rows per warp instruction -- measured
+//              20 % slower for the GRU cell and 30 % slower for the small layers), splits them, writes the hi and lo
 //              operand tiles in the canonical K-major layout of the tensor core (8-row x 16-byte core matrices; 16-byte
 //              column group g of a tile of R rows at g * 16 R, row r of it at + 16 r: core matrices contiguous, SBO = 128 B,
 //              LBO = 16 R);
@@ -45,7 +45,12 @@ constexpr int kTileM = 128;        // rows per tile = accumulator lanes
 constexpr int kChunkK = PDP_NN_CHUNK_K;   // K elements per stage (16 or 32): kChunkK / 4 column groups of 16 bytes, kChunkK / 8 MMA k-steps
 constexpr int kHalfK = kChunkK / 2;       // elements of a row chunk per producer thread (two threads per row)
 constexpr int kThreads = 608;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 and 18 MMA issuers, 17 B producer
-constexpr int kPrefetch = kChunkK == 16 ? 4 : 2;       // chunks of A loads in flight per producer thread
+#ifndef PDP_NN_RAW_DEPTH
+#define PDP_NN_RAW_DEPTH 6
+#endif
+constexpr int kRawDepth = PDP_NN_RAW_DEPTH;            // chunks of operand rows in flight per producer thread (cp.async ring, 8 KB each)
+constexpr int kRawBytes = kRawDepth * 256 * kHalfK * 4;
+constexpr int kMaxChunks = 64;                          // K <= 1024
 constexpr int kMaxNTot = 320;      // accumulator columns per pass.  Two buffers in the 512 columns of tensor memory: at 0 and 256
                                    // when a pass has <= 256 columns; wider passes (the GRU cell: 4 gates x 76 units = 304) put the
                                    // second buffer at 512 - n_tot, and the columns the two share are drained first (see the epilogue)
@@ -111,11 +116,14 @@ __device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
 #ifdef PDP_NN_TIMING
 __device__ long long g_nn_log[96][8];       // CTA 0, first 96 chunks: 0 producer sees empty, 1 producer arrives, 2 B copy issued, 3 issuer sees full, 4 MMAs issued, 5 commit done
 #define NN_LOG(chunk_, ev_) do { if (blockIdx.x == 0 && (chunk_) < 96) g_nn_log[chunk_][ev_] = clock64(); } while (0)
+__device__ long long g_nn_plog[96][32];     // CTA 0, first 96 chunks, producer warp w: [w] data in registers, [8 + w] empty seen, [16 + w] arrived
+#define NN_PLOG(chunk_, ev_) do { if (blockIdx.x == 0 && (chunk_) < 96 && lane == 0) g_nn_plog[chunk_][8 * (ev_) + warp] = clock64(); } while (0)
 __device__ unsigned long long g_nn_wait[8];     // cycles waited: 0 A-prod on empty, 1 B-prod on empty, 2 issuer on full_a, 3 on full_b, 4 on acc_empty, 5 epilogue on acc_full, 6 issuer total, 7 epilogue busy
 #define MB_WAIT_T(bar, par, slot) do { const long long _t0 = clock64(); mb_wait<((slot) < 2 || (slot) > 4)>(bar, par); if ((threadIdx.x & 31) == 0) atomicAdd(&g_nn_wait[slot], (unsigned long long)(clock64() - _t0)); } while (0)
 #else
 #define MB_WAIT_T(bar, par, slot) mb_wait<((slot) < 2 || (slot) > 4)>(bar, par)     // slots 2-4: the MMA issuer polls without backing off
 #define NN_LOG(chunk_, ev_) do {} while (0)
+#define NN_PLOG(chunk_, ev_) do {} while (0)
 #endif
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
@@ -185,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2], bar_ovl[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t issue_turn;                  // number of the chunk whose MMAs may be issued next
+    __shared__ int2 s_cd[2][kMaxChunks];             // per half chunk: {source (-1: element by element), column in it}
     __shared__ float s_bias[768];                   // the layer's (padded) bias: passes * n_tot values
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a broadcast: the compiler treats the role dispatch as warp-uniform)
@@ -193,6 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     const uint32_t b_bytes = 2u * (uint32_t)P.n_tot * kChunkK * 4u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     for (int i = tid; i < P.passes * P.n_tot; i += kThreads) s_bias[i] = __ldg(P.bias + i);
+    for (int i = tid; i < 2 * P.k_chunks; i += kThreads) {
+        const int c = i >> 1, hf = i & 1;
+        int k = c * kChunkK + kHalfK * hf, si = 0;
+        while (si < 2 && k >= P.ks[si]) { k -= P.ks[si]; ++si; }
+        const bool copy = k + kHalfK <= P.ks[si] && !((k | P.ks[si]) & 1) && !((uintptr_t)P.src[si] & 7);
+        s_cd[hf][c] = make_int2(copy ? si : -1, k);
+    }
     if (tid == 0) {
         issue_turn = 0u;
         for (int s = 0; s < S; ++s) { mb_init(&bar_full[s], 9); mb_init(&bar_empty[s], 1); }     // full: 8 A-producer warps + the weight copy (arrive + bytes)
@@ -215,82 +231,107 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     const int n_ovl = P.n_tot > 256 ? 2 * P.n_tot - 512 : 0;
     // every role walks the same sequence of (tile, pass, chunk) and keeps its own ring position
     if (warp < 8) {
-        // ---------------- A producers: threads r and r + 128 <-> row r of the tile, column groups {0,1} / {2,3} of the chunk
+        // ---------------- A producers: threads r and r + 128 <-> row r of the tile, column groups {0,1} / {2,3} of the chunk.
+        // A thread's 32 bytes of a chunk travel global -> shared memory as four 8-byte asynchronous copies (cp.async) into a
+        // ring of thread-private slots, kRawDepth chunks ahead, and are picked up with cp.async.wait_group: no register is
+        // held for data in flight, and the oldest group is the only one waited for.  (With the prefetched chunks in
+        // registers the unrolled ring shared scoreboards between its stages: every fourth chunk waited for the youngest
+        // loads, 1 000 - 2 700 cycles, and the address arithmetic of the loads took 480 cycles per chunk, both measured with
+        // the -DPDP_NN_TIMING build.)  Where the 8 columns come from is looked up per chunk in a table built at kernel start:
+        // one source at an even offset with rows of even length -> copies; anything else (a span across two sources, an odd
+        // offset, rows of odd length) element by element through registers.
         const int r = tid & 127, half = tid >> 7;
         int s = 0; uint32_t ph = 0;
-        // where the 8 columns [k0, k0 + 8) of a row come from: one source at an even offset with 8-byte aligned rows ->
-        // four 64-bit loads; anything else (a span across two sources, an odd offset, rows of odd length) element by element
-        auto load8 = [&](int64_t row, int k0, float (&v)[kHalfK]) {
-            int k = k0, si = 0;
-            while (si < 2 && k >= P.ks[si]) { k -= P.ks[si]; ++si; }
-            if (k + kHalfK <= P.ks[si] && !((k | P.ks[si]) & 1)) {
-                const float2* p2 = reinterpret_cast<const float2*>(P.src[si] + row * P.ks[si] + k);
-#pragma unroll
-                for (int j = 0; j < kHalfK / 2; ++j) { const float2 t2 = __ldg(p2 + j); v[2 * j] = t2.x; v[2 * j + 1] = t2.y; }
-            } else {
-#pragma unroll
-                for (int j = 0; j < kHalfK; ++j) v[j] = a_elem(P, row, k0 + j);
-            }
-        };
-        // kPrefetch chunks of loads are in flight per thread (a ring of register buffers, refilled as it is consumed): the
-        // rows come from HBM, and with one chunk in flight a thread would move 32 bytes per memory latency
-        constexpr int D = kPrefetch;
-        float buf[D][kHalfK];
         const int64_t tile_step = (int64_t)gridDim.x * kTileM;
         const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
         const int64_t total = my_tiles * units;
-        int64_t pf_row = (int64_t)blockIdx.x * kTileM + r;      // prefetch cursor: row of this thread in the tile, chunk unit
-        int pf_u = 0;
-        int64_t c_row = pf_row;                                  // consumer cursor
-        int c_u = 0;
+        const uint32_t raw_sa = s_u32(smem + (size_t)S * stage_bytes) + 8u * (uint32_t)tid;     // slot (level, j) at + 8 * 256 * (4 level + j)
+        int64_t pf_row = (int64_t)blockIdx.x * kTileM + r;      // prefetch cursor: row of this thread, chunk of the pass, pass
+        int pf_c = 0, pf_p = 0;
+        const float *rp0 = nullptr, *rp1 = nullptr, *rp2 = nullptr;      // this thread's row in the three sources
+        auto row_ptrs = [&]() {
+            rp0 = P.src[0] + pf_row * P.ks[0];
+            rp1 = P.ks[1] ? P.src[1] + pf_row * P.ks[1] : nullptr;
+            rp2 = P.ks[2] ? P.src[2] + pf_row * P.ks[2] : nullptr;
+        };
+        row_ptrs();
+        auto fetch = [&](int level) {
+            if (pf_row < P.rows) {
+                const int2 e = s_cd[half][pf_c];
+                const uint32_t dst = raw_sa + 8u * 256u * 4u * (uint32_t)level;
+                if (e.x >= 0) {
+                    const float* p = (e.x == 0 ? rp0 : (e.x == 1 ? rp1 : rp2)) + e.y;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            if (d < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + kHalfK * half, buf[d]);
-            if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
-        }
-        for (int64_t g0 = 0; g0 < total; g0 += D) {
+                    for (int j = 0; j < kHalfK / 2; ++j)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * 256u * (uint32_t)j), "l"(p + 2 * j) : "memory");
+                } else {
+                    const int k0 = pf_c * kChunkK + kHalfK * half;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                if (g0 + d >= total) break;
-                const bool live = c_row < P.rows;
-                float v[kHalfK];
-#pragma unroll
-                for (int j = 0; j < kHalfK; ++j) v[j] = live ? buf[d][j] : 0.f;
-                if (g0 + d + D < total && pf_row < P.rows) load8(pf_row, (pf_u % P.k_chunks) * kChunkK + kHalfK * half, buf[d]);
-                if (++pf_u == units) { pf_u = 0; pf_row += tile_step; }
-                MB_WAIT_T(&bar_empty[s], ph ^ 1u, 0);
-                if (tid == 0) NN_LOG((int)(g0 + d), 0);
-                unsigned char* st = smem + (size_t)s * stage_bytes;
-#pragma unroll
-                for (int gg = 0; gg < kHalfK / 4; ++gg) {
-                    const int g = (kHalfK / 4) * half + gg;
-                    uint4 hi, lo;
-                    uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
-                    uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float x = v[4 * gg + j];
-                        const uint32_t hb = __float_as_uint(x) & 0xffffe000u;
-                        hp[j] = hb;
-                        lp[j] = __float_as_uint(x - __uint_as_float(hb)) & 0xffffe000u;
+                    for (int j = 0; j < kHalfK / 2; ++j) {
+                        const float x0 = a_elem(P, pf_row, k0 + 2 * j), x1 = a_elem(P, pf_row, k0 + 2 * j + 1);
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst + 8u * 256u * (uint32_t)j), "f"(x0), "f"(x1) : "memory");
                     }
-#if PDP_NN_SWIZZLE
-                    // rows of 64 bytes, the 16-byte unit g of row r at unit g ^ ((r >> 1) & 3): Swizzle<2,4,3>
-                    const size_t off = (size_t)r * 64 + (size_t)((g ^ ((r >> 1) & 3)) << 4);
-#else
-                    const size_t off = (size_t)g * (kTileM * 16) + (size_t)r * 16;
-#endif
-                    *reinterpret_cast<uint4*>(st + off) = hi;
-                    *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + off) = lo;
                 }
-                fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mb_arrive(&bar_full[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
-                if (tid == 0) NN_LOG((int)(g0 + d), 1);
-                if (++s == S) { s = 0; ph ^= 1u; }
-                if (++c_u == units) { c_u = 0; c_row += tile_step; }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (++pf_c == P.k_chunks) {
+                pf_c = 0;
+                if (++pf_p == P.passes) { pf_p = 0; pf_row += tile_step; row_ptrs(); }
+            }
+        };
+        for (int d = 0; d < kRawDepth; ++d) fetch(d);        // (groups past the end are empty: the count stays uniform)
+        int64_t c_row = (int64_t)blockIdx.x * kTileM + r;        // consumer cursor
+        int c_u = 0, level = 0;
+#if PDP_NN_SWIZZLE
+        // rows of 64 bytes, the 16-byte unit g of row r at unit g ^ ((r >> 1) & 3): Swizzle<2,4,3>
+        const uint32_t off0 = (uint32_t)(r * 64 + (((2 * half) ^ ((r >> 1) & 3)) << 4)), off1 = (uint32_t)(r * 64 + (((2 * half + 1) ^ ((r >> 1) & 3)) << 4));
+#else
+        const uint32_t off0 = (uint32_t)((2 * half) * (kTileM * 16) + r * 16), off1 = (uint32_t)((2 * half + 1) * (kTileM * 16) + r * 16);
+#endif
+        for (int64_t g0 = 0; g0 < total; ++g0) {
+            const bool live = c_row < P.rows;
+            asm volatile("cp.async.wait_group %0;" ::"n"(kRawDepth - 1) : "memory");
+            float v[kHalfK];
+            {
+                const uint32_t src = raw_sa + 8u * 256u * 4u * (uint32_t)level;
+#pragma unroll
+                for (int j = 0; j < kHalfK / 2; ++j)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[2 * j]), "=f"(v[2 * j + 1]) : "r"(src + 8u * 256u * (uint32_t)j) : "memory");
+            }
+            uint4 hi[2], lo[2];
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+                uint32_t* hp = reinterpret_cast<uint32_t*>(&hi[gg]);
+                uint32_t* lp = reinterpret_cast<uint32_t*>(&lo[gg]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = live ? v[4 * gg + j] : 0.f;
+                    const uint32_t hb = __float_as_uint(x) & 0xffffe000u;
+                    hp[j] = hb;
+                    lp[j] = __float_as_uint(x - __uint_as_float(hb)) & 0xffffe000u;
+                }
+            }
+            NN_PLOG((int)g0, 3);
+            fetch(level);                                        // the slot just read takes the chunk kRawDepth further on
+            if (++level == kRawDepth) level = 0;
+            NN_PLOG((int)g0, 0);
+            MB_WAIT_T(&bar_empty[s], ph ^ 1u, 0);
+            NN_PLOG((int)g0, 1);
+            if (tid == 0) NN_LOG((int)g0, 0);
+            unsigned char* st = smem + (size_t)s * stage_bytes;
+            *reinterpret_cast<uint4*>(st + off0) = hi[0];
+            *reinterpret_cast<uint4*>(st + off1) = hi[1];
+            *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + off0) = lo[0];
+            *reinterpret_cast<uint4*>(st + (size_t)(kTileM * kChunkK * 4) + off1) = lo[1];
+            fence_async_smem();          // these generic-proxy writes are read by the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mb_arrive(&bar_full[s]);      // one arrival per warp: 256 arrivals on one barrier word serialise
+            NN_PLOG((int)g0, 2);
+            if (tid == 0) NN_LOG((int)g0, 1);
+            if (++s == S) { s = 0; ph ^= 1u; }
+            if (++c_u == units) { c_u = 0; c_row += tile_step; }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == 17 && lane == 0) {
         // ---------------- B producer: one bulk copy per chunk
         int s = 0; uint32_t ph = 0;
@@ -517,7 +558,7 @@ int launch(EdgeNNArgs& P, int epi, cudaStream_t stream) {
         cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { pdp_set_error("pdp_edge_nn: no CUDA device"); return PDP_ERR_CUDA; }
     if (cc < 10) { pdp_set_error("pdp_edge_nn: tcgen05 needs sm_100a"); return PDP_ERR_UNSUPPORTED; }
     const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
-    const size_t smem = stage * P.stages;
+    const size_t smem = stage * P.stages + kRawBytes;
     void* kern = epi == EPI_GRU ? (void*)k_edge_nn<EPI_GRU> : (void*)k_edge_nn<EPI_LINEAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: shared memory %zu: %s", smem, cudaGetErrorString(e)); return PDP_ERR_CUDA; }
@@ -563,7 +604,7 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
     P.rows = rows; P.w_img = w_img; P.bias = bias;
     P.n_blk = n_blk; P.n_mma = n_mma; P.n_tot = n_blk * n_mma; P.passes = passes;
     if (P.k_total <= 0 || !w_img || !bias || n_blk < 16 || (n_blk & 15) || n_mma < 1 || P.n_tot > kMaxNTot || passes < 1 ||
-        (k1 > 0 && !x1) || (k2 > 0 && !x2) || (k3 > 0 && !x3) || ((uintptr_t)w_img & 15) || passes * n_blk * n_mma > 768) {
+        (k1 > 0 && !x1) || (k2 > 0 && !x2) || (k3 > 0 && !x3) || ((uintptr_t)w_img & 15) || passes * n_blk * n_mma > 768 || P.k_chunks > kMaxChunks) {
         pdp_set_error("%s: bad argument (k=%d n_blk=%d n_mma=%d passes=%d)", who, P.k_total, n_blk, n_mma, passes);
         return false;
     }
@@ -572,7 +613,7 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
     // epilogue live on L1 hits (GRU cell over 1.2 M rows: 4 stages 4.14 ms, 3 stages 3.61 ms, 2 stages 3.50 ms)
     int st = (int)((100 * 1024) / stage);
     P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
-    if (const char* e = getenv("PDP_B200_NN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4 && (size_t)v * stage <= 200 * 1024) P.stages = v; }   // (profiling)
+    if (const char* e = getenv("PDP_B200_NN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4 && (size_t)v * stage + kRawBytes <= 220 * 1024) P.stages = v; }   // (profiling)
     return true;
 }
 
@@ -583,6 +624,9 @@ bool fill_common(EdgeNNArgs& P, const float* x1, int k1, const float* x2, int k2
 #ifdef PDP_NN_TIMING
 extern "C" int pdp_edge_nn_event_log(long long* host_96x8) {
     return cudaMemcpyFromSymbol(host_96x8, g_nn_log, sizeof(long long) * 96 * 8) == cudaSuccess ? PDP_OK : PDP_ERR_CUDA;
+}
+extern "C" int pdp_edge_nn_producer_log(long long* host_96x24) {
+    return cudaMemcpyFromSymbol(host_96x24, g_nn_plog, sizeof(long long) * 96 * 32) == cudaSuccess ? PDP_OK : PDP_ERR_CUDA;
 }
 extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
     if (host8 && cudaMemcpyFromSymbol(host8, g_nn_wait, sizeof(unsigned long long) * 8) != cudaSuccess) return PDP_ERR_CUDA;
@@ -596,7 +640,7 @@ extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
 extern "C" int pdp_edge_nn_chunk_k(void) { return kChunkK; }
 // 1: the weight images are rows of 64 bytes with the 16-byte units of row n at unit ^ ((n >> 1) & 3); 0: column groups of [n_tot][16 bytes]
 extern "C" int pdp_edge_nn_swizzle(void) { return PDP_NN_SWIZZLE; }
-static_assert(!PDP_NN_SWIZZLE || kChunkK == 16, "the 64-byte swizzle is the layout of 16-element K chunks");
+static_assert(kChunkK == 16, "the operand staging and the 64-byte swizzle are written for 16-element K chunks");
 
 extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* x3, int32_t k3, int64_t rows,
                                     const float* w_img, const float* bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,

@@ -34,3 +34,14 @@ print("CTA 0, chunks 40..71 (cycles since the first event): producer sees empty 
 for c in range(40, 72):
     print("  chunk %2d: " % c + "  ".join("%8d" % (ev[c, k] - t0) for k in range(6)) + "   full-empty %6d  mma-full %6d   empty(c+4) - issued(c) %6d" % (ev[c, 3] - ev[c, 0], ev[c, 4] - ev[c, 3], ev[c + 4, 0] - ev[c, 4]))
 print("chunk period (MMAs issued, chunks 40..71): %.0f cycles" % ((ev[71, 4] - ev[40, 4]) / 31.0))
+try:
+    plog = (ctypes.c_longlong * (96 * 32))()
+    L.pdp_edge_nn_producer_log(plog)
+    pv = np.array(list(plog), dtype=np.int64).reshape(96, 4, 8)
+    print("producer warps 0..7, chunks 44..56, cycles: previous arrive -> operands in registers | -> next loads issued (reached the wait) | -> saw empty | -> arrived")
+    for c in range(44, 57):
+        print("  chunk %2d  data " % c + " ".join("%5d" % (pv[c, 3, w] - pv[c - 1, 2, w]) for w in range(8)) + "   loads " +
+              " ".join("%5d" % (pv[c, 0, w] - pv[c, 3, w]) for w in range(8)) + "   empty " + " ".join("%5d" % (pv[c, 1, w] - pv[c, 0, w]) for w in range(8)) +
+              "   arrive " + " ".join("%5d" % (pv[c, 2, w] - pv[c, 1, w]) for w in range(8)))
+except Exception as e:
+    print("no producer log:", e)
