@@ -15,6 +15,12 @@ def edge_problem_mask(sat_problem, active_mask):
     return active_mask.reshape(-1)[prob].to(torch.float32).unsqueeze(1)
 
 
+def _blend(mask, new, old):
+    """mask * new + (1 - mask) * old for a 0/1 row mask [E,1] (frozen problems keep their state, reference
+    pdp_propagate.py:75,87) in one elementwise kernel: lerp returns `new` where mask = 1 and `old` where mask = 0 exactly."""
+    return torch.lerp(old, new, mask)
+
+
 class NeuralMessagePasser(nn.Module):
     """The neural propagator of `np-nd-np` (reference pdp_propagate.py:17-108): two deep-set aggregators, one per
     message direction.  Dense layers are library GEMMs; the segmented sums are the library's kernels."""
@@ -51,10 +57,10 @@ class NeuralMessagePasser(nn.Module):
         ef = sat_problem._edge_feature
         # variables --> functions (reference :69-78)
         new_f = self._variable_aggregator((dvs, ef), ef, ctx, True, edge_mask)
-        function_state = new_f if mask is None else mask * new_f + (1 - mask) * function_state
+        function_state = new_f if mask is None else _blend(mask, new_f, function_state)
         # functions --> variables (reference :80-89)
         new_v = self._function_aggregator((dfs, ef), ef, ctx, False, edge_mask)
-        variable_state = new_v if mask is None else mask * new_v + (1 - mask) * variable_state
+        variable_state = new_v if mask is None else _blend(mask, new_v, variable_state)
         return variable_state, function_state
 
     def get_init_state(self, graph_map, batch_variable_map, batch_function_map, edge_feature, graph_feat,

@@ -107,7 +107,11 @@ if os.path.exists(rep2):
              "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
              "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
              "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-             "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+             "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+             "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+             "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+             "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
     rows_gru = 300000
     lines2 = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep2,
                              os.path.join(ROOT, "pdp_solver_b200", "csrc", "pdp_edge_nn.o"), "k_edge_nnILi1", "24"],
@@ -115,9 +119,9 @@ if os.path.exists(rep2):
     with open(os.path.join(P, tag + "_edge_gru_ncu.md"), "w") as f:
         f.write("# ncu --set full: k_edge_nn<GRU> (pdp_edge_gru_forward: tcgen05 kind::tf32, three-term split, TMEM accumulators)\n\n")
         f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:k_edge_nn -c 1 python tools/prof_edge_nn.py %d` "
-                "(GRU cell 151 | 150 -> 150 over %d rows: 3 passes x 19 K-chunks x 3 tf32 terms of M128 x N256 x K8 MMAs per tile of 128 rows = "
+                "(GRU cell 151 | 150 -> 150 over %d rows: 2 passes x 19 K-chunks x 3 tf32 terms of M128 x N(256+48) x K8 MMAs per tile of 128 rows = "
                 "%.3g tensor flop in the launch).  Numbers under the profiler are not bench values; `%s_edge_nn_timing.log` has the CUDA-event times.\n\n"
-                % (rows_gru, rows_gru, 2.0 * rows_gru * 304 * 768 * 3, tag))
+                % (rows_gru, rows_gru, 2.0 * rows_gru * 304 * 608 * 3, tag))
         f.write("| metric | value | unit |\n|---|---|---|\n")
         for n in want2:
             if n in m2:
