@@ -29,7 +29,6 @@
 //              `empty` barrier; after the pass's last chunk it commits to the accumulator buffer's barrier;
 //   warps 8-15 epilogue: tcgen05.ld of the accumulator rows (thread = row, two warps per lane quadrant), bias / activation /
 //              GRU gate arithmetic, 64-bit stores; then hand the accumulator buffer back.
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -39,10 +38,8 @@
 namespace {
 
 constexpr int kTileM = 128;        // rows per tile = accumulator lanes
-#ifndef PDP_NN_CHUNK_K
-#define PDP_NN_CHUNK_K 16     // (32 halves the per-chunk barrier traffic but leaves two stages: GRU 5.2 ms vs 4.25 ms at 1.2 M rows)
-#endif
-constexpr int kChunkK = PDP_NN_CHUNK_K;   // K elements per stage (16 or 32): kChunkK / 4 column groups of 16 bytes, kChunkK / 8 MMA k-steps
+constexpr int kChunkK = 16;        // K elements per stage: one 64-byte row of the swizzled operand tiles, two MMA k-steps
+                                   // (32 halves the per-chunk barrier traffic but leaves two stages: measured 20 % slower)
 constexpr int kHalfK = kChunkK / 2;       // elements of a row chunk per producer thread (two threads per row)
 constexpr int kThreads = 608;      // warps 0-7 A producers, 8-15 epilogue (lane quadrant = warp mod 4), 16 and 18 MMA issuers, 17 B producer
 #ifndef PDP_NN_RAW_DEPTH
@@ -60,7 +57,6 @@ enum { EPI_LINEAR = 0, EPI_GRU = 1 };
 enum { ACT_NONE = 0, ACT_LOGSIGMOID = 1 };
 
 struct EdgeNNArgs {
-    alignas(64) CUtensorMap tmap_w;   // the weight image as a 2-D tensor [rows of 64 floats]: one chunk = one box (PDP_NN_TMAP)
     const float* src[3];       // row-major sources of the A rows, concatenated along K
     int32_t ks[3];             // their column counts (0: unused)
     int32_t k_total;           // sum of ks
@@ -103,16 +99,6 @@ __device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
         }
     }
 }
-#ifndef PDP_NN_SWIZZLE
-#define PDP_NN_SWIZZLE 1      // operand tiles in the 64-byte swizzled K-major layout (0: no swizzle, K chunks of 16 only with 1)
-#endif
-#ifndef PDP_NN_TMAP
-#define PDP_NN_TMAP 0         // 1: weights by tiled TMA (tensor map, UTMALDG) instead of the linear bulk copy (measured: 4.45 vs 4.11 ms
-                             // for the GRU cell over 1.2 M rows -- the copy is not what limits the pipeline)
-#endif
-#ifndef PDP_NN_TERMS
-#define PDP_NN_TERMS 3      // (profiling experiments only: fewer terms = wrong results)
-#endif
 #ifdef PDP_NN_TIMING
 __device__ long long g_nn_log[96][8];       // CTA 0, first 96 chunks: 0 producer sees empty, 1 producer arrives, 2 B copy issued, 3 issuer sees full, 4 MMAs issued, 5 commit done
 #define NN_LOG(chunk_, ev_) do { if (blockIdx.x == 0 && (chunk_) < 96) g_nn_log[chunk_][ev_] = clock64(); } while (0)
@@ -127,11 +113,6 @@ __device__ unsigned long long g_nn_wait[8];     // cycles waited: 0 A-prod on em
 #endif
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
-}
-// tiled TMA: the box at (0, row) of a 2-D tensor map -> shared memory (rows of 256 bytes: the box is a contiguous range)
-__device__ __forceinline__ void tmap_load_2d(void* dst, const CUtensorMap* tm, int row, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(s_u32(bar)) : "memory");
 }
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
@@ -282,12 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         for (int d = 0; d < kRawDepth; ++d) fetch(d);        // (groups past the end are empty: the count stays uniform)
         int64_t c_row = (int64_t)blockIdx.x * kTileM + r;        // consumer cursor
         int c_u = 0, level = 0;
-#if PDP_NN_SWIZZLE
         // rows of 64 bytes, the 16-byte unit g of row r at unit g ^ ((r >> 1) & 3): Swizzle<2,4,3>
         const uint32_t off0 = (uint32_t)(r * 64 + (((2 * half) ^ ((r >> 1) & 3)) << 4)), off1 = (uint32_t)(r * 64 + (((2 * half + 1) ^ ((r >> 1) & 3)) << 4));
-#else
-        const uint32_t off0 = (uint32_t)((2 * half) * (kTileM * 16) + r * 16), off1 = (uint32_t)((2 * half + 1) * (kTileM * 16) + r * 16);
-#endif
         for (int64_t g0 = 0; g0 < total; ++g0) {
             const bool live = c_row < P.rows;
             asm volatile("cp.async.wait_group %0;" ::"n"(kRawDepth - 1) : "memory");
@@ -340,13 +317,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             for (int u = 0; u < units; ++u, ++gb) {
                 MB_WAIT_T(&bar_empty[s], ph ^ 1u, 1);
                 NN_LOG(gb, 2);
-#if PDP_NN_TMAP
-                mb_expect_tx(&bar_full[s], b_bytes);
-                tmap_load_2d(smem + (size_t)s * stage_bytes + a_bytes, &P.tmap_w, u * (int)(b_bytes >> 8), &bar_full[s]);
-#else
                 mb_expect_tx(&bar_full[s], b_bytes);
                 bulk_load(smem + (size_t)s * stage_bytes + a_bytes, reinterpret_cast<const unsigned char*>(P.w_img) + (size_t)u * b_bytes, b_bytes, &bar_full[s]);
-#endif
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -362,16 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         const int me = (warp == 16) ? 0 : 1;
         const int w0 = P.n_tot < kMmaN ? P.n_tot : kMmaN, w1 = P.n_tot - w0;      // columns of the two MMAs of a k-step and term
         const uint32_t idesc0 = instr_desc(kTileM, w0), idesc1 = instr_desc(kTileM, w1 > 0 ? w1 : 16);
-        const uint32_t lbo_a = kTileM * 16;
-#if PDP_NN_SWIZZLE
         // K-major, 64-byte swizzle: rows of 64 bytes, 8-row atoms of 512 bytes one after the other (SBO = 512); a k-step of 8
         // elements = 32 bytes further along the row (the hardware applies the XOR to the address it computes)
         const uint64_t desc_hi_a = smem_desc(0, 16, 512, 4), desc_hi_b = smem_desc(0, 16, 512, 4);
         const uint32_t kstep4 = 32u >> 4, nrow4 = 64u >> 4;
-#else
-        const uint32_t lbo_b = (uint32_t)P.n_tot * 16;
-        const uint64_t desc_hi_a = smem_desc(0, lbo_a, 128), desc_hi_b = smem_desc(0, lbo_b, 128);
-#endif
         const uint32_t smem_a4 = s_u32(smem) >> 4, stage4 = stage_bytes >> 4;
         const uint32_t a_lo4 = (kTileM * kChunkK * 4) >> 4, b_off4 = a_bytes >> 4, b_lo4 = ((uint32_t)P.n_tot * kChunkK * 4) >> 4;
         int s = 0; uint32_t ph = 0, acc_ph0 = 0u, acc_ph1 = 0u, ovl_ph0 = 0u, ovl_ph1 = 0u;
@@ -399,16 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
 #pragma unroll
                         for (int ks = 0; ks < kChunkK / 8; ++ks) {
 #pragma unroll
-                            for (int term = 0; term < PDP_NN_TERMS; ++term) {      // hi hi, lo hi, hi lo
-#if PDP_NN_SWIZZLE
+                            for (int term = 0; term < 3; ++term) {      // hi hi, lo hi, hi lo
                                 const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * kstep4;
                                 const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * kstep4;
                                 const uint32_t nb4 = (uint32_t)w0 * nrow4;
-#else
-                                const uint32_t a4 = sa4 + (term == 1 ? a_lo4 : 0u) + ks * 2u * (lbo_a >> 4);
-                                const uint32_t b4 = sa4 + b_off4 + (term == 2 ? b_lo4 : 0u) + ks * 2u * (lbo_b >> 4);
-                                const uint32_t nb4 = (uint32_t)w0;
-#endif
                                 const uint32_t acc = (c == 0 && ks == 0 && term == 0) ? 0u : 1u;
                                 if (leader) {
                                     tc_mma_tf32(tacc, desc_hi_a | a4, desc_hi_b | b4, idesc0, acc);
@@ -562,30 +522,6 @@ int launch(EdgeNNArgs& P, int epi, cudaStream_t stream) {
     void* kern = epi == EPI_GRU ? (void*)k_edge_nn<EPI_GRU> : (void*)k_edge_nn<EPI_LINEAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: shared memory %zu: %s", smem, cudaGetErrorString(e)); return PDP_ERR_CUDA; }
-#if PDP_NN_TMAP
-    {
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qr;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
-                pdp_set_error("pdp_edge_nn: cuTensorMapEncodeTiled not available"); return PDP_ERR_CUDA;
-            }
-            encode = (EncodeFn)fn;
-        }
-        const size_t b_bytes = 2u * (size_t)P.n_tot * kChunkK * 4u;
-        const cuuint64_t rows_total = (cuuint64_t)P.passes * P.k_chunks * (b_bytes >> 8);
-        const cuuint64_t gdim[2] = {64, rows_total};
-        const cuuint64_t gstr[1] = {256};
-        const cuuint32_t box[2] = {64, (cuuint32_t)(b_bytes >> 8)};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult cr = encode(const_cast<CUtensorMap*>(&P.tmap_w), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P.w_img), gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { pdp_set_error("pdp_edge_nn: cuTensorMapEncodeTiled -> %d (box rows %u)", (int)cr, box[1]); return PDP_ERR_CUDA; }
-    }
-#endif
     const int64_t n_tiles = (P.rows + kTileM - 1) / kTileM;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     if (epi == EPI_GRU) k_edge_nn<EPI_GRU><<<grid, kThreads, smem, stream>>>(P);
@@ -639,7 +575,7 @@ extern "C" int pdp_edge_nn_wait_counters(unsigned long long* host8, int reset) {
 // K elements per chunk of the weight image (the host side builds the images accordingly)
 extern "C" int pdp_edge_nn_chunk_k(void) { return kChunkK; }
 // 1: the weight images are rows of 64 bytes with the 16-byte units of row n at unit ^ ((n >> 1) & 3); 0: column groups of [n_tot][16 bytes]
-extern "C" int pdp_edge_nn_swizzle(void) { return PDP_NN_SWIZZLE; }
+extern "C" int pdp_edge_nn_swizzle(void) { return 1; }
 static_assert(kChunkK == 16, "the operand staging and the 64-byte swizzle are written for 16-element K chunks");
 
 extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2, int32_t k2, const float* x3, int32_t k3, int64_t rows,

@@ -41,14 +41,6 @@ __device__ __forceinline__ bool blk_idle(const pdp_state& s, int b0, int b1) {
 #ifndef PDP_UNROLL_WO
 #define PDP_UNROLL_WO 4    // write-out: slots per thread in flight
 #endif
-#ifndef PDP_L2_PREFETCH
-#define PDP_L2_PREFETCH 2    // what of the next block is pulled into L2 while the current block is worked on: 0 nothing,
-                             // 1 tables and messages, 2 tables only (measured on 8 x n = 1M: 1 loses 3 % to 0 -- the messages of 296 CTAs
-                             // crowd each other out of L2 before they are used)
-#endif
-#ifndef PDP_INPASS_SCORE
-#define PDP_INPASS_SCORE 1
-#endif
 #ifndef PDP_COLD
 #define PDP_COLD __forceinline__
 #endif
@@ -99,16 +91,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the whole CTA waits for a phase: one warp polls the barrier word, the others sleep at the block barrier (a polling warp
 // takes issue slots from the SM's other CTA: 512 polling threads were 4.5 % of the kernel's instructions).  The polling
 // warp's acquire and the block barrier order the copied bytes before every thread's reads.
-#ifndef PDP_WAIT_WARP0
-#define PDP_WAIT_WARP0 1
-#endif
 __device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
-#if PDP_WAIT_WARP0
     if (threadIdx.x < 32) mbar_wait(bar, parity);
     __syncthreads();
-#else
-    mbar_wait(bar, parity);
-#endif
 }
 
 // explicit shared-window accesses (32-bit addresses).  The node phases index the planes through the position table; as
@@ -231,16 +216,13 @@ __device__ __forceinline__ void ph_write_out_t(int t, int wlo, int wend, uint32_
         }
     }
 }
-#ifndef PDP_WO_NOMARK
-#define PDP_WO_NOMARK 1
-#endif
 template <int G>
 __device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, int wlo, int wend, const float* plane, const uint2* wrun_s, int w0,
                                              const int32_t* adj_s, int r0, const int32_t* adj_g, const float* old, float* out, bool marks) {
     const uint32_t plane_sa = smem_u32(plane) - 4u * (uint32_t)B.e0;
     const uint32_t wrun_sa = smem_u32(wrun_s) - 8u * (uint32_t)w0;
     if (adj_s) {
-        if (PDP_WO_NOMARK && !marks) ph_write_out_t<G, true, false>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
+        if (!marks) ph_write_out_t<G, true, false>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
         else ph_write_out_t<G, true, true>(t, wlo, wend, plane_sa, wrun_sa, smem_u32(adj_s) - 4u * (uint32_t)r0, adj_g, old, out);
     } else ph_write_out_t<G, false, true>(t, wlo, wend, plane_sa, wrun_sa, 0u, adj_g, old, out);
 }
@@ -248,13 +230,13 @@ __device__ __forceinline__ void ph_write_out(int t, const BlkGeo& B, int wlo, in
 // the edge-mask bits of the block's region (indexed by layout position) -> sign bits of the plane (its values are >= +0 or
 // NaN).  Only the words that have a bit set cost anything.  The first two words of every thread (all of them at the block
 // sizes of the two-CTA configuration) are fetched BEFORE the CTA waits for the block's copies: their latency hides there.
-struct MaskWords { uint32_t m[2]; };
+struct MaskWords { uint32_t m0, m1; };
 template <int G>
 __device__ __forceinline__ MaskWords ph_mask_fetch(int t, const uint32_t* __restrict__ mask, const BlkGeo& B) {
     MaskWords M;
     const int W0 = B.e0 >> 5, W1 = (B.e0 + B.ne - 1) >> 5;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) { const int i = W0 + t + k * G; M.m[k] = (i <= W1) ? __ldcg(mask + i) : 0u; }
+    M.m0 = (W0 + t <= W1) ? __ldcg(mask + W0 + t) : 0u;
+    M.m1 = (W0 + t + G <= W1) ? __ldcg(mask + W0 + t + G) : 0u;
     return M;
 }
 template <int G>
@@ -263,7 +245,7 @@ __device__ __forceinline__ void ph_apply_mask(int t, const uint32_t* __restrict_
     const int W0 = B.e0 >> 5, W1 = (B.e0 + B.ne - 1) >> 5, wend = B.e0 + B.ne;
     int k = 0;
     for (int i = W0 + t; i <= W1; i += G, ++k) {
-        uint32_t m = (k < 2) ? M.m[k < 1 ? 0 : 1] : __ldcg(mask + i);
+        uint32_t m = (k == 0) ? M.m0 : ((k == 1) ? M.m1 : __ldcg(mask + i));
         while (m) {
             const int pos = 32 * i + __ffs(m) - 1;
             m &= m - 1;
@@ -452,11 +434,8 @@ __device__ __forceinline__ void ph_var_score(int t, const pdp_graph& g, const pd
 // own sign NaN, and every message of the variable reads both sums -- `same` the one of its sign, `opp` the other.)
 // MULTI: the block holds several problems: frozen ones are left alone (PDP_SLOT_SKIP), those on the sticky-NaN path get
 // the sticky sign.
-#ifndef PDP_VNODE_INLINE
-#define PDP_VNODE_INLINE __forceinline__
-#endif
 template <int G, bool MULTI, bool MASKED, bool PREV>
-__device__ PDP_VNODE_INLINE void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask,
+__device__ __forceinline__ void ph_var_node(int t, const pdp_graph& g, const pdp_state& s, const BlkGeo& B, bool use_mask,
                                             bool em_set, float* __restrict__ PA, float* __restrict__ PB, uint32_t stk_blk,
                                             KeyedReducer<StatAcc>& red, BlkStats& sm_st, bool local_stats) {
     const int lane = t & 31;
@@ -634,18 +613,6 @@ __device__ __forceinline__ void blk_stagger(int sm_rank, int cycles) {
     while (clock64() - t0 < cycles) __nanosleep(256);
 }
 
-// The planes of the NEXT block are filled while the current block is written out: the write-out goes through the plane in
-// PDP_WO_SEGS segments, a block barrier after each; what lies behind the barrier is dead and thread 0 issues the bulk copy
-// of the next block's words there (same mbarrier phase as the rest of that block's copies, opened with the byte count of
-// the whole block).  Only blocks that are certain to be processed are preloaded (their problems' activity does not change
-// inside a pass); the state below lives in thread 0.
-#ifndef PDP_WO_SEGS
-#define PDP_WO_SEGS 1
-#endif
-struct Preload {
-    int blk;        // block whose copies were opened ahead (-1: none)
-    int words;      // words of its (first) plane issued so far
-};
 // thread 0: will the blocked pass process block N?  1 yes, 2 no, 0 not looked at (a block of very many problems)
 __device__ __forceinline__ int blk_will_run(const pdp_state& s, const BlkGeo& N) {
     if (N.n1 <= N.n0 || N.ne <= 0) return 2;
@@ -672,7 +639,6 @@ template <int CTAS>
 __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_mask, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
-    constexpr int SEGW = (((Cfg::kBlkC + 8 + PDP_WO_SEGS - 1) / PDP_WO_SEGS) + 3) & ~3;   // plane words of a write-out segment
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* X0 = reinterpret_cast<float*>(smem);
     uint2* wrun_s = reinterpret_cast<uint2*>(smem + Cfg::kPlaneBytes);
@@ -684,7 +650,6 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
     __shared__ NextBlk sm_next[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
-    Preload pre{-1, 0};
     Feeder fd;
     fd.pending = (tid == 0) ? feed_draw<DYN>(&s.ctrl[CTRL_NEXT_CBLK], (int)blockIdx.x + (int)gridDim.x) : 0;
     if (tid < 2) sm_next[tid].blk = -1;
@@ -710,17 +675,16 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         const BlkStage S = blk_stage<CAP>(B);
         if (tid == 0) {
             fence_proxy_async_smem();      // the previous block's generic-proxy accesses of the planes precede these copies
-            if (pre.blk != blk) { mbar_expect_tx(bb.bar, (uint32_t)(S.nbytes + S.wbytes + S.rbytes)); pre.words = 0; }
-            if (4 * pre.words < S.nbytes) bulk_g2s(X0 + pre.words, qin + S.a0 + pre.words, S.nbytes - 4 * pre.words, bb.bar);
+            mbar_expect_tx(bb.bar, (uint32_t)(S.nbytes + S.wbytes + S.rbytes));
+            bulk_g2s(X0, qin + S.a0, S.nbytes, bb.bar);
             bulk_g2s(wrun_s, g.c_wrun + S.w0, S.wbytes, bb.bar);
             if (S.rbytes) bulk_g2s(adj_s, g.c_wadj + S.r0, S.rbytes, bb.bar);
-            pre.blk = -1;
         }
         float* X = X0 + S.shift;
         const bool masked = use_mask && (B.multi() || s.masked[B.b0]);
         const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
         const int ku = g.cb_k[blk];
-        MaskWords MW; MW.m[0] = 0u; MW.m[1] = 0u;
+        MaskWords MW; MW.m0 = 0u; MW.m1 = 0u;
         if (masked) MW = ph_mask_fetch<NT>(tid, g.qmask, B);
         mbar_wait_cta(bb.bar, bb.parity);
         bb.parity ^= 1u;
@@ -730,42 +694,16 @@ __device__ __forceinline__ void blk_clause_pass(const KArgs& A, int r, bool use_
         else ph_clause_node<NT, false>(tid, g, s, B, ku, X, stk_blk);
         __syncthreads();
         PHASE_ADD(1);
-        {
-            // write-out in segments of the plane.  After the first one thread 0 looks at the next block (descriptor for the
-            // hand-over, tables -> L2, its copies opened); behind every later one the next block's words move in.
-            BlkStage NS; NS.a0 = 0; NS.nbytes = 0; NS.wbytes = 0; NS.rbytes = 0;
-            const int wbeg = B.e0 - S.shift;      // slot of plane word 0
-#pragma unroll 1
-            for (int k = 0; k < PDP_WO_SEGS; ++k) {
-                const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
-                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, X, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.c_wadj, s.eta[r], eout, B.multi() || stk_blk != 0u);
-                if (k == 0 && tid == 0 && nx < g.ncb) {
-                    const BlkGeo N = clause_block(g, nx);
-                    const int st = blk_will_run(s, N);
-                    sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = st;
-                    if (PDP_L2_PREFETCH && N.ne > 0) {
-                        if (PDP_L2_PREFETCH == 1) bulk_prefetch_l2(qin + N.e0, 4 * N.ne);
-                        bulk_prefetch_l2(g.cfwd + N.t0, 2 * N.tn);
-                        bulk_prefetch_l2(g.c_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
-                        bulk_prefetch_l2(g.c_wadj + N.run0, 4 * N.nruns);
-                    }
-                    if (PDP_WO_SEGS > 1 && st == 1) {
-                        NS = blk_stage<CAP>(N);
-                        mbar_expect_tx(bb.bar, (uint32_t)(NS.nbytes + NS.wbytes + NS.rbytes));
-                        pre.blk = nx; pre.words = 0;
-                    }
-                }
-                if (k + 1 < PDP_WO_SEGS) {
-                    __syncthreads();
-                    if (tid == 0 && pre.blk >= 0) {
-                        const int upto = min((k + 1) * SEGW, NS.nbytes >> 2);
-                        if (upto > pre.words) {
-                            fence_proxy_async_smem();
-                            bulk_g2s(X0 + pre.words, qin + NS.a0 + pre.words, 4 * (upto - pre.words), bb.bar);
-                            pre.words = upto;
-                        }
-                    }
-                }
+        ph_write_out<NT>(tid, B, B.e0, B.e0 + B.ne, X, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.c_wadj, s.eta[r], eout, B.multi() || stk_blk != 0u);
+        // meanwhile thread 0 looks at the next block: its descriptor for the hand-over, its tables -> L2 (the tables only:
+        // pulling the messages in as well loses 3 % on 8 x n = 1M -- the regions of 296 CTAs crowd each other out of L2)
+        if (tid == 0 && nx < g.ncb) {
+            const BlkGeo N = clause_block(g, nx);
+            sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = blk_will_run(s, N);
+            if (N.ne > 0) {
+                bulk_prefetch_l2(g.cfwd + N.t0, 2 * N.tn);
+                bulk_prefetch_l2(g.c_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                bulk_prefetch_l2(g.c_wadj + N.run0, 4 * N.nruns);
             }
         }
         PHASE_ADD(2);
@@ -779,7 +717,6 @@ template <int CTAS>
 __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mask, bool has_prev, bool em_set, unsigned char* smem, int sm_rank, BulkBar& bb) {
     using Cfg = SweepCfg<CTAS>;
     constexpr int NT = Cfg::kThreads, CAP = Cfg::kAdjCap;
-    constexpr int SEGW = (((Cfg::kPlaneV + PDP_WO_SEGS - 1) / PDP_WO_SEGS) + 3) & ~3;
     const pdp_graph& g = A.g; const pdp_state& s = A.s;
     float* PA0 = reinterpret_cast<float*>(smem);   // eta(t), then q(t)
     float* PB0 = PA0 + Cfg::kPlaneV;               // eta(t-1), then y
@@ -795,7 +732,6 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
     __shared__ NextBlk sm_next[2];
     constexpr bool DYN = CTAS == 2;
     int par = 0;
-    Preload pre{-1, 0};
     Feeder fd;
     fd.pending = (tid == 0) ? feed_draw<DYN>(&s.ctrl[CTRL_NEXT_VBLK], (int)blockIdx.x + (int)gridDim.x) : 0;
     if (tid < 2) sm_next[tid].blk = -1;
@@ -821,15 +757,11 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         const BlkStage S = blk_stage<CAP>(B);
         if (tid == 0) {
             fence_proxy_async_smem();
-            if (pre.blk != blk) {
-                mbar_expect_tx(bb.bar, (uint32_t)(2 * S.nbytes + S.wbytes + S.rbytes));
-                bulk_g2s(PB0, eo + S.a0, S.nbytes, bb.bar);
-                pre.words = 0;
-            }
-            if (4 * pre.words < S.nbytes) bulk_g2s(PA0 + pre.words, en + S.a0 + pre.words, S.nbytes - 4 * pre.words, bb.bar);
+            mbar_expect_tx(bb.bar, (uint32_t)(2 * S.nbytes + S.wbytes + S.rbytes));
+            bulk_g2s(PB0, eo + S.a0, S.nbytes, bb.bar);
+            bulk_g2s(PA0, en + S.a0, S.nbytes, bb.bar);
             bulk_g2s(wrun_s, g.v_wrun + S.w0, S.wbytes, bb.bar);
             if (S.rbytes) bulk_g2s(adj_s, g.v_wadj + S.r0, S.rbytes, bb.bar);
-            pre.blk = -1;
         }
         float* PA = PA0 + S.shift;
         float* PB = PB0 + S.shift;
@@ -840,13 +772,13 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         if (local_stats) stats_slots_reset(sm_st, tid, B.b1 - B.b0 + 1);
         const bool masked = (use_mask || em_set) && (B.multi() || s.masked[B.b0]);
         const uint32_t stk_blk = (!B.multi() && s.nanflag[B.b0]) ? 0x80000000u : 0u;
-        const bool scoring = PDP_INPASS_SCORE && (s.want_score[B.b0] || s.want_score[B.b1]);
-        MaskWords MW; MW.m[0] = 0u; MW.m[1] = 0u;
+        const bool scoring = s.want_score[B.b0] || s.want_score[B.b1];
+        MaskWords MW; MW.m0 = 0u; MW.m1 = 0u;
         if (masked) MW = ph_mask_fetch<NT>(tid, g.vmask, B);
         mbar_wait_cta(bb.bar, bb.parity);
         bb.parity ^= 1u;
         if (masked) ph_apply_mask<NT>(tid, g.vmask, B, PA, MW);
-        if (masked || (local_stats && !PDP_WAIT_WARP0)) __syncthreads();
+        if (masked) __syncthreads();      // (the per-problem statistics slots were reset before the wait's barrier)
         PHASE_ADD(3);
         // SurveyScorer of problems about to converge, while the new surveys are still in the plane (the node phase
         // overwrites them); its own loop, so that the node phase's code is the same with and without it
@@ -861,45 +793,15 @@ __device__ __forceinline__ void blk_var_pass(const KArgs& A, int r, bool use_mas
         __syncthreads();
         PHASE_ADD(4);
         if (local_stats) stats_slots_commit(s, sm_st, tid, B.b1 - B.b0 + 1, B.b0);
-        {
-            // write-out in segments of plane PA (see the clause pass); the next block's old surveys move into PB (dead
-            // since the node phase) as soon as its copies are opened, its new surveys into PA behind the write-out
-            BlkStage NS; NS.a0 = 0; NS.nbytes = 0; NS.wbytes = 0; NS.rbytes = 0;
-            const int wbeg = B.e0 - S.shift;
-#pragma unroll 1
-            for (int k = 0; k < PDP_WO_SEGS; ++k) {
-                const int lo = max(B.e0, wbeg + k * SEGW), hi = min(B.e0 + B.ne, wbeg + (k + 1) * SEGW);
-                if (lo < hi) ph_write_out<NT>(tid, B, lo, hi, PA, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.v_wadj, s.qu, s.qu, B.multi() || stk_blk != 0u);
-                if (k == 0 && tid == 0 && nx < g.nvb) {
-                    const BlkGeo N = var_block(g, nx);
-                    const int st = blk_will_run(s, N);
-                    sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = st;
-                    if (PDP_L2_PREFETCH && N.ne > 0) {
-                        if (PDP_L2_PREFETCH == 1) { bulk_prefetch_l2(en + N.e0, 4 * N.ne); bulk_prefetch_l2(eo + N.e0, 4 * N.ne); }
-                        bulk_prefetch_l2(g.vfwd + N.t0, 2 * N.tn);
-                        bulk_prefetch_l2(g.vsort + N.n0, 8 * (N.n1 - N.n0));
-                        bulk_prefetch_l2(g.v_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
-                        bulk_prefetch_l2(g.v_wadj + N.run0, 4 * N.nruns);
-                    }
-                    if (PDP_WO_SEGS > 1 && st == 1) {
-                        NS = blk_stage<CAP>(N);
-                        fence_proxy_async_smem();
-                        mbar_expect_tx(bb.bar, (uint32_t)(2 * NS.nbytes + NS.wbytes + NS.rbytes));
-                        bulk_g2s(PB0, eo + NS.a0, NS.nbytes, bb.bar);
-                        pre.blk = nx; pre.words = 0;
-                    }
-                }
-                if (k + 1 < PDP_WO_SEGS) {
-                    __syncthreads();
-                    if (tid == 0 && pre.blk >= 0) {
-                        const int upto = min((k + 1) * SEGW, NS.nbytes >> 2);
-                        if (upto > pre.words) {
-                            fence_proxy_async_smem();
-                            bulk_g2s(PA0 + pre.words, en + NS.a0 + pre.words, 4 * (upto - pre.words), bb.bar);
-                            pre.words = upto;
-                        }
-                    }
-                }
+        ph_write_out<NT>(tid, B, B.e0, B.e0 + B.ne, PA, wrun_s, S.w0, S.rbytes ? adj_s : nullptr, S.r0, g.v_wadj, s.qu, s.qu, B.multi() || stk_blk != 0u);
+        if (tid == 0 && nx < g.nvb) {      // the next block's descriptor and tables (see the clause pass)
+            const BlkGeo N = var_block(g, nx);
+            sm_next[par].B = N; sm_next[par].blk = nx; sm_next[par].state = blk_will_run(s, N);
+            if (N.ne > 0) {
+                bulk_prefetch_l2(g.vfwd + N.t0, 2 * N.tn);
+                bulk_prefetch_l2(g.vsort + N.n0, 8 * (N.n1 - N.n0));
+                bulk_prefetch_l2(g.v_wrun + (N.e0 >> 5), 8 * (N.ne / 32 + 2));
+                bulk_prefetch_l2(g.v_wadj + N.run0, 4 * N.nruns);
             }
         }
         PHASE_ADD(5);

@@ -2,7 +2,7 @@
 
 A layer's weights are prepared once (and again whenever a parameter changes): split into the two tf32 terms
 (hi = W truncated to tf32, lo = W - hi truncated to tf32), padded, cut into K-chunks of 16 and stored chunk after chunk
-exactly as the kernel wants them in shared memory -- per chunk {hi, lo} x [4 column groups of 16 bytes][n_tot rows][4 floats]
+exactly as the kernel wants them in shared memory -- per chunk {hi, lo} x [n_tot rows][64 bytes, 16-byte units swizzled]
 -- so that one bulk copy per chunk brings them in.  The nn.Linear / nn.GRUCell modules stay the owners of the parameters
 (state-dict compatible with the reference); these objects only cache images of them."""
 import ctypes
@@ -28,24 +28,24 @@ def chunk_k():
 
 
 def _image(wp, passes, n_tot):
-    """wp: [passes * n_tot, k_pad] -> the shared-memory image of every (pass, K chunk): {hi, lo} x one operand tile.
-    No swizzle: [groups = chunk_k / 4][n_tot][4 floats] (column groups of 16 bytes).  64-byte swizzle (chunk_k = 16):
-    [n_tot][4 units][4 floats] with the 16-byte unit g of row n stored at unit g ^ ((n >> 1) & 3)."""
+    """wp: [passes * n_tot, k_pad] -> the shared-memory image of every (pass, K chunk): {hi, lo} x one operand tile in the
+    tensor core's K-major 64-byte-swizzled layout: [n_tot rows][4 units of 16 bytes][4 floats] with unit g of row n stored at
+    unit g ^ ((n >> 1) & 3)."""
     k_pad = wp.shape[1]
     ck = chunk_k()
     chunks = k_pad // ck
     hi, lo = _tf32_split(wp)
     both = torch.stack((hi, lo), 0)                                 # [2, P * n_tot, k_pad]
     both = both.view(2, passes, n_tot, chunks, ck // 4, 4)          # [term, pass, row, chunk, group, j]
-    if int(_lib.load().pdp_edge_nn_swizzle()):
-        rows = torch.arange(n_tot, device=wp.device)
-        slot = torch.arange(ck // 4, device=wp.device).view(1, -1) ^ ((rows >> 1) & 3).view(-1, 1)      # [row, group] -> unit
-        src = torch.empty_like(slot)
-        src.scatter_(1, slot, torch.arange(ck // 4, device=wp.device).view(1, -1).expand(n_tot, -1))    # unit -> group stored there
-        idx = src.view(1, 1, n_tot, 1, ck // 4, 1).expand(2, passes, n_tot, chunks, ck // 4, 4)
-        both = torch.gather(both, 4, idx)                           # [term, pass, row, chunk, unit, j]
-        return both.permute(1, 3, 0, 2, 4, 5).contiguous()         # [pass, chunk, term, row, unit, j]
-    return both.permute(1, 3, 0, 4, 2, 5).contiguous()             # [pass, chunk, term, group, row, j]
+    if not int(_lib.load().pdp_edge_nn_swizzle()):
+        raise _lib.PdpError("this library build expects un-swizzled weight images")
+    rows = torch.arange(n_tot, device=wp.device)
+    slot = torch.arange(ck // 4, device=wp.device).view(1, -1) ^ ((rows >> 1) & 3).view(-1, 1)      # [row, group] -> unit
+    src = torch.empty_like(slot)
+    src.scatter_(1, slot, torch.arange(ck // 4, device=wp.device).view(1, -1).expand(n_tot, -1))    # unit -> group stored there
+    idx = src.view(1, 1, n_tot, 1, ck // 4, 1).expand(2, passes, n_tot, chunks, ck // 4, 4)
+    both = torch.gather(both, 4, idx)                               # [term, pass, row, chunk, unit, j]
+    return both.permute(1, 3, 0, 2, 4, 5).contiguous()             # [pass, chunk, term, row, unit, j]
 
 
 def _ptr(t):
