@@ -313,12 +313,17 @@ def run_b200_arm(a, rank, world, local_rank):
 
     class Staged(object):
         """end-to-end leg: every step's batch is copied from pinned host memory inside the timed region, on a copy stream,
-        into one of two device buffers -- the copy of step i+1 runs under the kernels of step i (the same double buffering as
+        into one of two device buffers (allocated once, before the clock starts: cudaMalloc is not part of a step) -- the
+        copy of step i+1 runs under the kernels of step i (the same double buffering as
         FactorGraphTrainerBase._predict_epoch); the copy of step i+2 waits until step i has released its buffer"""
 
         def __init__(self, tensors):
-            self.host, self.bufs, self.ready, self.freed = tensors, [None, None], [None, None], [None, None]
+            self.host = tensors
+            with torch.cuda.stream(copy_stream):
+                self.bufs = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in tensors] for _ in range(2)]
+            self.ready, self.freed = [None, None], [None, None]
             self.spans = []
+            torch.cuda.synchronize()
 
         def copy_ms(self):
             "mean duration of one step's host-to-device copy on the copy stream (call after a synchronize)"
@@ -330,7 +335,8 @@ def run_b200_arm(a, rank, world, local_rank):
                     copy_stream.wait_event(self.freed[k & 1])
                 begin = torch.cuda.Event(enable_timing=True)
                 begin.record(copy_stream)
-                self.bufs[k & 1] = [t.to(dev, non_blocking=True) for t in self.host]
+                for dst, src in zip(self.bufs[k & 1], self.host):
+                    dst.copy_(src, non_blocking=True)
                 self.ready[k & 1] = torch.cuda.Event(enable_timing=True)
                 self.ready[k & 1].record(copy_stream)
                 self.spans.append((begin, self.ready[k & 1]))
@@ -348,6 +354,7 @@ def run_b200_arm(a, rank, world, local_rank):
             stats[k] = 0 if isinstance(stats[k], int) else 0.0
         for _ in range(a.warmup):
             one_step(tensors, from_host, False)
+        st = Staged(tensors) if from_host else None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -355,7 +362,6 @@ def run_b200_arm(a, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if from_host:
-            st = Staged(tensors)
             st.stage(0)
             for i in range(a.steps):
                 if i + 1 < a.steps:
