@@ -110,14 +110,15 @@ int pdp_edge_aggregate(pdp_ctx* ctx, int32_t by_variable, const float* d_state, 
 /* Dense per-edge layers of the neural model types on the tensor cores (tcgen05.mma kind::tf32, three-term split = fp32
  * accuracy; csrc/pdp_edge_nn.cu).  Context-free.  The rows' input is the concatenation [x1 | x2 | x3] of up to three
  * row-major device arrays (k_i columns each, 0 = unused).  w_img / bias: the weights pre-split and pre-tiled and the padded
- * bias, built once per layer by pdp_solver_b200/nn/tensor_ops.py (n_blk accumulator columns per MMA, n_mma blocks per
- * pass, `passes` passes over K).
+ * bias, built once per layer by pdp_solver_b200/nn/tensor_ops.py (n_blk * n_mma accumulator columns per pass -- a multiple of
+ * 16, at most 256 for the dense layer and 320 for the GRU cell -- and `passes` passes over K).
  * pdp_edge_mlp_forward: out[rows, n_out] = act([x1|x2|x3] W^T + b) * row_mask -- the nn.Linear (+ F.logsigmoid, act = 1) calls
  *   of MessageAggregator.forward, reference pdp/nn/util.py:51-77, and of the classifiers (act = 0).
  * pdp_edge_gru_forward: out[rows, hidden] = torch.nn.GRUCell([x1|x2], h), blended with h where row_mask is 0 -- the two cells of
- *   NeuralDecimator.forward, reference pdp/nn/pdp_decimate.py:51-87.  out must not alias h. */
+ *   NeuralDecimator.forward, reference pdp/nn/pdp_decimate.py:51-87.  A pass holds n_blk * n_mma / 4 hidden units, four
+ *   accumulator columns each (r, z, W_in x, W_hn h of the unit side by side; bias in the same order).  out must not alias h. */
 int pdp_edge_nn_swizzle(void);   /* 1: the weight images use the 64-byte swizzled operand layout (nn/tensor_ops.py follows) */
-int pdp_edge_nn_chunk_k(void);   /* K elements per chunk of the weight images (16 or 32): the host side tiles W accordingly */
+int pdp_edge_nn_chunk_k(void);   /* K elements per chunk of the weight images (16): the host side tiles W accordingly */
 int pdp_edge_mlp_forward(const float* d_x1, int32_t k1, const float* d_x2, int32_t k2, const float* d_x3, int32_t k3, int64_t rows,
                          const float* d_w_img, const float* d_bias, int32_t n_blk, int32_t n_mma, int32_t passes, int32_t n_out,
                          int32_t act, const float* d_row_mask, float* d_out, void* stream);
