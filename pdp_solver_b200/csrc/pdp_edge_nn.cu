@@ -74,6 +74,7 @@ struct EdgeNNArgs {
     const float* h_old;        // GRU: [rows, H] (also source 0 of A)
     float* out;                // [rows, n_out]
     int32_t stages;
+    int32_t out_tile;          // LINEAR: the tile's results are collected in shared memory and leave with one bulk store
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -406,6 +407,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         const bool vec2 = !(P.n_out & 1);
         uint32_t acc_ph[2] = {0u, 0u};
         int ab = 0;
+        // LINEAR: a tile's output rows are consecutive in global memory, so the warps collect them in a shared-memory image of
+        // the tile and one thread sends it off with ONE bulk store (cp.async.bulk.global.shared).  Thread-per-row stores touch
+        // 32 sectors per warp instruction and the L1 tag stage takes them one by one: with the row-strided operand loads
+        // they were what the layer was bound by.
+        const bool otile_on = EPI == EPI_LINEAR && P.out_tile != 0;
+        float* otile = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + kRawBytes);
         auto store16 = [&](float* dst, const float (&y)[16], int nvalid) {      // nvalid of the 16 values exist
             if (vec2 && nvalid == 16) {
 #pragma unroll
@@ -419,6 +426,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             const int64_t row = tile * kTileM + r;
             const bool live = row < P.rows;
             const float mk = (live && P.row_mask) ? __ldg(P.row_mask + row) : 1.f;
+            if (otile_on) {      // the previous tile's bulk store has read the image
+                if (tid == 256) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             for (int p = 0; p < P.passes; ++p) {
                 MB_WAIT_T(&bar_acc_full[ab], acc_ph[ab], 5);
                 acc_ph[ab] ^= 1u;
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                             if (P.row_mask) t *= mk;
                             y[j] = t;
                         }
-                        store16(P.out + row * P.n_out + n0, y, min(16, P.n_out - n0));
+                        store16(otile_on ? otile + (size_t)r * P.n_out + n0 : P.out + row * P.n_out + n0, y, min(16, P.n_out - n0));
                     }
                 } else {
                     // the pass holds hidden units [p * nh, (p + 1) * nh), four columns each: r, z, W_in x, W_hn h of the unit.  A
@@ -502,7 +513,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                 if (lane == 0) mb_arrive(&bar_acc_empty[ab]);
                 ab ^= 1;
             }
+            if (otile_on) {
+                fence_async_smem();                                  // the image was written through the generic proxy
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (tid == 256) {
+                    const int64_t row0 = tile * kTileM;
+                    const int64_t nrow = (P.rows - row0 < kTileM) ? (P.rows - row0) : kTileM;
+                    const uint32_t bytes = (uint32_t)(nrow * P.n_out * 4), b16 = bytes & ~15u;
+                    float* gdst = P.out + row0 * P.n_out;
+                    if (b16) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s_u32(otile)), "r"(b16) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    for (uint32_t i = b16 / 4; i < bytes / 4; ++i) gdst[i] = otile[i];      // (a last tile whose bytes are no multiple of 16)
+                }
+            }
         }
+        if (otile_on && tid == 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -518,7 +543,7 @@ int launch(EdgeNNArgs& P, int epi, cudaStream_t stream) {
         cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { pdp_set_error("pdp_edge_nn: no CUDA device"); return PDP_ERR_CUDA; }
     if (cc < 10) { pdp_set_error("pdp_edge_nn: tcgen05 needs sm_100a"); return PDP_ERR_UNSUPPORTED; }
     const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
-    const size_t smem = stage * P.stages + kRawBytes;
+    const size_t smem = stage * P.stages + kRawBytes + (P.out_tile ? (size_t)kTileM * P.n_out * 4 : 0);
     void* kern = epi == EPI_GRU ? (void*)k_edge_nn<EPI_GRU> : (void*)k_edge_nn<EPI_LINEAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { pdp_set_error("pdp_edge_nn: shared memory %zu: %s", smem, cudaGetErrorString(e)); return PDP_ERR_CUDA; }
@@ -587,6 +612,12 @@ extern "C" int pdp_edge_mlp_forward(const float* x1, int32_t k1, const float* x2
     if (!fill_common(P, x1, k1, x2, k2, x3, k3, rows, w_img, bias, n_blk, n_mma, passes, "pdp_edge_mlp_forward")) return PDP_ERR_ARG;
     if (!out || n_out < 1 || n_out > passes * P.n_tot || P.n_tot > 256) { pdp_set_error("pdp_edge_mlp_forward: bad output shape"); return PDP_ERR_ARG; }
     P.n_out = n_out; P.act = act; P.row_mask = row_mask; P.out = out;
+    {
+        const size_t stage = 2u * kTileM * kChunkK * 4u + 2u * (size_t)P.n_tot * kChunkK * 4u;
+        const char* e = getenv("PDP_B200_NN_OTILE");      // (profiling: 0 = thread-per-row stores)
+        P.out_tile = passes == 1 && !((uintptr_t)out & 15) && stage * P.stages + kRawBytes + (size_t)kTileM * n_out * 4 <= 227 * 1024 &&
+                     !(e && atoi(e) == 0);
+    }
     return launch(P, EPI_LINEAR, (cudaStream_t)stream);
 }
 

@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out; rm -f gpurun_out/tmp.log
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 >> gpurun_out/tmp.log
-timeout 300 python tools/prof_forward.py --module-only --reps 3 2>&1 | tail -7 >> gpurun_out/tmp.log
-timeout 300 python tools/prof_forward.py --reps 2 2>&1 | grep -B1 -A12 "^rep 1" | head -14 >> gpurun_out/tmp.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tensor_core or neural or npdnp" 2>&1 | tail -5 >> gpurun_out/tmp.log
+timeout 120 python tools/prof_edge_nn.py 2>&1 | grep "^E=" | tail -1 >> gpurun_out/tmp.log
+PDP_B200_NN_OTILE=0 timeout 120 python tools/prof_edge_nn.py 2>&1 | grep "^E=" | tail -1 >> gpurun_out/tmp.log
+timeout 300 python tools/prof_neural.py >> gpurun_out/tmp.log 2>&1
 cat gpurun_out/tmp.log
