@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         const int64_t tile_step = (int64_t)gridDim.x * kTileM;
         const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
         const int64_t total = my_tiles * units;
-        const uint32_t raw_sa = s_u32(smem + (size_t)S * stage_bytes) + 8u * (uint32_t)tid;     // slot (level, j) at + 8 * 256 * (4 level + j)
+        // ring level l: two 16-byte slots per thread, slot A of thread t at + 8192 l + 16 t, slot B 4096 further
+        const uint32_t raw_sa = s_u32(smem + (size_t)S * stage_bytes) + 16u * (uint32_t)tid;
         int64_t pf_row = (int64_t)blockIdx.x * kTileM + r;      // prefetch cursor: row of this thread, chunk of the pass, pass
         int pf_c = 0, pf_p = 0;
         const float *rp0 = nullptr, *rp1 = nullptr, *rp2 = nullptr;      // this thread's row in the three sources
@@ -237,22 +238,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             rp2 = P.ks[2] ? P.src[2] + pf_row * P.ks[2] : nullptr;
         };
         row_ptrs();
+        // The thread's 32 bytes are 8-byte aligned.  Where they are 16-byte aligned they go as two 16-byte copies (slot A, slot
+        // B); where not -- every other row of a 600-byte-row tensor -- the aligned middle goes as one 16-byte copy (slot A)
+        // and the two ends as 8-byte copies (the halves of slot B): 2.5 copies per thread and chunk instead of four of 8 bytes
+        // (what the layers wait for is the L1 tag stage taking the threads' sectors one by one).
         auto fetch = [&](int level) {
             if (pf_row < P.rows) {
                 const int2 e = s_cd[half][pf_c];
-                const uint32_t dst = raw_sa + 8u * 256u * 4u * (uint32_t)level;
+                const uint32_t dst = raw_sa + 8192u * (uint32_t)level;
                 if (e.x >= 0) {
                     const float* p = (e.x == 0 ? rp0 : (e.x == 1 ? rp1 : rp2)) + e.y;
-#pragma unroll
-                    for (int j = 0; j < kHalfK / 2; ++j)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * 256u * (uint32_t)j), "l"(p + 2 * j) : "memory");
+                    if (!((uintptr_t)p & 8)) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 4096u), "l"(p + 4) : "memory");
+                    } else {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p + 2) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 4096u), "l"(p) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 4104u), "l"(p + 6) : "memory");
+                    }
                 } else {
                     const int k0 = pf_c * kChunkK + kHalfK * half;
+                    float x[kHalfK];
 #pragma unroll
-                    for (int j = 0; j < kHalfK / 2; ++j) {
-                        const float x0 = a_elem(P, pf_row, k0 + 2 * j), x1 = a_elem(P, pf_row, k0 + 2 * j + 1);
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst + 8u * 256u * (uint32_t)j), "f"(x0), "f"(x1) : "memory");
-                    }
+                    for (int j = 0; j < kHalfK; ++j) x[j] = a_elem(P, pf_row, k0 + j);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4096u), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -262,8 +272,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             }
         };
         for (int d = 0; d < kRawDepth; ++d) fetch(d);        // (groups past the end are empty: the count stays uniform)
-        int64_t c_row = (int64_t)blockIdx.x * kTileM + r;        // consumer cursor
-        int c_u = 0, level = 0;
+        int64_t c_row = (int64_t)blockIdx.x * kTileM + r;        // consumer cursor: row, unit of the tile, chunk of the pass
+        int c_u = 0, c_c = 0, level = 0;
+        // bit 3 of the address of this thread's row in each source (the consumer re-derives which form the copies took)
+        uint32_t par0 = 0, par1 = 0, par2 = 0;
+        auto row_parity = [&]() {
+            par0 = (uint32_t)(((uintptr_t)(P.src[0] + c_row * P.ks[0]) >> 3) & 1);
+            par1 = P.ks[1] ? (uint32_t)(((uintptr_t)(P.src[1] + c_row * P.ks[1]) >> 3) & 1) : 0u;
+            par2 = P.ks[2] ? (uint32_t)(((uintptr_t)(P.src[2] + c_row * P.ks[2]) >> 3) & 1) : 0u;
+        };
+        row_parity();
         // rows of 64 bytes, the 16-byte unit g of row r at unit g ^ ((r >> 1) & 3): Swizzle<2,4,3>
         const uint32_t off0 = (uint32_t)(r * 64 + (((2 * half) ^ ((r >> 1) & 3)) << 4)), off1 = (uint32_t)(r * 64 + (((2 * half + 1) ^ ((r >> 1) & 3)) << 4));
         for (int64_t g0 = 0; g0 < total; ++g0) {
@@ -271,10 +289,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             asm volatile("cp.async.wait_group %0;" ::"n"(kRawDepth - 1) : "memory");
             float v[kHalfK];
             {
-                const uint32_t src = raw_sa + 8u * 256u * 4u * (uint32_t)level;
-#pragma unroll
-                for (int j = 0; j < kHalfK / 2; ++j)
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[2 * j]), "=f"(v[2 * j + 1]) : "r"(src + 8u * 256u * (uint32_t)j) : "memory");
+                const uint32_t src = raw_sa + 8192u * (uint32_t)level;
+                float a[4], bq[4];
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]) : "r"(src) : "memory");
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq[0]), "=f"(bq[1]), "=f"(bq[2]), "=f"(bq[3]) : "r"(src + 4096u) : "memory");
+                const int2 e = s_cd[half][c_c];
+                const bool sh = e.x >= 0 && ((((e.x == 0 ? par0 : (e.x == 1 ? par1 : par2)) + ((uint32_t)e.y >> 1)) & 1u) != 0u);
+                v[0] = sh ? bq[0] : a[0]; v[1] = sh ? bq[1] : a[1];
+                v[2] = sh ? a[0] : a[2];  v[3] = sh ? a[1] : a[3];
+                v[4] = sh ? a[2] : bq[0]; v[5] = sh ? a[3] : bq[1];
+                v[6] = bq[2]; v[7] = bq[3];
             }
             uint4 hi[2], lo[2];
 #pragma unroll
@@ -307,7 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
             NN_PLOG((int)g0, 2);
             if (tid == 0) NN_LOG((int)g0, 1);
             if (++s == S) { s = 0; ph ^= 1u; }
-            if (++c_u == units) { c_u = 0; c_row += tile_step; }
+            if (++c_c == P.k_chunks) c_c = 0;
+            if (++c_u == units) { c_u = 0; c_row += tile_step; row_parity(); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == 17 && lane == 0) {
@@ -410,7 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         // LINEAR: a tile's output rows are consecutive in global memory, so the warps collect them in a shared-memory image of
         // the tile and one thread sends it off with ONE bulk store (cp.async.bulk.global.shared).  Thread-per-row stores touch
         // 32 sectors per warp instruction and the L1 tag stage takes them one by one: with the row-strided operand loads
-        // they were what the layer was bound by.
+        // they were what the layer was bound by (0.66 -> 0.48 ms for 151 -> 100 over 1.2 M rows).  The GRU cell's tile (77 KB)
+        // only fits beside its stages with a shorter copy ring and no L1 to speak of: measured 3.1 ms against 2.6 ms, not done.
         const bool otile_on = EPI == EPI_LINEAR && P.out_tile != 0;
         float* otile = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + kRawBytes);
         auto store16 = [&](float* dst, const float (&y)[16], int nvalid) {      // nvalid of the 16 values exist
