@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t issue_turn;                  // number of the chunk whose MMAs may be issued next
     __shared__ int2 s_cd[2][kMaxChunks];             // per half chunk: {source (-1: element by element), column in it}
-    __shared__ float s_bias[768];                   // the layer's (padded) bias: passes * n_tot values
+    __shared__ __align__(16) float s_bias[768];                   // the layer's (padded) bias: passes * n_tot values
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a broadcast: the compiler treats the role dispatch as warp-uniform)
     const int S = P.stages;
@@ -441,8 +441,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
         float* otile = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + kRawBytes);
         auto store16 = [&](float* dst, const float (&y)[16], int nvalid) {      // nvalid of the 16 values exist
             if (vec2 && nvalid == 16) {
+                if (!((uintptr_t)dst & 15)) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) reinterpret_cast<float2*>(dst)[j] = make_float2(y[2 * j], y[2 * j + 1]);
+                    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) reinterpret_cast<float2*>(dst)[j] = make_float2(y[2 * j], y[2 * j + 1]);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (j < nvalid) dst[j] = y[j];
@@ -467,10 +472,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                         tc_ld16(tlane + (uint32_t)c0, v);
                         const int n0 = p * P.n_tot + c0;
                         if (!live || n0 >= P.n_out) continue;
-                        float y[16];
+                        float y[16], bq[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {      // (n0 is a multiple of 16: 64-byte aligned)
+                            const float4 b4 = reinterpret_cast<const float4*>(s_bias + n0)[j];
+                            bq[4 * j] = b4.x; bq[4 * j + 1] = b4.y; bq[4 * j + 2] = b4.z; bq[4 * j + 3] = b4.w;
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float t = v[j] + s_bias[n0 + j];
+                            float t = v[j] + bq[j];
                             if (P.act == ACT_LOGSIGMOID) t = logsigmoidf(t);
                             if (P.row_mask) t *= mk;
                             y[j] = t;
@@ -502,27 +512,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_nn(const __grid_constant__
                         const int nvalid = min(4, P.n_out - u0);
                         float ho[4], y[4];
                         const float* hp = P.h_old + row * P.n_out + u0;
-                        if (vec2 && nvalid == 4) {
+                        if (vec2 && nvalid == 4) {       // 16-byte aligned in every other row of a 600-byte-row tensor: one access, else two
+                            if (!((uintptr_t)hp & 15)) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(hp));
+                                ho[0] = t4.x; ho[1] = t4.y; ho[2] = t4.z; ho[3] = t4.w;
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 2; ++j) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(hp) + j); ho[2 * j] = t2.x; ho[2 * j + 1] = t2.y; }
+                                for (int j = 0; j < 2; ++j) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(hp) + j); ho[2 * j] = t2.x; ho[2 * j + 1] = t2.y; }
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) ho[j] = j < nvalid ? __ldg(hp + j) : 0.f;
                         }
-                        const float* bg = bs + 16 * grp;
+                        const float4* bg = reinterpret_cast<const float4*>(bs + 16 * grp);      // (n_tot is a multiple of 16: 64-byte aligned)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float rg = sigmoidf_(v[4 * j] + bg[4 * j]);
-                            const float zg = sigmoidf_(v[4 * j + 1] + bg[4 * j + 1]);
-                            const float ng = tanhf_(v[4 * j + 2] + bg[4 * j + 2] + rg * (v[4 * j + 3] + bg[4 * j + 3]));
+                            const float4 b4 = bg[j];
+                            const float rg = sigmoidf_(v[4 * j] + b4.x);
+                            const float zg = sigmoidf_(v[4 * j + 1] + b4.y);
+                            const float ng = tanhf_(v[4 * j + 2] + b4.z + rg * (v[4 * j + 3] + b4.w));
                             float hn = (1.f - zg) * ng + zg * ho[j];
                             if (P.row_mask) hn = mk * hn + (1.f - mk) * ho[j];
                             y[j] = hn;
                         }
                         float* dst = P.out + row * P.n_out + u0;
                         if (vec2 && nvalid == 4) {
-                            reinterpret_cast<float2*>(dst)[0] = make_float2(y[0], y[1]);
-                            reinterpret_cast<float2*>(dst)[1] = make_float2(y[2], y[3]);
+                            if (!((uintptr_t)dst & 15)) {
+                                *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+                            } else {
+                                reinterpret_cast<float2*>(dst)[0] = make_float2(y[0], y[1]);
+                                reinterpret_cast<float2*>(dst)[1] = make_float2(y[2], y[3]);
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) if (j < nvalid) dst[j] = y[j];
