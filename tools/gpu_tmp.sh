@@ -1,14 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out; tag=r2
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2z_tests.log
-cat gpurun_out/r2z_tests.log
-for w in config1 config2; do
-  timeout 900 python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/${tag}_bench_$w.json 2>> gpurun_out/${tag}_bench.err
-  tail -c 200 gpurun_out/${tag}_bench_$w.json
-done
-ncu --set full --clock-control none --import-source on -k regex:k_edge_nn -c 1 -f -o gpurun_out/${tag}_edge_gru \
-    python tools/prof_edge_nn.py 300000 > gpurun_out/${tag}_edge_gru.log 2>&1
-python tools/prof_edge_nn.py > gpurun_out/${tag}_edge_nn_timing.log 2>&1
-tail -4 gpurun_out/${tag}_edge_nn_timing.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+mkdir -p gpurun_out; rm -f gpurun_out/tmp.log
+for st in 2 4; do echo "stages $st" >> gpurun_out/tmp.log; PDP_B200_NN_STAGES=$st timeout 120 python tools/prof_edge_nn.py 2>&1 | grep "^E=" | tail -1 >> gpurun_out/tmp.log; done
+for v in rd8 rd4; do echo "$v" >> gpurun_out/tmp.log; PDP_B200_LIB=$PWD/pdp_solver_b200/csrc/libpdp_b200_alt_$v.so timeout 120 python tools/prof_edge_nn.py 2>&1 | grep "^E=" | tail -1 >> gpurun_out/tmp.log; done
+cat gpurun_out/tmp.log
