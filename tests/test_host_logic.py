@@ -136,3 +136,59 @@ def test_per_problem_max_and_argmax_follow_the_reference_rounding():
     bvm = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2], dtype=torch.int32)
     assert problem_argmax(x, bvm, 3).tolist() == [1, 3, 7]
     assert torch.allclose(problem_max(x, bvm, 3), torch.tensor([0.9, 0.0, 0.7]), atol=1e-6)
+
+
+def _decode_image(image, n_tot):
+    """inverse of nn/tensor_ops._image: [pass, chunk, term, row, unit, j] (64-byte swizzled rows) -> hi + lo as [pass, row, K]"""
+    import torch
+    passes, chunks, terms, rows, units, four = image.shape
+    assert (terms, rows, units, four) == (2, n_tot, 4, 4)
+    n = torch.arange(rows)
+    slot_of_group = torch.arange(4).view(1, 4) ^ ((n >> 1) & 3).view(-1, 1)              # [row, group] -> unit it is stored at
+    idx = slot_of_group.view(1, 1, 1, rows, 4, 1).expand(passes, chunks, 2, rows, 4, 4)
+    groups = torch.gather(image, 4, idx)                                                  # [pass, chunk, term, row, group, j]
+    w = groups.sum(2)                                                                     # hi + lo
+    return w.permute(0, 2, 1, 3, 4).reshape(passes, rows, chunks * 16)
+
+
+def test_tensor_core_weight_images_hold_the_layers_weights():
+    """Host side of the tcgen05 layers (nn/tensor_ops.py), no GPU: the GRU cell's image has four rows per hidden unit
+    (r, z, W_in x, W_hn h) with K ordered [h | x], the dense layer's image is W itself; hi + lo reproduces the fp32 weights
+    to 2^-21, both parts are tf32 numbers, padding is zero."""
+    import torch
+    from pdp_solver_b200.nn import tensor_ops
+    torch.manual_seed(3)
+    cell = torch.nn.GRUCell(151, 150)
+    tg = tensor_ops.TensorGRU(cell)
+    tg._prepare()
+    H, kx = 150, 151
+    assert (tg.passes, tg.n_blk * tg.n_mma) == (2, 304)
+    nh = tg.n_blk * tg.n_mma // 4
+    w = _decode_image(tg.image, 4 * nh)                     # [pass, 4 nh, K padded]
+    wih, whh = cell.weight_ih.detach(), cell.weight_hh.detach()
+    assert ((tg.image.view(torch.int32) & 0x1fff) == 0).all()           # tf32: the low 13 mantissa bits are clear
+    for p in range(tg.passes):
+        for u in (0, 1, 37, nh - 1):
+            unit = p * nh + u
+            rows = w[p, 4 * u: 4 * u + 4]
+            if unit >= H:
+                assert (rows == 0).all()
+                continue
+            want = torch.zeros(4, w.shape[2])
+            for gate in range(2):
+                want[gate, :H] = whh[gate * H + unit]
+                want[gate, H:H + kx] = wih[gate * H + unit]
+            want[2, H:H + kx] = wih[2 * H + unit]
+            want[3, :H] = whh[2 * H + unit]
+            assert torch.allclose(rows, want, rtol=2.0 ** -21, atol=0)
+            assert (rows[:, H + kx:] == 0).all()
+        bias = tg.bias[p]
+        unit = p * nh + 5
+        assert torch.allclose(bias[5], torch.stack((cell.bias_ih[unit] + cell.bias_hh[unit], cell.bias_ih[H + unit] + cell.bias_hh[H + unit],
+                                                    cell.bias_ih[2 * H + unit], cell.bias_hh[2 * H + unit])).detach())
+    lin = torch.nn.Linear(151, 100)
+    tl = tensor_ops.TensorLinear(lin)
+    tl._prepare()
+    wl = _decode_image(tl.image, tl.n_blk)[0]
+    assert tl.n_blk == 112 and torch.allclose(wl[:100, :151], lin.weight.detach(), rtol=2.0 ** -21, atol=0)
+    assert (wl[100:] == 0).all() and (wl[:, 151:] == 0).all() and torch.equal(tl.bias[:100], lin.bias.detach())
