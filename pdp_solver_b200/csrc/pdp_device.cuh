@@ -42,7 +42,6 @@ __device__ __forceinline__ int64_t gthreads() { return (int64_t)gridDim.x * bloc
 // named barriers (ids 1..15; 0 is __syncthreads): producer / consumer hand-over between warp groups
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void group_sync(int bar_id, int n) { if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, n); }
 
 // ------------------------------------------------------------------------------------------------
 // keyed reduction helper.  ACC needs: void reset(); void merge_shfl(unsigned mask) [warp-reduce over
@@ -65,12 +64,10 @@ struct KeyedReducer {
     // the same problem merge in registers and hand their partial to a block-level merge in shared
     // memory (one commit per block and problem run: a 1M-variable problem costs ~600 atomics per
     // pass instead of ~10^5); mixed warps commit per lane group.
-    // bar_id == 0: the whole CTA (__syncthreads); otherwise a named barrier of `gthr` threads whose local
-    // thread index is `t` (a warp group of the pipelined passes)
-    __device__ __forceinline__ void finish(const pdp_state& s, int bar_id = 0, int gthr = 0, int t = -1) {
+    __device__ __forceinline__ void finish(const pdp_state& s) {
         __shared__ ACC sm_acc[32];
         __shared__ int sm_key[32];
-        if (bar_id == 0) { gthr = blockDim.x; t = threadIdx.x; }
+        const int gthr = blockDim.x, t = threadIdx.x;
         const unsigned m = __match_any_sync(0xffffffffu, key);
         const bool uniform = (m == 0xffffffffu);
         const int warp = t >> 5, nwarp = (gthr + 31) >> 5;
@@ -82,7 +79,7 @@ struct KeyedReducer {
             if (lane_id() == (__ffs(m) - 1) && key >= 0) acc.commit(s, key);
             if (lane_id() == 0) sm_key[warp] = -1;
         }
-        group_sync(bar_id, gthr);
+        __syncthreads();
         if (t == 0) {
             int w = 0;
             while (w < nwarp) {
@@ -95,7 +92,7 @@ struct KeyedReducer {
                 w = v;
             }
         }
-        group_sync(bar_id, gthr);
+        __syncthreads();
         key = -1;       // everything has been committed: a later touch() starts from scratch
         acc.reset();
     }

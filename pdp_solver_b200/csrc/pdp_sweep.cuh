@@ -144,7 +144,7 @@ __device__ __forceinline__ BlkStage blk_stage(const BlkGeo& B) {
     return S;
 }
 
-// write-out: slots [wlo, wend) of the block's region (a segment of it); destinations ascend.  One slot per thread and
+// write-out: slots [wlo, wend) of the block's region (all of it); destinations ascend.  One slot per thread and
 // instruction (with several consecutive slots per thread a warp's stores would be strided and every destination sector
 // written several times).  Everything but the store (and the rare sticky re-read) is shared memory, addressed in the shared
 // window: plane_sa = address of slot 0's word (slot w at plane_sa + 4 w), wrun_sa = address of run table word 0 (word i at
