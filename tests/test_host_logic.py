@@ -192,3 +192,25 @@ def test_tensor_core_weight_images_hold_the_layers_weights():
     wl = _decode_image(tl.image, tl.n_blk)[0]
     assert tl.n_blk == 112 and torch.allclose(wl[:100, :151], lin.weight.detach(), rtol=2.0 ** -21, atol=0)
     assert (wl[100:] == 0).all() and (wl[:, 151:] == 0).all() and torch.equal(tl.bias[:100], lin.bias.detach())
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU only: the unmodified reference when it can be loaded, else the C port) prints one
+    JSON line with the bench contract's keys, `impl: reference`, a cpu_baseline describing the run and an e2e object
+    without copies."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "config4",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:
+        pytest.skip("reference arm unavailable: %s" % line["unavailable"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["metric"] == "edge_updates_per_s" and line["value"] > 0 and "workload" in line["config"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
